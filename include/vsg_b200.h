@@ -1,0 +1,146 @@
+/*
+ * vsg_b200.h -- C ABI of the B200-native VidSGG-BIG relation hot path (libvsgb200.so).
+ *
+ * The reference (Dawn-LX/VidSGG-BIG) is pure Python/PyTorch and has no FFI boundary; its
+ * contract for this path is three Python call signatures.  This header
+ * is the boundary the thin Python host layer (vidsgg_big_b200/*.py, ctypes) binds: plain
+ * pointers and sizes, no torch types.  Each entry point names the reference code it replaces
+ * (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - the caller owns every buffer including workspaces; nothing is allocated, nothing
+ *     synchronises, no host callbacks: calls are asynchronous on `stream` and re-entrant
+ *     per stream (the only exception is vsg_gemm_*'s tensor-map cache, guarded by a mutex);
+ *   - return value 0 = launched, <0 = error (see VSG_E_*); vsg_last_error() returns a
+ *     thread-local message for the last failing call;
+ *   - spans are CLOSED [s, e] int64 on the model side (dataloaders/dataloader_vidvrd.py:33-34)
+ *     and HALF-OPEN [s, e) on the evaluation side (VidVRDhelperEvalAPIs/README.md:7-47);
+ *   - track storage is packed/CSR: boxes[sum L][4] f32 xyxy pixels, off[n+1] int64 row offsets.
+ */
+#ifndef VSG_B200_H_
+#define VSG_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define VSG_OK 0
+#define VSG_E_INVALID (-1) /* bad argument (null pointer, negative size, misaligned buffer) */
+#define VSG_E_LAUNCH (-2)  /* CUDA reported an error at launch                               */
+#define VSG_E_UNSUPPORTED (-3)
+
+/* ---- library ---------------------------------------------------------------------------- */
+const char* vsg_last_error(void);
+int vsg_version(void);          /* 100*major + minor */
+int vsg_built_for_sm(void);     /* 100 (sm_100a)     */
+int vsg_device_sm_count(void);  /* multiprocessors of the current device, <0 on error */
+
+/* ---- geometry: pair enumeration, spans, trajectory vIoU ------ */
+
+/* Ordered pairs (s,o), s != o, row-major: replaces Base_C.trajid2pairid
+ * (models/model_pairwise_baseline.py:104-111, tools/train_vidor.py:73-78).
+ * pair_ids_out: int64[n*(n-1)][2]. */
+int vsg_pair_ids(int n, int64_t* pair_ids_out, void* stream);
+
+/* Closed-span intersection (broadcast): replaces utils/utils_func.py:347-373
+ * dura_intersection_ts(d1, d2, broadcast=True).  d1 int64[n1][2], d2 int64[n2][2];
+ * inter_out int64[n1][n2][2] = (max start, min end) -- inverted for non-overlapping pairs,
+ * exactly like the reference; mask_out uint8[n1][n2] = start<=end. */
+int vsg_dura_intersection(const int64_t* d1, int n1, const int64_t* d2, int n2,
+                          int64_t* inter_out, uint8_t* mask_out, void* stream);
+
+/* Same for dtype 0 = int64 / 1 = float32 spans (the grounding stage intersects normalised float spans,
+ * models/grd_model_v5.py:548) and for the element-wise mode broadcast=0 (n1 == n2, outputs [n1][2], [n1]). */
+int vsg_dura_intersection_ex(const void* d1, int n1, const void* d2, int n2, int broadcast, int dtype,
+                             void* inter_out, uint8_t* mask_out, void* stream);
+
+/* Per-track volume sum_f (x2-x1+1)*(y2-y1+1) over the FULL track (utils/utils_func.py:459-460).
+ * vol_out f32[n_tracks]. */
+int vsg_track_volumes(const float* boxes, const int64_t* off, int n_tracks, float* vol_out, void* stream);
+
+/* Batched trajectory-vIoU matrices, one per segment (= video):
+ * replaces the per-pair Python loop around vIoU_ts
+ *   models/model_0v10.py:565-581 (BIG_C.enti_viou_align), tools/train_vidor.py:107-122,
+ *   utils/utils_func.py:437-471 (vIoU_ts) and :347-373 (spans).
+ * Segment v pairs A tracks [segA[v], segA[v+1]) with B tracks [segB[v], segB[v+1]); its
+ * nA_v x nB_v outputs start at seg_out[v] (row-major).  Outputs (any may be NULL):
+ *   spans_out int64[P][2], mask_out uint8[P], viou_out f32[P] (0 where no temporal overlap),
+ *   inter_out f32[P] (raw intersection volume; variant 1 only),
+ * P = seg_out[n_seg].  volA / volB: f32 workspaces of n_tracks_A / n_tracks_B entries
+ * (filled by this call; pass the same pointer twice when A and B are the same table).
+ * variant: 0 = auto, 1 = warp-per-pair streaming kernel (2 = tiled: see vsg_traj_viou_matrix_tiled). */
+int vsg_traj_viou_matrix(const float* boxesA, const int64_t* offA, const int64_t* duraA, int n_tracks_A,
+                         const float* boxesB, const int64_t* offB, const int64_t* duraB, int n_tracks_B,
+                         const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
+                         int64_t n_pairs_total,
+                         int64_t* spans_out, uint8_t* mask_out, float* viou_out, float* inter_out,
+                         float* volA, float* volB, int variant, void* stream);
+
+/* Shared-memory tiled variant of vsg_traj_viou_matrix (same outputs).  n_tiles = sum over segments of
+ * ceil(nA_v/32)*ceil(nB_v/32); tile_off_ws: int64[n_seg+1] workspace. */
+int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* offA, const int64_t* duraA, int n_tracks_A,
+                               const float* boxesB, const int64_t* offB, const int64_t* duraB, int n_tracks_B,
+                               const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
+                               int64_t n_pairs_total, int64_t n_tiles,
+                               int64_t* spans_out, uint8_t* mask_out, float* viou_out,
+                               float* volA, float* volB, int64_t* tile_off_ws, void* stream);
+
+/* Base-C label assignment on top of a vIoU matrix: replaces the triple Python loop of
+ * tools/train_vidor.py:143-159.  viou f32[n][n_gt_traj]; gt_so int64[n_gt_pred][2] (GT subject /
+ * object track ids); labels_out uint8[n_gt_pred][n*(n-1)] in vsg_pair_ids order:
+ * 1 iff viou[s][gs] > th && viou[o][go] > th. */
+int vsg_pair_labels(const float* viou, int n, int n_gt_traj, const int64_t* gt_so, int n_gt_pred,
+                    float th, uint8_t* labels_out, void* stream);
+
+/* ---- evaluation: relation vIoU + greedy matching ---------------- */
+
+/* One packed evaluation problem over n_vid videos.  A "relation" is a row
+ * (triplet[3], sub_track, obj_track, start, end) with a HALF-OPEN duration; its two
+ * trajectories are the slices [start, end) of tracks in a track table
+ * (boxes[sum L][4], off[n_tracks+1], tstart[n_tracks] = first frame of each track).
+ * box_f64 = 0: boxes are f32, 1: boxes are f64 (dict path, arbitrary Python floats).
+ * All accumulation is f64 (the reference is Python float, common.py:65-106). */
+typedef struct VsgRelTable {
+  const void* boxes;        /* f32 or f64 [sum L][4]                                    */
+  const int64_t* off;       /* [n_tracks+1]                                             */
+  const int64_t* tstart;    /* [n_tracks]                                               */
+  const int64_t* rel;       /* [n_rel][7] = s_cat, p_cat, o_cat, sub_track, obj_track, start, end */
+  const int64_t* vid_off;   /* [n_vid+1] relation ranges per video                      */
+  int64_t n_rel;
+  int box_f64;
+  int vol_full_track;       /* 1: volumes over the relation's whole tracks (dict path: every relation owns its two
+                               lists, common.py:100-105); 0: over the [start,end) slice of shared tracks          */
+} VsgRelTable;
+
+/* Replaces eval_detection_scores / eval_detection_scores_v2
+ * (VidVRDhelperEvalAPIs/visual_relation_detection.py:7-34, :124-156) and common.viou
+ * (common.py:65-106) for all videos in one call:
+ *   1. stable descending sort of each video's predictions by score  -> order_out int32[n_pred]
+ *      (position k of video v holds the prediction index, local to the video, ranked k);
+ *   2. ov[p][g] = min(viou(sub), viou(obj)) for equal triplets, f64   -> ov_ws f64[sum n_pred_v*n_gt_v]
+ *      (ov_off int64[n_vid+1] gives each video's offset; -1 where triplets differ);
+ *   3. greedy assignment in rank order: >= thr and strictly better than the running max,
+ *      first GT wins ties, each GT consumed once
+ *      -> hit_out f64[n_pred] in rank order (score or -inf), gt2det_out int32[n_gt] (rank or -1).
+ * scores: f64[n_pred] (prediction scores, the sort key). */
+int vsg_rel_viou_match(const VsgRelTable* pred, const double* scores, const VsgRelTable* gt, int n_vid,
+                       const int64_t* ov_off, double thr,
+                       int32_t* order_out, double* ov_ws, double* hit_out, int32_t* gt2det_out,
+                       double* vol_pred_ws /* [n_pred][2] */, double* vol_gt_ws /* [n_gt][2] */,
+                       uint8_t* taken_ws /* [n_gt] */, void* stream);
+
+/* common.viou for a list of independent (traj_1, dur_1, traj_2, dur_2) problems, f64 boxes:
+ * boxes1/boxes2 f64 [sum len][4], off1/off2 int64[n+1], dur1/dur2 int64[n][2] half-open;
+ * out f64[n]. */
+int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t* dur1,
+                       const double* boxes2, const int64_t* off2, const int64_t* dur2,
+                       int n, double* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* VSG_B200_H_ */

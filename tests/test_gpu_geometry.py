@@ -1,0 +1,158 @@
+"""GPU parity: geometry kernels (C ABI) vs the oracle and the reference's golden outputs."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import geometry as og
+from vidsgg_big_b200 import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _geo():
+    from vidsgg_big_b200 import geometry
+    return geometry
+
+
+def test_pair_ids_bit_exact(golden):
+    g = _geo()
+    assert np.array_equal(g.trajid2pairid(7, DEV).cpu().numpy(), golden("geometry")["pair_ids_7"])
+    for n in (0, 1, 2, 3, 50, 181):
+        assert torch.equal(g.trajid2pairid(n, DEV).cpu(), og.pair_ids(n))
+
+
+def test_spans_bit_exact(golden):
+    g = _geo()
+    gg = golden("geometry")
+    rng = np.random.default_rng(11)
+    s = rng.integers(0, 200, size=(23, 1)); d1 = np.concatenate([s, s + rng.integers(0, 120, size=(23, 1))], 1)
+    s = rng.integers(0, 200, size=(17, 1)); d2 = np.concatenate([s, s + rng.integers(0, 120, size=(17, 1))], 1)
+    t1, t2 = torch.from_numpy(d1).to(DEV), torch.from_numpy(d2).to(DEV)
+    inter, mask = g.dura_intersection_ts(t1, t2)
+    assert inter.dtype == torch.long and mask.dtype == torch.bool
+    assert np.array_equal(inter.cpu().numpy(), gg["dura_inter"]) and np.array_equal(mask.cpu().numpy(), gg["dura_mask"])
+    inter, mask = g.dura_intersection_ts(t1[:17], t2, broadcast=False)
+    assert np.array_equal(inter.cpu().numpy(), gg["dura_inter_nb"]) and np.array_equal(mask.cpu().numpy(), gg["dura_mask_nb"])
+    k = torch.tensor([[0, 10], [5, 20], [30, 40]], device=DEV)
+    ki, km = g.dura_intersection_ts(k, k)
+    assert ki[0, 2].tolist() == [30, 10] and not bool(km[0, 2])        # inverted span kept, like the reference
+    # float spans (grounding), large int64 values
+    f1, f2 = (t1.float() / 320), (t2.float() / 320)
+    fi, fm = g.dura_intersection_ts(f1, f2)
+    oi, om = og.dura_intersection(f1.cpu(), f2.cpu())
+    assert torch.equal(fi.cpu(), oi) and torch.equal(fm.cpu(), om)
+    big = torch.tensor([[2**40, 2**40 + 5], [2**40 + 3, 2**41]], device=DEV)
+    bi, bm = g.dura_intersection_ts(big, big)
+    oi, om = og.dura_intersection(big.cpu(), big.cpu())
+    assert torch.equal(bi.cpu(), oi) and torch.equal(bm.cpu(), om)
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_viou_matrix_golden(golden, variant):
+    g = _geo()
+    gg = golden("geometry")
+    for tag, seed, n, vl in (("a", 101, 12, 160), ("b", 102, 20, 90)):
+        P = synth.make_proposal(seed, n, vl, 8, 36, with_features=False).to(DEV)
+        G = synth.make_gt_graph(seed, P, 133).to(DEV)
+        for side, (bx, du) in (("pp", (P.bboxes_list, P.traj_durations)), ("pg", (G.traj_bboxes, G.traj_durations))):
+            viou, inter, mask = g.traj_viou_matrix(P.bboxes_list, P.traj_durations, bx, du, variant=variant)
+            ref = gg["viou_%s_%s" % (side, tag)]
+            np.testing.assert_allclose(viou.cpu().numpy(), ref, rtol=1e-5, atol=1e-7)     # north_star: fp32 vIoU <= 1e-5 rel
+            assert np.array_equal(inter.cpu().numpy(), gg["inter_%s_%s" % (side, tag)])  # spans bit-exact
+            assert np.array_equal(mask.cpu().numpy(), ref_mask(gg["inter_%s_%s" % (side, tag)]))
+            assert np.all(viou.cpu().numpy()[~mask.cpu().numpy()] == 0.0)
+
+
+def ref_mask(inter):
+    return inter[..., 0] <= inter[..., 1]
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_viou_batched_ragged(variant):
+    """Several videos (ragged, incl. a 1-track video and a single-frame track) in one launch vs the oracle."""
+    g = _geo()
+    props, gts = [], []
+    for sd, n, vl in ((1, 33, 300), (2, 1, 40), (3, 70, 200), (4, 5, 17), (5, 40, 1200)):
+        P = synth.make_proposal(sd, n, vl, 8, 36, with_features=False, min_len=1)
+        props.append(P)
+        gts.append(synth.make_gt_graph(sd, P, 133))
+    A = g.TrackTable.from_containers([p.to(DEV) for p in props])
+    B = g.TrackTable.from_containers([x.to(DEV) for x in gts])
+    for X, Y, ylist in ((A, A, props), (A, B, gts)):
+        viou, spans, mask, seg, _ = g.traj_viou_batched(X, Y, variant=variant)
+        viou, spans, mask = viou.cpu(), spans.cpu(), mask.cpu()
+        for v, P in enumerate(props):
+            Q = ylist[v]
+            P.to("cpu"); Q.to("cpu")
+            qb = Q.bboxes_list if hasattr(Q, "bboxes_list") else Q.traj_bboxes
+            o_v, o_i, o_m = og.traj_viou_matrix(P.bboxes_list, P.traj_durations, qb, Q.traj_durations)
+            sl = slice(seg[v], seg[v + 1])
+            np.testing.assert_allclose(viou[sl].numpy(), o_v.reshape(-1).numpy(), rtol=1e-5, atol=1e-7)
+            assert torch.equal(spans[sl], o_i.reshape(-1, 2)) and torch.equal(mask[sl].bool(), o_m.reshape(-1))
+
+
+@pytest.mark.parametrize("variant", [1, 2])
+def test_viou_properties_large(variant):
+    """Stress-shaped (scaled) input: size-independent properties -- symmetry, diagonal == 1, range, agreement
+    between the two kernel variants, and a sampled comparison with the numpy oracle."""
+    g = _geo()
+    P = synth.make_proposal(9, 96, 4000, 8, 36, with_features=False, min_len=800).to(DEV)
+    T = g.TrackTable.from_containers([P])
+    viou, spans, mask, seg, _ = g.traj_viou_batched(T, T, variant=variant)
+    n = P.num_proposals
+    V = viou.view(n, n)
+    assert torch.allclose(V, V.t(), rtol=1e-6, atol=0)
+    assert torch.allclose(torch.diagonal(V), torch.ones(n, device=DEV), rtol=1e-6)
+    assert bool((V >= 0).all()) and bool((V <= 1 + 1e-6).all())
+    other, _, _, _, _ = g.traj_viou_batched(T, T, variant=3 - variant)
+    assert torch.allclose(viou, other, rtol=2e-6, atol=1e-9)
+    # sampled oracle rows
+    bx = P.bboxes.cpu().numpy(); du = P.traj_durations.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(P.lengths.numpy())])
+    rows = [0, 17, 95]
+    sub_off = np.concatenate([[0], np.cumsum([off[r + 1] - off[r] for r in rows])])
+    sub_bx = np.concatenate([bx[off[r]:off[r + 1]] for r in rows], 0)
+    ref = og.traj_viou_matrix_np(sub_bx, sub_off, du[rows], bx, off, du)
+    np.testing.assert_allclose(V[rows].cpu().numpy(), ref, rtol=1e-5, atol=1e-7)
+
+
+def test_vIoU_ts_single_pair():
+    g = _geo()
+    P = synth.make_proposal(21, 6, 80, 8, 36, with_features=False)
+    inter, mask = og.dura_intersection(P.traj_durations, P.traj_durations)
+    bl = P.bboxes_list
+    done = 0
+    for a in range(6):
+        for b in range(6):
+            if a == b or not mask[a, b]:
+                continue
+            ra = inter[a, b] - P.traj_durations[a, 0]; rb = inter[a, b] - P.traj_durations[b, 0]
+            ref = og.viou_single(bl[a], bl[b], ra, rb)
+            got = g.vIoU_ts(bl[a].to(DEV), bl[b].to(DEV), ra.to(DEV), rb.to(DEV))
+            assert abs(got.item() - ref.item()) <= 1e-5 * abs(ref.item()) + 1e-8
+            done += 1
+    assert done > 0
+
+
+def test_align_and_pair_labels(golden):
+    g = _geo()
+    ga = golden("align")
+    cfg = synth.tiny_vidvrd_config()
+    for sd in (401, 402, 403):
+        P = synth.make_proposal(sd, 14, 120, 8, cfg["num_enti_cats"], with_features=False)
+        G = synth.make_gt_graph(sd, P, cfg["num_pred_cats"], n_rel=(3, 12))
+        aligned, viou = g.enti_viou_align(G.adj_matrix.to(DEV), P.to(DEV), G.to(DEV), 0.5)
+        np.testing.assert_allclose(viou.cpu().numpy(), ga["viou_%d" % sd], rtol=1e-5, atol=1e-7)
+        assert np.array_equal(aligned.cpu().numpy(), ga["align_%d" % sd])
+        so = torch.argmax(G.adj_matrix, dim=-1).t().contiguous()
+        lab = g.pair_labels(viou, so, 0.5)
+        ref = og.pair_labels(torch.from_numpy(ga["viou_%d" % sd]), so.cpu(), 0.5)
+        assert torch.equal(lab.cpu(), ref)
+
+
+def test_errors_are_loud():
+    g = _geo()
+    from vidsgg_big_b200._cabi import VsgError
+    with pytest.raises(VsgError):
+        g.dura_intersection_ts(torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2, dtype=torch.long))   # CPU tensors

@@ -1,0 +1,90 @@
+"""ctypes binding of libvsgb200.so (include/vsg_b200.h).
+
+There is deliberately NO CPU fallback: if the library cannot be loaded or a call fails, the
+caller gets an exception.  Tensors are passed as raw device pointers (``tensor.data_ptr()``)
+plus the current CUDA stream; PyTorch is used only for device memory and streams.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libvsgb200.so")
+
+_lib: Optional[C.CDLL] = None
+
+p = C.c_void_p
+i32, i64, f32, f64 = C.c_int, C.c_int64, C.c_float, C.c_double
+
+
+class VsgRelTable(C.Structure):
+    _fields_ = [("boxes", p), ("off", p), ("tstart", p), ("rel", p), ("vid_off", p), ("n_rel", i64), ("box_f64", i32),
+                ("vol_full_track", i32)]
+
+
+class VsgError(RuntimeError):
+    pass
+
+
+# name -> (restype, argtypes); must list every symbol declared in include/vsg_b200.h
+SIGNATURES = {
+    "vsg_last_error": (C.c_char_p, []),
+    "vsg_version": (i32, []),
+    "vsg_built_for_sm": (i32, []),
+    "vsg_device_sm_count": (i32, []),
+    "vsg_pair_ids": (i32, [i32, p, p]),
+    "vsg_dura_intersection": (i32, [p, i32, p, i32, p, p, p]),
+    "vsg_track_volumes": (i32, [p, p, i32, p, p]),
+    "vsg_dura_intersection_ex": (i32, [p, i32, p, i32, i32, i32, p, p, p]),
+    "vsg_traj_viou_matrix": (i32, [p, p, p, i32, p, p, p, i32, p, p, p, i32, i64, p, p, p, p, p, p, i32, p]),
+    "vsg_traj_viou_matrix_tiled": (i32, [p, p, p, i32, p, p, p, i32, p, p, p, i32, i64, i64, p, p, p, p, p, p, p]),
+    "vsg_pair_labels": (i32, [p, i32, i32, p, i32, f32, p, p]),
+    "vsg_rel_viou_match": (i32, [C.POINTER(VsgRelTable), p, C.POINTER(VsgRelTable), i32, p, f64, p, p, p, p, p, p, p, p]),
+    "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
+}
+
+
+def lib() -> C.CDLL:
+    """Load (once) and return the library; raises if it is missing -- there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise VsgError("libvsgb200.so is not built (%s); run `python -m vidsgg_big_b200.build` -- "
+                           "this package has no CPU fallback" % LIB_PATH)
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        raise VsgError("%s failed (%d): %s" % (what, rc, lib().vsg_last_error().decode()))
+
+
+def ptr(t: Optional[torch.Tensor]):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise VsgError("expected a CUDA tensor (no CPU fallback); got device %s" % t.device)
+    if not t.is_contiguous():
+        raise VsgError("expected a contiguous tensor")
+    return C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(device=None):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise VsgError("vidsgg_big_b200 runs on CUDA tensors only (no CPU fallback); got %s" % t.device)

@@ -1,0 +1,433 @@
+// Geometry kernels: pair enumeration, span intersection, trajectory volume IoU.
+// SURVEY.md section 8a rows A2 (utils/utils_func.py:347-373), A3 (model_pairwise_baseline.py:104-111),
+// A4 (utils/utils_func.py:437-471 + the per-pair loop models/model_0v10.py:565-581),
+// A9 (tools/train_vidor.py:143-159).
+//
+// Data layout in HBM: tracks are packed CSR -- boxes[sum L][4] f32 (one float4 per frame, 16-byte
+// aligned), off[n+1] int64 -- so one warp reads 32 consecutive frames of a track as one 512-byte
+// coalesced request.  Every track of a video lives on the same absolute frame axis, so the overlap of
+// tracks a and b is frames [max(sa,sb), min(ea,eb)] at rows off[a] + f - sa and off[b] + f - sb.
+#include "common.cuh"
+
+namespace vsg {
+
+// ------------------------------------------------------------------------------------------
+__global__ void pair_ids_kernel(int n, int64_t* __restrict__ out) {
+  const int64_t total = (int64_t)n * (n - 1);
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t s = k / (n - 1);
+    const int64_t r = k - s * (n - 1);
+    const int64_t o = r + (r >= s ? 1 : 0);
+    reinterpret_cast<longlong2*>(out)[k] = make_longlong2(s, o);
+  }
+}
+
+__global__ void dura_intersection_kernel(const int64_t* __restrict__ d1, int n1, const int64_t* __restrict__ d2, int n2,
+                                         int64_t* __restrict__ inter, uint8_t* __restrict__ mask) {
+  const int64_t total = (int64_t)n1 * n2;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(k / n2), j = (int)(k - (int64_t)i * n2);
+    const longlong2 a = reinterpret_cast<const longlong2*>(d1)[i];
+    const longlong2 b = reinterpret_cast<const longlong2*>(d2)[j];
+    const int64_t s = a.x > b.x ? a.x : b.x;
+    const int64_t e = a.y < b.y ? a.y : b.y;
+    if (inter) reinterpret_cast<longlong2*>(inter)[k] = make_longlong2(s, e);
+    if (mask) mask[k] = (s <= e) ? 1 : 0;
+  }
+}
+
+template <typename T>
+__global__ void dura_intersection_generic_kernel(const T* __restrict__ d1, int n1, const T* __restrict__ d2, int n2, int broadcast,
+                                                 T* __restrict__ inter, uint8_t* __restrict__ mask) {
+  const int64_t total = broadcast ? (int64_t)n1 * n2 : n1;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int i = broadcast ? (int)(k / n2) : (int)k, j = broadcast ? (int)(k - (int64_t)i * n2) : (int)k;
+    const T s = d1[2 * i] > d2[2 * j] ? d1[2 * i] : d2[2 * j];
+    const T e = d1[2 * i + 1] < d2[2 * j + 1] ? d1[2 * i + 1] : d2[2 * j + 1];
+    if (inter) { inter[2 * k] = s; inter[2 * k + 1] = e; }
+    if (mask) mask[k] = (s <= e) ? 1 : 0;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Track volumes: one warp per track, float4 loads, chunked fp32 partials folded into fp64.
+__global__ void track_volume_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ off, int n_tracks,
+                                    float* __restrict__ vol) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int n_warps = (gridDim.x * blockDim.x) >> 5;
+  for (int t = warp; t < n_tracks; t += n_warps) {
+    const int64_t b = off[t], e = off[t + 1];
+    double acc = 0.0;
+    for (int64_t base = b; base < e; base += 32 * 8) {
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int64_t r = base + u * 32 + lane;
+        if (r < e) {
+          const float4 x = ldg_stream(boxes + r);
+          part += (x.z - x.x + 1.0f) * (x.w - x.y + 1.0f);
+        }
+      }
+      acc += (double)part;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) vol[t] = (float)acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 1: one warp per (a, b) pair; lanes stride the overlap.  Reads 32 bytes per overlapping
+// frame-pair (the "algorithmic bytes" of SURVEY 8d); tracks of a video are re-read from L2.
+__device__ __forceinline__ float inter_area(const float4 a, const float4 b) {
+  const float w = fmaxf((fminf(a.z, b.z) - fmaxf(a.x, b.x)) + 1.0f, 0.0f);
+  const float h = fmaxf((fminf(a.w, b.w) - fmaxf(a.y, b.y)) + 1.0f, 0.0f);
+  return w * h;
+}
+
+__global__ void __launch_bounds__(256)
+traj_viou_warp_kernel(const float4* __restrict__ boxesA, const int64_t* __restrict__ offA, const int64_t* __restrict__ duraA,
+                      const float4* __restrict__ boxesB, const int64_t* __restrict__ offB, const int64_t* __restrict__ duraB,
+                      const int32_t* __restrict__ segA, const int32_t* __restrict__ segB,
+                      const int64_t* __restrict__ seg_out, int n_seg, int64_t n_pairs,
+                      const float* __restrict__ volA, const float* __restrict__ volB,
+                      int64_t* __restrict__ spans, uint8_t* __restrict__ mask, float* __restrict__ viou,
+                      float* __restrict__ inter_out) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t p = warp; p < n_pairs; p += n_warps) {
+    const int v = find_segment(seg_out, n_seg, p);
+    const int nB = segB[v + 1] - segB[v];
+    const int64_t local = p - seg_out[v];
+    const int ia = segA[v] + (int)(local / nB);
+    const int ib = segB[v] + (int)(local % nB);
+    const longlong2 da = reinterpret_cast<const longlong2*>(duraA)[ia];
+    const longlong2 db = reinterpret_cast<const longlong2*>(duraB)[ib];
+    const int64_t s = da.x > db.x ? da.x : db.x;
+    const int64_t e = da.y < db.y ? da.y : db.y;
+    if (lane == 0) {
+      if (spans) reinterpret_cast<longlong2*>(spans)[p] = make_longlong2(s, e);
+      if (mask) mask[p] = (s <= e) ? 1 : 0;
+    }
+    if (!viou && !inter_out) continue;
+    if (s > e) {
+      if (lane == 0) {
+        if (viou) viou[p] = 0.0f;
+        if (inter_out) inter_out[p] = 0.0f;
+      }
+      continue;
+    }
+    const float4* pa = boxesA + offA[ia] + (s - da.x);
+    const float4* pb = boxesB + offB[ib] + (s - db.x);
+    const int64_t len = e - s + 1;
+    double acc = 0.0;
+    for (int64_t base = 0; base < len; base += 32 * 4) {
+      float4 a[4], b[4];
+      bool ok[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int64_t f = base + u * 32 + lane;
+        ok[u] = f < len;
+        if (ok[u]) {
+          a[u] = ldg_stream(pa + f);
+          b[u] = ldg_stream(pb + f);
+        }
+      }
+      float part = 0.f;
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (ok[u]) part += inter_area(a[u], b[u]);
+      acc += (double)part;
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      const float it = (float)acc;
+      if (viou) viou[p] = it / (volA[ia] + volB[ib] - it);
+      if (inter_out) inter_out[p] = it;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Variant 2: shared-memory tiled kernel for long, densely overlapping tracks (VidOR / stress shapes).
+// A CTA owns a TA x TB block of one segment's pair matrix and walks the block's time range in
+// windows of W frames.  Each window stages the TA + TB track slices once (frames where a track is
+// absent are filled with an empty box that intersects nothing), then every thread accumulates a
+// RA x RB register block of pairs: per frame RA + RB 128-bit shared loads feed RA*RB pairs, so HBM/L2
+// sees each box once per tile instead of once per pair.
+constexpr int T2_TA = 32, T2_TB = 32, T2_RA = 4, T2_RB = 4, T2_W = 32;
+constexpr int T2_THREADS = (T2_TA / T2_RA) * (T2_TB / T2_RB);  // 64
+constexpr int T2_PITCH = T2_W + 1;                             // float4 pitch: conflict-free 128-bit reads
+
+struct TileJob { int seg, a0, b0; };
+
+__global__ void __launch_bounds__(T2_THREADS)
+traj_viou_tile_kernel(const float4* __restrict__ boxesA, const int64_t* __restrict__ offA, const int64_t* __restrict__ duraA,
+                      const float4* __restrict__ boxesB, const int64_t* __restrict__ offB, const int64_t* __restrict__ duraB,
+                      const int32_t* __restrict__ segA, const int32_t* __restrict__ segB,
+                      const int64_t* __restrict__ seg_out, const int64_t* __restrict__ tile_off, int n_seg, int64_t n_tiles,
+                      const float* __restrict__ volA, const float* __restrict__ volB,
+                      int64_t* __restrict__ spans, uint8_t* __restrict__ mask, float* __restrict__ viou) {
+  __shared__ float4 sA[T2_TA * T2_PITCH];
+  __shared__ float4 sB[T2_TB * T2_PITCH];
+  __shared__ long long sStart[T2_TA + T2_TB], sEnd[T2_TA + T2_TB], sRow[T2_TA + T2_TB];
+  __shared__ long long sRange[2];
+  const int tid = threadIdx.x;
+  const int ta = tid / (T2_TB / T2_RB), tb = tid % (T2_TB / T2_RB);
+  const float4 EMPTY = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+
+  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    const int v = find_segment(tile_off, n_seg, tile);
+    const int nA = segA[v + 1] - segA[v], nB = segB[v + 1] - segB[v];
+    const int tilesB = (nB + T2_TB - 1) / T2_TB;
+    const int64_t lt = tile - tile_off[v];
+    const int a0 = (int)(lt / tilesB) * T2_TA, b0 = (int)(lt % tilesB) * T2_TB;
+    __syncthreads();  // previous tile finished with smem
+    if (tid < T2_TA + T2_TB) {
+      const bool isA = tid < T2_TA;
+      const int loc = isA ? a0 + tid : b0 + (tid - T2_TA);
+      const bool valid = loc < (isA ? nA : nB);
+      long long s = 1, e = 0, row = 0;
+      if (valid) {
+        const int g = (isA ? segA[v] : segB[v]) + loc;
+        const longlong2 d = reinterpret_cast<const longlong2*>(isA ? duraA : duraB)[g];
+        s = d.x; e = d.y; row = (isA ? offA : offB)[g];
+      }
+      sStart[tid] = s; sEnd[tid] = e; sRow[tid] = row;
+    }
+    __syncthreads();
+    if (tid == 0) {
+      // time range where at least one A track and one B track of the tile exist
+      long long as = LLONG_MAX, ae = LLONG_MIN, bs = LLONG_MAX, be = LLONG_MIN;
+      for (int i = 0; i < T2_TA; ++i) if (sStart[i] <= sEnd[i]) { as = min(as, sStart[i]); ae = max(ae, sEnd[i]); }
+      for (int i = T2_TA; i < T2_TA + T2_TB; ++i) if (sStart[i] <= sEnd[i]) { bs = min(bs, sStart[i]); be = max(be, sEnd[i]); }
+      sRange[0] = max(as, bs); sRange[1] = min(ae, be);
+    }
+    __syncthreads();
+    const long long f_lo = sRange[0], f_hi = sRange[1];
+    float acc[T2_RA][T2_RB];
+    double dacc[T2_RA][T2_RB];
+#pragma unroll
+    for (int i = 0; i < T2_RA; ++i)
+#pragma unroll
+      for (int j = 0; j < T2_RB; ++j) { acc[i][j] = 0.f; dacc[i][j] = 0.0; }
+
+    int win = 0;
+    for (long long f0 = f_lo; f0 <= f_hi; f0 += T2_W, ++win) {
+      __syncthreads();
+      // stage: (TA+TB) tracks x W frames; consecutive threads take consecutive frames of one track
+      for (int idx = tid; idx < (T2_TA + T2_TB) * T2_W; idx += T2_THREADS) {
+        const int trk = idx / T2_W, fo = idx % T2_W;
+        const long long f = f0 + fo;
+        float4 val = EMPTY;
+        if (f >= sStart[trk] && f <= sEnd[trk]) {
+          const float4* src = (trk < T2_TA ? boxesA : boxesB) + sRow[trk] + (f - sStart[trk]);
+          val = ldg_stream(src);
+        }
+        if (trk < T2_TA) sA[trk * T2_PITCH + fo] = val; else sB[(trk - T2_TA) * T2_PITCH + fo] = val;
+      }
+      __syncthreads();
+#pragma unroll 4
+      for (int fo = 0; fo < T2_W; ++fo) {
+        float4 a[T2_RA], b[T2_RB];
+#pragma unroll
+        for (int i = 0; i < T2_RA; ++i) a[i] = sA[(ta * T2_RA + i) * T2_PITCH + fo];
+#pragma unroll
+        for (int j = 0; j < T2_RB; ++j) b[j] = sB[(tb * T2_RB + j) * T2_PITCH + fo];
+#pragma unroll
+        for (int i = 0; i < T2_RA; ++i)
+#pragma unroll
+          for (int j = 0; j < T2_RB; ++j) acc[i][j] += inter_area(a[i], b[j]);
+      }
+      if ((win & 7) == 7) {  // fold fp32 partials (<= 256 frames) into fp64
+#pragma unroll
+        for (int i = 0; i < T2_RA; ++i)
+#pragma unroll
+          for (int j = 0; j < T2_RB; ++j) { dacc[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
+      }
+    }
+    // epilogue
+#pragma unroll
+    for (int i = 0; i < T2_RA; ++i) {
+      const int la = ta * T2_RA + i;
+      if (a0 + la >= nA) continue;
+#pragma unroll
+      for (int j = 0; j < T2_RB; ++j) {
+        const int lb = tb * T2_RB + j;
+        if (b0 + lb >= nB) continue;
+        const long long s = max(sStart[la], sStart[T2_TA + lb]);
+        const long long e = min(sEnd[la], sEnd[T2_TA + lb]);
+        const int64_t p = seg_out[v] + (int64_t)(a0 + la) * nB + (b0 + lb);
+        if (spans) reinterpret_cast<longlong2*>(spans)[p] = make_longlong2(s, e);
+        if (mask) mask[p] = (s <= e) ? 1 : 0;
+        if (viou) {
+          float r = 0.f;
+          if (s <= e) {
+            const float it = (float)(dacc[i][j] + (double)acc[i][j]);
+            r = it / (volA[segA[v] + a0 + la] + volB[segB[v] + b0 + lb] - it);
+          }
+          viou[p] = r;
+        }
+      }
+    }
+  }
+}
+
+// prefix of per-segment tile counts (tiny: one thread; n_seg <= a few thousand)
+__global__ void tile_offsets_kernel(const int32_t* __restrict__ segA, const int32_t* __restrict__ segB, int n_seg,
+                                    int64_t* __restrict__ tile_off) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    int64_t acc = 0;
+    for (int v = 0; v < n_seg; ++v) {
+      tile_off[v] = acc;
+      const int nA = segA[v + 1] - segA[v], nB = segB[v + 1] - segB[v];
+      acc += (int64_t)((nA + T2_TA - 1) / T2_TA) * ((nB + T2_TB - 1) / T2_TB);
+    }
+    tile_off[n_seg] = acc;
+  }
+}
+
+__global__ void pair_labels_kernel(const float* __restrict__ viou, int n, int n_gt_traj, const int64_t* __restrict__ gt_so,
+                                   int n_gt_pred, float th, uint8_t* __restrict__ out) {
+  const int64_t n_pairs = (int64_t)n * (n - 1);
+  const int64_t total = n_pairs * n_gt_pred;
+  for (int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; k < total; k += (int64_t)gridDim.x * blockDim.x) {
+    const int g = (int)(k / n_pairs);
+    const int64_t pr = k - (int64_t)g * n_pairs;
+    const int s = (int)(pr / (n - 1));
+    const int r = (int)(pr - (int64_t)s * (n - 1));
+    const int o = r + (r >= s ? 1 : 0);
+    const int gs = (int)gt_so[2 * g], go = (int)gt_so[2 * g + 1];
+    out[k] = (viou[(int64_t)s * n_gt_traj + gs] > th && viou[(int64_t)o * n_gt_traj + go] > th) ? 1 : 0;
+  }
+}
+
+static inline int grid_for(int64_t work_items, int threads, int per_sm) {
+  const int64_t blocks = (work_items + threads - 1) / threads;
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" int vsg_pair_ids(int n, int64_t* out, void* stream) {
+  VSG_REQUIRE(n >= 0, "vsg_pair_ids: n < 0");
+  if (n < 2) return VSG_OK;
+  VSG_REQUIRE(out != nullptr && aligned16(out), "vsg_pair_ids: out must be a 16-byte aligned device pointer");
+  pair_ids_kernel<<<grid_for((int64_t)n * (n - 1), 256, 8), 256, 0, (cudaStream_t)stream>>>(n, out);
+  return check_launch("vsg_pair_ids");
+}
+
+extern "C" int vsg_dura_intersection(const int64_t* d1, int n1, const int64_t* d2, int n2, int64_t* inter, uint8_t* mask,
+                                     void* stream) {
+  VSG_REQUIRE(n1 >= 0 && n2 >= 0, "vsg_dura_intersection: negative size");
+  if (n1 == 0 || n2 == 0) return VSG_OK;
+  VSG_REQUIRE(d1 && d2 && aligned16(d1) && aligned16(d2), "vsg_dura_intersection: spans must be 16-byte aligned");
+  VSG_REQUIRE(inter == nullptr || aligned16(inter), "vsg_dura_intersection: inter_out misaligned");
+  dura_intersection_kernel<<<grid_for((int64_t)n1 * n2, 256, 8), 256, 0, (cudaStream_t)stream>>>(d1, n1, d2, n2, inter, mask);
+  return check_launch("vsg_dura_intersection");
+}
+
+extern "C" int vsg_dura_intersection_ex(const void* d1, int n1, const void* d2, int n2, int broadcast, int dtype, void* inter,
+                                        uint8_t* mask, void* stream) {
+  VSG_REQUIRE(n1 >= 0 && n2 >= 0, "vsg_dura_intersection_ex: negative size");
+  VSG_REQUIRE(broadcast || n1 == n2, "vsg_dura_intersection_ex: row-wise mode needs n1 == n2");
+  VSG_REQUIRE(dtype == 0 || dtype == 1, "vsg_dura_intersection_ex: dtype must be 0 (int64) or 1 (float32)");
+  if (n1 == 0 || n2 == 0) return VSG_OK;
+  VSG_REQUIRE(d1 && d2, "vsg_dura_intersection_ex: null spans");
+  const int g = grid_for(broadcast ? (int64_t)n1 * n2 : n1, 256, 8);
+  if (dtype == 0)
+    dura_intersection_generic_kernel<int64_t><<<g, 256, 0, (cudaStream_t)stream>>>((const int64_t*)d1, n1, (const int64_t*)d2, n2,
+                                                                                    broadcast, (int64_t*)inter, mask);
+  else
+    dura_intersection_generic_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)d1, n1, (const float*)d2, n2, broadcast,
+                                                                                  (float*)inter, mask);
+  return check_launch("vsg_dura_intersection_ex");
+}
+
+extern "C" int vsg_track_volumes(const float* boxes, const int64_t* off, int n_tracks, float* vol, void* stream) {
+  VSG_REQUIRE(n_tracks >= 0, "vsg_track_volumes: n_tracks < 0");
+  if (n_tracks == 0) return VSG_OK;
+  VSG_REQUIRE(boxes && off && vol && aligned16(boxes), "vsg_track_volumes: null or misaligned pointer");
+  track_volume_kernel<<<grid_for((int64_t)n_tracks * 32, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(boxes), off, n_tracks, vol);
+  return check_launch("vsg_track_volumes");
+}
+
+extern "C" int vsg_traj_viou_matrix(const float* boxesA, const int64_t* offA, const int64_t* duraA, int nTA,
+                                    const float* boxesB, const int64_t* offB, const int64_t* duraB, int nTB,
+                                    const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
+                                    int64_t n_pairs, int64_t* spans, uint8_t* mask, float* viou, float* inter_out,
+                                    float* volA, float* volB, int variant, void* stream) {
+  VSG_REQUIRE(nTA >= 0 && nTB >= 0 && n_seg >= 0 && n_pairs >= 0, "vsg_traj_viou_matrix: negative size");
+  if (n_pairs == 0 || n_seg == 0) return VSG_OK;
+  VSG_REQUIRE(boxesA && offA && duraA && boxesB && offB && duraB && segA && segB && seg_out,
+              "vsg_traj_viou_matrix: null input pointer");
+  VSG_REQUIRE(aligned16(boxesA) && aligned16(boxesB) && aligned16(duraA) && aligned16(duraB),
+              "vsg_traj_viou_matrix: boxes / spans must be 16-byte aligned");
+  VSG_REQUIRE(spans == nullptr || aligned16(spans), "vsg_traj_viou_matrix: spans_out misaligned");
+  VSG_REQUIRE(viou == nullptr || (volA && volB), "vsg_traj_viou_matrix: volume workspaces required with viou_out");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (viou) {
+    int rc = vsg_track_volumes(boxesA, offA, nTA, volA, stream);
+    if (rc) return rc;
+    if (!(volB == volA && boxesB == boxesA)) {
+      rc = vsg_track_volumes(boxesB, offB, nTB, volB, stream);
+      if (rc) return rc;
+    }
+  }
+  if (variant == 0) variant = 1;
+  if (variant == 1) {
+    traj_viou_warp_kernel<<<grid_for(n_pairs * 32, 256, 8), 256, 0, st>>>(
+        reinterpret_cast<const float4*>(boxesA), offA, duraA, reinterpret_cast<const float4*>(boxesB), offB, duraB, segA, segB,
+        seg_out, n_seg, n_pairs, volA, volB, spans, mask, viou, inter_out);
+    return check_launch("vsg_traj_viou_matrix(warp)");
+  }
+  set_error("vsg_traj_viou_matrix: variant 2 needs vsg_traj_viou_matrix_tiled (tile-offset workspace)");
+  return VSG_E_UNSUPPORTED;
+}
+
+// Tiled variant with its extra workspace (tile_off int64[n_seg+1]); n_tiles_bound >= sum of per-segment tiles.
+extern "C" int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* offA, const int64_t* duraA, int nTA,
+                                          const float* boxesB, const int64_t* offB, const int64_t* duraB, int nTB,
+                                          const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
+                                          int64_t n_pairs, int64_t n_tiles, int64_t* spans, uint8_t* mask, float* viou,
+                                          float* volA, float* volB, int64_t* tile_off_ws, void* stream) {
+  VSG_REQUIRE(nTA >= 0 && nTB >= 0 && n_seg >= 0 && n_pairs >= 0 && n_tiles >= 0, "vsg_traj_viou_matrix_tiled: negative size");
+  if (n_pairs == 0 || n_seg == 0) return VSG_OK;
+  VSG_REQUIRE(boxesA && offA && duraA && boxesB && offB && duraB && segA && segB && seg_out && tile_off_ws,
+              "vsg_traj_viou_matrix_tiled: null input pointer");
+  VSG_REQUIRE(aligned16(boxesA) && aligned16(boxesB) && aligned16(duraA) && aligned16(duraB),
+              "vsg_traj_viou_matrix_tiled: boxes / spans must be 16-byte aligned");
+  VSG_REQUIRE(spans == nullptr || aligned16(spans), "vsg_traj_viou_matrix_tiled: spans_out misaligned");
+  VSG_REQUIRE(viou == nullptr || (volA && volB), "vsg_traj_viou_matrix_tiled: volume workspaces required");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (viou) {
+    int rc = vsg_track_volumes(boxesA, offA, nTA, volA, stream);
+    if (rc) return rc;
+    if (!(volB == volA && boxesB == boxesA)) {
+      rc = vsg_track_volumes(boxesB, offB, nTB, volB, stream);
+      if (rc) return rc;
+    }
+  }
+  tile_offsets_kernel<<<1, 32, 0, st>>>(segA, segB, n_seg, tile_off_ws);
+  const int64_t cap = (int64_t)sm_count() * 16;
+  const int grid = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
+  traj_viou_tile_kernel<<<grid, T2_THREADS, 0, st>>>(
+      reinterpret_cast<const float4*>(boxesA), offA, duraA, reinterpret_cast<const float4*>(boxesB), offB, duraB, segA, segB,
+      seg_out, tile_off_ws, n_seg, n_tiles, volA, volB, spans, mask, viou);
+  return check_launch("vsg_traj_viou_matrix_tiled");
+}
+
+extern "C" int vsg_pair_labels(const float* viou, int n, int n_gt_traj, const int64_t* gt_so, int n_gt_pred, float th,
+                               uint8_t* out, void* stream) {
+  VSG_REQUIRE(n >= 0 && n_gt_traj >= 0 && n_gt_pred >= 0, "vsg_pair_labels: negative size");
+  if (n < 2 || n_gt_pred == 0) return VSG_OK;
+  VSG_REQUIRE(viou && gt_so && out, "vsg_pair_labels: null pointer");
+  pair_labels_kernel<<<grid_for((int64_t)n * (n - 1) * n_gt_pred, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      viou, n, n_gt_traj, gt_so, n_gt_pred, th, out);
+  return check_launch("vsg_pair_labels");
+}

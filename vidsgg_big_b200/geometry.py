@@ -1,0 +1,212 @@
+"""Host-side mirror of the reference geometry helpers (SURVEY.md §8b "Geometry helpers"), backed by
+the sm_100a kernels of csrc/geometry.cu through the C ABI.  CUDA tensors only -- no CPU fallback.
+
+Reference functions mirrored (same names, argument meaning and results):
+  dura_intersection_ts   utils/utils_func.py:347-373
+  vIoU_ts                utils/utils_func.py:437-471
+  trajid2pairid          models/model_pairwise_baseline.py:104-111 / tools/train_vidor.py:73-78
+and the loops built on them:
+  traj_viou_matrix       models/model_0v10.py:565-581, tools/train_vidor.py:107-122 (one launch for a batch of videos)
+  enti_viou_align        models/model_0v10.py:559-604
+  prop_pair_to_gt_pred   tools/train_vidor.py:143-159 (labels as a dense uint8 matrix, see ``pair_labels``)
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _cabi
+from ._cabi import check, lib, ptr, require_cuda, stream_ptr
+
+TILE = 32  # csrc/geometry.cu T2_TA / T2_TB
+
+
+# --------------------------------------------------------------------------------------------
+class TrackTable(object):
+    """Packed tracks of a batch of videos in HBM: boxes f32[sum L,4], off i64[n+1], dura i64[n,2] (closed),
+    seg i32[V+1] (track range of each video)."""
+
+    def __init__(self, boxes, off, dura, seg, counts: List[int]):
+        self.boxes, self.off, self.dura, self.seg, self.counts = boxes, off, dura, seg, counts
+
+    @property
+    def n_tracks(self):
+        return int(self.dura.shape[0])
+
+    @classmethod
+    def from_containers(cls, items: Sequence, device=None) -> "TrackTable":
+        """``items``: TrajProposal / VideoGraph objects (packed ``bboxes``/``lengths``) of the batch."""
+        boxes_l, lens_l, dura_l, counts = [], [], [], []
+        for it in items:
+            bx = it.bboxes
+            du = it.traj_durations
+            device = device or bx.device
+            boxes_l.append(bx.to(device, torch.float32))
+            dura_l.append(du.to(device, torch.long))
+            lens_l.append(it.lengths)
+            counts.append(int(du.shape[0]))
+        require_cuda(*boxes_l)
+        boxes = boxes_l[0].contiguous() if len(boxes_l) == 1 else torch.cat(boxes_l, 0)
+        dura = dura_l[0].contiguous() if len(dura_l) == 1 else torch.cat(dura_l, 0)
+        lens = torch.cat([torch.as_tensor(l, dtype=torch.long) for l in lens_l]) if lens_l else torch.zeros(0, dtype=torch.long)
+        off = torch.zeros(lens.numel() + 1, dtype=torch.long)
+        off[1:] = torch.cumsum(lens, 0)
+        seg = torch.zeros(len(counts) + 1, dtype=torch.int32)
+        seg[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int32), 0)
+        return cls(boxes, off.to(device), dura, seg.to(device), counts)
+
+    @classmethod
+    def from_lists(cls, boxes_list: Sequence[torch.Tensor], dura: torch.Tensor) -> "TrackTable":
+        """Reference-style arguments of one video: list of [L_i,4] tensors + [n,2] closed spans."""
+        require_cuda(dura, *boxes_list)
+        n = len(boxes_list)
+        boxes = torch.cat([b.float() for b in boxes_list], 0) if n else torch.zeros(0, 4, device=dura.device)
+        lens = torch.tensor([int(b.shape[0]) for b in boxes_list], dtype=torch.long)
+        off = torch.zeros(n + 1, dtype=torch.long)
+        off[1:] = torch.cumsum(lens, 0)
+        seg = torch.tensor([0, n], dtype=torch.int32)
+        return cls(boxes.contiguous(), off.to(dura.device), dura.long().contiguous(), seg.to(dura.device), [n])
+
+
+def dura_intersection_ts(dura1: torch.Tensor, dura2: torch.Tensor, broadcast: bool = True):
+    """Closed-span intersection, bit-exact on int64 (utils/utils_func.py:347-373)."""
+    assert isinstance(dura1, torch.Tensor) and isinstance(dura2, torch.Tensor)
+    require_cuda(dura1, dura2)
+    n1, n2 = dura1.shape[0], dura2.shape[0]
+    if dura1.dtype == torch.long and dura2.dtype == torch.long:
+        dt, a, b = 0, dura1.contiguous(), dura2.contiguous()
+    else:
+        dt, a, b = 1, dura1.float().contiguous(), dura2.float().contiguous()
+    # the reference asserts every input span is valid (:351-353)
+    assert bool((a[:, 0] <= a[:, 1]).all()) and bool((b[:, 0] <= b[:, 1]).all())
+    if broadcast:
+        inter = torch.empty(n1, n2, 2, dtype=a.dtype, device=a.device)
+        mask = torch.empty(n1, n2, dtype=torch.uint8, device=a.device)
+    else:
+        assert n1 == n2
+        inter = torch.empty(n1, 2, dtype=a.dtype, device=a.device)
+        mask = torch.empty(n1, dtype=torch.uint8, device=a.device)
+    check(lib().vsg_dura_intersection_ex(ptr(a), n1, ptr(b), n2, 1 if broadcast else 0, dt, ptr(inter), ptr(mask),
+                                         stream_ptr(a.device)), "vsg_dura_intersection_ex")
+    return inter, mask.bool()
+
+
+def trajid2pairid(num_prop: int, device="cuda") -> torch.Tensor:
+    """All ordered (s,o), s != o, row-major, int64[n(n-1),2] (model_pairwise_baseline.py:104-111)."""
+    out = torch.empty(max(num_prop * (num_prop - 1), 0), 2, dtype=torch.long, device=device)
+    check(lib().vsg_pair_ids(int(num_prop), ptr(out), stream_ptr(out.device)), "vsg_pair_ids")
+    return out
+
+
+def track_volumes(table: TrackTable) -> torch.Tensor:
+    vol = torch.empty(table.n_tracks, dtype=torch.float32, device=table.boxes.device)
+    check(lib().vsg_track_volumes(ptr(table.boxes), ptr(table.off), table.n_tracks, ptr(vol), stream_ptr(vol.device)),
+          "vsg_track_volumes")
+    return vol
+
+
+def traj_viou_batched(A: TrackTable, B: TrackTable, want_spans=True, want_mask=True, want_viou=True,
+                      want_inter=False, variant: int = 1):
+    """vIoU matrices of every video of the batch in ONE launch.
+
+    Returns ``(viou f32[P], spans i64[P,2], mask u8[P], seg_out i64[V+1] (host list), inter f32[P])``; video ``v``'s
+    ``nA_v x nB_v`` block is rows ``seg_out[v]:seg_out[v+1]`` (row-major).  Entries not requested are None.
+    """
+    assert len(A.counts) == len(B.counts)
+    same = A is B
+    dev = A.boxes.device
+    sizes = [a * b for a, b in zip(A.counts, B.counts)]
+    seg_out_h = [0]
+    for s in sizes:
+        seg_out_h.append(seg_out_h[-1] + s)
+    P = seg_out_h[-1]
+    seg_out = torch.tensor(seg_out_h, dtype=torch.long).to(dev)
+    spans = torch.empty(P, 2, dtype=torch.long, device=dev) if want_spans else None
+    mask = torch.empty(P, dtype=torch.uint8, device=dev) if want_mask else None
+    viou = torch.empty(P, dtype=torch.float32, device=dev) if want_viou else None
+    inter = torch.empty(P, dtype=torch.float32, device=dev) if want_inter else None
+    volA = torch.empty(max(A.n_tracks, 1), dtype=torch.float32, device=dev)
+    volB = volA if same else torch.empty(max(B.n_tracks, 1), dtype=torch.float32, device=dev)
+    if variant == 2:
+        assert not want_inter
+        n_tiles = sum(((a + TILE - 1) // TILE) * ((b + TILE - 1) // TILE) for a, b in zip(A.counts, B.counts))
+        tile_ws = torch.empty(len(A.counts) + 1, dtype=torch.long, device=dev)
+        check(lib().vsg_traj_viou_matrix_tiled(
+            ptr(A.boxes), ptr(A.off), ptr(A.dura), A.n_tracks, ptr(B.boxes), ptr(B.off), ptr(B.dura), B.n_tracks,
+            ptr(A.seg), ptr(B.seg), ptr(seg_out), len(A.counts), P, n_tiles, ptr(spans), ptr(mask), ptr(viou),
+            ptr(volA), ptr(volB), ptr(tile_ws), stream_ptr(dev)), "vsg_traj_viou_matrix_tiled")
+    else:
+        check(lib().vsg_traj_viou_matrix(
+            ptr(A.boxes), ptr(A.off), ptr(A.dura), A.n_tracks, ptr(B.boxes), ptr(B.off), ptr(B.dura), B.n_tracks,
+            ptr(A.seg), ptr(B.seg), ptr(seg_out), len(A.counts), P, ptr(spans), ptr(mask), ptr(viou), ptr(inter),
+            ptr(volA), ptr(volB), variant, stream_ptr(dev)), "vsg_traj_viou_matrix")
+    return viou, spans, mask, seg_out_h, inter
+
+
+def traj_viou_matrix(boxes_a: Sequence[torch.Tensor], dura_a: torch.Tensor,
+                     boxes_b: Sequence[torch.Tensor], dura_b: torch.Tensor, variant: int = 1):
+    """One video, reference-style arguments.  Returns ``(viou f32[nA,nB], inter i64[nA,nB,2], mask bool[nA,nB])`` --
+    what the loop at models/model_0v10.py:569-581 produces (zeros where the spans do not overlap)."""
+    A = TrackTable.from_lists(boxes_a, dura_a)
+    B = TrackTable.from_lists(boxes_b, dura_b)
+    nA, nB = A.n_tracks, B.n_tracks
+    viou, spans, mask, _, _ = traj_viou_batched(A, B, variant=variant)
+    return viou.view(nA, nB), spans.view(nA, nB, 2), mask.view(nA, nB).bool()
+
+
+def vIoU_ts(traj_1: torch.Tensor, traj_2: torch.Tensor, dura_1, dura_2) -> torch.Tensor:
+    """Volume IoU of two trajectories given *relative* closed overlap spans (utils/utils_func.py:437-471):
+    full-track volumes (+1 pixel convention), intersection over the given slices only."""
+    assert isinstance(traj_1, torch.Tensor) and isinstance(traj_2, torch.Tensor)
+    require_cuda(traj_1, traj_2)
+    s1, e1 = int(dura_1[0]), int(dura_1[1])
+    s2, e2 = int(dura_2[0]), int(dura_2[1])
+    a = traj_1.float()[s1:e1 + 1].contiguous()
+    b = traj_2.float()[s2:e2 + 1].contiguous()
+    assert a.shape == b.shape
+    dev = traj_1.device
+    n = a.shape[0]
+    span = torch.tensor([[0, n - 1]], dtype=torch.long, device=dev)
+    A = TrackTable.from_lists([a], span)
+    B = TrackTable.from_lists([b], span)
+    _, _, _, _, inter = traj_viou_batched(A, B, want_spans=False, want_mask=False, want_viou=False, want_inter=True)
+    full = TrackTable.from_lists([traj_1.float().contiguous(), traj_2.float().contiguous()],
+                                 torch.tensor([[0, traj_1.shape[0] - 1], [0, traj_2.shape[0] - 1]], dtype=torch.long, device=dev))
+    vol = track_volumes(full)
+    it = inter[0]
+    return it / (vol[0] + vol[1] - it)
+
+
+def pair_labels(viou: torch.Tensor, gt_so: torch.Tensor, th: float) -> torch.Tensor:
+    """Base-C label assignment (tools/train_vidor.py:143-159): ``bool[n_gt_pred, n(n-1)]`` in ``trajid2pairid`` order."""
+    require_cuda(viou, gt_so)
+    n, ng = viou.shape
+    npred = gt_so.shape[0]
+    out = torch.zeros(npred, max(n * (n - 1), 0), dtype=torch.uint8, device=viou.device)
+    check(lib().vsg_pair_labels(ptr(viou.float().contiguous()), n, ng, ptr(gt_so.long().contiguous()), npred, float(th),
+                                ptr(out), stream_ptr(viou.device)), "vsg_pair_labels")
+    return out.bool()
+
+
+def enti_viou_align(gt_adj: torch.Tensor, proposal, gt_graph, positive_vIoU_th: float, gt_closed: bool = True):
+    """Training label assignment of models/model_0v10.py:559-604 on top of the vIoU-matrix kernel.
+
+    ``gt_graph.traj_durations`` must be closed spans (``gt_closed``); unlike the reference (:567) the input
+    is not mutated.  The force-assign / row-argmax steps (:583-602) are tiny index ops on the matrix.
+    """
+    assert gt_closed
+    A = TrackTable.from_containers([proposal])
+    B = TrackTable.from_containers([gt_graph], device=A.boxes.device)
+    nP, nG = A.n_tracks, B.n_tracks
+    viou, _, _, _, _ = traj_viou_batched(A, B, want_spans=False, want_mask=False)
+    viou = viou.view(nP, nG)
+    hit = viou > positive_vIoU_th
+    best_prop = torch.argmax(viou, dim=0)
+    orphan = hit.sum(dim=0) == 0
+    hit[best_prop[orphan], orphan.nonzero(as_tuple=True)[0]] = True
+    row_has = hit.sum(dim=1) > 0
+    best_gt = torch.argmax(viou, dim=1)
+    aligned = gt_adj.to(viou.device)[:, :, best_gt] * row_has[None, None, :].float()
+    return aligned, viou
