@@ -140,6 +140,25 @@ int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t*
                        const double* boxes2, const int64_t* off2, const int64_t* dur2,
                        int n, double* out, void* stream);
 
+/* ---- scoring: GEMM (kernels K4-K6) -------------------------------- */
+
+#define VSG_GEMM_SIMT 0   /* fp32 FFMA tiles (comparator / shapes TMA cannot describe)          */
+#define VSG_GEMM_TF32 1   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM                     */
+#define VSG_GEMM_3XTF32 2 /* fp32-faithful 3xTF32 split on tcgen05 (needs W_lo from vsg_split_tf32) */
+
+/* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ), fp32 row-major.
+ * Replaces every nn.Linear / 1x1 conv / conv tap of the hot path (models/model_0v10.py:446-458, :103-117,
+ * :178-225, :478-507; models/grd_model_v5.py:331-373).  idx(row) = rb_index[row] if rb_index else row % rb_period
+ * (used for the positional-embedding term of the decoder and the gathered frequency bias of the head).
+ * W_lo is only read in mode VSG_GEMM_3XTF32.  Requirements for the tensor-core modes: lda, ldw multiples of 4,
+ * A / W 16-byte aligned; otherwise the call silently uses the SIMT kernel (same result class). */
+int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
+             const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
+             int accumulate, float* C, int ldc, void* stream);
+
+/* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
+int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,77 @@
+"""GPU: the GEMM kernels (SIMT comparator, tcgen05 tf32, tcgen05 3xTF32) against an fp64 product."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+SHAPES = [  # M, N, K
+    (128, 128, 32), (128, 128, 64), (256, 128, 512), (300, 512, 2048), (37, 512, 512), (1000, 1536, 1024),
+    (192, 133, 3160), (4500, 512, 832), (1, 512, 2048), (129, 51, 512), (777, 128, 128), (20000, 512, 512),
+]
+TOL = {0: 2e-6, 1: 2e-3, 2: 4e-6}
+
+
+def _ref(A, W, bias):
+    return A.double() @ W.double().t() + (bias.double() if bias is not None else 0)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("shape", SHAPES, ids=["%dx%dx%d" % s for s in SHAPES])
+def test_gemm_modes(mode, shape):
+    from vidsgg_big_b200 import linalg
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(DEV)
+    wt = linalg.Weight(W, bias)
+    out = linalg.gemm(mode, A, wt)
+    torch.cuda.synchronize()
+    ref = _ref(A, W, bias)
+    err = (out.double() - ref).abs().max().item()
+    scale = ref.abs().max().item()
+    assert err <= TOL[mode] * scale, "mode %d shape %s: max err %.3e (scale %.3e)" % (mode, shape, err, scale)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_gemm_epilogue_options(mode):
+    from vidsgg_big_b200 import linalg
+    g = torch.Generator(device="cpu").manual_seed(5)
+    M, N, K = 384, 256, 320
+    A = torch.randn(M, K + 64, generator=g).to(DEV)            # A is a column slice of a wider buffer
+    W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(DEV)
+    rowb = torch.randn(192, N, generator=g).to(DEV)
+    idx = torch.randint(0, 192, (M,), generator=g).int().to(DEV)
+    wt = linalg.Weight(W, bias)
+    tol = TOL[mode]
+    base = _ref(A[:, 32:32 + K], W, bias)
+    # periodic row bias + relu, written into the right half of a wider output
+    out = torch.full((M, 2 * N), -7.0, device=DEV)
+    linalg.gemm(mode, A[:, 32:32 + K], wt, out=out[:, N:], relu=True, rowbias=rowb, rb_period=192)
+    ref = torch.relu(base + rowb.double()[torch.arange(M, device=DEV) % 192])
+    assert (out[:, N:].double() - ref).abs().max().item() <= tol * ref.abs().max().item()
+    assert bool((out[:, :N] == -7.0).all())
+    # indexed row bias + accumulate, no bias
+    out2 = torch.ones(M, N, device=DEV)
+    linalg.gemm(mode, A[:, 32:32 + K], wt, out=out2, rowbias=rowb, rb_index=idx, accumulate=True, bias=False)
+    ref2 = _ref(A[:, 32:32 + K], W, None) + rowb.double()[idx.long()] + 1.0
+    assert (out2.double() - ref2).abs().max().item() <= tol * ref2.abs().max().item()
+
+
+def test_gemm_3xtf32_is_fp32_class():
+    """3xTF32 must be fp32-class: error vs fp64 within 4x of an fp32 cuBLAS GEMM's, and far below plain tf32."""
+    from vidsgg_big_b200 import linalg
+    g = torch.Generator(device="cpu").manual_seed(9)
+    A = torch.randn(2048, 2048, generator=g).to(DEV)
+    W = torch.randn(512, 2048, generator=g).to(DEV) / 45.0
+    wt = linalg.Weight(W)
+    out = linalg.gemm(2, A, wt)
+    ref = A.double() @ W.double().t()
+    torch.backends.cuda.matmul.allow_tf32 = False
+    e32 = ((A @ W.t()).double() - ref).abs().max().item()
+    e3x = (out.double() - ref).abs().max().item()
+    e1x = (linalg.gemm(1, A, wt).double() - ref).abs().max().item()
+    print("fp32 err %.3e  3xtf32 err %.3e  tf32 err %.3e" % (e32, e3x, e1x))
+    assert e3x <= 4 * e32 + 1e-6 and e1x > 10 * e3x

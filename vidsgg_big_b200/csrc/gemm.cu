@@ -1,0 +1,546 @@
+// GEMM for the scoring stages: C[M,N] = act(A[M,K] * W[N,K]^T + bias[N] + rowbias[idx(row)][N]) (+ C), fp32 in HBM.
+//
+// Every dense contraction of BIG-C (models/model_0v10.py:446-458 per-frame MLPs and the k=3 conv as 3 taps,
+// :103-117 encoder, :178-225 decoder, :478-507 head) and of the grounding net (models/grd_model_v5.py:331-373)
+// is a "rows x shared weight" product, so rows of ALL tracks / queries / videos of a shard are stacked
+// into one M and run through this kernel.
+//
+// Precision modes (SURVEY.md section 7 "discrete decisions under reduced precision"):
+//   VSG_GEMM_SIMT   (0)  plain fp32 FFMA tiles -- the on-device comparator used by the tests;
+//   VSG_GEMM_TF32   (1)  tcgen05.mma kind::tf32, operands read as fp32 straight from TMA-staged smem;
+//   VSG_GEMM_3XTF32 (2)  fp32-faithful: A = Ah + Al split on the fly in smem by 4 transform warps, W = Wh + Wl
+//                        pre-split in HBM; D += Al*Wh + Ah*Wl + Ah*Wh (error ~2^-21, like an fp32 GEMM).
+//
+// tcgen05 kernel anatomy (one CTA per SM, persistent over 128x128 output tiles, BLOCK_K = 32 fp32 = one
+// 128-byte swizzle row):
+//   warp 0      TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier complete_tx)
+//   warp 1      MMA issuer (one elected lane; tcgen05.mma cta_group::1, M=128 N=128 K=8; tcgen05.commit frees stages)
+//   warp 2      TMEM allocator (256 columns = two 128-column fp32 accumulators, double buffered)
+//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / row-bias / ReLU -> global stores
+//   warps 8-11  (3xTF32 only) hi/lo split of the A stage in shared memory
+#include "common.cuh"
+#include <cuda.h>
+#include <mutex>
+#include <unordered_map>
+#include <string>
+#include <string.h>
+
+namespace vsg {
+
+constexpr int BM = 128, BN = 128, BK = 32;            // tile; BK fp32 = 128 bytes
+constexpr int TILE_BYTES = BM * BK * 4;               // 16 KB (A and B tiles are the same size)
+constexpr int UMMA_K = 8;                             // tf32
+constexpr int ACC_COLS = BN;                          // fp32 accumulator columns per stage
+constexpr int TMEM_COLS = 2 * ACC_COLS;               // double buffered
+constexpr uint64_t WATCHDOG_NS = 4000000000ull;       // watchdog: trap after 4 s instead of hanging the GPU
+
+struct GemmEpilogue {
+  const float* bias;        // [N] or null
+  const float* rowbias;     // [P][ld_rb] or null
+  const int32_t* rb_index;  // [M] row -> rowbias row, or null (then row % rb_period)
+  int rb_period;
+  int ld_rb;
+  int relu;
+  int accumulate;           // C += result (before activation)
+  float* C;
+  int ldc;
+  int M, N, K;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ uint64_t global_ns() {
+  uint64_t t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if ((++spins & 0x3FF) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WATCHDOG_NS) __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
+//   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B between 8-row groups
+//   | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
+// n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
+constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+// ---------------------------------------------------------------------------------------------------
+template <int MODE> struct Cfg;
+template <> struct Cfg<1> { static constexpr int STAGES = 6, TILES_PER_STAGE = 2, THREADS = 256; };
+template <> struct Cfg<2> { static constexpr int STAGES = 3, TILES_PER_STAGE = 4, THREADS = 384; };
+
+template <int MODE>
+__global__ void __launch_bounds__(Cfg<MODE>::THREADS, 1)
+gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+               const __grid_constant__ CUtensorMap mapBl, const GemmEpilogue ep) {
+  constexpr int STAGES = Cfg<MODE>::STAGES;
+  constexpr int STAGE_BYTES = Cfg<MODE>::TILES_PER_STAGE * TILE_BYTES;
+  // stage layout: [A | B_hi] (MODE 1) or [A(hi) | B_hi | A_lo | B_lo] (MODE 2)
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint64_t* full = bars;                   // TMA landed
+  uint64_t* empty = bars + STAGES;         // MMAs that read the stage retired
+  uint64_t* ready = bars + 2 * STAGES;     // (MODE 2) split done
+  uint64_t* acc_full = bars + 3 * STAGES;  // [2]
+  uint64_t* acc_empty = acc_full + 2;      // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
+  const int n_tiles = tiles_m * tiles_n;
+  const int kblocks = (ep.K + BK - 1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA);
+    tma_prefetch_desc(&mapBh);
+    if (MODE == 2) tma_prefetch_desc(&mapBl);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+      mbar_init(&ready[s], 128);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&acc_full[a], 1);
+      mbar_init(&acc_empty[a], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&empty[stage], phase ^ 1);
+          uint8_t* st = smem + stage * STAGE_BYTES;
+          mbar_expect_tx(&full[stage], (MODE == 2 ? 3 : 2) * TILE_BYTES);
+          tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK, m0);
+          tma_load_2d(smem_u32(st + TILE_BYTES), &mapBh, &full[stage], kb * BK, n0);
+          if (MODE == 2) tma_load_2d(smem_u32(st + 3 * TILE_BYTES), &mapBl, &full[stage], kb * BK, n0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(MODE == 2 ? &ready[stage] : &full[stage], phase);
+          tc_fence_after();
+          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + TILE_BYTES);
+          if (MODE == 2) {
+            const uint64_t a_lo = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, IDESC_TF32, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, 1u);
+          } else {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (kb == kblocks - 1) umma_commit(&acc_full[acc]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ================= epilogue =================
+    const int quad = warp & 3;              // TMEM lane quadrant this warp may read
+    const int row_in_tile = quad * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const int row = m0 + row_in_tile;
+      mbar_wait(&acc_full[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
+      const bool row_ok = row < ep.M;
+      const float* rb = nullptr;
+      if (row_ok && ep.rowbias) {
+        const int ri = ep.rb_index ? ep.rb_index[row] : (row % ep.rb_period);
+        rb = ep.rowbias + (size_t)ri * ep.ld_rb;
+      }
+      float* crow = ep.C + (size_t)(row_ok ? row : 0) * ep.ldc;
+      const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+#pragma unroll 1
+      for (int c = 0; c < BN / 32; ++c) {
+        uint32_t r[32];
+        tmem_ld32(taddr + c * 32, r);
+        tmem_ld_wait();
+        if (row_ok) {
+          const int col0 = n0 + c * 32;
+          if (col0 + 32 <= ep.N && vec_ok) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              if (ep.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (rb) {
+                v.x += rb[col0 + j]; v.y += rb[col0 + j + 1]; v.z += rb[col0 + j + 2]; v.w += rb[col0 + j + 3];
+              }
+              float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
+              if (ep.accumulate) {
+                const float4 o = *dst;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              *dst = v;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < ep.N) {
+                float v = __uint_as_float(r[j]);
+                if (ep.bias) v += ep.bias[col];
+                if (rb) v += rb[col];
+                if (ep.accumulate) v += crow[col];
+                if (ep.relu) v = fmaxf(v, 0.f);
+                crow[col] = v;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&acc_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (MODE == 2 && warp >= 8) {
+    // ================= A hi/lo split (element-wise, so it is oblivious to the 128B swizzle) =================
+    const int t = threadIdx.x - 256;  // 0..127
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        mbar_wait(&full[stage], phase);
+        float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + 2 * TILE_BYTES);
+#pragma unroll
+        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+          const int idx = i * 128 + t;
+          const float4 x = hi[idx];
+          float4 h, l;
+          h.x = __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u); l.x = x.x - h.x;
+          h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
+          h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
+          h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
+          hi[idx] = h;
+          lo[idx] = l;
+        }
+        fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&ready[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// SIMT fp32 reference GEMM (comparator; also the fallback for shapes TMA cannot describe, e.g. K % 4 != 0)
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__ W, int ldw, const GemmEpilogue ep) {
+  constexpr int TM = 64, TN = 64, TK = 16;
+  __shared__ float sA[TK][TM + 4];
+  __shared__ float sW[TK][TN + 4];
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int m0 = blockIdx.y * TM, n0 = blockIdx.x * TN;
+  float acc[4][4] = {};
+  for (int k0 = 0; k0 < ep.K; k0 += TK) {
+    for (int i = threadIdx.x; i < TM * TK; i += 256) {
+      const int r = i / TK, c = i % TK;
+      sA[c][r] = (m0 + r < ep.M && k0 + c < ep.K) ? A[(size_t)(m0 + r) * lda + k0 + c] : 0.f;
+      sW[c][r] = (n0 + r < ep.N && k0 + c < ep.K) ? W[(size_t)(n0 + r) * ldw + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < TK; ++k) {
+      float a[4], w[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { a[i] = sA[k][ty * 4 + i]; w[i] = sW[k][tx * 4 + i]; }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = m0 + ty * 4 + i;
+    if (row >= ep.M) continue;
+    const float* rb = nullptr;
+    if (ep.rowbias) rb = ep.rowbias + (size_t)(ep.rb_index ? ep.rb_index[row] : row % ep.rb_period) * ep.ld_rb;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int col = n0 + tx * 4 + j;
+      if (col >= ep.N) continue;
+      float v = acc[i][j];
+      if (ep.bias) v += ep.bias[col];
+      if (rb) v += rb[col];
+      float* dst = ep.C + (size_t)row * ep.ldc + col;
+      if (ep.accumulate) v += *dst;
+      if (ep.relu) v = fmaxf(v, 0.f);
+      *dst = v;
+    }
+  }
+}
+
+__global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict__ hi, float* __restrict__ lo, int64_t n) {
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float x = w[i];
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    hi[i] = h;
+    lo[i] = x - h;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side: tensor maps
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+struct MapKey {
+  const void* ptr; int rows, cols, ld;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld; }
+};
+struct MapKeyHash {
+  size_t operator()(const MapKey& k) const {
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.cols) * 131) ^ (std::hash<int>()(k.ld) * 1031);
+  }
+};
+static std::mutex g_map_mu;
+static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
+
+// 2-D fp32 row-major [rows][cols] with leading dimension ld; box = BK x 128 rows, SWIZZLE_128B, zero OOB fill
+static int get_tensor_map(const float* base, int rows, int cols, int ld, CUtensorMap* out) {
+  MapKey key{base, rows, cols, ld};
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    auto it = g_maps.find(key);
+    if (it != g_maps.end()) { *out = it->second; return VSG_OK; }
+  }
+  EncodeTiledFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return VSG_E_LAUNCH; }
+  cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMap m;
+  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld); return VSG_E_LAUNCH; }
+  {
+    std::lock_guard<std::mutex> g(g_map_mu);
+    if (g_maps.size() > 4096) g_maps.clear();
+    g_maps[key] = m;
+  }
+  *out = m;
+  return VSG_OK;
+}
+
+template <int MODE>
+static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, int ldw, const GemmEpilogue& ep, cudaStream_t st) {
+  CUtensorMap mA, mBh, mBl;
+  int rc = get_tensor_map(A, ep.M, ep.K, lda, &mA);
+  if (rc) return rc;
+  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, &mBh);
+  if (rc) return rc;
+  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, &mBl); if (rc) return rc; } else mBl = mBh;
+  constexpr int SMEM = Cfg<MODE>::STAGES * Cfg<MODE>::TILES_PER_STAGE * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static bool attr_set = false;
+  if (!attr_set) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+      set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
+      return VSG_E_LAUNCH;
+    }
+    attr_set = true;
+  }
+  const int tiles = ((ep.M + BM - 1) / BM) * ((ep.N + BN - 1) / BN);
+  const int grid = tiles < sm_count() ? tiles : sm_count();
+  gemm_tc_kernel<MODE><<<grid, Cfg<MODE>::THREADS, SMEM, st>>>(mA, mBh, mBl, ep);
+  return check_launch("vsg_gemm(tcgen05)");
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
+  VSG_REQUIRE(n >= 0, "vsg_split_tf32: n < 0");
+  if (n == 0) return VSG_OK;
+  VSG_REQUIRE(w && hi && lo, "vsg_split_tf32: null pointer");
+  int64_t blocks = (n + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  split_tf32_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, hi, lo, n);
+  return check_launch("vsg_split_tf32");
+}
+
+extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
+                        const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
+                        int accumulate, float* C, int ldc, void* stream) {
+  VSG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vsg_gemm: negative size");
+  if (M == 0 || N == 0) return VSG_OK;
+  VSG_REQUIRE(A && W_hi && C, "vsg_gemm: null matrix pointer");
+  VSG_REQUIRE(lda >= K && ldw >= K && ldc >= N, "vsg_gemm: leading dimension smaller than extent");
+  VSG_REQUIRE(rowbias == nullptr || rb_index != nullptr || rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
+  GemmEpilogue ep;
+  ep.bias = bias; ep.rowbias = rowbias; ep.rb_index = rb_index; ep.rb_period = rb_period; ep.ld_rb = ld_rb;
+  ep.relu = relu; ep.accumulate = accumulate; ep.C = C; ep.ldc = ldc; ep.M = M; ep.N = N; ep.K = K;
+  cudaStream_t st = (cudaStream_t)stream;
+  const bool tma_ok = (lda % 4 == 0) && (ldw % 4 == 0) && aligned16(A) && aligned16(W_hi) && K >= 1;
+  if (mode == 0 || !tma_ok) {
+    dim3 grid((N + 63) / 64, (M + 63) / 64);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W_hi, ldw, ep);
+    return check_launch("vsg_gemm(simt)");
+  }
+  if (mode == 1) return launch_tc<1>(A, lda, W_hi, nullptr, ldw, ep, st);
+  if (mode == 2) {
+    VSG_REQUIRE(W_lo && aligned16(W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
+    return launch_tc<2>(A, lda, W_hi, W_lo, ldw, ep, st);
+  }
+  set_error("vsg_gemm: unknown mode %d", mode);
+  return VSG_E_UNSUPPORTED;
+}

@@ -1,0 +1,56 @@
+"""Thin host wrapper of the GEMM entry points (csrc/gemm.cu).  CUDA tensors only."""
+from __future__ import annotations
+
+from ctypes import c_void_p
+from typing import Optional
+
+import torch
+
+from ._cabi import check, lib, ptr, require_cuda, stream_ptr
+
+SIMT, TF32, X3TF32 = 0, 1, 2
+MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32}
+
+
+class Weight(object):
+    """A [N,K] fp32 weight resident in HBM with its (optional) tf32 hi/lo split."""
+
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor] = None, split: bool = True):
+        require_cuda(w)
+        self.w = w.detach().float().contiguous()
+        self.bias = None if bias is None else bias.detach().float().contiguous()
+        self.N, self.K = self.w.shape
+        self.hi = self.lo = None
+        if split:
+            self.hi = torch.empty_like(self.w)
+            self.lo = torch.empty_like(self.w)
+            check(lib().vsg_split_tf32(ptr(self.w), ptr(self.hi), ptr(self.lo), self.w.numel(), stream_ptr(self.w.device)),
+                  "vsg_split_tf32")
+
+
+def _raw(t):
+    return None if t is None else c_void_p(t.data_ptr())
+
+
+def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
+         rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
+         accumulate: bool = False, bias: bool = True, K: Optional[int] = None) -> torch.Tensor:
+    """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
+    wider row-major buffers (their row stride is passed as the leading dimension)."""
+    require_cuda(A)
+    assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32
+    M = A.shape[0]
+    K = W.K if K is None else K
+    assert A.shape[1] >= K
+    if out is None:
+        out = torch.empty(M, W.N, dtype=torch.float32, device=A.device)
+    assert out.dim() == 2 and out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= W.N
+    lda = A.stride(0) if M > 1 else max(A.stride(0), K)
+    ldc = out.stride(0) if M > 1 else max(out.stride(0), W.N)
+    w_hi = W.hi if (mode == X3TF32 and W.hi is not None) else W.w
+    w_lo = W.lo if mode == X3TF32 else None
+    b = W.bias if bias else None
+    check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
+                         _raw(rb_index), int(rb_period), 0 if rowbias is None else rowbias.stride(0), 1 if relu else 0,
+                         1 if accumulate else 0, _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
+    return out
