@@ -159,6 +159,63 @@ int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* 
 /* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
 int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
 
+/* ---- BIG-C classification stage, non-GEMM kernels -------------------------
+ * Batch layout: rows = all box-frames of all tracks of all videos; off int64[N+1]; seg int32[V+1] track range
+ * per video; tmax int32[N] = longest track of the track's video; queries = V*Q rows, video-major. */
+
+/* 8-d motion features [ctx,dctx,cty,dcty,w,dw,h,dh] (models/model_0v10.py:401-420) fused with the first
+ * fc_bbox2enti layer (Linear 8->E + ReLU, :296-298).  wh f32[V][2]; W1 f32[E][8]; out f32[R][ldo];
+ * feat8_out optional f32[R][8]. */
+int vsg_bbox_feat_mlp1(const float* boxes, const int64_t* off, int n_tracks, int64_t n_rows, const int32_t* track_vid,
+                       const float* wh, const float* W1, const float* b1, int E, float* out, int ldo, float* feat8_out,
+                       void* stream);
+
+/* Time-mean over the STRETCHED sequence of feature columns [col0, col0+width) (model_0v10.py:470,
+ * model_0v7.py:473; stretch = stack_with_repeat_2d :18-46): out f32[N][ldo]. */
+int vsg_stretched_mean(const float* feat, int ldf, int col0, int width, const int64_t* off, const int32_t* tmax,
+                       int n_tracks, float* out, int ldo, void* stream);
+
+/* conv_feat2enti (k3,s2,p1 over stretched time) + adaptive_max_pool1d (model_0v10.py:450-457) from the three tap
+ * products Y f32[R][3E] (tap-major); out f32[N][E*pool] flattened channel-major (c*pool+p). */
+int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,
+                  int n_tracks, int pool, float* out, void* stream);
+
+/* out = LayerNorm(x + a)*gamma + beta (+ post[row % post_period])  (norm1/2/3 of model_0v10.py:111-115, :186-223;
+ * the "+ pos" of :189 is the post term).  a, post may be NULL.  D % 32 == 0, D <= 1024. */
+int vsg_add_layernorm(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
+                      const float* post, int post_period, int64_t rows, int D, float* out, int ldo, void* stream);
+
+/* out[r] = x[r % period]  (pred_query_init for every video, model_0v10.py:465). */
+int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* out, void* stream);
+
+/* softmax(Q K^T / sqrt(head_dim)) V per segment and head on packed rows (the core of nn.MultiheadAttention,
+ * model_0v10.py:109, :183; grd_model_v5.py:100-108).  Segments: seg_off int64[n_seg+1] or fixed_len rows each. */
+int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
+            int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, void* stream);
+
+/* Role attention (model_0v10.py:190-214): att = softmax_tracks * softmax_roles of <p2a, e2a>/sqrt(dim_enti),
+ * values f32[V*Q][2E] = att[r] @ enco.  Optional: att_out f32[V*Q][2][att_ld], so_out int32[V*Q][2] = per-role
+ * argmax as GLOBAL track ids (prediction_head :485). */
+int vsg_role_attention(const float* p2a, const float* e2a, const float* enco, const int32_t* seg, int n_vid, int Q, int E,
+                       int max_tracks, float inv_sqrt_d, float* values, float* att_out, int att_ld, int32_t* so_out,
+                       void* stream);
+
+/* Row-wise concat of up to 8 (optionally gathered) pieces: the prediction_head input (model_0v10.py:501/503). */
+int vsg_gather_concat(const float* const* src_host, const int32_t* const* idx_host, const int* idx_stride_host,
+                      const int* ld_host, const int* width_host, int n_pieces, int64_t rows, float* out, int ldo,
+                      void* stream);
+
+/* (s,o) track ids -> frequency-bias row scat*C+ocat and per-role category ids (model_0v10.py:486-487). */
+int vsg_so_category(const int32_t* so, const int64_t* cat_ids, int C, int64_t rows, int32_t* pair_index, int32_t* so_cat,
+                    void* stream);
+
+/* construct_triplet (model_0v10.py:707-785) for every video: outputs at video v start at row v*cap;
+ * counts int32[V][2] = (rows emitted, rows that passed the overlap filter; 0 => the reference returns None). */
+int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int topk, const int32_t* so, const int32_t* seg,
+                          int n_vid, const int64_t* dura, const int64_t* cat_ids, const float* enti_scores,
+                          int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
+                          void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -47,6 +47,16 @@ SIGNATURES = {
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
+    "vsg_bbox_feat_mlp1": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p, p]),
+    "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
+    "vsg_conv_pool": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
+    "vsg_add_layernorm": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p]),
+    "vsg_broadcast_rows": (i32, [p, i32, i32, i64, p, p]),
+    "vsg_mha": (i32, [p, i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, p, i32, p]),
+    "vsg_role_attention": (i32, [p, p, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),
+    "vsg_gather_concat": (i32, [C.POINTER(p), C.POINTER(p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i64, p, i32, p]),
+    "vsg_so_category": (i32, [p, p, i32, i64, p, p, p]),
+    "vsg_construct_triplet": (i32, [p, i32, i32, i32, i32, p, p, i32, p, p, p, p, p, p, p, p, i32, p]),
 }
 
 

@@ -1,0 +1,441 @@
+"""BIG-C classification stage on B200: host-side mirror of the reference ``BIG_C`` modules
+(models/model_0v10.py:239-785 for VidVRD, models/model_0v7.py:240-790 for VidOR; exported by the
+reference as ``BIG_C_vidvrd`` / ``BIG_C_vidor``, models/__init__.py:1-4).
+
+Same constructor (``BIG_C(config, is_train=False)``), same ``forward(proposal_list, gt_graph_list=None, topk)``
+signature and return value (list of ``None | (quintuples i64[m,5], scores f32[m,3], spans i64[m,2],
+query_ids i64[m])``), and it loads reference ``state_dict``s unchanged.  Everything between the packed
+inputs and the triplets runs in the hand-written sm_100a kernels of libvsgb200 (csrc/gemm.cu tcgen05 GEMMs,
+csrc/bigc.cu fused kernels); PyTorch only owns the device buffers.  Inference only: the training path
+(``_forward_train``, Hungarian matching) is out of this hot path's scope.
+
+Differences in *how* (never in *what*):
+  * all videos passed to one ``forward`` call are batched: their rows are stacked into single GEMMs;
+  * the stretched ``[n, Tmax, D]`` tensors of ``_preprocess_proposal`` are never materialised -- the per-frame
+    MLPs run on the unique frames and the conv / pool / time-mean kernels apply the stretch as an index map.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import linalg
+from ._cabi import VsgError, check, lib, ptr, require_cuda, stream_ptr
+from .containers import TrajProposal
+from .linalg import Weight, gemm
+
+_P = C.c_void_p
+
+
+def _raw(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class PackedVideos(object):
+    """Device-resident packed form of a batch of ``TrajProposal``s (see csrc/bigc.cu header comment)."""
+
+    def __init__(self, proposals: Sequence[TrajProposal], device):
+        self.proposals = list(proposals)
+        V = len(self.proposals)
+        lens = [p.lengths for p in self.proposals]
+        counts = [p.num_proposals for p in self.proposals]
+        all_len = torch.cat(lens) if V else torch.zeros(0, dtype=torch.long)
+        off = torch.zeros(all_len.numel() + 1, dtype=torch.long)
+        off[1:] = torch.cumsum(all_len, 0)
+        seg = torch.zeros(V + 1, dtype=torch.int32)
+        seg[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int32), 0)
+        tmax = torch.cat([torch.full((c,), int(l.max()), dtype=torch.int32) for c, l in zip(counts, lens)])
+        track_vid = torch.cat([torch.full((c,), i, dtype=torch.int32) for i, c in enumerate(counts)])
+        wh = torch.tensor([[float(p.video_wh[0]), float(p.video_wh[1])] for p in self.proposals], dtype=torch.float32)
+        cat = lambda xs: xs[0].contiguous() if len(xs) == 1 else torch.cat(xs, 0)
+        self.boxes = cat([p.bboxes.to(device, torch.float32) for p in self.proposals])
+        self.feats = cat([p.features.to(device, torch.float32) for p in self.proposals])
+        self.dura = cat([p.traj_durations.to(device, torch.long) for p in self.proposals])
+        self.cat_ids = cat([p.cat_ids.to(device, torch.long) for p in self.proposals])
+        self.scores = cat([p.scores.to(device, torch.float32) for p in self.proposals])
+        self.off, self.seg = off.to(device), seg.to(device)
+        self.seg64 = seg.long().to(device)
+        self.tmax, self.track_vid, self.wh = tmax.to(device), track_vid.to(device), wh.to(device)
+        self.V, self.N, self.R = V, int(all_len.numel()), int(all_len.sum())
+        self.max_tracks = max(counts) if counts else 0
+        self.counts = counts
+
+
+class BIG_C(object):
+    """Drop-in for the reference ``BIG_C`` in inference mode (see module docstring)."""
+
+    variant = "vidvrd"
+
+    def __init__(self, config: dict, is_train: bool = False, precision: str = "3xtf32"):
+        if is_train:
+            raise NotImplementedError("vidsgg_big_b200.BIG_C covers the inference hot path only (is_train=False)")
+        self.is_train = False
+        self.config = dict(config)
+        c = config
+        self.num_pred_cats, self.num_enti_cats = c["num_pred_cats"], c["num_enti_cats"]
+        self.dim_feat, self.dim_clsme = c["dim_feat"], c["dim_clsme"]
+        self.dim_enti, self.dim_pred, self.dim_att, self.dim_ffn = c["dim_enti"], c["dim_pred"], c["dim_att"], c["dim_ffn"]
+        self.enco_pool_len, self.n_enco_layers, self.n_deco_layers = c["enco_pool_len"], c["n_enco_layers"], c["n_deco_layers"]
+        self.n_att_head, self.num_querys = c["n_att_head"], c["num_querys"]
+        self.num_anchors = self.num_querys
+        if not (self.dim_enti == self.dim_pred == self.dim_att):
+            raise VsgError("kernels assume dim_enti == dim_pred == dim_att (true for every reference config)")
+        if self.dim_enti not in (64, 128, 512):
+            raise VsgError("role-attention kernel is instantiated for dim 64 / 128 / 512")
+        if self.dim_enti // self.n_att_head not in (16, 32, 64):
+            raise VsgError("attention kernel is instantiated for head_dim 16 / 32 / 64")
+        self.precision = precision
+        self.mode = linalg.MODES[precision]
+        self.topk = 10
+        self.device = None
+        self._w = None
+        self._state: Dict[str, torch.Tensor] = {}
+        self._init_variant(c)
+        # the reference loads these two tables from .npy files at construction (model_0v10.py:266, :283)
+        for key, path in (("EntiNameEmb", c.get("EntiNameEmb_path")), ("bias_matrix", c.get("bias_matrix_path"))):
+            if path is not None and isinstance(path, str) and path.endswith(".npy"):
+                self._state[key] = torch.from_numpy(np.load(path)).float()
+
+    def _init_variant(self, c):
+        self.dim_i3d = c.get("dim_i3d", None)
+        self.has_entiemb = True
+        self.extra_width = self.dim_i3d or 0
+        self.dim_z = self.dim_pred + 2 * self.dim_clsme + (4 if self.dim_i3d else 2) * self.dim_enti
+
+    # ---- nn.Module-like surface -------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else
+                                    (device.index if isinstance(device, torch.device) else int(device))))
+
+    def to(self, device):
+        self.device = torch.device(device)
+        if self._state:
+            self._prepare()
+        return self
+
+    def state_dict(self):
+        return dict(self._state)
+
+    def _expected_keys_static(self) -> List[str]:
+        k = []
+        if self.has_entiemb:
+            k.append("EntiNameEmb")
+        k += ["pos_embedding", "pred_query_init", "bias_matrix"]
+        for n in ("fc_feat2enti.0", "fc_feat2enti.2", "fc_bbox2enti.0", "fc_bbox2enti.2", "conv_feat2enti",
+                  "fc_enti2enco.0", "fc_enti2enco.2"):
+            k += [n + ".weight", n + ".bias"]
+        if self.variant == "vidvrd" and self.dim_i3d:
+            k += ["fc_i3d.0.weight", "fc_i3d.0.bias"]
+        for i in range(self.n_enco_layers):
+            p = "encoder_layers.%d." % i
+            k += [p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", p + "self_attn.out_proj.weight",
+                  p + "self_attn.out_proj.bias"]
+            for n in ("linear1", "linear2", "norm1", "norm2"):
+                k += [p + n + ".weight", p + n + ".bias"]
+        for i in range(self.n_deco_layers):
+            p = "decoder_layers.%d." % i
+            k += [p + "self_attn.in_proj_weight", p + "self_attn.in_proj_bias", p + "self_attn.out_proj.weight",
+                  p + "self_attn.out_proj.bias"]
+            for n in ("fc_rolewise.0.0", "fc_rolewise.0.2", "fc_rolewise.1.0", "fc_rolewise.1.2", "fc_enti2att", "fc_pred2att",
+                      "fc2.0", "fc2.3", "norm1", "norm2", "norm3"):
+                k += [p + n + ".weight", p + n + ".bias"]
+        if self.variant == "vidor":
+            k += ["fc_pred2logits.0.weight", "fc_pred2logits.0.bias", "fc_pred2logits.2.weight", "fc_pred2logits.2.bias"]
+        else:
+            k += ["fc_pred2logits.weight", "fc_pred2logits.bias"]
+        return k
+
+    def load_state_dict(self, state_dict: Dict[str, torch.Tensor], strict: bool = True):
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}   # tools/eval_vidor.py:59-68
+        if strict:
+            want = set(self._expected_keys_static())
+            missing, unexpected = sorted(want - set(sd)), sorted(set(sd) - want)
+            if missing or unexpected:
+                raise RuntimeError("Error(s) in loading state_dict for BIG_C: missing %s unexpected %s" % (missing, unexpected))
+        self._state = {k: v.detach().float().cpu() for k, v in sd.items()}
+        if self.device is not None:
+            self._prepare()
+        return self
+
+    # ---- weight staging in HBM --------------------------------------------------------------------
+    def _prepare(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise VsgError("BIG_C runs on a CUDA device only (no CPU fallback)")
+        st = {k: v.to(dev) for k, v in self._state.items()}
+        E, Pd, Q = self.dim_enti, self.dim_pred, self.num_querys
+        split = self.mode == linalg.X3TF32
+        W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
+        w = {}
+        w["bbox1_w"], w["bbox1_b"] = st["fc_bbox2enti.0.weight"].contiguous(), st["fc_bbox2enti.0.bias"].contiguous()
+        w["bbox2"], w["feat1"], w["feat2"] = W("fc_bbox2enti.2"), W("fc_feat2enti.0"), W("fc_feat2enti.2")
+        cw = st["conv_feat2enti.weight"]                                  # [E, 2E, 3] -> tap-major [3E, 2E]
+        w["conv"] = Weight(cw.permute(2, 0, 1).reshape(3 * E, 2 * E).contiguous(), None, split=split)
+        w["conv_b"] = st["conv_feat2enti.bias"].contiguous()
+        w["enco1"], w["enco2"] = W("fc_enti2enco.0"), W("fc_enti2enco.2")
+        if self.variant == "vidvrd" and self.dim_i3d:
+            w["i3d"] = W("fc_i3d.0")
+        w["enc"] = []
+        for i in range(self.n_enco_layers):
+            p = "encoder_layers.%d." % i
+            w["enc"].append(dict(
+                qkv=Weight(st[p + "self_attn.in_proj_weight"], st[p + "self_attn.in_proj_bias"], split=split),
+                out=W(p + "self_attn.out_proj"), l1=W(p + "linear1"), l2=W(p + "linear2"),
+                n1=(st[p + "norm1.weight"].contiguous(), st[p + "norm1.bias"].contiguous()),
+                n2=(st[p + "norm2.weight"].contiguous(), st[p + "norm2.bias"].contiguous())))
+        pos = st["pos_embedding"].contiguous()
+        w["pos"], w["query_init"] = pos, st["pred_query_init"].contiguous()
+        w["dec"] = []
+        for i in range(self.n_deco_layers):
+            p = "decoder_layers.%d." % i
+            qkv = Weight(st[p + "self_attn.in_proj_weight"], st[p + "self_attn.in_proj_bias"], split=split)
+            # q = k = (query + pos) W^T  ==  query W^T + (pos W^T): the pos term becomes a row-periodic bias (period Q)
+            posb = gemm(self.mode, pos, qkv, bias=False)
+            posb[:, 2 * Pd:] = 0.0
+            r2 = Weight(torch.cat([st[p + "fc_rolewise.0.2.weight"], st[p + "fc_rolewise.1.2.weight"]], 1).contiguous(),
+                        st[p + "fc_rolewise.0.2.bias"] + st[p + "fc_rolewise.1.2.bias"], split=split)
+            w["dec"].append(dict(
+                qkv=qkv, posb=posb.contiguous(), out=W(p + "self_attn.out_proj"),
+                p2a=W(p + "fc_pred2att"), e2a=W(p + "fc_enti2att"),
+                r1=(W(p + "fc_rolewise.0.0"), W(p + "fc_rolewise.1.0")), r2=r2,
+                f1=W(p + "fc2.0"), f2=W(p + "fc2.3"),
+                n1=(st[p + "norm1.weight"].contiguous(), st[p + "norm1.bias"].contiguous()),
+                n2=(st[p + "norm2.weight"].contiguous(), st[p + "norm2.bias"].contiguous()),
+                n3=(st[p + "norm3.weight"].contiguous(), st[p + "norm3.bias"].contiguous())))
+        w["bias_matrix"] = st["bias_matrix"].reshape(self.num_enti_cats * self.num_enti_cats, self.num_pred_cats).contiguous()
+        if self.has_entiemb:
+            w["entiemb"] = st["EntiNameEmb"].contiguous()
+        if self.variant == "vidor":
+            w["log1"], w["log2"] = W("fc_pred2logits.0"), W("fc_pred2logits.2")
+        else:
+            w["log"] = W("fc_pred2logits")
+        self._w = w
+
+    # ---- kernels ------------------------------------------------------------------------------------
+    def _add_ln(self, x, a, norm, post=None, period=0):
+        out = torch.empty_like(x)
+        check(lib().vsg_add_layernorm(_raw(x), x.stride(0), _raw(a), 0 if a is None else a.stride(0), _raw(norm[0]), _raw(norm[1]),
+                                      _raw(post), period, x.shape[0], x.shape[1], _raw(out), out.stride(0), stream_ptr(x.device)),
+              "vsg_add_layernorm")
+        return out
+
+    def _mha(self, qkv, d, seg_off, n_seg, fixed_len, max_len):
+        out = torch.empty(qkv.shape[0], d, dtype=torch.float32, device=qkv.device)
+        ld = qkv.stride(0)
+        check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * d), ld, C.c_void_p(qkv.data_ptr() + 8 * d), ld,
+                            _raw(seg_off), n_seg, fixed_len, max_len, self.n_att_head, d // self.n_att_head, _raw(out), d,
+                            stream_ptr(qkv.device)), "vsg_mha")
+        return out
+
+    def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
+        """model_0v10.py:434-475 for the whole batch.  Returns (logits [V*Q, P], so int32[V*Q,2], extras)."""
+        w, m, dev = self._w, self.mode, self.device
+        E, Pd, Q, F_in = self.dim_enti, self.dim_pred, self.num_querys, self.dim_feat
+        R, N, V = pk.R, pk.N, pk.V
+        sp = stream_ptr(dev)
+        L = lib()
+        if pk.feats.shape[1] < F_in + self.extra_width:
+            raise VsgError("features have %d columns, model needs %d" % (pk.feats.shape[1], F_in + self.extra_width))
+        # --- per-frame MLPs on the unique frames, written into the two halves of X [R, 2E]
+        X = torch.empty(R, 2 * E, dtype=torch.float32, device=dev)
+        h = torch.empty(R, E, dtype=torch.float32, device=dev)
+        check(L.vsg_bbox_feat_mlp1(_raw(pk.boxes), _raw(pk.off), N, R, _raw(pk.track_vid), _raw(pk.wh), _raw(w["bbox1_w"]),
+                                   _raw(w["bbox1_b"]), E, _raw(h), E, None, sp), "vsg_bbox_feat_mlp1")
+        gemm(m, h, w["bbox2"], out=X[:, :E], relu=True)
+        gemm(m, pk.feats, w["feat1"], out=h, relu=True, K=F_in)
+        gemm(m, h, w["feat2"], out=X[:, E:], relu=True)
+        # --- conv taps (one GEMM, N = 3E) + stretched conv / max-pool
+        Y = gemm(m, X, w["conv"], bias=False)
+        del X, h
+        pooled = torch.empty(N, E * self.enco_pool_len, dtype=torch.float32, device=dev)
+        check(L.vsg_conv_pool(_raw(Y), Y.stride(0), E, _raw(w["conv_b"]), _raw(pk.off), _raw(pk.tmax), N, self.enco_pool_len,
+                              _raw(pooled), sp), "vsg_conv_pool")
+        del Y
+        enti2enco = gemm(m, gemm(m, pooled, w["enco1"], relu=True), w["enco2"], relu=True)
+        # --- stretched time-mean of the extra columns (I3D / classeme)
+        extra = None
+        if self.extra_width:
+            extra = torch.empty(N, self.extra_width, dtype=torch.float32, device=dev)
+            check(L.vsg_stretched_mean(_raw(pk.feats), pk.feats.stride(0), F_in, self.extra_width, _raw(pk.off), _raw(pk.tmax), N,
+                                       _raw(extra), self.extra_width, sp), "vsg_stretched_mean")
+        # --- encoder (post-norm, tokens = tracks of a video)
+        x = enti2enco
+        for lw in w["enc"]:
+            qkv = gemm(m, x, lw["qkv"])
+            att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks)
+            x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"])
+            x = self._add_ln(x, gemm(m, gemm(m, x, lw["l1"], relu=True), lw["l2"]), lw["n2"])
+        enco = x
+        # --- decoder
+        VQ = V * Q
+        query = torch.empty(VQ, Pd, dtype=torch.float32, device=dev)
+        check(L.vsg_broadcast_rows(_raw(w["query_init"]), Q, Pd, VQ, _raw(query), sp), "vsg_broadcast_rows")
+        so = torch.empty(VQ, 2, dtype=torch.int32, device=dev)
+        att_out = torch.zeros(VQ, 2, max(pk.max_tracks, 1), dtype=torch.float32, device=dev) if want_att else None
+        values = torch.empty(VQ, 2 * E, dtype=torch.float32, device=dev)
+        hid = torch.empty(VQ, 2 * Pd, dtype=torch.float32, device=dev)
+        n_dec = len(w["dec"])
+        for li, lw in enumerate(w["dec"]):
+            last = li == n_dec - 1
+            qkv = gemm(m, query, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
+            att = self._mha(qkv, Pd, None, V, Q, Q)
+            query = self._add_ln(query, gemm(m, att, lw["out"]), lw["n1"], post=w["pos"], period=Q)
+            p2a = gemm(m, query, lw["p2a"])
+            e2a = gemm(m, enco, lw["e2a"])
+            check(L.vsg_role_attention(_raw(p2a), _raw(e2a), _raw(enco), _raw(pk.seg), V, Q, E, pk.max_tracks,
+                                       float(1.0 / np.sqrt(self.dim_enti)), _raw(values),
+                                       _raw(att_out) if last else None, 0 if att_out is None else att_out.shape[2],
+                                       _raw(so) if last else None, sp), "vsg_role_attention")
+            gemm(m, values[:, :E], lw["r1"][0], out=hid[:, :Pd], relu=True)
+            gemm(m, values[:, E:], lw["r1"][1], out=hid[:, Pd:], relu=True)
+            query = self._add_ln(query, gemm(m, hid, lw["r2"]), lw["n2"])
+            query = self._add_ln(query, gemm(m, gemm(m, query, lw["f1"], relu=True), lw["f2"]), lw["n3"])
+        logits = self._prediction_head(pk, query, so, enti2enco, extra)
+        return logits, so, dict(query=query, att=att_out, enti2enco=enti2enco, enco=enco, extra=extra)
+
+    def _concat(self, pieces, rows, ldo):
+        n = len(pieces)
+        src = (_P * n)(*[C.c_void_p(p[0].data_ptr()) for p in pieces])
+        idx = (_P * n)(*[None if p[1] is None else C.c_void_p(p[1].data_ptr()) for p in pieces])
+        istr = (C.c_int * n)(*[2 for _ in pieces])
+        ld = (C.c_int * n)(*[int(p[0].stride(0)) for p in pieces])
+        wd = (C.c_int * n)(*[int(p[2]) for p in pieces])
+        out = torch.empty(rows, ldo, dtype=torch.float32, device=self.device)
+        check(lib().vsg_gather_concat(src, idx, istr, ld, wd, n, rows, _raw(out), ldo, stream_ptr(self.device)), "vsg_gather_concat")
+        return out
+
+    def _so_cats(self, pk, so):
+        VQ = so.shape[0]
+        pair_index = torch.empty(VQ, dtype=torch.int32, device=self.device)
+        so_cat = torch.empty(VQ, 2, dtype=torch.int32, device=self.device)
+        check(lib().vsg_so_category(_raw(so), _raw(pk.cat_ids), self.num_enti_cats, VQ, _raw(pair_index), _raw(so_cat),
+                                    stream_ptr(self.device)), "vsg_so_category")
+        return pair_index, so_cat
+
+    def _prediction_head(self, pk, query, so, enti_feat, extra):
+        """model_0v10.py:478-507."""
+        w, m = self._w, self.mode
+        E, Pd = self.dim_enti, self.dim_pred
+        VQ = query.shape[0]
+        pair_index, so_cat = self._so_cats(pk, so)
+        s_idx, o_idx = so, so[:, 1:]                      # strided views: element r*2 (+1)
+        sc_idx, oc_idx = so_cat, so_cat[:, 1:]
+        emb = w["entiemb"]
+        if self.dim_i3d:
+            i3d = gemm(m, extra, w["i3d"], relu=True)   # fc_i3d commutes with the row gather
+            pieces = [(query, None, Pd), (i3d, s_idx, E), (i3d, o_idx, E), (enti_feat, s_idx, E), (enti_feat, o_idx, E),
+                      (emb, sc_idx, self.dim_clsme), (emb, oc_idx, self.dim_clsme)]
+        else:
+            pieces = [(query, None, Pd), (emb, sc_idx, self.dim_clsme), (emb, oc_idx, self.dim_clsme),
+                      (enti_feat, s_idx, E), (enti_feat, o_idx, E)]
+        ldz = (self.dim_z + 3) // 4 * 4
+        Z = self._concat(pieces, VQ, ldz)
+        return gemm(m, Z, w["log"], rowbias=w["bias_matrix"], rb_index=pair_index, K=self.dim_z)
+
+    def _construct_triplets(self, pk, logits, so, topk):
+        """model_0v10.py:707-785 for every video; one D2H read of the per-video counts."""
+        V, Q = pk.V, self.num_querys
+        cap = Q * topk
+        dev = self.device
+        quint = torch.empty(V * cap, 5, dtype=torch.long, device=dev)
+        scores = torch.empty(V * cap, 3, dtype=torch.float32, device=dev)
+        spans = torch.empty(V * cap, 2, dtype=torch.long, device=dev)
+        qids = torch.empty(V * cap, dtype=torch.long, device=dev)
+        counts = torch.empty(V, 2, dtype=torch.int32, device=dev)
+        check(lib().vsg_construct_triplet(_raw(logits), logits.stride(0), self.num_pred_cats, Q, topk, _raw(so), _raw(pk.seg), V,
+                                          _raw(pk.dura), _raw(pk.cat_ids), _raw(pk.scores), _raw(quint), _raw(scores), _raw(spans),
+                                          _raw(qids), _raw(counts), cap, stream_ptr(dev)), "vsg_construct_triplet")
+        cnt = counts.cpu().tolist()
+        out = []
+        for v in range(V):
+            n_out, n_pos = cnt[v]
+            if n_pos == 0:
+                out.append(None)                         # no overlapping pair (model_0v10.py:733-734)
+                continue
+            s = slice(v * cap, v * cap + n_out)
+            out.append((quint[s], scores[s], spans[s], qids[s]))
+        return out
+
+    # ---- public API -----------------------------------------------------------------------------------
+    def forward(self, proposal_list, gt_graph_list=None, topk=None, max_rows: int = 2_000_000):
+        if self._w is None:
+            raise VsgError("BIG_C has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
+        self.topk = self.default_topk if topk is None else topk
+        props = [p if isinstance(p, TrajProposal) else TrajProposal.from_reference(p) for p in proposal_list]
+        results: List[Optional[tuple]] = [None] * len(props)
+        live = [i for i, p in enumerate(props) if p.num_proposals > 0]   # num_proposals == 0 -> None (:377-380)
+        # sub-batches bounded by rows so the intermediate buffers stay within budget
+        batch, rows = [], 0
+        def flush():
+            nonlocal batch, rows
+            if not batch:
+                return
+            pk = PackedVideos([props[i] for i in batch], self.device)
+            logits, so, _ = self._encode2decode(pk)
+            for i, r in zip(batch, self._construct_triplets(pk, logits, so, self.topk)):
+                results[i] = r
+            batch, rows = [], 0
+        for i in live:
+            r = int(props[i].lengths.sum())
+            if batch and rows + r > max_rows:
+                flush()
+            batch.append(i)
+            rows += r
+        flush()
+        return results
+
+    __call__ = forward
+    default_topk = 10
+
+    def forward_debug(self, proposal):
+        """(pred_queries, pred_logits [Q,P], att_matrx [2,Q,n]) of one video, like ``encode2decode`` (:434-475)."""
+        pk = PackedVideos([proposal], self.device)
+        logits, so, ex = self._encode2decode(pk, want_att=True)
+        n = proposal.num_proposals
+        att = ex["att"][:, :, :n].permute(1, 0, 2).contiguous()
+        return ex["query"], logits[:, :self.num_pred_cats], att, so, ex
+
+
+class BIG_C_vidvrd(BIG_C):
+    variant = "vidvrd"
+
+
+class BIG_C_vidor(BIG_C):
+    """models/model_0v7.py: no I3D branch, optional classeme (from features or from EntiNameEmb), 2-layer classifier,
+    default topk=3."""
+    variant = "vidor"
+    default_topk = 3
+
+    def _init_variant(self, c):
+        self.dim_i3d = None
+        self.use_clsme = c["use_clsme"]
+        self.has_entiemb = c.get("EntiNameEmb_path", None) is not None
+        self.extra_width = self.dim_clsme if (self.use_clsme and not self.has_entiemb) else 0
+        self.dim_z = self.dim_pred + 2 * self.dim_enti + (2 * self.dim_clsme if self.use_clsme else 0)
+
+    def _prediction_head(self, pk, query, so, enti_feat, extra):
+        """model_0v7.py:483-513."""
+        w, m = self._w, self.mode
+        E, Pd = self.dim_enti, self.dim_pred
+        VQ = query.shape[0]
+        pair_index, so_cat = self._so_cats(pk, so)
+        s_idx, o_idx = so, so[:, 1:]
+        if self.use_clsme:
+            if self.has_entiemb:
+                cl = [(w["entiemb"], so_cat, self.dim_clsme), (w["entiemb"], so_cat[:, 1:], self.dim_clsme)]
+            else:
+                cl = [(extra, s_idx, self.dim_clsme), (extra, o_idx, self.dim_clsme)]
+            pieces = [(query, None, Pd)] + cl + [(enti_feat, s_idx, E), (enti_feat, o_idx, E)]
+        else:
+            pieces = [(query, None, Pd), (enti_feat, s_idx, E), (enti_feat, o_idx, E)]
+        ldz = (self.dim_z + 3) // 4 * 4
+        Z = self._concat(pieces, VQ, ldz)
+        hid = gemm(m, Z, w["log1"], relu=True, K=self.dim_z)
+        return gemm(m, hid, w["log2"], rowbias=w["bias_matrix"], rb_index=pair_index)

@@ -1,0 +1,719 @@
+// BIG-C classification stage: every non-GEMM kernel (the GEMMs are csrc/gemm.cu).
+//
+// All kernels work on a BATCH of videos in packed form:
+//   rows     = all box-frames of all tracks of all videos (R = sum L);  off[N+1] row offsets per track
+//   tracks   = N over all videos; seg[V+1] track range per video; tmax[N] = longest track of the track's video
+//   queries  = V * Q rows (Q = num_querys, video-major)
+// The reference stretches each track to the video's longest track by repeating frames
+// (models/model_0v10.py:18-46): frame i of an L-frame track appears ceil((Tmax-i)/L) times.  Here the stretch
+// is never materialised: with q = Tmax / L, rem = Tmax % L, frame i is repeated q+1 times if i < rem else q times,
+// and stretched position j maps to   src(j) = j / (q+1)                     if j < rem*(q+1)
+//                                            rem + (j - rem*(q+1)) / q      otherwise.
+#include "common.cuh"
+#include <float.h>
+
+namespace vsg {
+
+__device__ __forceinline__ int find_track(const int64_t* __restrict__ off, int n, int64_t row) {
+  return find_segment(off, n, row);
+}
+
+struct Stretch {
+  int L, q, rem, split;  // split = rem*(q+1)
+  __device__ __forceinline__ Stretch(int L_, int Tmax) : L(L_) { q = Tmax / L_; rem = Tmax - q * L_; split = rem * (q + 1); }
+  __device__ __forceinline__ int src(int j) const { return j < split ? j / (q + 1) : rem + (j - split) / q; }
+  __device__ __forceinline__ int reps(int i) const { return i < rem ? q + 1 : q; }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// A5: 8-d motion features (model_0v10.py:401-420) fused with the first fc_bbox2enti layer (8 -> E, ReLU).
+// One warp per row; lane owns channels lane, lane+32, ...
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ off, int n_tracks, int64_t n_rows,
+                      const int32_t* __restrict__ track_vid, const float* __restrict__ wh,  // wh[V][2]
+                      const float* __restrict__ W1, const float* __restrict__ b1, int E,    // W1 [E][8]
+                      float* __restrict__ out, int ldo, float* __restrict__ feat8_out /* optional [R][8] */) {
+  extern __shared__ float sw[];  // W1 transposed [8][E] + b1[E]
+  for (int i = threadIdx.x; i < E * 8; i += blockDim.x) sw[(i % 8) * E + i / 8] = W1[i];
+  for (int i = threadIdx.x; i < E; i += blockDim.x) sw[8 * E + i] = b1[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < n_rows; r += n_warps) {
+    const int t = find_track(off, n_tracks, r);
+    const bool last = (r + 1 == off[t + 1]);
+    const int v = track_vid[t];
+    const float w = wh[2 * v], h = wh[2 * v + 1];
+    float4 a = boxes[r];
+    float4 b = last ? a : boxes[r + 1];
+    a.x = a.x / w; a.z = a.z / w; a.y = a.y / h; a.w = a.w / h;
+    b.x = b.x / w; b.z = b.z / w; b.y = b.y / h; b.w = b.w / h;
+    float f[8];
+    const float cx = (a.z + a.x) / 2, cy = (a.w + a.y) / 2, bw = a.z - a.x, bh = a.w - a.y;
+    const float cx2 = (b.z + b.x) / 2, cy2 = (b.w + b.y) / 2, bw2 = b.z - b.x, bh2 = b.w - b.y;
+    f[0] = cx; f[1] = last ? 0.f : cx2 - cx;
+    f[2] = cy; f[3] = last ? 0.f : cy2 - cy;
+    f[4] = bw; f[5] = last ? 0.f : bw2 - bw;
+    f[6] = bh; f[7] = last ? 0.f : bh2 - bh;
+    if (feat8_out && lane < 8) feat8_out[r * 8 + lane] = f[lane];
+    float* o = out + r * (int64_t)ldo;
+    for (int c = lane; c < E; c += 32) {
+      float acc = sw[8 * E + c];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc = fmaf(f[k], sw[k * E + c], acc);
+      o[c] = fmaxf(acc, 0.f);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Time-mean of the extra feature columns over the STRETCHED sequence (model_0v10.py:470, model_0v7.py:473):
+// mean_j x[src(j)] = sum_i reps(i) * x[i] / Tmax.   One CTA per track, threads over channels.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+stretched_mean_kernel(const float* __restrict__ feat, int ldf, int col0, int width, const int64_t* __restrict__ off,
+                      const int32_t* __restrict__ tmax, float* __restrict__ out, int ldo) {
+  const int t = blockIdx.x;
+  const int64_t r0 = off[t];
+  const int L = (int)(off[t + 1] - r0);
+  const Stretch st(L, tmax[t]);
+  for (int c = threadIdx.x; c < width; c += blockDim.x) {
+    float acc = 0.f;
+    const float* p = feat + r0 * (int64_t)ldf + col0 + c;
+    for (int i = 0; i < L; ++i) acc = fmaf((float)st.reps(i), p[(int64_t)i * ldf], acc);
+    out[(int64_t)t * ldo + c] = acc / (float)tmax[t];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// conv_feat2enti (k=3, stride 2, pad 1 over stretched time) + adaptive_max_pool1d(pool) (model_0v10.py:450-457)
+// from the three per-frame tap products Y[r][k*E + c] = sum_ci W[c][ci][k] * X[r][ci] (one GEMM).
+// out position t:  Y0[src(2t-1)] + Y1[src(2t)] + Y2[src(2t+1)] (+ bias), zero padding outside [0, Tmax).
+// One CTA per (track, pool bin); threads own 4 channels; consecutive positions that gather the same three
+// source frames are skipped, so a track costs O(L) loads however far it is stretched.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+conv_pool_kernel(const float* __restrict__ Y, int ldy, int E, const float* __restrict__ bias, const int64_t* __restrict__ off,
+                 const int32_t* __restrict__ tmax, int pool, float* __restrict__ out /* [N][E*pool] channel-major */) {
+  const int t = blockIdx.x / pool, p = blockIdx.x % pool;
+  const int64_t r0 = off[t];
+  const int L = (int)(off[t + 1] - r0);
+  const int Tmax = tmax[t];
+  const Stretch st(L, Tmax);
+  const int Tc = (Tmax - 1) / 2 + 1;
+  const int ts = (p * Tc) / pool;
+  const int te = ((p + 1) * Tc + pool - 1) / pool;
+  for (int c4 = threadIdx.x; c4 < E / 4; c4 += blockDim.x) {
+    float4 best = make_float4(-FLT_MAX, -FLT_MAX, -FLT_MAX, -FLT_MAX);
+    int pa = -2, pb = -2, pc = -2;
+    for (int tt = ts; tt < te; ++tt) {
+      const int ja = 2 * tt - 1, jb = 2 * tt, jc = 2 * tt + 1;
+      const int a = ja >= 0 ? st.src(ja) : -1;
+      const int b = st.src(jb);
+      const int c = jc < Tmax ? st.src(jc) : -1;
+      if (a == pa && b == pb && c == pc) continue;
+      pa = a; pb = b; pc = c;
+      float4 v = *reinterpret_cast<const float4*>(Y + (r0 + b) * (int64_t)ldy + E + 4 * c4);
+      if (a >= 0) {
+        const float4 x = *reinterpret_cast<const float4*>(Y + (r0 + a) * (int64_t)ldy + 4 * c4);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      if (c >= 0) {
+        const float4 x = *reinterpret_cast<const float4*>(Y + (r0 + c) * (int64_t)ldy + 2 * E + 4 * c4);
+        v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
+      }
+      best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y); best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
+    }
+    const float4 bb = *reinterpret_cast<const float4*>(bias + 4 * c4);
+    float* o = out + (int64_t)t * E * pool;
+    o[(4 * c4 + 0) * pool + p] = best.x + bb.x;
+    o[(4 * c4 + 1) * pool + p] = best.y + bb.y;
+    o[(4 * c4 + 2) * pool + p] = best.z + bb.z;
+    o[(4 * c4 + 3) * pool + p] = best.w + bb.w;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// out = LayerNorm(x + a) * gamma + beta (+ post[row % post_period])   (eps 1e-5, biased variance).
+// One warp per row, D <= 1024, D % 32 == 0.  `a` may be null.
+// ---------------------------------------------------------------------------------------------------
+template <int MAXPL>
+__global__ void __launch_bounds__(256)
+add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a, int lda, const float* __restrict__ gamma,
+                     const float* __restrict__ beta, const float* __restrict__ post, int post_period, int64_t rows, int D,
+                     float* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int per = D / 32;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    float v[MAXPL];
+    float s = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+      if (i < per) {
+        const int c = lane + 32 * i;
+        float t = x[r * ldx + c];
+        if (a) t += a[r * lda + c];
+        v[i] = t;
+        s += t;
+      }
+    }
+    const float mean = warp_sum(s) / (float)D;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i)
+      if (i < per) { const float d = v[i] - mean; q += d * d; }
+    const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+#pragma unroll
+    for (int i = 0; i < MAXPL; ++i) {
+      if (i < per) {
+        const int c = lane + 32 * i;
+        float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
+        if (post) y += post[(r % post_period) * (int64_t)D + c];
+        out[r * ldo + c] = y;
+      }
+    }
+  }
+}
+
+// out[r][c] = x[r % period][c]   (query initialisation: pred_query_init broadcast to every video)
+__global__ void broadcast_rows_kernel(const float* __restrict__ x, int period, int D, int64_t rows, float* __restrict__ out) {
+  const int64_t total = rows * (D / 4);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / (D / 4);
+    const int c4 = (int)(i - r * (D / 4));
+    reinterpret_cast<float4*>(out)[i] = reinterpret_cast<const float4*>(x)[(r % period) * (D / 4) + c4];
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Multi-head self-attention core on packed rows (nn.MultiheadAttention semantics without the projections):
+// for every segment s (rows seg_off[s]..seg_off[s+1]) and head h:  O = softmax(Q K^T / sqrt(dh)) V.
+// Q/K/V are column blocks of (possibly the same) row-major buffers.  One CTA per (segment, head, 32-query block);
+// keys/values are walked in chunks of KC rows staged in shared memory with an online softmax, so the
+// segment length is unbounded.  One warp per query at a time; lanes split keys for QK^T and dims for PV.
+// ---------------------------------------------------------------------------------------------------
+template <int DH>
+__global__ void __launch_bounds__(256)
+mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp, int ldv,
+           const int64_t* __restrict__ seg_off, int fixed_len, int n_head, float scale, float* __restrict__ Op, int ldo) {
+  constexpr int KC = DH >= 64 ? 64 : 128;   // keeps K/V chunks + scratch under the 48 KB static limit
+  constexpr int PITCH = DH + 1;
+  __shared__ float sK[KC * PITCH];
+  __shared__ float sV[KC * PITCH];
+  __shared__ float sP[8][KC];
+  __shared__ float sQ[8][DH];
+  const int seg = blockIdx.x, head = blockIdx.y;
+  const int64_t row0 = seg_off ? seg_off[seg] : (int64_t)seg * fixed_len;
+  const int n = seg_off ? (int)(seg_off[seg + 1] - row0) : fixed_len;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q_base = blockIdx.z * 32;
+  if (q_base >= n) return;
+  const int hc = head * DH;
+  constexpr int OD = (DH + 31) / 32;  // output dims per lane
+  // each warp owns queries q_base + warp, +8, +16, +24
+  float m_run[4], l_run[4], o_acc[4][OD];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    m_run[i] = -INFINITY; l_run[i] = 0.f;
+#pragma unroll
+    for (int d = 0; d < OD; ++d) o_acc[i][d] = 0.f;
+  }
+  for (int k0 = 0; k0 < n; k0 += KC) {
+    const int kc = min(KC, n - k0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < kc * DH; i += blockDim.x) {
+      const int kr = i / DH, d = i % DH;
+      sK[kr * PITCH + d] = Kp[(row0 + k0 + kr) * ldk + hc + d];
+      sV[kr * PITCH + d] = Vp[(row0 + k0 + kr) * ldv + hc + d];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int qi = 0; qi < 4; ++qi) {
+      const int q = q_base + warp + 8 * qi;
+      if (q >= n) continue;  // warp-uniform
+      for (int d = lane; d < DH; d += 32) sQ[warp][d] = Qp[(row0 + q) * ldq + hc + d] * scale;
+      __syncwarp();
+      float sc[KC / 32];
+      float cmax = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < KC / 32; ++j) {
+        const int kr = lane + 32 * j;
+        float s = -INFINITY;
+        if (kr < kc) {
+          s = 0.f;
+#pragma unroll
+          for (int d = 0; d < DH; ++d) s = fmaf(sQ[warp][d], sK[kr * PITCH + d], s);
+        }
+        sc[j] = s;
+        cmax = fmaxf(cmax, s);
+      }
+      cmax = warp_max(cmax);
+      const float m_new = fmaxf(m_run[qi], cmax);
+      const float corr = expf(m_run[qi] - m_new);
+      float psum = 0.f;
+#pragma unroll
+      for (int j = 0; j < KC / 32; ++j) {
+        const int kr = lane + 32 * j;
+        const float pv = (kr < kc) ? expf(sc[j] - m_new) : 0.f;
+        sP[warp][kr] = pv;
+        psum += pv;
+      }
+      psum = warp_sum(psum);
+      l_run[qi] = l_run[qi] * corr + psum;
+      m_run[qi] = m_new;
+      __syncwarp();
+#pragma unroll
+      for (int dd = 0; dd < OD; ++dd) {
+        const int d = lane + 32 * dd;
+        float acc = o_acc[qi][dd] * corr;
+        if (d < DH) {
+          for (int kr = 0; kr < kc; ++kr) acc = fmaf(sP[warp][kr], sV[kr * PITCH + d], acc);
+        }
+        o_acc[qi][dd] = acc;
+      }
+      __syncwarp();
+    }
+  }
+#pragma unroll
+  for (int qi = 0; qi < 4; ++qi) {
+    const int q = q_base + warp + 8 * qi;
+    if (q >= n) continue;
+#pragma unroll
+    for (int dd = 0; dd < OD; ++dd) {
+      const int d = lane + 32 * dd;
+      if (d < DH) Op[(row0 + q) * ldo + hc + d] = o_acc[qi][dd] / l_run[qi];
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Role attention of RoleAttnDecoderLayer (model_0v10.py:190-214) for every video:
+//   logits[r][q][e] = <p2a[q][r-half], e2a[e][r-half]> / sqrt(dim_enti)
+//   att = softmax_e(logits) * softmax_r(logits);   values[r][q] = sum_e att[r][q][e] * enco[e]
+// One CTA per (video, 8-query block), one warp per query; lanes 0-15 hold the subject half of the 512-d
+// projections, lanes 16-31 the object half.  Writes values as [row][r*E + c] (the input layout of the two
+// fc_rolewise first layers), and on request the attention matrix and its per-role argmax (prediction_head :485).
+// ---------------------------------------------------------------------------------------------------
+constexpr int RA_MAX_TRACKS = 256;
+
+template <int E>
+__global__ void __launch_bounds__(256)
+role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e2a, const float* __restrict__ enco,
+                      const int32_t* __restrict__ seg, int Q, float inv_sqrt_d, float* __restrict__ values,
+                      float* __restrict__ att_out /* [V*Q][2][max_n] or null */, int att_ld,
+                      int32_t* __restrict__ so_out /* [V*Q][2] global track ids, or null */) {
+  constexpr int PER = E / 32;  // 16 dims per lane
+  __shared__ float sL[8][2][RA_MAX_TRACKS];
+  const int v = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.y * 8 + warp;
+  if (q >= Q) return;
+  const int t0 = seg[v], n = seg[v + 1] - t0;
+  const int64_t qrow = (int64_t)v * Q + q;
+  float pq[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) pq[i] = p2a[qrow * E + lane * PER + i];
+  // pass 1: logits
+  for (int e = 0; e < n; ++e) {
+    const float4* er = reinterpret_cast<const float4*>(e2a + (int64_t)(t0 + e) * E + lane * PER);
+    float acc = 0.f;
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+      const float4 x = er[i];
+      acc = fmaf(pq[4 * i], x.x, acc); acc = fmaf(pq[4 * i + 1], x.y, acc);
+      acc = fmaf(pq[4 * i + 2], x.z, acc); acc = fmaf(pq[4 * i + 3], x.w, acc);
+    }
+    // reduce within each half-warp (role)
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if ((lane & 15) == 0) sL[warp][lane >> 4][e] = acc * inv_sqrt_d;
+  }
+  __syncwarp();
+  // softmax over tracks per role (lanes stride e), then softmax over roles per track
+  float mx[2] = {-INFINITY, -INFINITY};
+  for (int e = lane; e < n; e += 32) { mx[0] = fmaxf(mx[0], sL[warp][0][e]); mx[1] = fmaxf(mx[1], sL[warp][1][e]); }
+  mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
+  float sm[2] = {0.f, 0.f};
+  for (int e = lane; e < n; e += 32) { sm[0] += expf(sL[warp][0][e] - mx[0]); sm[1] += expf(sL[warp][1][e] - mx[1]); }
+  sm[0] = warp_sum(sm[0]); sm[1] = warp_sum(sm[1]);
+  float best[2] = {-INFINITY, -INFINITY};
+  int best_e[2] = {0x7fffffff, 0x7fffffff};
+  for (int e = lane; e < n; e += 32) {
+    const float l0 = sL[warp][0][e], l1 = sL[warp][1][e];
+    const float m = fmaxf(l0, l1);
+    const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+    const float a0 = (expf(l0 - mx[0]) / sm[0]) * (e0 / (e0 + e1));
+    const float a1 = (expf(l1 - mx[1]) / sm[1]) * (e1 / (e0 + e1));
+    sL[warp][0][e] = a0; sL[warp][1][e] = a1;
+    if (a0 > best[0]) { best[0] = a0; best_e[0] = e; }
+    if (a1 > best[1]) { best[1] = a1; best_e[1] = e; }
+    if (att_out) { att_out[(qrow * 2 + 0) * att_ld + e] = a0; att_out[(qrow * 2 + 1) * att_ld + e] = a1; }
+  }
+  if (so_out) {
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ob = __shfl_xor_sync(0xffffffffu, best[r], o);
+        const int oe = __shfl_xor_sync(0xffffffffu, best_e[r], o);
+        if (ob > best[r] || (ob == best[r] && oe < best_e[r])) { best[r] = ob; best_e[r] = oe; }
+      }
+    }
+    if (lane == 0) { so_out[qrow * 2] = t0 + best_e[0]; so_out[qrow * 2 + 1] = t0 + best_e[1]; }
+  }
+  __syncwarp();
+  // pass 2: values[r] = sum_e att[r][e] * enco[e]; every lane owns 16 dims of BOTH roles
+  float acc0[PER], acc1[PER];
+#pragma unroll
+  for (int i = 0; i < PER; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
+  for (int e = 0; e < n; ++e) {
+    const float a0 = sL[warp][0][e], a1 = sL[warp][1][e];
+    const float4* er = reinterpret_cast<const float4*>(enco + (int64_t)(t0 + e) * E + lane * PER);
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+      const float4 x = er[i];
+      acc0[4 * i] = fmaf(a0, x.x, acc0[4 * i]); acc0[4 * i + 1] = fmaf(a0, x.y, acc0[4 * i + 1]);
+      acc0[4 * i + 2] = fmaf(a0, x.z, acc0[4 * i + 2]); acc0[4 * i + 3] = fmaf(a0, x.w, acc0[4 * i + 3]);
+      acc1[4 * i] = fmaf(a1, x.x, acc1[4 * i]); acc1[4 * i + 1] = fmaf(a1, x.y, acc1[4 * i + 1]);
+      acc1[4 * i + 2] = fmaf(a1, x.z, acc1[4 * i + 2]); acc1[4 * i + 3] = fmaf(a1, x.w, acc1[4 * i + 3]);
+    }
+  }
+  float* o0 = values + qrow * (2 * E) + lane * PER;
+  float* o1 = o0 + E;
+#pragma unroll
+  for (int i = 0; i < PER / 4; ++i) {
+    reinterpret_cast<float4*>(o0)[i] = make_float4(acc0[4 * i], acc0[4 * i + 1], acc0[4 * i + 2], acc0[4 * i + 3]);
+    reinterpret_cast<float4*>(o1)[i] = make_float4(acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Head input: Z[row] = concat of up to 8 pieces, each a (possibly gathered) row of a source matrix
+// (prediction_head concat, model_0v10.py:501/503, model_0v7.py:506/508).  idx < 0 => identity row.
+// ---------------------------------------------------------------------------------------------------
+struct ConcatPiece { const float* src; const int32_t* idx; int idx_stride; int ld; int width; int col0; };
+struct ConcatArgs { ConcatPiece p[8]; int n; };
+
+__global__ void gather_concat_kernel(ConcatArgs a, int64_t rows, float* __restrict__ out, int ldo) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    for (int k = 0; k < a.n; ++k) {
+      const ConcatPiece& pc = a.p[k];
+      const int64_t sr = pc.idx ? (int64_t)pc.idx[r * pc.idx_stride] : r;
+      const float* s = pc.src + sr * pc.ld;
+      float* d = out + r * ldo + pc.col0;
+      for (int c = lane; c < pc.width; c += 32) d[c] = s[c];
+    }
+  }
+}
+
+// so (global track ids [rows][2]) -> cat pair index scat*C+ocat and the per-role category ids
+__global__ void so_category_kernel(const int32_t* __restrict__ so, const int64_t* __restrict__ cat_ids, int C, int64_t rows,
+                                   int32_t* __restrict__ pair_index, int32_t* __restrict__ so_cat) {
+  for (int64_t r = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int sc = (int)cat_ids[so[2 * r]], oc = (int)cat_ids[so[2 * r + 1]];
+    pair_index[r] = sc * C + oc;
+    so_cat[2 * r] = sc; so_cat[2 * r + 1] = oc;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// A8 construct_triplet (model_0v10.py:707-785), one CTA per video:
+//   softmax over predicate classes, top-k, drop (s,o) without temporal overlap or s == o, dedup the quintuple
+//   [pred, scat, ocat, sid, oid] keeping the max predicate probability (first on ties), emit in lexicographic
+//   key order (== torch.unique(dim=0)), drop background (pred == 0) last.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TR_MAX = 2048;  // >= Q * topk
+
+struct TripletOut {
+  int64_t* quint;   // [V*cap][5]
+  float* scores;    // [V*cap][3]
+  int64_t* spans;   // [V*cap][2]
+  int64_t* qids;    // [V*cap]
+  int32_t* counts;  // [V][2] = (rows emitted, rows that passed the overlap filter)
+  int cap;
+};
+
+__device__ __forceinline__ bool trip_less(unsigned long long ka, float sa, unsigned ja, unsigned long long kb, float sb, unsigned jb) {
+  if (ka != kb) return ka < kb;
+  if (sa != sb) return sa > sb;
+  return ja < jb;
+}
+
+__global__ void __launch_bounds__(512)
+construct_triplet_kernel(const float* __restrict__ logits, int ld_logits, int P, int Q, int topk,
+                         const int32_t* __restrict__ so, const int32_t* __restrict__ seg, const int64_t* __restrict__ dura,
+                         const int64_t* __restrict__ cat_ids, const float* __restrict__ enti_scores, TripletOut out) {
+  __shared__ unsigned long long sKey[TR_MAX];
+  __shared__ float sScore[TR_MAX];
+  __shared__ unsigned sIdx[TR_MAX];
+  __shared__ int sFlag[TR_MAX];
+  __shared__ int sCount[2];
+  const int v = blockIdx.x;
+  const int t0 = seg[v];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, n_warps = blockDim.x >> 5;
+  const int m = Q * topk;
+  if (threadIdx.x < 2) sCount[threadIdx.x] = 0;
+  for (int i = threadIdx.x; i < TR_MAX; i += blockDim.x) { sKey[i] = ~0ull; sScore[i] = 0.f; sIdx[i] = 0xffffffffu; }
+  __syncthreads();
+  // ---- softmax + top-k per query (warp per query, up to 8 classes per lane) ----
+  for (int q = warp; q < Q; q += n_warps) {
+    const int64_t row = (int64_t)v * Q + q;
+    float x[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < P ? logits[row * ld_logits + c] : -INFINITY;
+      mx = fmaxf(mx, x[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < P ? expf(x[i] - mx) : -1.f;
+      if (c < P) sum += x[i];
+    }
+    sum = warp_sum(sum);
+    const int s_id = so[2 * row] - t0, o_id = so[2 * row + 1] - t0;
+    const longlong2 ds = reinterpret_cast<const longlong2*>(dura)[t0 + s_id];
+    const longlong2 dz = reinterpret_cast<const longlong2*>(dura)[t0 + o_id];
+    const bool overlap = (s_id != o_id) && (max(ds.x, dz.x) <= min(ds.y, dz.y));
+    const unsigned long long tail = ((unsigned long long)cat_ids[t0 + s_id] << 36) | ((unsigned long long)cat_ids[t0 + o_id] << 24) |
+                                    ((unsigned long long)s_id << 12) | (unsigned long long)o_id;
+    for (int k = 0; k < topk; ++k) {
+      float bv = -2.f;
+      int bc = 0x7fffffff;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int c = lane + 32 * i;
+        if (x[i] > bv) { bv = x[i]; bc = c; }   // ascending c within a lane => first max kept
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+        const int oc = __shfl_xor_sync(0xffffffffu, bc, o);
+        if (ov > bv || (ov == bv && oc < bc)) { bv = ov; bc = oc; }
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (lane + 32 * i == bc) x[i] = -1.f;
+      if (lane == 0 && overlap) {
+        const int j = q * topk + k;
+        sKey[j] = ((unsigned long long)bc << 48) | tail;
+        sScore[j] = bv / sum;
+        sIdx[j] = (unsigned)j;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- bitonic sort of TR_MAX entries by (key asc, score desc, original index asc) ----
+  for (int size = 2; size <= TR_MAX; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int i = threadIdx.x; i < TR_MAX / 2; i += blockDim.x) {
+        const int lo = 2 * i - (i & (stride - 1));
+        const int hi = lo + stride;
+        const bool asc = ((lo & size) == 0);
+        const unsigned long long ka = sKey[lo], kb = sKey[hi];
+        const float sa = sScore[lo], sb = sScore[hi];
+        const unsigned ja = sIdx[lo], jb = sIdx[hi];
+        const bool a_first = trip_less(ka, sa, ja, kb, sb, jb);
+        if (a_first != asc) {
+          sKey[lo] = kb; sKey[hi] = ka; sScore[lo] = sb; sScore[hi] = sa; sIdx[lo] = jb; sIdx[hi] = ja;
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // ---- run heads (= group winners), background filter, ordered compaction ----
+  for (int i = threadIdx.x; i < TR_MAX; i += blockDim.x) {
+    const bool valid = sKey[i] != ~0ull;
+    const bool head = valid && (i == 0 || sKey[i - 1] != sKey[i]);
+    sFlag[i] = (head && (sKey[i] >> 48) != 0) ? 1 : 0;
+    if (valid) atomicAdd(&sCount[1], 1);
+  }
+  __syncthreads();
+  if (warp == 0) {  // exclusive scan of TR_MAX flags by one warp (64 per lane)
+    constexpr int PER = TR_MAX / 32;
+    int local = 0;
+    for (int i = 0; i < PER; ++i) local += sFlag[lane * PER + i];
+    int incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += t;
+    }
+    int run = incl - local;
+    for (int i = 0; i < PER; ++i) {
+      const int f = sFlag[lane * PER + i];
+      sFlag[lane * PER + i] = f ? run : -1;
+      run += f;
+    }
+    if (lane == 31) sCount[0] = incl;
+  }
+  __syncthreads();
+  const int64_t base = (int64_t)v * out.cap;
+  for (int i = threadIdx.x; i < TR_MAX; i += blockDim.x) {
+    const int pos = sFlag[i];
+    if (pos < 0) continue;
+    const unsigned long long key = sKey[i];
+    const int pred = (int)(key >> 48), sc = (int)((key >> 36) & 0xfff), oc = (int)((key >> 24) & 0xfff);
+    const int sid = (int)((key >> 12) & 0xfff), oid = (int)(key & 0xfff);
+    int64_t* qd = out.quint + (base + pos) * 5;
+    qd[0] = pred; qd[1] = sc; qd[2] = oc; qd[3] = sid; qd[4] = oid;
+    float* sd = out.scores + (base + pos) * 3;
+    sd[0] = sScore[i]; sd[1] = enti_scores[t0 + sid]; sd[2] = enti_scores[t0 + oid];
+    const longlong2 ds = reinterpret_cast<const longlong2*>(dura)[t0 + sid];
+    const longlong2 dz = reinterpret_cast<const longlong2*>(dura)[t0 + oid];
+    out.spans[(base + pos) * 2] = max(ds.x, dz.x);
+    out.spans[(base + pos) * 2 + 1] = min(ds.y, dz.y);
+    out.qids[base + pos] = sIdx[i] / topk;
+  }
+  if (threadIdx.x == 0) { out.counts[2 * v] = sCount[0]; out.counts[2 * v + 1] = sCount[1]; }
+  (void)m;
+}
+
+static inline int grid_cap(int64_t blocks, int per_sm) {
+  const int64_t cap = (int64_t)sm_count() * per_sm;
+  return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" int vsg_bbox_feat_mlp1(const float* boxes, const int64_t* off, int n_tracks, int64_t n_rows, const int32_t* track_vid,
+                                  const float* wh, const float* W1, const float* b1, int E, float* out, int ldo, float* feat8_out,
+                                  void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && n_rows >= 0 && E > 0, "vsg_bbox_feat_mlp1: bad size");
+  if (n_rows == 0) return VSG_OK;
+  VSG_REQUIRE(boxes && off && track_vid && wh && W1 && b1 && out && aligned16(boxes), "vsg_bbox_feat_mlp1: null/misaligned pointer");
+  const size_t smem = (size_t)9 * E * sizeof(float);
+  VSG_REQUIRE(smem <= 48 * 1024, "vsg_bbox_feat_mlp1: E too large");
+  bbox_feat_mlp1_kernel<<<grid_cap((n_rows + 7) / 8, 8), 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(boxes), off, n_tracks, n_rows, track_vid, wh, W1, b1, E, out, ldo, feat8_out);
+  return check_launch("vsg_bbox_feat_mlp1");
+}
+
+extern "C" int vsg_stretched_mean(const float* feat, int ldf, int col0, int width, const int64_t* off, const int32_t* tmax,
+                                  int n_tracks, float* out, int ldo, void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && width >= 0, "vsg_stretched_mean: bad size");
+  if (n_tracks == 0 || width == 0) return VSG_OK;
+  VSG_REQUIRE(feat && off && tmax && out, "vsg_stretched_mean: null pointer");
+  stretched_mean_kernel<<<n_tracks, 256, 0, (cudaStream_t)stream>>>(feat, ldf, col0, width, off, tmax, out, ldo);
+  return check_launch("vsg_stretched_mean");
+}
+
+extern "C" int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,
+                             int n_tracks, int pool, float* out, void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && pool > 0 && E > 0 && E % 4 == 0 && ldy % 4 == 0, "vsg_conv_pool: bad size");
+  if (n_tracks == 0) return VSG_OK;
+  VSG_REQUIRE(Y && bias && off && tmax && out && aligned16(Y) && aligned16(bias), "vsg_conv_pool: null/misaligned pointer");
+  conv_pool_kernel<<<n_tracks * pool, 128, 0, (cudaStream_t)stream>>>(Y, ldy, E, bias, off, tmax, pool, out);
+  return check_launch("vsg_conv_pool");
+}
+
+extern "C" int vsg_add_layernorm(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
+                                 const float* post, int post_period, int64_t rows, int D, float* out, int ldo, void* stream) {
+  VSG_REQUIRE(rows >= 0 && D > 0 && D % 32 == 0 && D <= 1024, "vsg_add_layernorm: D must be a multiple of 32, <= 1024");
+  if (rows == 0) return VSG_OK;
+  VSG_REQUIRE(x && gamma && beta && out, "vsg_add_layernorm: null pointer");
+  VSG_REQUIRE(post == nullptr || post_period > 0, "vsg_add_layernorm: post needs a period");
+  const int g = grid_cap((rows + 7) / 8, 8);
+  if (D <= 128)
+    add_layernorm_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+  else if (D <= 512)
+    add_layernorm_kernel<16><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+  else
+    add_layernorm_kernel<32><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+  return check_launch("vsg_add_layernorm");
+}
+
+extern "C" int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* out, void* stream) {
+  VSG_REQUIRE(rows >= 0 && period > 0 && D > 0 && D % 4 == 0, "vsg_broadcast_rows: bad size");
+  if (rows == 0) return VSG_OK;
+  VSG_REQUIRE(x && out && aligned16(x) && aligned16(out), "vsg_broadcast_rows: null/misaligned pointer");
+  broadcast_rows_kernel<<<grid_cap((rows * (D / 4) + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(x, period, D, rows, out);
+  return check_launch("vsg_broadcast_rows");
+}
+
+extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
+                       int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, void* stream) {
+  VSG_REQUIRE(n_seg >= 0 && n_head > 0 && max_len >= 0, "vsg_mha: bad size");
+  if (n_seg == 0 || max_len == 0) return VSG_OK;
+  VSG_REQUIRE(Q && K && V && O, "vsg_mha: null pointer");
+  VSG_REQUIRE(seg_off != nullptr || fixed_len > 0, "vsg_mha: need seg_off or fixed_len");
+  const float scale = 1.0f / sqrtf((float)head_dim);
+  dim3 grid(n_seg, n_head, (max_len + 31) / 32);
+  if (head_dim == 64) mha_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
+  else if (head_dim == 16) mha_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
+  else if (head_dim == 32) mha_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
+  else { set_error("vsg_mha: head_dim %d unsupported (16, 32, 64)", head_dim); return VSG_E_UNSUPPORTED; }
+  return check_launch("vsg_mha");
+}
+
+extern "C" int vsg_role_attention(const float* p2a, const float* e2a, const float* enco, const int32_t* seg, int n_vid, int Q, int E,
+                                  int max_tracks, float inv_sqrt_d, float* values, float* att_out, int att_ld, int32_t* so_out,
+                                  void* stream) {
+  VSG_REQUIRE(n_vid >= 0 && Q > 0, "vsg_role_attention: bad size");
+  if (n_vid == 0) return VSG_OK;
+  VSG_REQUIRE(p2a && e2a && enco && seg && values, "vsg_role_attention: null pointer");
+  VSG_REQUIRE(max_tracks <= RA_MAX_TRACKS, "vsg_role_attention: more than %d tracks in a video", RA_MAX_TRACKS);
+  VSG_REQUIRE(aligned16(e2a) && aligned16(enco) && aligned16(values), "vsg_role_attention: misaligned pointer");
+  dim3 grid(n_vid, (Q + 7) / 8);
+  if (E == 512) role_attention_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
+  else if (E == 64) role_attention_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
+  else if (E == 128) role_attention_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
+  else { set_error("vsg_role_attention: dim %d unsupported (64, 128, 512)", E); return VSG_E_UNSUPPORTED; }
+  return check_launch("vsg_role_attention");
+}
+
+extern "C" int vsg_gather_concat(const float* const* src, const int32_t* const* idx, const int* idx_stride, const int* ld,
+                                 const int* width, int n_pieces, int64_t rows, float* out, int ldo, void* stream) {
+  VSG_REQUIRE(n_pieces >= 1 && n_pieces <= 8 && rows >= 0, "vsg_gather_concat: 1..8 pieces");
+  if (rows == 0) return VSG_OK;
+  ConcatArgs a;
+  a.n = n_pieces;
+  int col = 0;
+  for (int k = 0; k < n_pieces; ++k) {
+    VSG_REQUIRE(src[k] != nullptr, "vsg_gather_concat: null source");
+    a.p[k].src = src[k]; a.p[k].idx = idx[k]; a.p[k].idx_stride = idx_stride[k]; a.p[k].ld = ld[k]; a.p[k].width = width[k];
+    a.p[k].col0 = col;
+    col += width[k];
+  }
+  VSG_REQUIRE(col <= ldo, "vsg_gather_concat: pieces wider than the output row");
+  gather_concat_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(a, rows, out, ldo);
+  return check_launch("vsg_gather_concat");
+}
+
+extern "C" int vsg_so_category(const int32_t* so, const int64_t* cat_ids, int C, int64_t rows, int32_t* pair_index, int32_t* so_cat,
+                               void* stream) {
+  VSG_REQUIRE(rows >= 0 && C > 0, "vsg_so_category: bad size");
+  if (rows == 0) return VSG_OK;
+  VSG_REQUIRE(so && cat_ids && pair_index && so_cat, "vsg_so_category: null pointer");
+  so_category_kernel<<<grid_cap((rows + 255) / 256, 8), 256, 0, (cudaStream_t)stream>>>(so, cat_ids, C, rows, pair_index, so_cat);
+  return check_launch("vsg_so_category");
+}
+
+extern "C" int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int topk, const int32_t* so, const int32_t* seg,
+                                     int n_vid, const int64_t* dura, const int64_t* cat_ids, const float* enti_scores,
+                                     int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
+                                     void* stream) {
+  VSG_REQUIRE(n_vid >= 0 && P > 0 && P <= 256 && Q > 0 && topk > 0 && topk <= P, "vsg_construct_triplet: bad size (P <= 256)");
+  VSG_REQUIRE(Q * topk <= TR_MAX && cap >= Q * topk, "vsg_construct_triplet: Q*topk must be <= %d and <= cap", TR_MAX);
+  if (n_vid == 0) return VSG_OK;
+  VSG_REQUIRE(logits && so && seg && dura && cat_ids && enti_scores && quint && scores && spans && qids && counts,
+              "vsg_construct_triplet: null pointer");
+  VSG_REQUIRE(aligned16(dura), "vsg_construct_triplet: spans misaligned");
+  TripletOut o{quint, scores, spans, qids, counts, cap};
+  construct_triplet_kernel<<<n_vid, 512, 0, (cudaStream_t)stream>>>(logits, ld_logits, P, Q, topk, so, seg, dura, cat_ids,
+                                                                   enti_scores, o);
+  return check_launch("vsg_construct_triplet");
+}
