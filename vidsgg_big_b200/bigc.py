@@ -248,16 +248,23 @@ class BIG_C(object):
         h = torch.empty(R, E, dtype=torch.float32, device=dev)
         check(L.vsg_bbox_feat_mlp1(_raw(pk.boxes), _raw(pk.off), N, R, _raw(pk.track_vid), _raw(pk.wh), _raw(w["bbox1_w"]),
                                    _raw(w["bbox1_b"]), E, _raw(h), E, None, sp), "vsg_bbox_feat_mlp1")
+        dbg = getattr(self, "_dbg", None)
+        if dbg is not None:
+            dbg["bbox_h1"] = h.clone()
         gemm(m, h, w["bbox2"], out=X[:, :E], relu=True)
         gemm(m, pk.feats, w["feat1"], out=h, relu=True, K=F_in)
         gemm(m, h, w["feat2"], out=X[:, E:], relu=True)
         # --- conv taps (one GEMM, N = 3E) + stretched conv / max-pool
         Y = gemm(m, X, w["conv"], bias=False)
+        if dbg is not None:
+            dbg["X"], dbg["Y"] = X.clone(), Y.clone()
         del X, h
         pooled = torch.empty(N, E * self.enco_pool_len, dtype=torch.float32, device=dev)
         check(L.vsg_conv_pool(_raw(Y), Y.stride(0), E, _raw(w["conv_b"]), _raw(pk.off), _raw(pk.tmax), N, self.enco_pool_len,
                               _raw(pooled), sp), "vsg_conv_pool")
         del Y
+        if dbg is not None:
+            dbg["pooled"] = pooled.clone()
         enti2enco = gemm(m, gemm(m, pooled, w["enco1"], relu=True), w["enco2"], relu=True)
         # --- stretched time-mean of the extra columns (I3D / classeme)
         extra = None
@@ -272,6 +279,8 @@ class BIG_C(object):
             att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks)
             x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"])
             x = self._add_ln(x, gemm(m, gemm(m, x, lw["l1"], relu=True), lw["l2"]), lw["n2"])
+            if dbg is not None:
+                dbg.setdefault("enc_layers", []).append(x.clone())
         enco = x
         # --- decoder
         VQ = V * Q
@@ -297,6 +306,8 @@ class BIG_C(object):
             gemm(m, values[:, E:], lw["r1"][1], out=hid[:, Pd:], relu=True)
             query = self._add_ln(query, gemm(m, hid, lw["r2"]), lw["n2"])
             query = self._add_ln(query, gemm(m, gemm(m, query, lw["f1"], relu=True), lw["f2"]), lw["n3"])
+            if dbg is not None:
+                dbg.setdefault("dec_layers", []).append(query.clone())
         logits = self._prediction_head(pk, query, so, enti2enco, extra)
         return logits, so, dict(query=query, att=att_out, enti2enco=enti2enco, enco=enco, extra=extra)
 

@@ -300,6 +300,20 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
 // ---------------------------------------------------------------------------------------------------
 constexpr int RA_MAX_TRACKS = 256;
 
+template <int PER>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&x)[PER]) {
+  if constexpr (PER % 4 == 0) {
+#pragma unroll
+    for (int i = 0; i < PER / 4; ++i) {
+      const float4 v = reinterpret_cast<const float4*>(p)[i];
+      x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < PER; ++i) x[i] = p[i];
+  }
+}
+
 template <int E>
 __global__ void __launch_bounds__(256)
 role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e2a, const float* __restrict__ enco,
@@ -319,14 +333,12 @@ role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e
   for (int i = 0; i < PER; ++i) pq[i] = p2a[qrow * E + lane * PER + i];
   // pass 1: logits
   for (int e = 0; e < n; ++e) {
-    const float4* er = reinterpret_cast<const float4*>(e2a + (int64_t)(t0 + e) * E + lane * PER);
+    const float* er = e2a + (int64_t)(t0 + e) * E + lane * PER;
+    float xr[PER];
+    load_row<PER>(er, xr);
     float acc = 0.f;
 #pragma unroll
-    for (int i = 0; i < PER / 4; ++i) {
-      const float4 x = er[i];
-      acc = fmaf(pq[4 * i], x.x, acc); acc = fmaf(pq[4 * i + 1], x.y, acc);
-      acc = fmaf(pq[4 * i + 2], x.z, acc); acc = fmaf(pq[4 * i + 3], x.w, acc);
-    }
+    for (int i = 0; i < PER; ++i) acc = fmaf(pq[i], xr[i], acc);
     // reduce within each half-warp (role)
 #pragma unroll
     for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
@@ -372,23 +384,15 @@ role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e
   for (int i = 0; i < PER; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
   for (int e = 0; e < n; ++e) {
     const float a0 = sL[warp][0][e], a1 = sL[warp][1][e];
-    const float4* er = reinterpret_cast<const float4*>(enco + (int64_t)(t0 + e) * E + lane * PER);
+    float xr[PER];
+    load_row<PER>(enco + (int64_t)(t0 + e) * E + lane * PER, xr);
 #pragma unroll
-    for (int i = 0; i < PER / 4; ++i) {
-      const float4 x = er[i];
-      acc0[4 * i] = fmaf(a0, x.x, acc0[4 * i]); acc0[4 * i + 1] = fmaf(a0, x.y, acc0[4 * i + 1]);
-      acc0[4 * i + 2] = fmaf(a0, x.z, acc0[4 * i + 2]); acc0[4 * i + 3] = fmaf(a0, x.w, acc0[4 * i + 3]);
-      acc1[4 * i] = fmaf(a1, x.x, acc1[4 * i]); acc1[4 * i + 1] = fmaf(a1, x.y, acc1[4 * i + 1]);
-      acc1[4 * i + 2] = fmaf(a1, x.z, acc1[4 * i + 2]); acc1[4 * i + 3] = fmaf(a1, x.w, acc1[4 * i + 3]);
-    }
+    for (int i = 0; i < PER; ++i) { acc0[i] = fmaf(a0, xr[i], acc0[i]); acc1[i] = fmaf(a1, xr[i], acc1[i]); }
   }
   float* o0 = values + qrow * (2 * E) + lane * PER;
   float* o1 = o0 + E;
 #pragma unroll
-  for (int i = 0; i < PER / 4; ++i) {
-    reinterpret_cast<float4*>(o0)[i] = make_float4(acc0[4 * i], acc0[4 * i + 1], acc0[4 * i + 2], acc0[4 * i + 3]);
-    reinterpret_cast<float4*>(o1)[i] = make_float4(acc1[4 * i], acc1[4 * i + 1], acc1[4 * i + 2], acc1[4 * i + 3]);
-  }
+  for (int i = 0; i < PER; ++i) { o0[i] = acc0[i]; o1[i] = acc1[i]; }
 }
 
 // ---------------------------------------------------------------------------------------------------
