@@ -1,0 +1,377 @@
+#!/usr/bin/env python
+"""bench.py -- videos/sec of the per-video relation hot path (classify [+ ground] + vIoU eval) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # CPU arm: the oracle port of the reference
+
+A "step" is one pass of the hot path over one batch of synthetic videos (BASELINE.json configs[1]: a VidVRD-test
+shaped batch, default 200 videos per GPU): pair geometry (n x n spans + trajectory vIoU), BIG-C classification
+(model_0v10 dims of experiments/exp2) incl. triplet construction, and eval_visual_relation-style vIoU matching of
+the resulting predictions against synthetic GT.  Prints ONE JSON line (see README / DESIGN.md section "Measurement").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from vidsgg_big_b200 import synth  # noqa: E402
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--videos", type=int, default=200, help="videos per GPU per step (weak scaling)")
+    ap.add_argument("--workload", default="vidvrd", choices=["vidvrd", "vidor"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32_simt"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="videos in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------------
+# workload
+# ------------------------------------------------------------------------------------------------------
+def workload_cfg(kind):
+    if kind == "vidvrd":
+        cfg = synth.vidvrd_config()
+        return cfg, dict(feat_total=cfg["dim_feat"] + cfg["dim_i3d"], min_len=20, max_len=150, shape=synth.vidvrd_video_shape,
+                         topk=10, name="VidVRD-test-shaped batch, BIG-C exp2 dims (RoI 2048 + I3D 832), 5-50 tracklets, 20-150 frames")
+    cfg = synth.vidor_config()
+    return cfg, dict(feat_total=cfg["dim_feat"] + cfg["dim_clsme"], min_len=15, max_len=600, shape=synth.vidor_video_shape,
+                     topk=3, name="VidOR-val-shaped batch, BIG-C exp5 dims (RoI 1024 + classeme 300), 10-180 tracklets")
+
+
+def make_videos(kind, n_videos, base_seed, device, pinned=False):
+    """Proposals (boxes etc. from the seeded host generator) whose features are row views of ONE buffer, plus GT graphs."""
+    cfg, wl = workload_cfg(kind)
+    props, graphs = [], []
+    for i in range(n_videos):
+        seed = base_seed + i
+        rng = np.random.default_rng(seed)
+        vlen, n = wl["shape"](rng)
+        P = synth.make_proposal(seed, n, vlen, wl["feat_total"], cfg["num_enti_cats"], min_len=wl["min_len"],
+                                max_len=wl["max_len"], with_features=False)
+        graphs.append(synth.make_gt_graph(seed, P, cfg["num_pred_cats"]))
+        props.append(P)
+    rows = sum(int(p.lengths.sum()) for p in props)
+    g = torch.Generator(device=device).manual_seed(base_seed)
+    feats = torch.randn(rows, wl["feat_total"], generator=g, device=device, dtype=torch.float32) * 0.5
+    if pinned:
+        host = torch.empty(rows, wl["feat_total"], dtype=torch.float32, pin_memory=True)
+        host.copy_(feats)
+        feats = host
+    r = 0
+    for p in props:
+        L = int(p.lengths.sum())
+        p.features = feats[r:r + L]
+        p.dim_feat = wl["feat_total"]
+        r += L
+    return cfg, wl, props, graphs, feats
+
+
+def algorithmic_bytes_geometry(props):
+    """sum over overlapping (a,b) of 32*ov + 16*(sumL_A + sumL_B) + nA*nB*(16+1+4)."""
+    total = 0
+    for p in props:
+        d = p.traj_durations.cpu().numpy()
+        s = np.maximum(d[:, None, 0], d[None, :, 0]); e = np.minimum(d[:, None, 1], d[None, :, 1])
+        ov = np.clip(e - s + 1, 0, None)
+        total += 32 * int(ov.sum()) + 16 * 2 * int(p.lengths.sum()) + d.shape[0] * d.shape[0] * 21
+    return total
+
+
+class Clocks(object):
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows if len(r) >= 6 for i in range(4) if r[2 + i].lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+                "samples": len(sm)}
+
+
+# ------------------------------------------------------------------------------------------------------
+# the step (our arm)
+# ------------------------------------------------------------------------------------------------------
+class Pipeline(object):
+    def __init__(self, kind, precision, device):
+        from vidsgg_big_b200 import bigc
+        self.cfg, self.wl = workload_cfg(kind)
+        cls = bigc.BIG_C_vidor if kind == "vidor" else bigc.BIG_C_vidvrd
+        self.model = cls(self.cfg, is_train=False, precision=precision)
+        self.model.load_state_dict(synth.make_bigc_state(1, self.cfg))
+        self.model.to(device)
+        self.device = device
+
+    def step(self, props, graphs, timers=None):
+        """One pass over a batch that is resident in HBM.  Returns (metrics, n_triplets)."""
+        from vidsgg_big_b200 import evalapi, geometry
+        tt = geometry.TrackTable.from_containers(props)
+        if timers is not None:
+            timers["geo0"].record()
+        viou, spans, mask, seg, _ = geometry.traj_viou_batched(tt, tt)                 # pair geometry, all videos, one launch
+        if timers is not None:
+            timers["geo1"].record()
+        trips = self.model(props, topk=self.wl["topk"])                                # BIG-C + triplet construction
+        trips3 = [None if t is None else (t[0], t[1].mean(-1), t[2]) for t in trips]   # score = mean of the 3 (eval_vidvrd.py:136)
+        gt_t = geometry.TrackTable.from_containers(graphs, device=self.device)
+        PR = evalapi.PackedRelations.from_triplets(tt, trips3)
+        GT = evalapi.PackedRelations.from_gt_graphs(gt_t, graphs)
+        m_ap, rec, mprec = evalapi.evaluate_packed(PR, GT)                             # vIoU matching + AP / recall (D2H of hits)
+        return (float(m_ap), float(rec[50]), float(rec[100])), int(PR.n_rel), viou
+
+
+def to_device_copy(props, graphs, device):
+    """Host -> device copies of one batch (e2e leg): features from pinned memory in one transfer, the rest tiny."""
+    import copy
+    feats_host = props[0].features
+    total = sum(int(p.lengths.sum()) for p in props)
+    base = props[0].features.as_strided((total, props[0].features.shape[1]), props[0].features.stride())
+    dev_feats = base.to(device, non_blocking=True)
+    out_p, out_g, r, nbytes = [], [], 0, dev_feats.numel() * 4
+    for p in props:
+        q = copy.copy(p)
+        L = int(p.lengths.sum())
+        q.features = dev_feats[r:r + L]
+        r += L
+        q.bboxes = p.bboxes.to(device, non_blocking=True)
+        q.cat_ids = p.cat_ids.to(device); q.scores = p.scores.to(device); q.traj_durations = p.traj_durations.to(device)
+        nbytes += q.bboxes.numel() * 4 + q.cat_ids.numel() * 8 + q.scores.numel() * 4 + q.traj_durations.numel() * 8
+        out_p.append(q)
+    for g in graphs:
+        h = copy.copy(g)
+        h.to(device)
+        nbytes += h.bboxes.numel() * 4 + h.traj_durations.numel() * 8 + h.pred_durations.numel() * 4 + h.adj_matrix.numel() * 4
+        out_g.append(h)
+    return out_p, out_g, nbytes
+
+
+# ------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference (torch-CPU / python loops), all host threads
+# ------------------------------------------------------------------------------------------------------
+def cpu_pass(kind, props, graphs, st, cfg, wl):
+    """What the reference does per video on the host: stretched BIG-C forward, per-pair vIoU loop, dict conversion, eval."""
+    from oracle import bigc as ob, convert as oc, evalapi as oe, geometry as og
+    en, pn = oc.default_names("e", 256), oc.default_names("p", 256)
+    gts, prs = {}, {}
+    with torch.no_grad():
+        for p, g in zip(props, graphs):
+            og.traj_viou_matrix(p.bboxes_list, p.traj_durations, p.bboxes_list, p.traj_durations)
+            r = ob.forward(st, cfg, [p], wl["topk"])[0]
+            t3 = None if r is None else (r[0], r[1].mean(-1), r[2])
+            prs.update(oc.to_eval_format_pr(p, t3, en, pn))
+            gts.update(oc.to_eval_format_gt(g, en, pn))
+    return oe.evaluate(gts, prs)
+
+
+def cpu_baseline(kind, n_sample, repeats=1):
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu")
+    st = synth.make_bigc_state(1, cfg)
+    cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl)                     # warm-up
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        cpu_pass(kind, props, graphs, st, cfg, wl)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return n_sample / best, best
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    cfg, wl = workload_cfg(args.workload)
+    times = []
+    for i in range(args.warmup + args.steps):
+        v, dt = cpu_baseline(args.workload, args.cpu_sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    value = args.cpu_sample / (ms / 1e3)
+    cores = torch.get_num_threads()
+    sample = "%d videos of the workload per step (seeds 1000..), oracle port of the reference incl. python loops" % args.cpu_sample
+    print(json.dumps({
+        "impl": "reference", "metric": "videos/sec (classify+ground+vIoU)", "value": value, "unit": "videos/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": wl["name"], "stages": ["pair_geometry", "bigc_classify", "triplets", "viou_eval"], "videos_per_step": args.cpu_sample},
+        "cpu_baseline": {"value": value, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    import torch.distributed as dist
+    from vidsgg_big_b200 import linalg, _cabi
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    _cabi.lib()
+
+    # CPU baseline first (rank 0, N=1 only), so it does not overlap the GPU timing
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, dt = cpu_baseline(args.workload, args.cpu_sample)
+        cpu = {"value": v, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
+               "sample": "%d videos of the same workload (seeds 1000..), %.1f s of CPU work" % (args.cpu_sample, dt)}
+
+    pipe = Pipeline(args.workload, args.precision, device)
+    cfg, wl, props, graphs, feats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device)
+    for g in graphs:
+        g.to(device)
+    for p in props:
+        f = p.features
+        p.to(device)
+        p.features = f
+    geo_bytes = algorithmic_bytes_geometry(props)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        metrics, n_trip, _ = pipe.step(props, graphs)
+    # ---- timed region: K steps, inputs resident in HBM (they exceed L2 by far: no flush needed) ----
+    clocks = Clocks(local)
+    if rank == 0:
+        clocks.start()
+    launches0 = int(_cabi.lib().vsg_launch_count())
+    barrier()
+    t0 = torch.cuda.Event(enable_timing=True); t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    for _ in range(args.steps):
+        metrics, n_trip, _ = pipe.step(props, graphs)
+    t1.record()
+    barrier()
+    ms_total = t0.elapsed_time(t1)
+    clk = clocks.stop() if rank == 0 else None
+    n_launches = int(_cabi.lib().vsg_launch_count()) - launches0
+    ms = torch.tensor([ms_total], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_step = float(ms.item()) / args.steps
+    value = args.videos * world / (ms_step / 1e3)
+
+    # ---- per-kernel roofline legs (separate, instrumented steps; CUDA events on the launch stream) ----
+    linalg._Profile.begin()
+    timers = {"geo0": torch.cuda.Event(enable_timing=True), "geo1": torch.cuda.Event(enable_timing=True)}
+    pipe.step(props, graphs, timers)
+    n_gemm, gemm_flops, gemm_ms = linalg._Profile.end()
+    geo_ms = timers["geo0"].elapsed_time(timers["geo1"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    tc_peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    peak_src = "measured" if peaks else "fallback"
+    gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
+    geo_gbs = geo_bytes / (geo_ms * 1e-3) / 1e9 if geo_ms > 0 else 0.0
+    roofline = {"kernel": "gemm_tc_kernel (tcgen05 %s)" % args.precision, "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak,
+                "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": None, "peak_source": peak_src + " bf16 dense sustained",
+                "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms_step,
+                "note": "achieved = useful 2MNK flops; 3xTF32 issues 3 tf32 MMAs per useful one and tf32 peak is half of bf16",
+                "also": {"kernel": "traj_viou_warp_kernel (+track volumes)", "bound": "hbm", "achieved": geo_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": geo_gbs / hbm_peak, "ms": geo_ms, "algorithmic_bytes": geo_bytes}}
+
+    # ---- e2e: same metric through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
+    e2e = None
+    if not args.no_e2e:
+        del props, feats
+        torch.cuda.empty_cache()
+        cfg, wl, hprops, hgraphs, hfeats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device, pinned=True)
+        h2d = 0
+        for i in range(2):
+            dp, dg, h2d = to_device_copy(hprops, hgraphs, device)
+            pipe.step(dp, dg)
+        barrier()
+        w0 = time.perf_counter()
+        n_e2e = max(2, min(args.steps, 5))
+        for _ in range(n_e2e):
+            dp, dg, h2d = to_device_copy(hprops, hgraphs, device)
+            metrics_e, n_trip_e, _ = pipe.step(dp, dg)
+            del dp, dg
+        barrier()
+        dt = (time.perf_counter() - w0) / n_e2e
+        tdt = torch.tensor([dt], device=device)
+        if world > 1:
+            dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
+        d2h = n_trip_e * (8 + 4) * 2 + args.videos * 8            # hit scores + order + gt2det reads, per-video counts
+        e2e = {"value": args.videos * world / float(tdt.item()), "unit": "videos/s", "h2d_bytes_per_step": int(h2d),
+               "d2h_bytes_per_step": int(d2h), "steps": n_e2e}
+
+    if rank == 0:
+        out = {
+            "metric": "videos/sec (classify+ground+vIoU)", "value": value, "unit": "videos/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (tcgen05 %s, fp32 accumulate)" % args.precision, "data": "synthetic",
+            "config": {"workload": wl["name"], "videos_per_gpu": args.videos, "precision": args.precision,
+                       "stages": ["pair_geometry", "bigc_classify", "triplets", "viou_eval"], "grounding": "not in this workload (VidVRD has no grounding stage)",
+                       "l2": "inputs (%.1f GB per GPU) exceed L2" % (sum(int(p.lengths.sum()) for p in hprops) * wl["feat_total"] * 4 / 1e9 if not args.no_e2e else 0.0),
+                       "result": {"mAP": metrics[0], "R@50": metrics[1], "R@100": metrics[2], "triplets": n_trip}},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launches,
+            "clocks": clk,
+        }
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

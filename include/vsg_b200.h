@@ -38,6 +38,7 @@ const char* vsg_last_error(void);
 int vsg_version(void);          /* 100*major + minor */
 int vsg_built_for_sm(void);     /* 100 (sm_100a)     */
 int vsg_device_sm_count(void);  /* multiprocessors of the current device, <0 on error */
+long long vsg_launch_count(void); /* kernels launched by this library in this process (monotonic) */
 
 /* ---- geometry: pair enumeration, spans, trajectory vIoU ------ */
 

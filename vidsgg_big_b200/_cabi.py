@@ -36,6 +36,7 @@ SIGNATURES = {
     "vsg_version": (i32, []),
     "vsg_built_for_sm": (i32, []),
     "vsg_device_sm_count": (i32, []),
+    "vsg_launch_count": (C.c_longlong, []),
     "vsg_pair_ids": (i32, [i32, p, p]),
     "vsg_dura_intersection": (i32, [p, i32, p, i32, p, p, p]),
     "vsg_track_volumes": (i32, [p, p, i32, p, p]),

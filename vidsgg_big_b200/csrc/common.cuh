@@ -11,7 +11,10 @@ namespace vsg {
 
 void set_error(const char* fmt, ...);
 
-inline int check_launch(const char* what) {
+void count_launches(int n);
+
+inline int check_launch(const char* what, int n_kernels = 1) {
+  count_launches(n_kernels);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));

@@ -419,7 +419,7 @@ extern "C" int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* of
   traj_viou_tile_kernel<<<grid, T2_THREADS, 0, st>>>(
       reinterpret_cast<const float4*>(boxesA), offA, duraA, reinterpret_cast<const float4*>(boxesB), offB, duraB, segA, segB,
       seg_out, tile_off_ws, n_seg, n_tiles, volA, volB, spans, mask, viou);
-  return check_launch("vsg_traj_viou_matrix_tiled");
+  return check_launch("vsg_traj_viou_matrix_tiled", 2);
 }
 
 extern "C" int vsg_pair_labels(const float* viou, int n, int n_gt_traj, const int64_t* gt_so, int n_gt_pred, float th,

@@ -1,6 +1,7 @@
 // Library-level entry points: error reporting, version, device query.
 #include "common.cuh"
 #include <string.h>
+#include <atomic>
 
 namespace vsg {
 
@@ -12,6 +13,10 @@ void set_error(const char* fmt, ...) {
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
 }
+
+static std::atomic<long long> g_launches{0};
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
+long long launches() { return g_launches.load(std::memory_order_relaxed); }
 
 int sm_count() {
   static int cached[64] = {0};
@@ -25,8 +30,10 @@ int sm_count() {
   return cached[dev];
 }
 
+long long launches();
 }  // namespace vsg
 
+extern "C" long long vsg_launch_count(void) { return vsg::launches(); }
 extern "C" const char* vsg_last_error(void) { return vsg::g_err; }
 extern "C" int vsg_version(void) { return 1; }
 extern "C" int vsg_built_for_sm(void) { return 100; }

@@ -240,7 +240,7 @@ extern "C" int vsg_rel_viou_match(const VsgRelTable* pred, const double* scores,
   VSG_REQUIRE(ng == 0 || taken_ws, "vsg_rel_viou_match: null taken workspace");
   greedy_match_kernel<<<(n_vid * 32 + 127) / 128, 128, 0, st>>>(pred->vid_off, gt->vid_off, n_vid, ov_off, ov_ws, order, scores,
                                                                thr, hit, gt2det, taken_ws);
-  return check_launch("vsg_rel_viou_match");
+  return check_launch("vsg_rel_viou_match", 1 + (np > 0 ? 2 : 0) + (ng > 0 ? 1 : 0) + ((np > 0 && ng > 0) ? 1 : 0));
 }
 
 extern "C" int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t* dur1, const double* boxes2,

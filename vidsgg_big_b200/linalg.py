@@ -32,6 +32,30 @@ def _raw(t):
     return None if t is None else c_void_p(t.data_ptr())
 
 
+class _Profile(object):
+    """Optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg)."""
+    enabled = False
+    records = []          # (start_event, end_event, useful_flops, mode)
+
+    @classmethod
+    def begin(cls):
+        cls.enabled, cls.records = True, []
+
+    @classmethod
+    def end(cls):
+        """-> (n_launches, useful_flops, kernel_ms) after synchronising."""
+        cls.enabled = False
+        torch.cuda.synchronize()
+        ms = sum(s.elapsed_time(e) for s, e, _, _ in cls.records)
+        fl = sum(f for _, _, f, _ in cls.records)
+        n = len(cls.records)
+        cls.records = []
+        return n, fl, ms
+
+
+LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py's gpu_launches)
+
+
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
          accumulate: bool = False, bias: bool = True, K: Optional[int] = None) -> torch.Tensor:
@@ -50,7 +74,14 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
     w_hi = W.hi if (mode == X3TF32 and W.hi is not None) else W.w
     w_lo = W.lo if mode == X3TF32 else None
     b = W.bias if bias else None
+    LAUNCHES[0] += 1
+    if _Profile.enabled:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
     check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
                          _raw(rb_index), int(rb_period), 0 if rowbias is None else rowbias.stride(0), 1 if relu else 0,
                          1 if accumulate else 0, _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
+    if _Profile.enabled:
+        ev1.record()
+        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, mode))
     return out
