@@ -147,7 +147,8 @@ int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t*
 #define VSG_GEMM_TF32 1   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM                     */
 #define VSG_GEMM_3XTF32 2 /* fp32-faithful 3xTF32 split on tcgen05 (needs W_lo from vsg_split_tf32) */
 
-/* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ), fp32 row-major.
+/* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ) (+ residual[M][N]),
+ * fp32 row-major; the residual is added after the activation (QANet blocks, models/grd_model_v5.py:118-135).
  * Replaces every nn.Linear / 1x1 conv / conv tap of the hot path (models/model_0v10.py:446-458, :103-117,
  * :178-225, :478-507; models/grd_model_v5.py:331-373).  idx(row) = rb_index[row] if rb_index else row % rb_period
  * (used for the positional-embedding term of the decoder and the gathered frequency bias of the head).
@@ -155,7 +156,7 @@ int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t*
  * A / W 16-byte aligned; otherwise the call silently uses the SIMT kernel (same result class). */
 int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
              const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
-             int accumulate, float* C, int ldc, void* stream);
+             int accumulate, const float* residual, int ld_res, float* C, int ldc, void* stream);
 
 /* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
 int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
@@ -216,6 +217,40 @@ int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int 
                           int n_vid, const int64_t* dura, const int64_t* cat_ids, const float* enti_scores,
                           int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
                           void* stream);
+
+/* ---- grounding stage, non-GEMM kernels (models/grd_model_v5.py) -----------
+ * Row-major [rows][H] over ragged sequences seq_off int64[n_seq+1] (video clips / 3 query words / clips per query). */
+
+/* pos[r] = index of row r inside its sequence, rem[r] = rows left after it. */
+int vsg_seq_positions(const int64_t* seq_off, int n_seq, int64_t rows, int32_t* pos, int32_t* rem, void* stream);
+
+/* prepare_data + query_fc + temp_fc (:310-328, :337-339) with the word embeddings pre-projected:
+ * out f32[3*nq][H] (sub, pred, obj word of each query), so_norm f32[nq][2] = span / video_len. */
+int vsg_grd_query_init(const int64_t* quint, const int64_t* spans, const float* vlen, const int32_t* q_vid, int nq,
+                       const float* proj_enti, const float* proj_pred, const float* Wt, const float* bt, int H, float* out,
+                       float* so_norm, void* stream);
+
+/* PosEncoder (:58-78) + normb (:116-118): res = x + sin(pos*freq+phase), out = LayerNorm(res). */
+int vsg_pos_add_ln(const float* x, const int32_t* pos, const float* freq, const float* phase, const float* gamma,
+                   const float* beta, int64_t rows, int H, float* res, float* out, void* stream);
+
+/* Depthwise Conv1d (groups = channels, pad k/2) along each sequence (:44); w f32[H][k]. */
+int vsg_dwconv(const float* in, const int32_t* pos, const int32_t* rem, const float* w, const float* b, int k, int64_t rows,
+               int H, float* out, void* stream);
+
+/* Context-query attention (:345-363), (S_r S_c^T) V re-associated through the 3 query words:
+ * out f32[sum nq_v*T_v][4H] = [v, A, A*v, B*v]. */
+int vsg_cq_attention(const float* v, const float* pv, const float* q, const int64_t* vid_off, const int32_t* q_vid,
+                     const int64_t* comb_off, int nq, int H, int max_T, float* out, void* stream);
+
+/* Post-network part of _forward_test_single (:533-576) incl. temporal_pooling (:697-737) and the multi-bin NMS (:667-695):
+ * pooled f32[nq][B+1][2], probs f32[nq][B+1], mask u8[nq][B+1]; err_count += #(query,bin) with an empty pooling set
+ * (the reference raises there).  clip_tab f32[sum T_v] = torch.linspace(0,1,T_v) per video. */
+int vsg_grounding_post(const float* regr, const float* conf, const float* cls, const int64_t* comb_off, const float* so_norm,
+                       const float* clip_tab, const int64_t* vid_off, const int32_t* q_vid, int nq, int num_bins,
+                       int regr_activated /* 1: regr already passed through the sigmoid */, float score_th,
+                       float tiou_th, float bins_th, float nms_th, float* pooled, float* probs, uint8_t* mask, int32_t* err_count,
+                       void* stream);
 
 #ifdef __cplusplus
 }

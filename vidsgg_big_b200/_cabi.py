@@ -46,7 +46,7 @@ SIGNATURES = {
     "vsg_pair_labels": (i32, [p, i32, i32, p, i32, f32, p, p]),
     "vsg_rel_viou_match": (i32, [C.POINTER(VsgRelTable), p, C.POINTER(VsgRelTable), i32, p, f64, p, p, p, p, p, p, p, p]),
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
-    "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p]),
+    "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
     "vsg_bbox_feat_mlp1": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p, p]),
     "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
@@ -57,6 +57,12 @@ SIGNATURES = {
     "vsg_role_attention": (i32, [p, p, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),
     "vsg_gather_concat": (i32, [C.POINTER(p), C.POINTER(p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i64, p, i32, p]),
     "vsg_so_category": (i32, [p, p, i32, i64, p, p, p]),
+    "vsg_seq_positions": (i32, [p, i32, i64, p, p, p]),
+    "vsg_grd_query_init": (i32, [p, p, p, p, i32, p, p, p, p, i32, p, p, p]),
+    "vsg_pos_add_ln": (i32, [p, p, p, p, p, p, i64, i32, p, p, p]),
+    "vsg_dwconv": (i32, [p, p, p, p, p, i32, i64, i32, p, p]),
+    "vsg_cq_attention": (i32, [p, p, p, p, p, p, i32, i32, i32, p, p]),
+    "vsg_grounding_post": (i32, [p, p, p, p, p, p, p, p, i32, i32, i32, f32, f32, f32, f32, p, p, p, p, p]),
     "vsg_construct_triplet": (i32, [p, i32, i32, i32, i32, p, p, i32, p, p, p, p, p, p, p, p, i32, p]),
 }
 

@@ -42,6 +42,8 @@ struct GemmEpilogue {
   int ld_rb;
   int relu;
   int accumulate;           // C += result (before activation)
+  const float* residual;    // [M][ld_res] added AFTER the activation, or null
+  int ld_res;
   float* C;
   int ldc;
   int M, N, K;
@@ -277,6 +279,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         rb = ep.rowbias + (size_t)ri * ep.ld_rb;
       }
       float* crow = ep.C + (size_t)(row_ok ? row : 0) * ep.ldc;
+      const float* res = (row_ok && ep.residual) ? ep.residual + (size_t)row * ep.ld_res : nullptr;
       const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                           ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
 #pragma unroll 1
@@ -303,6 +306,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
               }
               if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
               *dst = v;
             }
           } else {
@@ -315,6 +319,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (rb) v += rb[col];
                 if (ep.accumulate) v += crow[col];
                 if (ep.relu) v = fmaxf(v, 0.f);
+                if (res) v += res[col];
                 crow[col] = v;
               }
             }
@@ -408,6 +413,7 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       float* dst = ep.C + (size_t)row * ep.ldc + col;
       if (ep.accumulate) v += *dst;
       if (ep.relu) v = fmaxf(v, 0.f);
+      if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
       *dst = v;
     }
   }
@@ -520,7 +526,7 @@ extern "C" int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, v
 
 extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
                         const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
-                        int accumulate, float* C, int ldc, void* stream) {
+                        int accumulate, const float* residual, int ld_res, float* C, int ldc, void* stream) {
   VSG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vsg_gemm: negative size");
   if (M == 0 || N == 0) return VSG_OK;
   VSG_REQUIRE(A && W_hi && C, "vsg_gemm: null matrix pointer");
@@ -528,7 +534,7 @@ extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, co
   VSG_REQUIRE(rowbias == nullptr || rb_index != nullptr || rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
   GemmEpilogue ep;
   ep.bias = bias; ep.rowbias = rowbias; ep.rb_index = rb_index; ep.rb_period = rb_period; ep.ld_rb = ld_rb;
-  ep.relu = relu; ep.accumulate = accumulate; ep.C = C; ep.ldc = ldc; ep.M = M; ep.N = N; ep.K = K;
+  ep.relu = relu; ep.accumulate = accumulate; ep.residual = residual; ep.ld_res = ld_res; ep.C = C; ep.ldc = ldc; ep.M = M; ep.N = N; ep.K = K;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tma_ok = (lda % 4 == 0) && (ldw % 4 == 0) && aligned16(A) && aligned16(W_hi) && K >= 1;
   if (mode == 0 || !tma_ok) {

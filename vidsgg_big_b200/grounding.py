@@ -1,0 +1,311 @@
+"""Grounding stage on B200: host-side mirror of the reference ``DEBUG`` module (models/grd_model_v5.py:140-737,
+exported as ``DEBUG`` by models/__init__.py:4) in inference mode.
+
+    model = DEBUG(config, is_train=False); model.load_state_dict(sd); model.cuda()
+    pooled_se, bins_probs, bins_mask = model(video_feature_list, data_list, score_th, tiou_th, bins_th, nms_th,
+                                             with_gt_data=False)
+
+with ``data_list[i] = (quintuples i64[m,5], spans i64[m,2], video_len)`` -- the call made by
+tools/eval_vidor.py:239-242.  Returns ``f32[m,k+1,2]`` (normalised 0..1), ``f32[m,k+1]``, ``bool[m,k+1]`` or
+``(None, None)``.  Unlike the reference (which asserts a batch of one, :211) any number of videos can be passed;
+then a list of triples is returned.  All compute runs in libvsgb200 kernels (csrc/gemm.cu, csrc/grounding.cu,
+csrc/bigc.cu MHA / LayerNorm); inference only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import linalg
+from ._cabi import VsgError, check, lib, stream_ptr
+from .linalg import Weight, gemm
+
+
+def _raw(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def expand_after_grounding(quintuples, cls_scores3, pooled_se, bins_probs, bins_mask, video_len):
+    """Driver-side expansion of tools/eval_vidor.py:245-253 (tiny index ops on the kernel outputs):
+    score = mean(cls scores) * bin prob, span = round(pooled * video_len) as int64, rows selected by the mask."""
+    nb = bins_probs.shape[1]
+    q = quintuples[:, None, :].repeat(1, nb, 1)[bins_mask, :]
+    s = (cls_scores3.mean(-1)[:, None] * bins_probs)[bins_mask]
+    sp = torch.round((pooled_se * video_len)[bins_mask, :]).type(torch.long)
+    return q, s, sp
+
+
+class DEBUG(object):
+    def __init__(self, config: dict, is_train: bool = False, precision: str = "3xtf32"):
+        if is_train:
+            raise NotImplementedError("vidsgg_big_b200.DEBUG covers the inference hot path only (is_train=False)")
+        self.is_train = False
+        self.config = dict(config)
+        self.dim_feat, self.dim_clsme = config["dim_feat"], config["dim_clsme"]
+        self.dim_hidden, self.num_bins = config["dim_hidden"], config["num_bins"]
+        if self.dim_hidden != 128:
+            raise VsgError("context-query kernel is instantiated for dim_hidden == 128 (the reference value)")
+        self.precision, self.mode = precision, linalg.MODES[precision]
+        self.device = None
+        self._w = None
+        self._state: Dict[str, torch.Tensor] = {}
+        for key in ("EntiNameEmb", "PredNameEmb"):
+            path = config.get(key + "_path")
+            if isinstance(path, str) and path.endswith(".npy"):
+                self._state[key] = torch.from_numpy(np.load(path)).float()
+
+    # ---- nn.Module-like surface ---------------------------------------------------------------------
+    def eval(self):
+        return self
+
+    def cuda(self, device=None):
+        return self.to(torch.device("cuda", torch.cuda.current_device() if device is None else
+                                    (device.index if isinstance(device, torch.device) else int(device))))
+
+    def to(self, device):
+        self.device = torch.device(device)
+        if len(self._state) > 2:
+            self._prepare()
+        return self
+
+    def state_dict(self):
+        return dict(self._state)
+
+    def _expected_keys(self) -> List[str]:
+        k = ["EntiNameEmb", "PredNameEmb"]
+        for n in ("video_fc", "query_fc", "temp_fc", "vq_fc"):
+            k += [n + ".weight", n + ".bias"]
+        for enc in ("video_encoder", "query_encoder", "combined_encoder"):
+            for c in range(4):
+                for part in ("depth_wise", "point_wise"):
+                    k += ["%s.convs.%d.%s.weight" % (enc, c, part), "%s.convs.%d.%s.bias" % (enc, c, part)]
+            k += [enc + ".mh_attn.in_proj_weight", enc + ".mh_attn.in_proj_bias", enc + ".mh_attn.out_proj.weight",
+                  enc + ".mh_attn.out_proj.bias", enc + ".fc.weight", enc + ".fc.bias", enc + ".normb.weight", enc + ".normb.bias"]
+            for c in range(4):
+                k += ["%s.norm_seq.%d.weight" % (enc, c), "%s.norm_seq.%d.bias" % (enc, c)]
+            k += [enc + ".norme.weight", enc + ".norme.bias"]
+        k.append("proj2sim.weight")
+        for head in ("cls_head", "conf_head", "regr_head"):
+            for c in range(4):
+                for part in ("depth_wise", "point_wise"):
+                    k += ["%s.%d.0.%s.weight" % (head, c, part), "%s.%d.0.%s.bias" % (head, c, part)]
+            for part in ("depth_wise", "point_wise"):
+                k += ["%s.4.%s.weight" % (head, part), "%s.4.%s.bias" % (head, part)]
+        return k
+
+    def load_state_dict(self, state_dict, strict: bool = True):
+        sd = {(k[7:] if k.startswith("module.") else k): v for k, v in state_dict.items()}
+        if strict:
+            want = set(self._expected_keys())
+            missing, unexpected = sorted(want - set(sd)), sorted(set(sd) - want)
+            if missing or unexpected:
+                raise RuntimeError("Error(s) in loading state_dict for DEBUG: missing %s unexpected %s" % (missing, unexpected))
+        self._state = {k: v.detach().float().cpu() for k, v in sd.items()}
+        if self.device is not None:
+            self._prepare()
+        return self
+
+    # ---- weights in HBM ---------------------------------------------------------------------------------
+    def _prepare(self):
+        dev = self.device
+        if dev.type != "cuda":
+            raise VsgError("DEBUG runs on a CUDA device only (no CPU fallback)")
+        st = {k: v.to(dev) for k, v in self._state.items()}
+        H = self.dim_hidden
+        split = self.mode == linalg.X3TF32
+        W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
+        w = {"video_fc": W("video_fc"), "vq_fc": W("vq_fc")}
+        qfc = W("query_fc")
+        # query_fc is linear, so project the two embedding tables once instead of every query word
+        w["proj_enti"] = gemm(self.mode, st["EntiNameEmb"].contiguous(), qfc)
+        w["proj_pred"] = gemm(self.mode, st["PredNameEmb"].contiguous(), qfc)
+        w["temp_w"], w["temp_b"] = st["temp_fc.weight"].contiguous(), st["temp_fc.bias"].contiguous()
+        w["proj2sim"] = Weight(st["proj2sim.weight"], None, split=split)
+
+        def dws(prefix):
+            dw = st[prefix + ".depth_wise.weight"]
+            pw = st[prefix + ".point_wise.weight"]
+            return dict(dw_w=dw.reshape(dw.shape[0], dw.shape[2]).contiguous(), dw_b=st[prefix + ".depth_wise.bias"].contiguous(),
+                        k=int(dw.shape[2]), pw=Weight(pw.reshape(pw.shape[0], pw.shape[1]).contiguous(), st[prefix + ".point_wise.bias"], split=split))
+
+        def norm(name):
+            return st[name + ".weight"].contiguous(), st[name + ".bias"].contiguous()
+
+        for enc in ("video_encoder", "query_encoder", "combined_encoder"):
+            w[enc] = dict(convs=[dws("%s.convs.%d" % (enc, c)) for c in range(4)],
+                          qkv=Weight(st[enc + ".mh_attn.in_proj_weight"], st[enc + ".mh_attn.in_proj_bias"], split=split),
+                          out=W(enc + ".mh_attn.out_proj"), fc=W(enc + ".fc"), normb=norm(enc + ".normb"),
+                          norm_seq=[norm("%s.norm_seq.%d" % (enc, c)) for c in range(4)], norme=norm(enc + ".norme"))
+        for head in ("cls_head", "conf_head", "regr_head"):
+            w[head] = [dws("%s.%d.0" % (head, c)) for c in range(4)] + [dws("%s.4" % head)]
+        # PosEncoder tables exactly as the reference builds them (python doubles -> float32 tensor, :61-64)
+        freqs = [10000 ** (-i / H) if i % 2 == 0 else -10000 ** ((1 - i) / H) for i in range(H)]
+        phases = [0 if i % 2 == 0 else np.pi / 2 for i in range(H)]
+        w["freq"], w["phase"] = torch.Tensor(freqs).to(dev), torch.Tensor(phases).to(dev)
+        self._w = w
+
+    # ---- building blocks --------------------------------------------------------------------------------
+    def _ln(self, x, norm):
+        out = torch.empty_like(x)
+        check(lib().vsg_add_layernorm(_raw(x), x.stride(0), None, 0, _raw(norm[0]), _raw(norm[1]), None, 0, x.shape[0], x.shape[1],
+                                      _raw(out), out.stride(0), stream_ptr(x.device)), "vsg_add_layernorm")
+        return out
+
+    def _dwconv(self, x, cw, pos, rem):
+        out = torch.empty_like(x)
+        check(lib().vsg_dwconv(_raw(x), _raw(pos), _raw(rem), _raw(cw["dw_w"]), _raw(cw["dw_b"]), cw["k"], x.shape[0], x.shape[1],
+                               _raw(out), stream_ptr(x.device)), "vsg_dwconv")
+        return out
+
+    def _seq(self, seq_off_host: np.ndarray):
+        dev = self.device
+        seq_off = torch.from_numpy(np.ascontiguousarray(seq_off_host.astype(np.int64))).to(dev)
+        rows = int(seq_off_host[-1])
+        pos = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+        rem = torch.empty(max(rows, 1), dtype=torch.int32, device=dev)
+        check(lib().vsg_seq_positions(_raw(seq_off), len(seq_off_host) - 1, rows, _raw(pos), _raw(rem), stream_ptr(dev)), "vsg_seq_positions")
+        lens = np.diff(seq_off_host)
+        return dict(off=seq_off, n=len(seq_off_host) - 1, rows=rows, pos=pos, rem=rem, max_len=int(lens.max()) if lens.size else 0)
+
+    def _qanet(self, ew, x, sq):
+        """QANetEncoderLayer.forward (:110-137) on rows [rows, H] of ragged sequences."""
+        w, m, H = self._w, self.mode, self.dim_hidden
+        res = torch.empty_like(x)
+        out = torch.empty_like(x)
+        check(lib().vsg_pos_add_ln(_raw(x), _raw(sq["pos"]), _raw(w["freq"]), _raw(w["phase"]), _raw(ew["normb"][0]), _raw(ew["normb"][1]),
+                                   x.shape[0], H, _raw(res), _raw(out), stream_ptr(x.device)), "vsg_pos_add_ln")
+        for i in range(4):
+            t = self._dwconv(out, ew["convs"][i], sq["pos"], sq["rem"])
+            res = gemm(m, t, ew["convs"][i]["pw"], relu=True, residual=res)          # relu(conv) + res  (:120-122)
+            out = self._ln(res, ew["norm_seq"][i])
+        qkv = gemm(m, out, ew["qkv"])
+        att = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
+        ld = qkv.stride(0)
+        check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld, _raw(sq["off"]),
+                            sq["n"], 0, sq["max_len"], 8, H // 8, _raw(att), H, stream_ptr(x.device)), "vsg_mha")
+        res = gemm(m, att, ew["out"], residual=res)                                 # attn + res (:129-130)
+        out = self._ln(res, ew["norme"])
+        return gemm(m, out, ew["fc"], relu=True, residual=res)                      # relu(fc(LN)) + res (:133-136)
+
+    def _head(self, hw, x, sq):
+        y = x
+        for c in range(4):
+            y = gemm(self.mode, self._dwconv(y, hw[c], sq["pos"], sq["rem"]), hw[c]["pw"], relu=True)
+        return gemm(self.mode, self._dwconv(y, hw[4], sq["pos"], sq["rem"]), hw[4]["pw"])
+
+    # ---- batched forward ----------------------------------------------------------------------------------
+    def _forward_videos(self, feats: Sequence[torch.Tensor], datas: Sequence[tuple], th, want_net: bool = False):
+        w, m, H, B, dev = self._w, self.mode, self.dim_hidden, self.num_bins, self.device
+        L = lib()
+        sp = stream_ptr(dev)
+        T = [int(f.shape[0]) for f in feats]
+        nq = [int(d[0].shape[0]) for d in datas]
+        NQ = sum(nq)
+        vid_off_h = np.concatenate([[0], np.cumsum(T)]).astype(np.int64)
+        q_vid_h = np.repeat(np.arange(len(T)), nq).astype(np.int32)
+        comb_off_h = np.concatenate([[0], np.cumsum(np.repeat(T, nq))]).astype(np.int64)
+        vf = feats[0].to(dev, torch.float32).contiguous() if len(feats) == 1 else torch.cat([f.to(dev, torch.float32) for f in feats], 0)
+        quint = torch.cat([d[0].to(dev, torch.long) for d in datas], 0).contiguous()
+        spans = torch.cat([d[1].to(dev, torch.long) for d in datas], 0).contiguous()
+        vlen = torch.tensor([float(d[2]) for d in datas], dtype=torch.float32, device=dev)
+        q_vid = torch.from_numpy(q_vid_h).to(dev)
+        clip = torch.cat([torch.linspace(0, 1, t) for t in T]).to(dev)          # (:705) host-evaluated table, see grounding.cu
+        sv, sq3, sc = self._seq(vid_off_h), self._seq(np.arange(NQ + 1, dtype=np.int64) * 3), self._seq(comb_off_h)
+        # --- embeddings
+        v0 = gemm(m, vf, w["video_fc"])
+        q0 = torch.empty(3 * NQ, H, dtype=torch.float32, device=dev)
+        so_norm = torch.empty(NQ, 2, dtype=torch.float32, device=dev)
+        check(L.vsg_grd_query_init(_raw(quint), _raw(spans), _raw(vlen), _raw(q_vid), NQ, _raw(w["proj_enti"]), _raw(w["proj_pred"]),
+                                   _raw(w["temp_w"]), _raw(w["temp_b"]), H, _raw(q0), _raw(so_norm), sp), "vsg_grd_query_init")
+        v = self._qanet(w["video_encoder"], v0, sv)
+        q = self._qanet(w["query_encoder"], q0, sq3)
+        # --- context-query attention -> vq_fc -> combined encoder
+        pv = gemm(m, v, w["proj2sim"], bias=False)
+        comb_in = torch.empty(sc["rows"], 4 * H, dtype=torch.float32, device=dev)
+        check(L.vsg_cq_attention(_raw(v), _raw(pv), _raw(q), _raw(sv["off"]), _raw(q_vid), _raw(sc["off"]), NQ, H, max(T), _raw(comb_in), sp),
+              "vsg_cq_attention")
+        comb = self._qanet(w["combined_encoder"], gemm(m, comb_in, w["vq_fc"]), sc)
+        del comb_in
+        regr, conf, cls = self._head(w["regr_head"], comb, sc), self._head(w["conf_head"], comb, sc), self._head(w["cls_head"], comb, sc)
+        out = self._post(regr, conf, cls, sc["off"], so_norm, clip, sv["off"], q_vid, NQ, nq, th, regr_activated=False)
+        if want_net:
+            return out, (regr, conf, cls, so_norm)
+        return out
+
+    def _post(self, regr, conf, cls, comb_off, so_norm, clip, vid_off, q_vid, NQ, nq, th, regr_activated):
+        """Everything after the network (:533-576) in one kernel."""
+        L, dev, B = lib(), self.device, self.num_bins
+        sp = stream_ptr(dev)
+        pooled = torch.empty(NQ, B + 1, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(NQ, B + 1, dtype=torch.float32, device=dev)
+        mask = torch.empty(NQ, B + 1, dtype=torch.uint8, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        check(L.vsg_grounding_post(_raw(regr), _raw(conf), _raw(cls), _raw(comb_off), _raw(so_norm), _raw(clip), _raw(vid_off), _raw(q_vid),
+                                   NQ, B, 1 if regr_activated else 0, float(th[0]), float(th[1]), float(th[2]), float(th[3]), _raw(pooled), _raw(probs), _raw(mask),
+                                   _raw(err), sp), "vsg_grounding_post")
+        if int(err.item()) > 0:
+            # the reference raises in temporal_pooling when no clip survives (:726, min() of an empty tensor)
+            raise RuntimeError("temporal_pooling: %d (query, bin) pairs have an empty pooling set" % int(err.item()))
+        out, r = [], 0
+        for n in nq:
+            out.append((pooled[r:r + n], probs[r:r + n], mask[r:r + n].bool()))
+            r += n
+        return out
+
+    def postprocess(self, regrs, conf_logits, cls_logits, so_norm, th=(0.9, 0.5, 0.2, 0.8)):
+        """Post-network stage alone for one video, on ``forward_propagation``-style outputs
+        (regrs f32[nq,T,2B] AFTER the sigmoid, logits f32[nq,T,B], so_norm f32[nq,2])."""
+        dev = self.device
+        nq, T, _ = conf_logits.shape
+        comb_off = (torch.arange(nq + 1, dtype=torch.long) * T).to(dev)
+        vid_off = torch.tensor([0, T], dtype=torch.long, device=dev)
+        q_vid = torch.zeros(nq, dtype=torch.int32, device=dev)
+        clip = torch.linspace(0, 1, T).to(dev)
+        f = lambda t: t.to(dev, torch.float32).reshape(nq * T, -1).contiguous()
+        return self._post(f(regrs), f(conf_logits), f(cls_logits), comb_off, so_norm.to(dev, torch.float32).contiguous(), clip, vid_off,
+                          q_vid, nq, [nq], th, regr_activated=True)[0]
+
+    def forward(self, video_feature_list, data_list, score_th=0.5, tiou_th=0.5, bins_th=0.1, nms_th=0.5, with_gt_data=True,
+                max_rows: int = 1_500_000):
+        if with_gt_data:
+            raise NotImplementedError("with_gt_data=True evaluates the grounding stage alone on GT queries (grd_model_v5.py:198-202); "
+                                      "only the inference path with_gt_data=False is on the hot path")
+        if self._w is None:
+            raise VsgError("DEBUG has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
+        assert len(video_feature_list) == len(data_list)
+        single = len(video_feature_list) == 1
+        th = (score_th, tiou_th, bins_th, nms_th)
+        self.bin_conf_th, self.score_th, self.tiou_th, self.nms_th = bins_th, score_th, tiou_th, nms_th
+        results: List[Optional[tuple]] = [None] * len(data_list)
+        live = [i for i, d in enumerate(data_list) if d[0] is not None and d[0].shape[0] > 0]
+        batch, rows = [], 0
+
+        def flush():
+            nonlocal batch, rows
+            if batch:
+                outs = self._forward_videos([video_feature_list[i] for i in batch], [data_list[i] for i in batch], th)
+                for i, o in zip(batch, outs):
+                    results[i] = o
+            batch, rows = [], 0
+        for i in live:
+            r = int(video_feature_list[i].shape[0]) * int(data_list[i][0].shape[0])
+            if batch and rows + r > max_rows:
+                flush()
+            batch.append(i)
+            rows += r
+        flush()
+        if single:
+            return results[0] if results[0] is not None else (None, None)
+        return results
+
+    __call__ = forward
+
+    def forward_propagation_debug(self, video_feature, quintuples, spans, video_len, th=(0.9, 0.5, 0.2, 0.8)):
+        """(regrs after sigmoid, conf_logits, cls_logits) as ``forward_propagation`` (:331-373) returns them, for tests."""
+        out, (regr, conf, cls, so_norm) = self._forward_videos([video_feature], [(quintuples, spans, video_len)], th, want_net=True)
+        nq, T = quintuples.shape[0], video_feature.shape[0]
+        B = self.num_bins
+        return torch.sigmoid(regr).view(nq, T, 2 * B), conf.view(nq, T, B), cls.view(nq, T, B), so_norm, out[0]

@@ -58,7 +58,8 @@ LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py'
 
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
-         accumulate: bool = False, bias: bool = True, K: Optional[int] = None) -> torch.Tensor:
+         accumulate: bool = False, bias: bool = True, K: Optional[int] = None,
+         residual: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
     wider row-major buffers (their row stride is passed as the leading dimension)."""
     require_cuda(A)
@@ -80,7 +81,8 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         ev0.record()
     check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
                          _raw(rb_index), int(rb_period), 0 if rowbias is None else rowbias.stride(0), 1 if relu else 0,
-                         1 if accumulate else 0, _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
+                         1 if accumulate else 0, _raw(residual), 0 if residual is None else residual.stride(0),
+                         _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
     if _Profile.enabled:
         ev1.record()
         _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, mode))
