@@ -175,3 +175,22 @@ def test_bigc_state_dict_strictness():
     m.load_state_dict({"module." + k: v for k, v in st.items()})        # DataParallel prefix is stripped
     with pytest.raises(NotImplementedError):
         bigc.BIG_C_vidvrd(cfg, is_train=True)
+
+
+def test_forward_packed_equals_forward():
+    from vidsgg_big_b200 import evalapi, geometry
+    cfg = synth.tiny_vidvrd_config()
+    st = synth.make_bigc_state(7, cfg)
+    model = _model(cfg, st, "3xtf32")
+    props = [bigc_inputs(cfg, 950 + i, n, vl, None).to(DEV) for i, (n, vl) in enumerate([(7, 40), (12, 64), (1, 25), (20, 90)])]
+    with torch.no_grad():
+        ref = model(props, topk=5)
+        packed = model.forward_packed(props, topk=5)
+    for a, b in zip(ref, packed.per_video()):
+        assert (a is None) == (b is None)
+        if a is not None:
+            assert all(torch.equal(x, y) for x, y in zip(a, b))
+    tt = geometry.TrackTable.from_containers(props)
+    A = evalapi.PackedRelations.from_packed_triplets(tt, packed)
+    B = evalapi.PackedRelations.from_triplets(tt, [None if t is None else (t[0], t[1].mean(-1), t[2]) for t in ref])
+    assert torch.equal(A.rel, B.rel) and torch.equal(A.vid_off, B.vid_off) and torch.allclose(A.scores, B.scores)

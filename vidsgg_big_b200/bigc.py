@@ -82,6 +82,30 @@ class PackedVideos(object):
         self.counts = counts
 
 
+class PackedTriplets(object):
+    """Triplets of a batch of videos as written by the kernel: video v owns rows [v*cap, v*cap + counts[v,0])."""
+
+    def __init__(self, quint, scores, spans, qids, counts_host, cap):
+        self.quint, self.scores, self.spans, self.qids, self.counts, self.cap = quint, scores, spans, qids, counts_host, cap
+
+    def compact(self):
+        """Dense rows of all videos (video-major) + host offsets: 4 gathers for the whole batch."""
+        n = self.counts[:, 0].astype(np.int64)
+        off = np.zeros(n.size + 1, np.int64)
+        off[1:] = np.cumsum(n)
+        idx = np.repeat(np.arange(n.size, dtype=np.int64) * self.cap - off[:-1], n) + np.arange(off[-1], dtype=np.int64)
+        idx_d = torch.from_numpy(idx).to(self.quint.device)
+        return self.quint[idx_d], self.scores[idx_d], self.spans[idx_d], self.qids[idx_d], off
+
+    def per_video(self):
+        out = []
+        for v in range(self.counts.shape[0]):
+            n_out, n_pos = int(self.counts[v, 0]), int(self.counts[v, 1])
+            s = slice(v * self.cap, v * self.cap + n_out)
+            out.append(None if n_pos == 0 else (self.quint[s], self.scores[s], self.spans[s], self.qids[s]))
+        return out
+
+
 class BIG_C(object):
     """Drop-in for the reference ``BIG_C`` in inference mode (see module docstring)."""
 
@@ -367,7 +391,7 @@ class BIG_C(object):
         Z = self._concat(pieces, VQ, ldz)
         return gemm(m, Z, w["log"], rowbias=w["bias_matrix"], rb_index=pair_index, K=self.dim_z)
 
-    def _construct_triplets(self, pk, logits, so, topk):
+    def _construct_triplets(self, pk, logits, so, topk, packed=False):
         """model_0v10.py:707-785 for every video; one D2H read of the per-video counts."""
         V, Q = pk.V, self.num_querys
         cap = Q * topk
@@ -380,6 +404,8 @@ class BIG_C(object):
         check(lib().vsg_construct_triplet(_raw(logits), logits.stride(0), self.num_pred_cats, Q, topk, _raw(so), _raw(pk.seg), V,
                                           _raw(pk.dura), _raw(pk.cat_ids), _raw(pk.scores), _raw(quint), _raw(scores), _raw(spans),
                                           _raw(qids), _raw(counts), cap, stream_ptr(dev)), "vsg_construct_triplet")
+        if packed:
+            return PackedTriplets(quint, scores, spans, qids, counts.cpu().numpy(), cap)
         cnt = counts.cpu().tolist()
         out = []
         for v in range(V):
@@ -421,6 +447,17 @@ class BIG_C(object):
 
     __call__ = forward
     default_topk = 10
+
+    def forward_packed(self, proposal_list, topk=None):
+        """Same computation as ``forward`` for a batch of non-empty videos, but the result stays packed on the device
+        (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``."""
+        if self._w is None:
+            raise VsgError("BIG_C has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
+        self.topk = self.default_topk if topk is None else topk
+        assert all(p.num_proposals > 0 for p in proposal_list)
+        pk = PackedVideos(proposal_list, self.device)
+        logits, so, _ = self._encode2decode(pk)
+        return self._construct_triplets(pk, logits, so, self.topk, packed=True)
 
     def forward_debug(self, proposal):
         """(pred_queries, pred_logits [Q,P], att_matrx [2,Q,n]) of one video, like ``encode2decode`` (:434-475)."""

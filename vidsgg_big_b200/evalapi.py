@@ -116,6 +116,19 @@ class PackedRelations(object):
                    torch.tensor(vid_off, dtype=torch.long).to(dev), scores, vol_full_track=False)
 
     @classmethod
+    def from_packed_triplets(cls, table, packed, seg_host=None):
+        """Batched twin of ``from_triplets`` for ``BIG_C.forward_packed`` output (bigc.PackedTriplets): a handful of
+        device ops for the whole batch.  Score = mean of the three scores (tools/eval_vidvrd.py:136)."""
+        dev = table.boxes.device
+        q, s3, sp, _, off = packed.compact()
+        counts = np.diff(off)
+        base = np.concatenate([[0], np.cumsum(table.counts)])[:-1].astype(np.int64)
+        base_rows = torch.from_numpy(np.repeat(base, counts)).to(dev)
+        rel = torch.stack([q[:, 1], q[:, 0], q[:, 2], q[:, 3] + base_rows, q[:, 4] + base_rows, sp[:, 0], sp[:, 1] + 1], 1).contiguous()
+        return cls(table.boxes, table.off, table.dura[:, 0].contiguous(), rel, torch.from_numpy(off).to(dev),
+                   s3.mean(-1).double().contiguous(), vol_full_track=False)
+
+    @classmethod
     def from_gt_graphs(cls, table, graphs: Sequence):
         """``table``: TrackTable of the batch's GT tracks; relation = (traj cats, pred cat, closed pred span)."""
         dev = table.boxes.device
