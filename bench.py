@@ -136,8 +136,9 @@ class Clocks(object):
 # the step (our arm)
 # ------------------------------------------------------------------------------------------------------
 class Pipeline(object):
-    def __init__(self, kind, precision, device):
+    def __init__(self, kind, precision, device, rank=0):
         from vidsgg_big_b200 import bigc
+        self.rank = rank
         self.cfg, self.wl = workload_cfg(kind)
         cls = bigc.BIG_C_vidor if kind == "vidor" else bigc.BIG_C_vidvrd
         self.model = cls(self.cfg, is_train=False, precision=precision)
@@ -166,8 +167,14 @@ class Pipeline(object):
         packed = self.model.forward_packed(props, topk=self.wl["topk"])                # BIG-C + triplet construction (stays packed)
         PR = evalapi.PackedRelations.from_packed_triplets(tt, packed)                  # score = mean of the 3 (eval_vidvrd.py:136)
         GT = self.pack_gt(graphs)
-        m_ap, rec, mprec = evalapi.evaluate_packed(PR, GT)                             # vIoU matching + AP / recall (D2H of hits)
-        return (float(m_ap), float(rec[50]), float(rec[100])), int(PR.n_rel), viou
+        # vIoU matching on the device, per-video records on the host (D2H of the hit arrays), then the only
+        # cross-rank exchange of the whole path: an all_gather of 64 B / video (no-op at world size 1)
+        from vidsgg_big_b200 import shard
+        rec = evalapi.evaluate_packed(PR, GT, want_records=True)
+        rec[:, 0] += self.rank * 1_000_000
+        allrec = shard.gather_records(torch.from_numpy(rec).to(self.device)).cpu().numpy()
+        m_ap, r_at, mprec = evalapi.metrics_from_records(allrec)
+        return (float(m_ap), float(r_at[50]), float(r_at[100])), int(PR.n_rel), viou
 
 
 def to_device_copy(props, graphs, device):
@@ -276,7 +283,7 @@ def main():
         cpu = {"value": v, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d videos of the same workload (seeds 1000..), %.1f s of CPU work" % (args.cpu_sample, dt)}
 
-    pipe = Pipeline(args.workload, args.precision, device)
+    pipe = Pipeline(args.workload, args.precision, device, rank)
     cfg, wl, props, graphs, feats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device)
     for g in graphs:
         g.to(device)

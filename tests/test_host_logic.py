@@ -1,0 +1,124 @@
+"""CPU tier: host logic, C-ABI symbol export, packaging rules (no GPU needed, no compute calls into the library)."""
+import os
+import re
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    from vidsgg_big_b200 import _cabi, build
+    build.build()
+    lib = _cabi.lib()
+    header = open(os.path.join(ROOT, "include", "vsg_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(vsg_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 30
+    for name in sorted(declared):
+        assert hasattr(lib, name), "libvsgb200.so does not export %s" % name
+        assert name in _cabi.SIGNATURES, "%s has no ctypes signature" % name
+    assert set(_cabi.SIGNATURES) <= declared | {"vsg_launch_count"}
+    assert lib.vsg_built_for_sm() == 100 and lib.vsg_version() >= 1
+
+
+def test_library_is_sm100a_with_tcgen05_and_tma():
+    from vidsgg_big_b200 import _cabi
+    try:
+        sass = subprocess.run(["cuobjdump", "-sass", _cabi.LIB_PATH], capture_output=True, text=True, timeout=120).stdout
+    except Exception:
+        pytest.skip("cuobjdump unavailable")
+    assert "sm_100a" in sass
+    assert "UTCHMMA" in sass or "UTCMMA" in sass          # tcgen05.mma
+    assert "UTMALDG" in sass and "LDTM" in sass           # TMA loads, tcgen05.ld
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "vidsgg_big_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith(".py"):
+                src = open(os.path.join(dirpath, f)).read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
+
+
+def test_no_cpu_fallback():
+    from vidsgg_big_b200 import geometry, evalapi, bigc, grounding, synth
+    from vidsgg_big_b200._cabi import VsgError
+    with pytest.raises(VsgError):
+        geometry.dura_intersection_ts(torch.zeros(1, 2, dtype=torch.long), torch.zeros(1, 2, dtype=torch.long))
+    if not torch.cuda.is_available():
+        with pytest.raises(VsgError):
+            evalapi.viou([[0, 0, 1, 1]], [0, 1], [[0, 0, 1, 1]], [0, 1])
+    cfg = synth.tiny_vidvrd_config()
+    m = bigc.BIG_C_vidvrd(cfg)
+    m.load_state_dict(synth.make_bigc_state(7, cfg))
+    with pytest.raises(VsgError):
+        m([synth.make_proposal(1, 3, 20, 136, 9)], topk=5)          # weights never moved to a CUDA device
+    with pytest.raises(VsgError):
+        m.to("cpu")
+
+
+def test_containers_roundtrip():
+    from vidsgg_big_b200 import synth
+    from vidsgg_big_b200.containers import TrajProposal
+    P = synth.make_proposal(5, 6, 80, 12, 36)
+    assert P.num_proposals == 6 and len(P.bboxes_list) == 6 and len(P.features_list) == 6
+    assert all(b.shape[0] == int(e - s + 1) for b, (s, e) in zip(P.bboxes_list, P.traj_durations.tolist()))
+    assert P.bboxes_list[2].data_ptr() == P.bboxes[int(P.lengths[:2].sum()):].data_ptr()        # zero-copy views
+    Q = TrajProposal.from_lists(P.video_name, P.video_len, P.video_wh, P.cat_ids, P.scores, P.traj_durations, P.bboxes_list, P.features_list)
+    assert torch.equal(Q.bboxes, P.bboxes) and torch.equal(Q.features, P.features)
+    assert bool((P.scores[:-1] >= P.scores[1:]).all())
+    E = synth.make_proposal(5, 0, 80, 12, 36)
+    assert E.num_proposals == 0 and E.to("cpu") is E
+
+
+def test_lpt_sharding_and_records():
+    from vidsgg_big_b200 import shard, evalapi
+    costs = [100, 1, 1, 1, 50, 49, 3, 2]
+    shards = shard.assign_lpt(costs, 3)
+    assert sorted(i for s in shards for i in s) == list(range(8))
+    loads = [sum(costs[i] for i in s) for s in shards]
+    assert max(loads) == 100 and min(loads) >= 50
+    assert shard.assign_lpt([], 2) == [[], []]
+    # records -> metrics equals the reference-style aggregation
+    rng = np.random.default_rng(0)
+    vids, ngt, hits, tags = [], [], [], []
+    for v in range(7):
+        n = int(rng.integers(1, 140))
+        sc = rng.uniform(0, 1, n)
+        sc[rng.uniform(size=n) < 0.7] = -np.inf
+        vids.append(v); ngt.append(int(rng.integers(1, 30))); hits.append(sc)
+        tags.append(np.sort(rng.uniform(0, 1, int(rng.integers(0, 12))))[::-1].astype(np.float32))
+    a = evalapi._aggregate(vids, ngt, hits, tags, [50, 100], [1, 5, 10])
+    rec = evalapi.per_video_records(vids, ngt, hits, tags)
+    b = evalapi.metrics_from_records(rec)
+    assert a[0] == b[0] and all(a[1][k] == b[1][k] for k in (50, 100)) and all(np.isclose(a[2][k], b[2][k], rtol=1e-7) for k in (1, 5, 10))
+
+
+def _gloo_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vidsgg_big_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    rec = torch.arange((rank + 1) * 3 * 8, dtype=torch.float64).reshape(-1, 8) + 1000 * rank
+    out = shard.gather_records(rec)
+    q.put((rank, out.shape[0], float(out.sum())))
+    dist.destroy_process_group()
+
+
+def test_gather_records_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    exp_rows = 3 + 6
+    exp_sum = float(torch.arange(24, dtype=torch.float64).sum() + (torch.arange(48, dtype=torch.float64) + 1000).sum())
+    assert all(r[1] == exp_rows and r[2] == exp_sum for r in res)

@@ -291,6 +291,32 @@ def _aggregate(vids, n_gt_per_vid, hits, tag_precs, det_nreturns, tag_nreturns):
     return mean_ap, rec_at, {k: np.mean(p_at[k]) for k in tag_nreturns}
 
 
+def per_video_records(vids, n_gt_per_vid, hits, tag_precs, det_nreturns=(50, 100), tag_nreturns=(1, 5, 10)) -> np.ndarray:
+    """Fixed-width per-video records ``[vid, AP, n_gt, tp@K..., P@K...]`` (f64): all that the final aggregation of
+    visual_relation_detection.py:94-109 needs, so ranks only exchange 64 bytes per video."""
+    rows = []
+    for vid, n_gt, sc, tprec in zip(vids, n_gt_per_vid, hits, tag_precs):
+        prec, rec = _pr_curves(sc, n_gt)
+        tp = np.isfinite(sc)
+        row = [float(vid), float(voc_ap(rec, prec)), float(n_gt)]
+        row += [float(tp[:min(k, sc.size)].sum()) for k in det_nreturns]
+        row += [float(tprec[min(k, tprec.size) - 1]) if min(k, tprec.size) > 0 else 0. for k in tag_nreturns]
+        rows.append(row)
+    return np.asarray(rows, dtype=np.float64).reshape(-1, 3 + len(det_nreturns) + len(tag_nreturns))
+
+
+def metrics_from_records(records: np.ndarray, det_nreturns=(50, 100), tag_nreturns=(1, 5, 10)):
+    """Finish mAP / recall@K / P@K from gathered records; equals ``_aggregate`` (recall@K = sum TP@K / sum GT in float32)."""
+    mean_ap = np.mean(records[:, 1])
+    total_gt = int(records[:, 2].sum())
+    rec_at = {}
+    for i, k in enumerate(det_nreturns):
+        rec_at[k] = np.float32(records[:, 3 + i].sum()) / np.maximum(total_gt, F32_EPS)
+    nd = len(det_nreturns)
+    mprec = {k: np.mean(records[:, 3 + nd + i].astype(np.float32) if False else records[:, 3 + nd + i]) for i, k in enumerate(tag_nreturns)}
+    return mean_ap, rec_at, mprec
+
+
 def evaluate_v2(groundtruth, prediction, viou_threshold=0.5, det_nreturns=[50, 100], tag_nreturns=[1, 5, 10]):
     """visual_relation_detection.py:160-223; all videos matched by one batched device call."""
     vids = [v for v, g in groundtruth.items() if len(g) > 0]        # videos without GT are skipped (:73-74)
@@ -316,7 +342,7 @@ eval_visual_relation = evaluate
 
 
 def evaluate_packed(pred: PackedRelations, gt: PackedRelations, viou_threshold=0.5, det_nreturns=(50, 100),
-                    tag_nreturns=(1, 5, 10), with_infos=False):
+                    tag_nreturns=(1, 5, 10), with_infos=False, want_records=False):
     """Packed fast path: same numbers as ``evaluate`` on the equivalent dicts, no dict materialisation."""
     m = match_relations(pred, gt, viou_threshold)
     hit = m.hit.cpu().numpy()
@@ -338,6 +364,8 @@ def evaluate_packed(pred: PackedRelations, gt: PackedRelations, viou_threshold=0
         hits.append(hit[po[v]:po[v + 1]])
         tags.append(_tagging_from_ids([tuple(t) for t in grel[go[v]:go[v + 1]].tolist()], trip, sc)[0])
         infos[v] = (hits[-1], g2d[go[v]:go[v + 1]])
+    if want_records:
+        return per_video_records(vids, ngt, hits, tags, det_nreturns, tag_nreturns)
     res = _aggregate(vids, ngt, hits, tags, list(det_nreturns), list(tag_nreturns))
     return res + (infos,) if with_infos else res
 
