@@ -325,19 +325,32 @@ class BIG_C(object):
         enco = x
         # --- decoder
         VQ = V * Q
-        query = torch.empty(VQ, Pd, dtype=torch.float32, device=dev)
-        check(L.vsg_broadcast_rows(_raw(w["query_init"]), Q, Pd, VQ, _raw(query), sp), "vsg_broadcast_rows")
         so = torch.empty(VQ, 2, dtype=torch.int32, device=dev)
         att_out = torch.zeros(VQ, 2, max(pk.max_tracks, 1), dtype=torch.float32, device=dev) if want_att else None
         values = torch.empty(VQ, 2 * E, dtype=torch.float32, device=dev)
         hid = torch.empty(VQ, 2 * Pd, dtype=torch.float32, device=dev)
         n_dec = len(w["dec"])
+
+        def bcast(x):
+            out = torch.empty(VQ, x.shape[1], dtype=torch.float32, device=dev)
+            check(L.vsg_broadcast_rows(_raw(x), Q, x.shape[1], VQ, _raw(out), sp), "vsg_broadcast_rows")
+            return out
+
+        query = None
         for li, lw in enumerate(w["dec"]):
             last = li == n_dec - 1
-            qkv = gemm(m, query, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
-            att = self._mha(qkv, Pd, None, V, Q, Q)
-            query = self._add_ln(query, gemm(m, att, lw["out"]), lw["n1"], post=w["pos"], period=Q)
-            p2a = gemm(m, query, lw["p2a"])
+            # layer 0: the queries of every video are still pred_query_init, so its self-attention block and
+            # fc_pred2att are video-independent -- computed once on Q rows, then broadcast
+            x = w["query_init"] if li == 0 else query
+            nv = 1 if li == 0 else V
+            qkv = gemm(m, x, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
+            att = self._mha(qkv, Pd, None, nv, Q, Q)
+            x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"], post=w["pos"], period=Q)
+            p2a = gemm(m, x, lw["p2a"])
+            if li == 0:
+                query, p2a = bcast(x), bcast(p2a)
+            else:
+                query = x
             e2a = gemm(m, enco, lw["e2a"])
             check(L.vsg_role_attention(_raw(p2a), _raw(e2a), _raw(enco), _raw(pk.seg), V, Q, E, pk.max_tracks,
                                        float(1.0 / np.sqrt(self.dim_enti)), _raw(values),

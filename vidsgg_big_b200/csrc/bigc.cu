@@ -192,100 +192,147 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ x, int period, i
 // ---------------------------------------------------------------------------------------------------
 // Multi-head self-attention core on packed rows (nn.MultiheadAttention semantics without the projections):
 // for every segment s (rows seg_off[s]..seg_off[s+1]) and head h:  O = softmax(Q K^T / sqrt(dh)) V.
-// Q/K/V are column blocks of (possibly the same) row-major buffers.  One CTA per (segment, head, 32-query block);
-// keys/values are walked in chunks of KC rows staged in shared memory with an online softmax, so the
-// segment length is unbounded.  One warp per query at a time; lanes split keys for QK^T and dims for PV.
+// Q/K/V are column blocks of (possibly the same) row-major buffers.
+//
+// One CTA (8 warps) per (segment, head, 64-query block); keys are walked in super-chunks of 128 with an online
+// softmax, so the segment length is unbounded.  Per super-chunk:
+//   phase A  warp (kg, qh): lane = one key of key group kg, its K row lives in REGISTERS (read straight from
+//            global/L2); the 32 queries of half qh are broadcast from shared memory -> 1 FMA per MAC, the
+//            scores land transposed in St[key][query];
+//   phase B  warp w owns 8 queries: chunk max / exp / running-sum update (lanes stride the keys), then PV with
+//            the 8 probabilities of a key fetched by two broadcast LDS.128 and V[key][lane(+32)] from smem:
+//            16 FMAs per 4 shared loads.
 // ---------------------------------------------------------------------------------------------------
+constexpr int MHA_QB = 64, MHA_SK = 128, MHA_PITCH = 68;
+
 template <int DH>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 2)
 mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp, int ldv,
            const int64_t* __restrict__ seg_off, int fixed_len, int n_head, float scale, float* __restrict__ Op, int ldo) {
-  constexpr int KC = DH >= 64 ? 64 : 128;   // keeps K/V chunks + scratch under the 48 KB static limit
-  constexpr int PITCH = DH + 1;
-  __shared__ float sK[KC * PITCH];
-  __shared__ float sV[KC * PITCH];
-  __shared__ float sP[8][KC];
-  __shared__ float sQ[8][DH];
+  extern __shared__ __align__(16) float mha_smem[];
+  float* Qs = mha_smem;                         // [64][DH] pre-scaled
+  float* Vs = Qs + MHA_QB * DH;                 // [128][DH]
+  float* St = Vs + MHA_SK * DH;                 // [128][68] scores / probabilities, transposed (key-major)
   const int seg = blockIdx.x, head = blockIdx.y;
   const int64_t row0 = seg_off ? seg_off[seg] : (int64_t)seg * fixed_len;
   const int n = seg_off ? (int)(seg_off[seg + 1] - row0) : fixed_len;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int q_base = blockIdx.z * 32;
+  const int q_base = blockIdx.z * MHA_QB;
   if (q_base >= n) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hc = head * DH;
-  constexpr int OD = (DH + 31) / 32;  // output dims per lane
-  // each warp owns queries q_base + warp, +8, +16, +24
-  float m_run[4], l_run[4], o_acc[4][OD];
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    m_run[i] = -INFINITY; l_run[i] = 0.f;
-#pragma unroll
-    for (int d = 0; d < OD; ++d) o_acc[i][d] = 0.f;
+  constexpr int OD = (DH + 31) / 32;
+  constexpr int D4 = DH / 4;
+  // queries of this block (zero rows beyond n)
+  for (int i = threadIdx.x; i < MHA_QB * D4; i += 256) {
+    const int q = i / D4, d4 = i % D4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q_base + q < n) {
+      v = *reinterpret_cast<const float4*>(Qp + (row0 + q_base + q) * ldq + hc + 4 * d4);
+      v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
+    }
+    reinterpret_cast<float4*>(Qs)[i] = v;
   }
-  for (int k0 = 0; k0 < n; k0 += KC) {
-    const int kc = min(KC, n - k0);
-    __syncthreads();
-    for (int i = threadIdx.x; i < kc * DH; i += blockDim.x) {
-      const int kr = i / DH, d = i % DH;
-      sK[kr * PITCH + d] = Kp[(row0 + k0 + kr) * ldk + hc + d];
-      sV[kr * PITCH + d] = Vp[(row0 + k0 + kr) * ldv + hc + d];
+  float m_run[8], l_run[8], o_acc[8][OD];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    m_run[j] = -INFINITY; l_run[j] = 0.f;
+#pragma unroll
+    for (int d = 0; d < OD; ++d) o_acc[j][d] = 0.f;
+  }
+  const int kg = warp & 3, qh = warp >> 2;
+  for (int k0 = 0; k0 < n; k0 += MHA_SK) {
+    const int kc = min(MHA_SK, n - k0);
+    __syncthreads();  // previous chunk fully consumed (and Qs visible on the first pass)
+    for (int i = threadIdx.x; i < MHA_SK * D4; i += 256) {
+      const int kr = i / D4, d4 = i % D4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (kr < kc) v = *reinterpret_cast<const float4*>(Vp + (row0 + k0 + kr) * ldv + hc + 4 * d4);
+      reinterpret_cast<float4*>(Vs)[i] = v;
+    }
+    // ---- phase A ----
+    {
+      const int key = kg * 32 + lane;
+      if (kg * 32 < kc) {          // warp-uniform
+        float kreg[DH];
+        const bool valid = key < kc;
+        const float* kp = Kp + (row0 + k0 + (valid ? key : 0)) * ldk + hc;
+#pragma unroll
+        for (int d4 = 0; d4 < D4; ++d4) {
+          const float4 v = *reinterpret_cast<const float4*>(kp + 4 * d4);
+          kreg[4 * d4] = v.x; kreg[4 * d4 + 1] = v.y; kreg[4 * d4 + 2] = v.z; kreg[4 * d4 + 3] = v.w;
+        }
+        float* srow = St + key * MHA_PITCH + qh * 32;
+#pragma unroll 4
+        for (int q = 0; q < 32; ++q) {
+          const float4* qp = reinterpret_cast<const float4*>(Qs + (qh * 32 + q) * DH);
+          float acc = 0.f;
+#pragma unroll
+          for (int d4 = 0; d4 < D4; ++d4) {
+            const float4 x = qp[d4];
+            acc = fmaf(kreg[4 * d4], x.x, acc); acc = fmaf(kreg[4 * d4 + 1], x.y, acc);
+            acc = fmaf(kreg[4 * d4 + 2], x.z, acc); acc = fmaf(kreg[4 * d4 + 3], x.w, acc);
+          }
+          srow[q] = valid ? acc : -INFINITY;
+        }
+      }
     }
     __syncthreads();
+    // ---- phase B: warp owns queries 8*warp .. 8*warp+7 ----
+    if (q_base + 8 * warp < n) {    // warp-uniform
+      const int nk_groups = (kc + 31) / 32;
 #pragma unroll
-    for (int qi = 0; qi < 4; ++qi) {
-      const int q = q_base + warp + 8 * qi;
-      if (q >= n) continue;  // warp-uniform
-      for (int d = lane; d < DH; d += 32) sQ[warp][d] = Qp[(row0 + q) * ldq + hc + d] * scale;
-      __syncwarp();
-      float sc[KC / 32];
-      float cmax = -INFINITY;
+      for (int j = 0; j < 8; ++j) {
+        const int q = 8 * warp + j;
+        float sc[MHA_SK / 32];
+        float cmax = -INFINITY;
 #pragma unroll
-      for (int j = 0; j < KC / 32; ++j) {
-        const int kr = lane + 32 * j;
-        float s = -INFINITY;
-        if (kr < kc) {
-          s = 0.f;
-#pragma unroll
-          for (int d = 0; d < DH; ++d) s = fmaf(sQ[warp][d], sK[kr * PITCH + d], s);
+        for (int i = 0; i < MHA_SK / 32; ++i) {
+          sc[i] = (i < nk_groups) ? St[(lane + 32 * i) * MHA_PITCH + q] : -INFINITY;
+          cmax = fmaxf(cmax, sc[i]);
         }
-        sc[j] = s;
-        cmax = fmaxf(cmax, s);
-      }
-      cmax = warp_max(cmax);
-      const float m_new = fmaxf(m_run[qi], cmax);
-      const float corr = expf(m_run[qi] - m_new);
-      float psum = 0.f;
+        cmax = warp_max(cmax);
+        const float m_new = fmaxf(m_run[j], cmax);
+        const float corr = expf(m_run[j] - m_new);
+        float psum = 0.f;
 #pragma unroll
-      for (int j = 0; j < KC / 32; ++j) {
-        const int kr = lane + 32 * j;
-        const float pv = (kr < kc) ? expf(sc[j] - m_new) : 0.f;
-        sP[warp][kr] = pv;
-        psum += pv;
-      }
-      psum = warp_sum(psum);
-      l_run[qi] = l_run[qi] * corr + psum;
-      m_run[qi] = m_new;
-      __syncwarp();
-#pragma unroll
-      for (int dd = 0; dd < OD; ++dd) {
-        const int d = lane + 32 * dd;
-        float acc = o_acc[qi][dd] * corr;
-        if (d < DH) {
-          for (int kr = 0; kr < kc; ++kr) acc = fmaf(sP[warp][kr], sV[kr * PITCH + d], acc);
+        for (int i = 0; i < MHA_SK / 32; ++i) {
+          if (i < nk_groups) {
+            const float pv = expf(sc[i] - m_new);      // -inf -> 0 for keys beyond kc
+            St[(lane + 32 * i) * MHA_PITCH + q] = pv;
+            psum += pv;
+          }
         }
-        o_acc[qi][dd] = acc;
+        psum = warp_sum(psum);
+        l_run[j] = l_run[j] * corr + psum;
+        m_run[j] = m_new;
+#pragma unroll
+        for (int d = 0; d < OD; ++d) o_acc[j][d] *= corr;
       }
       __syncwarp();
+      if (lane < DH) {
+        for (int kr = 0; kr < kc; ++kr) {
+          const float4 p0 = *reinterpret_cast<const float4*>(St + kr * MHA_PITCH + 8 * warp);
+          const float4 p1 = *reinterpret_cast<const float4*>(St + kr * MHA_PITCH + 8 * warp + 4);
+#pragma unroll
+          for (int d = 0; d < OD; ++d) {
+            const float v = Vs[kr * DH + lane + 32 * d];
+            o_acc[0][d] = fmaf(p0.x, v, o_acc[0][d]); o_acc[1][d] = fmaf(p0.y, v, o_acc[1][d]);
+            o_acc[2][d] = fmaf(p0.z, v, o_acc[2][d]); o_acc[3][d] = fmaf(p0.w, v, o_acc[3][d]);
+            o_acc[4][d] = fmaf(p1.x, v, o_acc[4][d]); o_acc[5][d] = fmaf(p1.y, v, o_acc[5][d]);
+            o_acc[6][d] = fmaf(p1.z, v, o_acc[6][d]); o_acc[7][d] = fmaf(p1.w, v, o_acc[7][d]);
+          }
+        }
+      }
     }
   }
 #pragma unroll
-  for (int qi = 0; qi < 4; ++qi) {
-    const int q = q_base + warp + 8 * qi;
+  for (int j = 0; j < 8; ++j) {
+    const int q = q_base + 8 * warp + j;
     if (q >= n) continue;
 #pragma unroll
-    for (int dd = 0; dd < OD; ++dd) {
-      const int d = lane + 32 * dd;
-      if (d < DH) Op[(row0 + q) * ldo + hc + d] = o_acc[qi][dd] / l_run[qi];
+    for (int d = 0; d < OD; ++d) {
+      const int dd = lane + 32 * d;
+      if (dd < DH) Op[(row0 + q) * ldo + hc + dd] = o_acc[j][d] / l_run[j];
     }
   }
 }
@@ -655,11 +702,27 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
   VSG_REQUIRE(Q && K && V && O, "vsg_mha: null pointer");
   VSG_REQUIRE(seg_off != nullptr || fixed_len > 0, "vsg_mha: need seg_off or fixed_len");
   const float scale = 1.0f / sqrtf((float)head_dim);
-  dim3 grid(n_seg, n_head, (max_len + 31) / 32);
-  if (head_dim == 64) mha_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
-  else if (head_dim == 16) mha_kernel<16><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
-  else if (head_dim == 32) mha_kernel<32><<<grid, 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo);
+  VSG_REQUIRE((ldq % 4) == 0 && (ldk % 4) == 0 && (ldv % 4) == 0 && aligned16(Q) && aligned16(K) && aligned16(V),
+              "vsg_mha: Q/K/V must be 16-byte aligned with leading dimensions that are multiples of 4");
+  dim3 grid(n_seg, n_head, (max_len + MHA_QB - 1) / MHA_QB);
+  const size_t smem = (size_t)(MHA_QB * head_dim + MHA_SK * head_dim + MHA_SK * MHA_PITCH) * sizeof(float);
+#define VSG_MHA_LAUNCH(DH_)                                                                                              \
+  do {                                                                                                                   \
+    static bool attr_done = false;                                                                                       \
+    if (!attr_done) {                                                                                                    \
+      if (cudaFuncSetAttribute(mha_kernel<DH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {  \
+        set_error("vsg_mha: cannot raise dynamic shared memory to %zu", smem);                                           \
+        return VSG_E_LAUNCH;                                                                                             \
+      }                                                                                                                  \
+      attr_done = true;                                                                                                  \
+    }                                                                                                                    \
+    mha_kernel<DH_><<<grid, 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo); \
+  } while (0)
+  if (head_dim == 64) VSG_MHA_LAUNCH(64);
+  else if (head_dim == 32) VSG_MHA_LAUNCH(32);
+  else if (head_dim == 16) VSG_MHA_LAUNCH(16);
   else { set_error("vsg_mha: head_dim %d unsupported (16, 32, 64)", head_dim); return VSG_E_UNSUPPORTED; }
+#undef VSG_MHA_LAUNCH
   return check_launch("vsg_mha");
 }
 
