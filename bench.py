@@ -81,6 +81,12 @@ def make_videos(kind, n_videos, base_seed, device, pinned=False):
         p.features = feats[r:r + L]
         p.dim_feat = wl["feat_total"]
         r += L
+    if kind == "vidor":      # I3D clip features for the grounding stage: f32[T, 1024] * 0.05, T = ceil(video_len / 8)
+        for p in props:
+            T = (p.video_len + 7) // 8
+            p.i3d = (torch.randn(T, 1024, generator=g, device=device, dtype=torch.float32) * 0.05)
+            if pinned:
+                p.i3d = p.i3d.cpu().pin_memory()
     return cfg, wl, props, graphs, feats
 
 
@@ -137,8 +143,13 @@ class Clocks(object):
 # ------------------------------------------------------------------------------------------------------
 class Pipeline(object):
     def __init__(self, kind, precision, device, rank=0):
-        from vidsgg_big_b200 import bigc
-        self.rank = rank
+        from vidsgg_big_b200 import bigc, grounding
+        self.rank, self.kind = rank, kind
+        if kind == "vidor":
+            gcfg = synth.grounding_config()
+            self.grd = grounding.DEBUG(gcfg, is_train=False, precision=precision)
+            self.grd.load_state_dict(synth.make_grounding_state(21, gcfg))
+            self.grd.to(device)
         self.cfg, self.wl = workload_cfg(kind)
         cls = bigc.BIG_C_vidor if kind == "vidor" else bigc.BIG_C_vidvrd
         self.model = cls(self.cfg, is_train=False, precision=precision)
@@ -165,7 +176,15 @@ class Pipeline(object):
         if timers is not None:
             timers["geo1"].record()
         packed = self.model.forward_packed(props, topk=self.wl["topk"])                # BIG-C + triplet construction (stays packed)
-        PR = evalapi.PackedRelations.from_packed_triplets(tt, packed)                  # score = mean of the 3 (eval_vidvrd.py:136)
+        if self.kind == "vidor":
+            # grounding stage on the classification output (tools/eval_vidor.py:218-257), all videos batched
+            q, s3, sp, _, off = packed.compact()
+            datas = [(q[off[i]:off[i + 1]], sp[off[i]:off[i + 1]], props[i].video_len) for i in range(len(props))]
+            assert all(d[0].shape[0] > 0 for d in datas)
+            pooled, probs, mask = self.grd.forward_packed([p.i3d for p in props], datas, **synth.GROUNDING_INFERENCE)
+            PR = evalapi.PackedRelations.from_grounded(tt, packed, pooled, probs, mask, [p.video_len for p in props])
+        else:
+            PR = evalapi.PackedRelations.from_packed_triplets(tt, packed)              # score = mean of the 3 (eval_vidvrd.py:136)
         GT = self.pack_gt(graphs)
         # vIoU matching on the device, per-video records on the host (D2H of the hit arrays), then the only
         # cross-rank exchange of the whole path: an all_gather of 64 B / video (no-op at world size 1)
@@ -192,6 +211,9 @@ def to_device_copy(props, graphs, device):
         r += L
         q.bboxes = p.bboxes.to(device, non_blocking=True)
         q.cat_ids = p.cat_ids.to(device); q.scores = p.scores.to(device); q.traj_durations = p.traj_durations.to(device)
+        if hasattr(p, "i3d"):
+            q.i3d = p.i3d.to(device, non_blocking=True)
+            nbytes += q.i3d.numel() * 4
         nbytes += q.bboxes.numel() * 4 + q.cat_ids.numel() * 8 + q.scores.numel() * 4 + q.traj_durations.numel() * 8
         out_p.append(q)
     for g in graphs:
@@ -205,9 +227,10 @@ def to_device_copy(props, graphs, device):
 # ------------------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference (torch-CPU / python loops), all host threads
 # ------------------------------------------------------------------------------------------------------
-def cpu_pass(kind, props, graphs, st, cfg, wl):
-    """What the reference does per video on the host: stretched BIG-C forward, per-pair vIoU loop, dict conversion, eval."""
-    from oracle import bigc as ob, convert as oc, evalapi as oe, geometry as og
+def cpu_pass(kind, props, graphs, st, cfg, wl, gst=None):
+    """What the reference does per video on the host: stretched BIG-C forward, per-pair vIoU loop, (grounding incl. its
+    python pooling loops,) dict conversion, eval."""
+    from oracle import bigc as ob, convert as oc, evalapi as oe, geometry as og, grounding as ogr
     en, pn = oc.default_names("e", 256), oc.default_names("p", 256)
     gts, prs = {}, {}
     with torch.no_grad():
@@ -215,6 +238,9 @@ def cpu_pass(kind, props, graphs, st, cfg, wl):
             og.traj_viou_matrix(p.bboxes_list, p.traj_durations, p.bboxes_list, p.traj_durations)
             r = ob.forward(st, cfg, [p], wl["topk"])[0]
             t3 = None if r is None else (r[0], r[1].mean(-1), r[2])
+            if kind == "vidor" and r is not None:
+                pooled, probs, mask = ogr.forward(gst, synth.grounding_config(), [p.i3d], [(r[0], r[2], p.video_len)], **synth.GROUNDING_INFERENCE)
+                t3 = ogr.expand_after_grounding(r[0], r[1], pooled, probs, mask, p.video_len)
             prs.update(oc.to_eval_format_pr(p, t3, en, pn))
             gts.update(oc.to_eval_format_gt(g, en, pn))
     return oe.evaluate(gts, prs)
@@ -224,11 +250,12 @@ def cpu_baseline(kind, n_sample, repeats=1):
     torch.set_num_threads(os.cpu_count() or 1)
     cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu")
     st = synth.make_bigc_state(1, cfg)
-    cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl)                     # warm-up
+    gst = synth.make_grounding_state(21, synth.grounding_config()) if kind == "vidor" else None
+    cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl, gst)                # warm-up
     best = None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_pass(kind, props, graphs, st, cfg, wl)
+        cpu_pass(kind, props, graphs, st, cfg, wl, gst)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
     return n_sample / best, best
@@ -292,6 +319,7 @@ def main():
         p.to(device)
         p.features = f
     geo_bytes = algorithmic_bytes_geometry(props)
+    in_bytes = feats.numel() * 4
 
     def barrier():
         if world > 1:
@@ -376,8 +404,9 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 (tcgen05 %s, fp32 accumulate)" % args.precision, "data": "synthetic",
             "config": {"workload": wl["name"], "videos_per_gpu": args.videos, "precision": args.precision,
-                       "stages": ["pair_geometry", "bigc_classify", "triplets", "viou_eval"], "grounding": "not in this workload (VidVRD has no grounding stage)",
-                       "l2": "inputs (%.1f GB per GPU) exceed L2" % (sum(int(p.lengths.sum()) for p in hprops) * wl["feat_total"] * 4 / 1e9 if not args.no_e2e else 0.0),
+                       "stages": ["pair_geometry", "bigc_classify", "triplets"] + (["grounding"] if args.workload == "vidor" else []) + ["viou_eval"],
+                       "grounding": "grd_model_v5 dims, 10 bins" if args.workload == "vidor" else "not in this workload (VidVRD has no grounding stage)",
+                       "l2": "inputs (%.1f GB per GPU) exceed L2" % (in_bytes / 1e9),
                        "result": {"mAP": metrics[0], "R@50": metrics[1], "R@100": metrics[2], "triplets": n_trip}},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launches,
             "clocks": clk,

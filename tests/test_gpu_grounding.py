@@ -87,3 +87,34 @@ def test_grounding_api_errors():
         m([torch.zeros(4, 1024, device=DEV)], [(torch.zeros(1, 5, dtype=torch.long), torch.zeros(1, 2, dtype=torch.long), 10)])
     empty = (torch.zeros(0, 5, dtype=torch.long), torch.zeros(0, 2, dtype=torch.long), 10)
     assert m([torch.zeros(4, 1024, device=DEV)], [empty], with_gt_data=False) == (None, None)
+
+
+def test_classify_then_ground_packed_equals_driver_expansion():
+    """BIG-C (VidOR) -> grounding -> relations: the packed batched path builds exactly the relations that the reference
+    driver's per-video expansion (tools/eval_vidor.py:245-253) + to_eval_format_pr would evaluate."""
+    from vidsgg_big_b200 import bigc, evalapi, geometry, grounding
+    cfg = synth.vidor_config()
+    model = bigc.BIG_C_vidor(cfg, precision="3xtf32")
+    model.load_state_dict(synth.make_bigc_state(2, cfg)); model.cuda()
+    grd = _model("3xtf32")
+    props, feats = [], []
+    for sd, n, vl in ((701, 8, 120), (702, 14, 260)):
+        P = synth.make_proposal(sd, n, vl, 1324, 81, min_len=15).to(DEV)
+        props.append(P); feats.append(synth.make_video_feature(sd, vl).to(DEV))
+    with torch.no_grad():
+        packed = model.forward_packed(props, topk=3)
+        per_video = packed.per_video()
+        q, s3, sp, _, off = packed.compact()
+        datas = [(q[off[i]:off[i + 1]], sp[off[i]:off[i + 1]], props[i].video_len) for i in range(2)]
+        pooled, probs, mask = grd.forward_packed(feats, datas, **INF)
+    tt = geometry.TrackTable.from_containers(props)
+    A = evalapi.PackedRelations.from_grounded(tt, packed, pooled, probs, mask, [p.video_len for p in props])
+    trips, r = [], 0
+    for i, pv in enumerate(per_video):
+        m = pv[0].shape[0]
+        trips.append(grounding.expand_after_grounding(pv[0], pv[1], pooled[r:r + m], probs[r:r + m], mask[r:r + m], props[i].video_len))
+        r += m
+    B = evalapi.PackedRelations.from_triplets(tt, trips)
+    assert torch.equal(A.rel, B.rel) and torch.equal(A.vid_off, B.vid_off)
+    assert torch.allclose(A.scores, B.scores, rtol=1e-6)
+    assert A.n_rel >= sum(t[0].shape[0] for t in per_video)          # at least one bin per query

@@ -129,6 +129,28 @@ class PackedRelations(object):
                    s3.mean(-1).double().contiguous(), vol_full_track=False)
 
     @classmethod
+    def from_grounded(cls, table, packed, pooled_se, bins_probs, bins_mask, video_lens):
+        """Classification output (bigc.PackedTriplets) + grounding output of the same queries (concatenated in video
+        order) -> relations, i.e. the expansion of tools/eval_vidor.py:245-253 for the whole batch:
+        score = mean(cls scores) * bin prob, span = round(pooled * video_len), one relation per kept bin."""
+        dev = table.boxes.device
+        q, s3, sp, _, off = packed.compact()
+        counts = np.diff(off)
+        V = counts.size
+        base = np.concatenate([[0], np.cumsum(table.counts)])[:-1].astype(np.int64)
+        base_rows = torch.from_numpy(np.repeat(base, counts)).to(dev)
+        vid_rows = torch.from_numpy(np.repeat(np.arange(V, dtype=np.int64), counts)).to(dev)
+        vlen = torch.as_tensor(np.asarray(video_lens, dtype=np.float32)).to(dev)[vid_rows]            # per query
+        qi, bi = bins_mask.nonzero(as_tuple=True)                                                       # row-major, like [mask]
+        score = (s3.mean(-1)[:, None] * bins_probs)[qi, bi]
+        span = torch.round(pooled_se[qi, bi, :] * vlen[qi, None]).long()
+        rel = torch.stack([q[qi, 1], q[qi, 0], q[qi, 2], q[qi, 3] + base_rows[qi], q[qi, 4] + base_rows[qi], span[:, 0], span[:, 1] + 1], 1)
+        per_vid = torch.bincount(vid_rows[qi], minlength=V).cpu().numpy()
+        vid_off = np.concatenate([[0], np.cumsum(per_vid)]).astype(np.int64)
+        return cls(table.boxes, table.off, table.dura[:, 0].contiguous(), rel.contiguous(), torch.from_numpy(vid_off).to(dev),
+                   score.double().contiguous(), vol_full_track=False)
+
+    @classmethod
     def from_gt_graphs(cls, table, graphs: Sequence):
         """``table``: TrackTable of the batch's GT tracks; relation = (traj cats, pred cat, closed pred span)."""
         dev = table.boxes.device

@@ -303,6 +303,27 @@ class DEBUG(object):
 
     __call__ = forward
 
+    def forward_packed(self, video_feature_list, data_list, score_th=0.5, tiou_th=0.5, bins_th=0.1, nms_th=0.5,
+                       max_rows: int = 1_500_000):
+        """Batched fast path: every video must have >= 1 query.  Returns the concatenated
+        ``(pooled_se f32[NQ,k+1,2], bins_probs f32[NQ,k+1], bins_mask bool[NQ,k+1])`` in video order."""
+        th = (score_th, tiou_th, bins_th, nms_th)
+        outs, batch, rows = [], [], 0
+
+        def flush():
+            nonlocal batch, rows
+            if batch:
+                outs.extend(self._forward_videos([video_feature_list[i] for i in batch], [data_list[i] for i in batch], th))
+            batch, rows = [], 0
+        for i in range(len(data_list)):
+            r = int(video_feature_list[i].shape[0]) * int(data_list[i][0].shape[0])
+            if batch and rows + r > max_rows:
+                flush()
+            batch.append(i)
+            rows += r
+        flush()
+        return (torch.cat([o[0] for o in outs], 0), torch.cat([o[1] for o in outs], 0), torch.cat([o[2] for o in outs], 0))
+
     def forward_propagation_debug(self, video_feature, quintuples, spans, video_len, th=(0.9, 0.5, 0.2, 0.8)):
         """(regrs after sigmoid, conf_logits, cls_logits) as ``forward_propagation`` (:331-373) returns them, for tests."""
         out, (regr, conf, cls, so_norm) = self._forward_videos([video_feature], [(quintuples, spans, video_len)], th, want_net=True)
