@@ -77,3 +77,22 @@ def test_gemm_3xtf32_is_fp32_class():
     e1x = (linalg.gemm(1, A, wt).double() - ref).abs().max().item()
     print("fp32 err %.3e  3xtf32 err %.3e  tf32 err %.3e" % (e32, e3x, e1x))
     assert e3x <= 40 * e32 + 1e-6 and e1x > 20 * e3x
+
+
+def test_tf32_mma_ignores_low_mantissa_bits():
+    """The 3xTF32 kernel leaves the raw fp32 A tile in shared memory as the 'high' operand.  That is only valid if
+    tcgen05 kind::tf32 ignores the low 13 mantissa bits: the result must be BIT-IDENTICAL to the variant that masks them."""
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(11)
+    A = torch.randn(1000, 1024, generator=g).to(DEV)
+    W = torch.randn(384, 1024, generator=g).to(DEV) / 32.0
+    wt = linalg.Weight(W)
+    old = lib().vsg_gemm_set_store_hi(1)
+    try:
+        masked = linalg.gemm(2, A, wt).clone()
+        lib().vsg_gemm_set_store_hi(0)
+        raw = linalg.gemm(2, A, wt).clone()
+    finally:
+        lib().vsg_gemm_set_store_hi(old)
+    assert torch.equal(masked, raw)

@@ -47,6 +47,7 @@ struct GemmEpilogue {
   float* C;
   int ldc;
   int M, N, K;
+  int store_hi;             // 3xTF32: also write the masked high part back (0 = rely on the MMA ignoring the low 13 bits)
 };
 
 // ---------------------------------------------------------------------------------------------------
@@ -349,7 +350,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           h.y = __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u); l.y = x.y - h.y;
           h.z = __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u); l.z = x.z - h.z;
           h.w = __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u); l.w = x.w - h.w;
-          hi[idx] = h;
+          if (ep.store_hi) hi[idx] = h;
           lo[idx] = l;
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
@@ -514,6 +515,10 @@ static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, 
 
 using namespace vsg;
 
+static int g_store_hi = 0;
+/* debug/validation knob: 1 = the 3xTF32 split also rewrites the A tile with its masked high part */
+extern "C" int vsg_gemm_set_store_hi(int on) { int old = g_store_hi; g_store_hi = on ? 1 : 0; return old; }
+
 extern "C" int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream) {
   VSG_REQUIRE(n >= 0, "vsg_split_tf32: n < 0");
   if (n == 0) return VSG_OK;
@@ -534,6 +539,7 @@ extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, co
   VSG_REQUIRE(rowbias == nullptr || rb_index != nullptr || rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
   GemmEpilogue ep;
   ep.bias = bias; ep.rowbias = rowbias; ep.rb_index = rb_index; ep.rb_period = rb_period; ep.ld_rb = ld_rb;
+  ep.store_hi = g_store_hi;
   ep.relu = relu; ep.accumulate = accumulate; ep.residual = residual; ep.ld_res = ld_res; ep.C = C; ep.ldc = ldc; ep.M = M; ep.N = N; ep.K = K;
   cudaStream_t st = (cudaStream_t)stream;
   const bool tma_ok = (lda % 4 == 0) && (ldw % 4 == 0) && aligned16(A) && aligned16(W_hi) && K >= 1;
