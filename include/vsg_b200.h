@@ -161,6 +161,8 @@ int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* 
 /* Validation knob for VSG_GEMM_3XTF32: 1 = the in-kernel split also rewrites the A tile with its masked high part;
  * 0 (default) relies on tcgen05 kind::tf32 ignoring the low 13 mantissa bits (checked bit-exact by tests). Returns the old value. */
 int vsg_gemm_set_store_hi(int on);
+/* Validation knob: 128 forces the 128x128-tile kernel for every shape, 0 (default) picks 128x256 tiles where N allows. */
+int vsg_gemm_force_bn(int bn);
 
 /* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
 int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);

@@ -96,3 +96,24 @@ def test_tf32_mma_ignores_low_mantissa_bits():
     finally:
         lib().vsg_gemm_set_store_hi(old)
     assert torch.equal(masked, raw)
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_wide_tiles_equal_narrow_tiles(mode):
+    """The 128x256-tile kernel and the 128x128-tile kernel accumulate every output element over K in the same order:
+    results must be bit-identical."""
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(13)
+    for (M, N, K) in ((1000, 512, 1024), (300, 1536, 512), (192, 133, 3160), (4097, 256, 96)):
+        A = torch.randn(M, K, generator=g).to(DEV)
+        W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+        b = torch.randn(N, generator=g).to(DEV)
+        wt = linalg.Weight(W, b)
+        wide = linalg.gemm(mode, A, wt, relu=True).clone()
+        old = lib().vsg_gemm_force_bn(128)
+        try:
+            narrow = linalg.gemm(mode, A, wt, relu=True).clone()
+        finally:
+            lib().vsg_gemm_force_bn(old)
+        assert torch.equal(wide, narrow), (M, N, K)

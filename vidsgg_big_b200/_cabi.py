@@ -49,6 +49,7 @@ SIGNATURES = {
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
     "vsg_gemm_set_store_hi": (i32, [i32]),
+    "vsg_gemm_force_bn": (i32, [i32]),
     "vsg_bbox_feat_mlp1": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p, p]),
     "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
     "vsg_conv_pool": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),

@@ -27,11 +27,11 @@
 
 namespace vsg {
 
-constexpr int BM = 128, BN = 128, BK = 32;            // tile; BK fp32 = 128 bytes
-constexpr int TILE_BYTES = BM * BK * 4;               // 16 KB (A and B tiles are the same size)
+constexpr int BM = 128, BK = 32;                      // tile rows; BK fp32 = 128 bytes = one swizzle row
+constexpr int TILE_A = BM * BK * 4;                   // 16 KB
 constexpr int UMMA_K = 8;                             // tf32
-constexpr int ACC_COLS = BN;                          // fp32 accumulator columns per stage
-constexpr int TMEM_COLS = 2 * ACC_COLS;               // double buffered
+// BN (tile columns = MMA N) is a template parameter: 256 where N allows it -- an SS-mode M=128 MMA reads
+// (128 + N) * 32 B of shared memory per N/2 cycles, i.e. 128 B/clk at N=128 (all of the smem bandwidth) but 96 B/clk at N=256.
 constexpr uint64_t WATCHDOG_NS = 4000000000ull;       // watchdog: trap after 4 s instead of hanging the GPU
 
 struct GemmEpilogue {
@@ -153,19 +153,30 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-constexpr uint32_t IDESC_TF32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+template <int BN_>
+constexpr uint32_t idesc_tf32() { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
 
 // ---------------------------------------------------------------------------------------------------
-template <int MODE> struct Cfg;
-template <> struct Cfg<1> { static constexpr int STAGES = 6, TILES_PER_STAGE = 2, THREADS = 256; };
-template <> struct Cfg<2> { static constexpr int STAGES = 3, TILES_PER_STAGE = 4, THREADS = 384; };
+template <int MODE, int BN_> struct Cfg {
+  static constexpr int TILE_B = BN_ * BK * 4;                                    // 16 / 32 KB
+  static constexpr int STAGE_BYTES = (MODE == 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo])
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/2 (3xTF32)
+  static constexpr int THREADS = MODE == 2 ? 384 : 256;
+  static constexpr int OFF_BH = TILE_A, OFF_AL = TILE_A + TILE_B, OFF_BL = 2 * TILE_A + TILE_B;
+  static constexpr int TMEM_COLS = 2 * BN_;                                      // double-buffered fp32 accumulator
+};
 
-template <int MODE>
-__global__ void __launch_bounds__(Cfg<MODE>::THREADS, 1)
+template <int MODE, int BN_>
+__global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const GemmEpilogue ep) {
-  constexpr int STAGES = Cfg<MODE>::STAGES;
-  constexpr int STAGE_BYTES = Cfg<MODE>::TILES_PER_STAGE * TILE_BYTES;
+  using CF = Cfg<MODE, BN_>;
+  constexpr int STAGES = CF::STAGES;
+  constexpr int STAGE_BYTES = CF::STAGE_BYTES;
+  constexpr int BN = BN_;
+  constexpr int ACC_COLS = BN_;
+  constexpr int TMEM_COLS = CF::TMEM_COLS;
+  constexpr uint32_t IDESC_TF32 = idesc_tf32<BN_>();
   // stage layout: [A | B_hi] (MODE 1) or [A(hi) | B_hi | A_lo | B_lo] (MODE 2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -218,10 +229,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], (MODE == 2 ? 3 : 2) * TILE_BYTES);
+          mbar_expect_tx(&full[stage], TILE_A + (MODE == 2 ? 2 : 1) * CF::TILE_B);
           tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK, m0);
-          tma_load_2d(smem_u32(st + TILE_BYTES), &mapBh, &full[stage], kb * BK, n0);
-          if (MODE == 2) tma_load_2d(smem_u32(st + 3 * TILE_BYTES), &mapBl, &full[stage], kb * BK, n0);
+          tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK, n0);
+          if (MODE == 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK, n0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -241,9 +252,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(MODE == 2 ? &ready[stage] : &full[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + TILE_BYTES);
+          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + CF::OFF_BH);
           if (MODE == 2) {
-            const uint64_t a_lo = make_smem_desc(st + 2 * TILE_BYTES), b_lo = make_smem_desc(st + 3 * TILE_BYTES);
+            const uint64_t a_lo = make_smem_desc(st + CF::OFF_AL), b_lo = make_smem_desc(st + CF::OFF_BL);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
 #pragma unroll
@@ -340,9 +351,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < kblocks; ++kb) {
         mbar_wait(&full[stage], phase);
         float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
-        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + 2 * TILE_BYTES);
+        float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + CF::OFF_AL);
 #pragma unroll
-        for (int i = 0; i < TILE_BYTES / 16 / 128; ++i) {
+        for (int i = 0; i < TILE_A / 16 / 128; ++i) {
           const int idx = i * 128 + t;
           const float4 x = hi[idx];
           float4 h, l;
@@ -449,20 +460,21 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld; }
+  const void* ptr; int rows, cols, ld, box_rows;
+  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
-    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.cols) * 131) ^ (std::hash<int>()(k.ld) * 1031);
+    return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.cols) * 131) ^ (std::hash<int>()(k.ld) * 1031) ^
+           (std::hash<int>()(k.box_rows) * 7919);
   }
 };
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D fp32 row-major [rows][cols] with leading dimension ld; box = BK x 128 rows, SWIZZLE_128B, zero OOB fill
-static int get_tensor_map(const float* base, int rows, int cols, int ld, CUtensorMap* out) {
-  MapKey key{base, rows, cols, ld};
+// 2-D fp32 row-major [rows][cols] with leading dimension ld; box = BK x box_rows, SWIZZLE_128B, zero OOB fill
+static int get_tensor_map(const float* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
+  MapKey key{base, rows, cols, ld, box_rows};
   {
     std::lock_guard<std::mutex> g(g_map_mu);
     auto it = g_maps.find(key);
@@ -472,7 +484,7 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, CUtenso
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return VSG_E_LAUNCH; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)BM};
+  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
@@ -488,34 +500,41 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, CUtenso
   return VSG_OK;
 }
 
-template <int MODE>
+template <int MODE, int BN_>
 static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, int ldw, const GemmEpilogue& ep, cudaStream_t st) {
+  using CF = Cfg<MODE, BN_>;
   CUtensorMap mA, mBh, mBl;
-  int rc = get_tensor_map(A, ep.M, ep.K, lda, &mA);
+  int rc = get_tensor_map(A, ep.M, ep.K, lda, BM, &mA);
   if (rc) return rc;
-  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, &mBh);
+  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, BN_, &mBh);
   if (rc) return rc;
-  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, &mBl); if (rc) return rc; } else mBl = mBh;
-  constexpr int SMEM = Cfg<MODE>::STAGES * Cfg<MODE>::TILES_PER_STAGE * TILE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, BN_, &mBl); if (rc) return rc; } else mBl = mBh;
+  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
     attr_set = true;
   }
-  const int tiles = ((ep.M + BM - 1) / BM) * ((ep.N + BN - 1) / BN);
+  const int tiles = ((ep.M + BM - 1) / BM) * ((ep.N + BN_ - 1) / BN_);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_tc_kernel<MODE><<<grid, Cfg<MODE>::THREADS, SMEM, st>>>(mA, mBh, mBl, ep);
+  gemm_tc_kernel<MODE, BN_><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, ep);
   return check_launch("vsg_gemm(tcgen05)");
 }
+
+// N=256 tiles whenever they do not add MMA work over N=128 tiles
+static inline bool use_bn256(int N) { return 2 * ((N + 255) / 256) <= (N + 127) / 128; }
 
 }  // namespace vsg
 
 using namespace vsg;
 
 static int g_store_hi = 0;
+static int g_force_bn = 0;
+/* debug/validation knob: 128 forces the N=128 tile kernel everywhere, 0 = automatic */
+extern "C" int vsg_gemm_force_bn(int bn) { int old = g_force_bn; g_force_bn = bn; return old; }
 /* debug/validation knob: 1 = the 3xTF32 split also rewrites the A tile with its masked high part */
 extern "C" int vsg_gemm_set_store_hi(int on) { int old = g_store_hi; g_store_hi = on ? 1 : 0; return old; }
 
@@ -548,10 +567,11 @@ extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, co
     gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W_hi, ldw, ep);
     return check_launch("vsg_gemm(simt)");
   }
-  if (mode == 1) return launch_tc<1>(A, lda, W_hi, nullptr, ldw, ep, st);
+  const bool wide = use_bn256(N) && g_force_bn != 128;
+  if (mode == 1) return wide ? launch_tc<1, 256>(A, lda, W_hi, nullptr, ldw, ep, st) : launch_tc<1, 128>(A, lda, W_hi, nullptr, ldw, ep, st);
   if (mode == 2) {
     VSG_REQUIRE(W_lo && aligned16(W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
-    return launch_tc<2>(A, lda, W_hi, W_lo, ldw, ep, st);
+    return wide ? launch_tc<2, 256>(A, lda, W_hi, W_lo, ldw, ep, st) : launch_tc<2, 128>(A, lda, W_hi, W_lo, ldw, ep, st);
   }
   set_error("vsg_gemm: unknown mode %d", mode);
   return VSG_E_UNSUPPORTED;
