@@ -153,8 +153,9 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-template <int BN_>
-constexpr uint32_t idesc_tf32() { return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(BM >> 4) << 24); }
+template <int BN_> struct IDesc {
+  static constexpr uint32_t tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+};
 
 // ---------------------------------------------------------------------------------------------------
 template <int MODE, int BN_> struct Cfg {
@@ -176,7 +177,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int BN = BN_;
   constexpr int ACC_COLS = BN_;
   constexpr int TMEM_COLS = CF::TMEM_COLS;
-  constexpr uint32_t IDESC_TF32 = idesc_tf32<BN_>();
+  constexpr uint32_t IDESC_TF32 = IDesc<BN_>::tf32;
   // stage layout: [A | B_hi] (MODE 1) or [A(hi) | B_hi | A_lo | B_lo] (MODE 2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
