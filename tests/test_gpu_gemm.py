@@ -100,8 +100,8 @@ def test_tf32_mma_ignores_low_mantissa_bits():
 
 @pytest.mark.parametrize("mode", [1, 2])
 def test_wide_tiles_equal_narrow_tiles(mode):
-    """The 128x256-tile kernel and the 128x128-tile kernel accumulate every output element over K in the same order:
-    results must be bit-identical."""
+    """The 128x256-tile kernel against the 128x128-tile kernel: bit-identical in tf32 mode (same accumulation order over K);
+    in 3xTF32 mode the wide kernel walks K in blocks of 16 instead of 32, which reorders the three partial products."""
     from vidsgg_big_b200 import linalg
     from vidsgg_big_b200._cabi import lib
     g = torch.Generator(device="cpu").manual_seed(13)
@@ -116,4 +116,7 @@ def test_wide_tiles_equal_narrow_tiles(mode):
             narrow = linalg.gemm(mode, A, wt, relu=True).clone()
         finally:
             lib().vsg_gemm_force_bn(old)
-        assert torch.equal(wide, narrow), (M, N, K)
+        if mode == 1:
+            assert torch.equal(wide, narrow), (M, N, K)
+        else:
+            assert (wide - narrow).abs().max().item() <= 1e-5 * narrow.abs().max().item(), (M, N, K)

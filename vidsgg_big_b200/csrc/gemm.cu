@@ -27,9 +27,11 @@
 
 namespace vsg {
 
-constexpr int BM = 128, BK = 32;                      // tile rows; BK fp32 = 128 bytes = one swizzle row
-constexpr int TILE_A = BM * BK * 4;                   // 16 KB
+constexpr int BM = 128;                               // tile rows
 constexpr int UMMA_K = 8;                             // tf32
+// BK (fp32 per stage row) is a template parameter: 32 (128-byte rows, SWIZZLE_128B) or 16 (64-byte rows, SWIZZLE_64B).
+// The 3xTF32 kernel with 256-wide tiles uses BK=16 so that 4 pipeline stages fit (2 stages of BK=32 cannot cover the
+// TMA + split latency).
 // BN (tile columns = MMA N) is a template parameter: 256 where N allows it -- an SS-mode M=128 MMA reads
 // (128 + N) * 32 B of shared memory per N/2 cycles, i.e. 128 B/clk at N=128 (all of the smem bandwidth) but 96 B/clk at N=256.
 constexpr uint64_t WATCHDOG_NS = 4000000000ull;       // watchdog: trap after 4 s instead of hanging the GPU
@@ -142,13 +144,15 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 // K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor layout):
 //   [0,14) start>>4 | [16,30) LBO>>4 (unused for swizzled K-major) | [32,46) SBO>>4 = 1024 B between 8-row groups
 //   | [46,48) version = 1 | [61,64) layout = 2 (SWIZZLE_128B)
+//   SWIZZLE_64B (BK = 16): SBO = 512 B, layout = 4
+template <int BK_>
 __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
   d |= (uint64_t)1 << 16;
-  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)((8 * BK_ * 4) >> 4) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)(BK_ == 32 ? 2 : 4) << 61;
   return d;
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
@@ -159,9 +163,11 @@ template <int BN_> struct IDesc {
 
 // ---------------------------------------------------------------------------------------------------
 template <int MODE, int BN_> struct Cfg {
-  static constexpr int TILE_B = BN_ * BK * 4;                                    // 16 / 32 KB
+  static constexpr int BK = (MODE == 2 && BN_ == 256) ? 16 : 32;
+  static constexpr int TILE_A = BM * BK * 4;
+  static constexpr int TILE_B = BN_ * BK * 4;
   static constexpr int STAGE_BYTES = (MODE == 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo])
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/2 (3xTF32)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32)
   static constexpr int THREADS = MODE == 2 ? 384 : 256;
   static constexpr int OFF_BH = TILE_A, OFF_AL = TILE_A + TILE_B, OFF_BL = 2 * TILE_A + TILE_B;
   static constexpr int TMEM_COLS = 2 * BN_;                                      // double-buffered fp32 accumulator
@@ -175,6 +181,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int STAGES = CF::STAGES;
   constexpr int STAGE_BYTES = CF::STAGE_BYTES;
   constexpr int BN = BN_;
+  constexpr int BK = CF::BK;
+  constexpr int TILE_A = CF::TILE_A;
   constexpr int ACC_COLS = BN_;
   constexpr int TMEM_COLS = CF::TMEM_COLS;
   constexpr uint32_t IDESC_TF32 = IDesc<BN_>::tf32;
@@ -253,9 +261,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           mbar_wait(MODE == 2 ? &ready[stage] : &full[stage], phase);
           tc_fence_after();
           const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc(st), b_hi = make_smem_desc(st + CF::OFF_BH);
+          const uint64_t a_hi = make_smem_desc<BK>(st), b_hi = make_smem_desc<BK>(st + CF::OFF_BH);
           if (MODE == 2) {
-            const uint64_t a_lo = make_smem_desc(st + CF::OFF_AL), b_lo = make_smem_desc(st + CF::OFF_BL);
+            const uint64_t a_lo = make_smem_desc<BK>(st + CF::OFF_AL), b_lo = make_smem_desc<BK>(st + CF::OFF_BL);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
 #pragma unroll
@@ -461,21 +469,23 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows;
-  bool operator==(const MapKey& o) const { return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows; }
+  const void* ptr; int rows, cols, ld, box_rows, box_cols;
+  bool operator==(const MapKey& o) const {
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+  }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.cols) * 131) ^ (std::hash<int>()(k.ld) * 1031) ^
-           (std::hash<int>()(k.box_rows) * 7919);
+           (std::hash<int>()(k.box_rows) * 7919) ^ (std::hash<int>()(k.box_cols) * 104729);
   }
 };
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
 // 2-D fp32 row-major [rows][cols] with leading dimension ld; box = BK x box_rows, SWIZZLE_128B, zero OOB fill
-static int get_tensor_map(const float* base, int rows, int cols, int ld, int box_rows, CUtensorMap* out) {
-  MapKey key{base, rows, cols, ld, box_rows};
+static int get_tensor_map(const float* base, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out) {
+  MapKey key{base, rows, cols, ld, box_rows, box_cols};
   {
     std::lock_guard<std::mutex> g(g_map_mu);
     auto it = g_maps.find(key);
@@ -485,11 +495,12 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, int box
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return VSG_E_LAUNCH; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
-  cuuint32_t box[2] = {(cuuint32_t)BK, (cuuint32_t)box_rows};
+  cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
   CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld); return VSG_E_LAUNCH; }
   {
@@ -505,11 +516,11 @@ template <int MODE, int BN_>
 static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, int ldw, const GemmEpilogue& ep, cudaStream_t st) {
   using CF = Cfg<MODE, BN_>;
   CUtensorMap mA, mBh, mBl;
-  int rc = get_tensor_map(A, ep.M, ep.K, lda, BM, &mA);
+  int rc = get_tensor_map(A, ep.M, ep.K, lda, BM, CF::BK, &mA);
   if (rc) return rc;
-  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, BN_, &mBh);
+  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, BN_, CF::BK, &mBh);
   if (rc) return rc;
-  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, BN_, &mBl); if (rc) return rc; } else mBl = mBh;
+  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
