@@ -196,7 +196,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* acc_full = bars + 3 * STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* epi_stage = reinterpret_cast<float*>(smem + STAGES * STAGE_BYTES + 256);   // 4 warps x [32][33] floats
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
@@ -294,39 +293,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
-      (void)row;
-      // Transposed through a padded per-warp smem tile so that every global access of the epilogue (C, bias, row bias,
-      // residual) is a coalesced 128-byte row segment instead of 32 scattered 16-byte pieces.
-      float* sb = epi_stage + (warp - 4) * (32 * 33);
-      const int rows_here = min(32, ep.M - (m0 + quad * 32));   // warp-uniform, may be <= 0
+      const bool row_ok = row < ep.M;
+      const float* rb = nullptr;
+      if (row_ok && ep.rowbias) {
+        const int ri = ep.rb_index ? ep.rb_index[row] : (row % ep.rb_period);
+        rb = ep.rowbias + (size_t)ri * ep.ld_rb;
+      }
+      float* crow = ep.C + (size_t)(row_ok ? row : 0) * ep.ldc;
+      const float* res = (row_ok && ep.residual) ? ep.residual + (size_t)row * ep.ld_res : nullptr;
+      const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
+                          ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        const int col = n0 + c * 32 + lane;
-        if (n0 + c * 32 >= ep.N || rows_here <= 0) continue;     // warp-uniform
+        if (row_ok) {
+          const int col0 = n0 + c * 32;
+          if (col0 + 32 <= ep.N && vec_ok) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) sb[lane * 33 + j] = __uint_as_float(r[j]);
-        __syncwarp();
-        const bool col_ok = col < ep.N;
-        const float bias_v = (ep.bias && col_ok) ? ep.bias[col] : 0.f;
-        for (int rr = 0; rr < rows_here; ++rr) {
-          const int grow = m0 + quad * 32 + rr;
-          float v = sb[rr * 33 + lane] + bias_v;
-          if (col_ok) {
-            if (ep.rowbias) {
-              const int ri = ep.rb_index ? ep.rb_index[grow] : (grow % ep.rb_period);
-              v += ep.rowbias[(size_t)ri * ep.ld_rb + col];
+            for (int j = 0; j < 32; j += 4) {
+              float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+              if (ep.bias) {
+                const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              }
+              if (rb) {
+                v.x += rb[col0 + j]; v.y += rb[col0 + j + 1]; v.z += rb[col0 + j + 2]; v.w += rb[col0 + j + 3];
+              }
+              float4* dst = reinterpret_cast<float4*>(crow + col0 + j);
+              if (ep.accumulate) {
+                const float4 o = *dst;
+                v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+              }
+              if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+              *dst = v;
             }
-            float* dst = ep.C + (size_t)grow * ep.ldc + col;
-            if (ep.accumulate) v += *dst;
-            if (ep.relu) v = fmaxf(v, 0.f);
-            if (ep.residual) v += ep.residual[(size_t)grow * ep.ld_res + col];
-            *dst = v;
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int col = col0 + j;
+              if (col < ep.N) {
+                float v = __uint_as_float(r[j]);
+                if (ep.bias) v += ep.bias[col];
+                if (rb) v += rb[col];
+                if (ep.accumulate) v += crow[col];
+                if (ep.relu) v = fmaxf(v, 0.f);
+                if (res) v += res[col];
+                crow[col] = v;
+              }
+            }
           }
         }
-        __syncwarp();
       }
       tc_fence_before();
       mbar_arrive(&acc_empty[acc]);
@@ -502,7 +521,7 @@ static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, 
   rc = get_tensor_map(Wh, ep.N, ep.K, ldw, BN_, CF::BK, &mBh);
   if (rc) return rc;
   if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
-  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/ + 4 * 32 * 33 * 4 /*epilogue staging*/;
+  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
