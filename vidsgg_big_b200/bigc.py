@@ -461,14 +461,18 @@ class BIG_C(object):
     __call__ = forward
     default_topk = 10
 
-    def forward_packed(self, proposal_list, topk=None):
+    def pack(self, proposal_list) -> "PackedVideos":
+        """Index arrays / packed views of a batch (reusable across calls while the batch is resident in HBM)."""
+        return PackedVideos(proposal_list, self.device)
+
+    def forward_packed(self, proposal_list, topk=None, packed_videos=None):
         """Same computation as ``forward`` for a batch of non-empty videos, but the result stays packed on the device
         (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``."""
         if self._w is None:
             raise VsgError("BIG_C has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
         self.topk = self.default_topk if topk is None else topk
         assert all(p.num_proposals > 0 for p in proposal_list)
-        pk = PackedVideos(proposal_list, self.device)
+        pk = packed_videos if packed_videos is not None else PackedVideos(proposal_list, self.device)
         logits, so, _ = self._encode2decode(pk)
         return self._construct_triplets(pk, logits, so, self.topk, packed=True)
 

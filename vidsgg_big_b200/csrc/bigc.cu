@@ -378,18 +378,29 @@ role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e
   float pq[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) pq[i] = p2a[qrow * E + lane * PER + i];
-  // pass 1: logits
-  for (int e = 0; e < n; ++e) {
-    const float* er = e2a + (int64_t)(t0 + e) * E + lane * PER;
-    float xr[PER];
-    load_row<PER>(er, xr);
-    float acc = 0.f;
+  // pass 1: logits; 4 tracks per iteration so that 16 independent 128-bit loads are in flight per lane
+  for (int e0 = 0; e0 < n; e0 += 4) {
+    float xr[4][PER];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) acc = fmaf(pq[i], xr[i], acc);
+    for (int u = 0; u < 4; ++u) load_row<PER>(e2a + (int64_t)(t0 + min(e0 + u, n - 1)) * E + lane * PER, xr[u]);
+    float acc[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      acc[u] = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) acc[u] = fmaf(pq[i], xr[u][i], acc[u]);
+    }
     // reduce within each half-warp (role)
 #pragma unroll
-    for (int o = 8; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if ((lane & 15) == 0) sL[warp][lane >> 4][e] = acc * inv_sqrt_d;
+    for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc[u] += __shfl_xor_sync(0xffffffffu, acc[u], o);
+    }
+    if ((lane & 15) == 0) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (e0 + u < n) sL[warp][lane >> 4][e0 + u] = acc[u] * inv_sqrt_d;
+    }
   }
   __syncwarp();
   // softmax over tracks per role (lanes stride e), then softmax over roles per track
@@ -429,12 +440,17 @@ role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e
   float acc0[PER], acc1[PER];
 #pragma unroll
   for (int i = 0; i < PER; ++i) { acc0[i] = 0.f; acc1[i] = 0.f; }
-  for (int e = 0; e < n; ++e) {
-    const float a0 = sL[warp][0][e], a1 = sL[warp][1][e];
-    float xr[PER];
-    load_row<PER>(enco + (int64_t)(t0 + e) * E + lane * PER, xr);
+  for (int e0 = 0; e0 < n; e0 += 4) {
+    float xr[4][PER];
 #pragma unroll
-    for (int i = 0; i < PER; ++i) { acc0[i] = fmaf(a0, xr[i], acc0[i]); acc1[i] = fmaf(a1, xr[i], acc1[i]); }
+    for (int u = 0; u < 4; ++u) load_row<PER>(enco + (int64_t)(t0 + min(e0 + u, n - 1)) * E + lane * PER, xr[u]);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const bool ok = e0 + u < n;
+      const float a0 = ok ? sL[warp][0][e0 + u] : 0.f, a1 = ok ? sL[warp][1][e0 + u] : 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { acc0[i] = fmaf(a0, xr[u][i], acc0[i]); acc1[i] = fmaf(a1, xr[u][i], acc1[i]); }
+    }
   }
   float* o0 = values + qrow * (2 * E) + lane * PER;
   float* o1 = o0 + E;
