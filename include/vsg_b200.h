@@ -81,14 +81,15 @@ int vsg_traj_viou_matrix(const float* boxesA, const int64_t* offA, const int64_t
                          int64_t* spans_out, uint8_t* mask_out, float* viou_out, float* inter_out,
                          float* volA, float* volB, int variant, void* stream);
 
-/* Shared-memory tiled variant of vsg_traj_viou_matrix (same outputs).  n_tiles = sum over segments of
- * ceil(nA_v/32)*ceil(nB_v/32); tile_off_ws: int64[n_seg+1] workspace. */
+/* Shared-memory tiled variant of vsg_traj_viou_matrix (same outputs; deterministic).  seg_len int64[n_seg] = frames on each
+ * segment's absolute frame axis (video_len; every span must lie in [0, seg_len)).  Workspaces: jobs_ws (n_seg+1)*24 bytes,
+ * njobs_ws int64[1], part_ws f32[n_jobs_bound*1024] with n_jobs_bound >= sum_v ceil(nA_v/32)*ceil(nB_v/32)*ceil(seg_len_v/256). */
 int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* offA, const int64_t* duraA, int n_tracks_A,
                                const float* boxesB, const int64_t* offB, const int64_t* duraB, int n_tracks_B,
-                               const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
-                               int64_t n_pairs_total, int64_t n_tiles,
-                               int64_t* spans_out, uint8_t* mask_out, float* viou_out,
-                               float* volA, float* volB, int64_t* tile_off_ws, void* stream);
+                               const int32_t* segA, const int32_t* segB, const int64_t* seg_out, const int64_t* seg_len,
+                               int n_seg, int64_t n_pairs_total, int64_t n_jobs_bound,
+                               int64_t* spans_out, uint8_t* mask_out, float* viou_out, float* volA, float* volB,
+                               void* jobs_ws, int64_t* njobs_ws, float* part_ws, void* stream);
 
 /* Base-C label assignment on top of a vIoU matrix: replaces the triple Python loop of
  * tools/train_vidor.py:143-159.  viou f32[n][n_gt_traj]; gt_so int64[n_gt_pred][2] (GT subject /

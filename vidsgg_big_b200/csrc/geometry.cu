@@ -151,24 +151,51 @@ traj_viou_warp_kernel(const float4* __restrict__ boxesA, const int64_t* __restri
 
 // ------------------------------------------------------------------------------------------
 // Variant 2: shared-memory tiled kernel for long, densely overlapping tracks (VidOR / stress shapes).
-// A CTA owns a TA x TB block of one segment's pair matrix and walks the block's time range in
-// windows of W frames.  Each window stages the TA + TB track slices once (frames where a track is
-// absent are filled with an empty box that intersects nothing), then every thread accumulates a
-// RA x RB register block of pairs: per frame RA + RB 128-bit shared loads feed RA*RB pairs, so HBM/L2
-// sees each box once per tile instead of once per pair.
-constexpr int T2_TA = 32, T2_TB = 32, T2_RA = 4, T2_RB = 4, T2_W = 32;
+// Job = (segment, 32x32 block of its pair matrix, chunk of T2_CH absolute frames).  A CTA stages the TA + TB track
+// slices of the chunk window by window (W frames; frames where a track is absent are filled with an empty box
+// that intersects nothing), and every thread accumulates a 4x4 register block of pairs: per frame 8 128-bit shared
+// loads feed 16 pairs, so L2/HBM see each box once per tile row/column instead of once per pair.  The fp32 chunk
+// partials go to a workspace and a second kernel sums them in a fixed order (deterministic) in fp64.
+constexpr int T2_TA = 32, T2_TB = 32, T2_RA = 4, T2_RB = 4, T2_W = 32, T2_CH = 256;
 constexpr int T2_THREADS = (T2_TA / T2_RA) * (T2_TB / T2_RB);  // 64
 constexpr int T2_PITCH = T2_W + 1;                             // float4 pitch: conflict-free 128-bit reads
 
-struct TileJob { int seg, a0, b0; };
+// per-segment job table: tiles_b, chunks, first job; built by one small kernel
+struct SegJobs { int tiles_a, tiles_b, chunks; long long first_job; };
+
+__global__ void seg_jobs_kernel(const int32_t* __restrict__ segA, const int32_t* __restrict__ segB, const int64_t* __restrict__ seg_len,
+                                int n_seg, SegJobs* __restrict__ jobs, int64_t* __restrict__ n_jobs) {
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    long long acc = 0;
+    for (int v = 0; v < n_seg; ++v) {
+      const int nA = segA[v + 1] - segA[v], nB = segB[v + 1] - segB[v];
+      SegJobs j;
+      j.tiles_a = (nA + T2_TA - 1) / T2_TA; j.tiles_b = (nB + T2_TB - 1) / T2_TB;
+      j.chunks = (int)((seg_len[v] + T2_CH - 1) / T2_CH);
+      if (j.chunks < 1) j.chunks = 1;
+      j.first_job = acc;
+      jobs[v] = j;
+      acc += (long long)j.tiles_a * j.tiles_b * j.chunks;
+    }
+    jobs[n_seg].first_job = acc;
+    *n_jobs = acc;
+  }
+}
+
+__device__ __forceinline__ int find_seg_job(const SegJobs* __restrict__ jobs, int n_seg, long long job) {
+  int lo = 0, hi = n_seg;
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if (jobs[mid].first_job <= job) lo = mid; else hi = mid;
+  }
+  return lo;
+}
 
 __global__ void __launch_bounds__(T2_THREADS)
 traj_viou_tile_kernel(const float4* __restrict__ boxesA, const int64_t* __restrict__ offA, const int64_t* __restrict__ duraA,
                       const float4* __restrict__ boxesB, const int64_t* __restrict__ offB, const int64_t* __restrict__ duraB,
-                      const int32_t* __restrict__ segA, const int32_t* __restrict__ segB,
-                      const int64_t* __restrict__ seg_out, const int64_t* __restrict__ tile_off, int n_seg, int64_t n_tiles,
-                      const float* __restrict__ volA, const float* __restrict__ volB,
-                      int64_t* __restrict__ spans, uint8_t* __restrict__ mask, float* __restrict__ viou) {
+                      const int32_t* __restrict__ segA, const int32_t* __restrict__ segB, const SegJobs* __restrict__ jobs, int n_seg,
+                      const int64_t* __restrict__ n_jobs_ptr, float* __restrict__ part /* [jobs][TA*TB] */) {
   __shared__ float4 sA[T2_TA * T2_PITCH];
   __shared__ float4 sB[T2_TB * T2_PITCH];
   __shared__ long long sStart[T2_TA + T2_TB], sEnd[T2_TA + T2_TB], sRow[T2_TA + T2_TB];
@@ -176,14 +203,17 @@ traj_viou_tile_kernel(const float4* __restrict__ boxesA, const int64_t* __restri
   const int tid = threadIdx.x;
   const int ta = tid / (T2_TB / T2_RB), tb = tid % (T2_TB / T2_RB);
   const float4 EMPTY = make_float4(1e30f, 1e30f, -1e30f, -1e30f);
+  const long long n_jobs = *n_jobs_ptr;
 
-  for (int64_t tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    const int v = find_segment(tile_off, n_seg, tile);
+  for (long long job = blockIdx.x; job < n_jobs; job += gridDim.x) {
+    const int v = find_seg_job(jobs, n_seg, job);
+    const SegJobs sj = jobs[v];
+    const long long lj = job - sj.first_job;
+    const int chunk = (int)(lj % sj.chunks);
+    const int tile = (int)(lj / sj.chunks);
+    const int a0 = (tile / sj.tiles_b) * T2_TA, b0 = (tile % sj.tiles_b) * T2_TB;
     const int nA = segA[v + 1] - segA[v], nB = segB[v + 1] - segB[v];
-    const int tilesB = (nB + T2_TB - 1) / T2_TB;
-    const int64_t lt = tile - tile_off[v];
-    const int a0 = (int)(lt / tilesB) * T2_TA, b0 = (int)(lt % tilesB) * T2_TB;
-    __syncthreads();  // previous tile finished with smem
+    __syncthreads();  // previous job finished with smem
     if (tid < T2_TA + T2_TB) {
       const bool isA = tid < T2_TA;
       const int loc = isA ? a0 + tid : b0 + (tid - T2_TA);
@@ -198,30 +228,30 @@ traj_viou_tile_kernel(const float4* __restrict__ boxesA, const int64_t* __restri
     }
     __syncthreads();
     if (tid == 0) {
-      // time range where at least one A track and one B track of the tile exist
+      // frames of this chunk where at least one A track and one B track of the tile exist
       long long as = LLONG_MAX, ae = LLONG_MIN, bs = LLONG_MAX, be = LLONG_MIN;
       for (int i = 0; i < T2_TA; ++i) if (sStart[i] <= sEnd[i]) { as = min(as, sStart[i]); ae = max(ae, sEnd[i]); }
       for (int i = T2_TA; i < T2_TA + T2_TB; ++i) if (sStart[i] <= sEnd[i]) { bs = min(bs, sStart[i]); be = max(be, sEnd[i]); }
-      sRange[0] = max(as, bs); sRange[1] = min(ae, be);
+      // chunks tile the absolute frame axis from the segment's first frame; seg_len bounds it (host-provided)
+      sRange[0] = max(max(as, bs), (long long)chunk * T2_CH);
+      sRange[1] = min(min(ae, be), (long long)(chunk + 1) * T2_CH - 1);
     }
     __syncthreads();
     const long long f_lo = sRange[0], f_hi = sRange[1];
     float acc[T2_RA][T2_RB];
-    double dacc[T2_RA][T2_RB];
 #pragma unroll
     for (int i = 0; i < T2_RA; ++i)
 #pragma unroll
-      for (int j = 0; j < T2_RB; ++j) { acc[i][j] = 0.f; dacc[i][j] = 0.0; }
+      for (int j = 0; j < T2_RB; ++j) acc[i][j] = 0.f;
 
-    int win = 0;
-    for (long long f0 = f_lo; f0 <= f_hi; f0 += T2_W, ++win) {
+    for (long long f0 = f_lo; f0 <= f_hi; f0 += T2_W) {
       __syncthreads();
       // stage: (TA+TB) tracks x W frames; consecutive threads take consecutive frames of one track
       for (int idx = tid; idx < (T2_TA + T2_TB) * T2_W; idx += T2_THREADS) {
         const int trk = idx / T2_W, fo = idx % T2_W;
         const long long f = f0 + fo;
         float4 val = EMPTY;
-        if (f >= sStart[trk] && f <= sEnd[trk]) {
+        if (f <= f_hi && f >= sStart[trk] && f <= sEnd[trk]) {
           const float4* src = (trk < T2_TA ? boxesA : boxesB) + sRow[trk] + (f - sStart[trk]);
           val = ldg_stream(src);
         }
@@ -240,51 +270,45 @@ traj_viou_tile_kernel(const float4* __restrict__ boxesA, const int64_t* __restri
 #pragma unroll
           for (int j = 0; j < T2_RB; ++j) acc[i][j] += inter_area(a[i], b[j]);
       }
-      if ((win & 7) == 7) {  // fold fp32 partials (<= 256 frames) into fp64
-#pragma unroll
-        for (int i = 0; i < T2_RA; ++i)
-#pragma unroll
-          for (int j = 0; j < T2_RB; ++j) { dacc[i][j] += (double)acc[i][j]; acc[i][j] = 0.f; }
-      }
     }
-    // epilogue
+    float* o = part + job * (T2_TA * T2_TB);
 #pragma unroll
-    for (int i = 0; i < T2_RA; ++i) {
-      const int la = ta * T2_RA + i;
-      if (a0 + la >= nA) continue;
-#pragma unroll
-      for (int j = 0; j < T2_RB; ++j) {
-        const int lb = tb * T2_RB + j;
-        if (b0 + lb >= nB) continue;
-        const long long s = max(sStart[la], sStart[T2_TA + lb]);
-        const long long e = min(sEnd[la], sEnd[T2_TA + lb]);
-        const int64_t p = seg_out[v] + (int64_t)(a0 + la) * nB + (b0 + lb);
-        if (spans) reinterpret_cast<longlong2*>(spans)[p] = make_longlong2(s, e);
-        if (mask) mask[p] = (s <= e) ? 1 : 0;
-        if (viou) {
-          float r = 0.f;
-          if (s <= e) {
-            const float it = (float)(dacc[i][j] + (double)acc[i][j]);
-            r = it / (volA[segA[v] + a0 + la] + volB[segB[v] + b0 + lb] - it);
-          }
-          viou[p] = r;
-        }
-      }
-    }
+    for (int i = 0; i < T2_RA; ++i)
+      *reinterpret_cast<float4*>(o + (ta * T2_RA + i) * T2_TB + tb * T2_RB) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   }
 }
 
-// prefix of per-segment tile counts (tiny: one thread; n_seg <= a few thousand)
-__global__ void tile_offsets_kernel(const int32_t* __restrict__ segA, const int32_t* __restrict__ segB, int n_seg,
-                                    int64_t* __restrict__ tile_off) {
-  if (blockIdx.x == 0 && threadIdx.x == 0) {
-    int64_t acc = 0;
-    for (int v = 0; v < n_seg; ++v) {
-      tile_off[v] = acc;
-      const int nA = segA[v + 1] - segA[v], nB = segB[v + 1] - segB[v];
-      acc += (int64_t)((nA + T2_TA - 1) / T2_TA) * ((nB + T2_TB - 1) / T2_TB);
+// sums the chunk partials of every pair in chunk order (fp64) and writes spans / mask / vIoU
+__global__ void traj_viou_tile_finalize_kernel(const int64_t* __restrict__ duraA, const int64_t* __restrict__ duraB,
+                                               const int32_t* __restrict__ segA, const int32_t* __restrict__ segB,
+                                               const int64_t* __restrict__ seg_out, const SegJobs* __restrict__ jobs, int n_seg,
+                                               int64_t n_pairs, const float* __restrict__ part, const float* __restrict__ volA,
+                                               const float* __restrict__ volB, int64_t* __restrict__ spans, uint8_t* __restrict__ mask,
+                                               float* __restrict__ viou) {
+  for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < n_pairs; p += (int64_t)gridDim.x * blockDim.x) {
+    const int v = find_segment(seg_out, n_seg, p);
+    const int nB = segB[v + 1] - segB[v];
+    const int64_t local = p - seg_out[v];
+    const int la = (int)(local / nB), lb = (int)(local % nB);
+    const int ia = segA[v] + la, ib = segB[v] + lb;
+    const longlong2 da = reinterpret_cast<const longlong2*>(duraA)[ia];
+    const longlong2 db = reinterpret_cast<const longlong2*>(duraB)[ib];
+    const int64_t s = da.x > db.x ? da.x : db.x, e = da.y < db.y ? da.y : db.y;
+    if (spans) reinterpret_cast<longlong2*>(spans)[p] = make_longlong2(s, e);
+    if (mask) mask[p] = (s <= e) ? 1 : 0;
+    if (!viou) continue;
+    float r = 0.f;
+    if (s <= e) {
+      const SegJobs sj = jobs[v];
+      const int tile = (la / T2_TA) * sj.tiles_b + (lb / T2_TB);
+      const float* src = part + (sj.first_job + (long long)tile * sj.chunks) * (T2_TA * T2_TB) + (la % T2_TA) * T2_TB + (lb % T2_TB);
+      double acc = 0.0;
+      const int c0 = (int)(s / T2_CH), c1 = (int)(e / T2_CH);      // only chunks that intersect the overlap hold non-zeros
+      for (int c = c0; c <= c1 && c < sj.chunks; ++c) acc += (double)src[(long long)c * (T2_TA * T2_TB)];
+      const float it = (float)acc;
+      r = it / (volA[ia] + volB[ib] - it);
     }
-    tile_off[n_seg] = acc;
+    viou[p] = r;
   }
 }
 
@@ -390,21 +414,25 @@ extern "C" int vsg_traj_viou_matrix(const float* boxesA, const int64_t* offA, co
   return VSG_E_UNSUPPORTED;
 }
 
-// Tiled variant with its extra workspace (tile_off int64[n_seg+1]); n_tiles_bound >= sum of per-segment tiles.
+// Tiled variant.  seg_len int64[n_seg]: frames spanned by each segment's absolute frame axis (video_len; spans must lie in
+// [0, seg_len)).  Workspaces: jobs_ws >= (n_seg+1)*24 bytes, njobs_ws int64[1], part_ws f32[n_jobs_bound*1024] where
+// n_jobs_bound >= sum_v ceil(nA_v/32)*ceil(nB_v/32)*ceil(seg_len_v/256) (computed by the host wrapper).
 extern "C" int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* offA, const int64_t* duraA, int nTA,
                                           const float* boxesB, const int64_t* offB, const int64_t* duraB, int nTB,
-                                          const int32_t* segA, const int32_t* segB, const int64_t* seg_out, int n_seg,
-                                          int64_t n_pairs, int64_t n_tiles, int64_t* spans, uint8_t* mask, float* viou,
-                                          float* volA, float* volB, int64_t* tile_off_ws, void* stream) {
-  VSG_REQUIRE(nTA >= 0 && nTB >= 0 && n_seg >= 0 && n_pairs >= 0 && n_tiles >= 0, "vsg_traj_viou_matrix_tiled: negative size");
+                                          const int32_t* segA, const int32_t* segB, const int64_t* seg_out, const int64_t* seg_len,
+                                          int n_seg, int64_t n_pairs, int64_t n_jobs_bound, int64_t* spans, uint8_t* mask,
+                                          float* viou, float* volA, float* volB, void* jobs_ws, int64_t* njobs_ws, float* part_ws,
+                                          void* stream) {
+  VSG_REQUIRE(nTA >= 0 && nTB >= 0 && n_seg >= 0 && n_pairs >= 0 && n_jobs_bound >= 0, "vsg_traj_viou_matrix_tiled: negative size");
   if (n_pairs == 0 || n_seg == 0) return VSG_OK;
-  VSG_REQUIRE(boxesA && offA && duraA && boxesB && offB && duraB && segA && segB && seg_out && tile_off_ws,
+  VSG_REQUIRE(boxesA && offA && duraA && boxesB && offB && duraB && segA && segB && seg_out && seg_len && jobs_ws && njobs_ws && part_ws,
               "vsg_traj_viou_matrix_tiled: null input pointer");
-  VSG_REQUIRE(aligned16(boxesA) && aligned16(boxesB) && aligned16(duraA) && aligned16(duraB),
-              "vsg_traj_viou_matrix_tiled: boxes / spans must be 16-byte aligned");
+  VSG_REQUIRE(aligned16(boxesA) && aligned16(boxesB) && aligned16(duraA) && aligned16(duraB) && aligned16(part_ws),
+              "vsg_traj_viou_matrix_tiled: boxes / spans / workspace must be 16-byte aligned");
   VSG_REQUIRE(spans == nullptr || aligned16(spans), "vsg_traj_viou_matrix_tiled: spans_out misaligned");
   VSG_REQUIRE(viou == nullptr || (volA && volB), "vsg_traj_viou_matrix_tiled: volume workspaces required");
   cudaStream_t st = (cudaStream_t)stream;
+  int launches = 2;
   if (viou) {
     int rc = vsg_track_volumes(boxesA, offA, nTA, volA, stream);
     if (rc) return rc;
@@ -413,13 +441,19 @@ extern "C" int vsg_traj_viou_matrix_tiled(const float* boxesA, const int64_t* of
       if (rc) return rc;
     }
   }
-  tile_offsets_kernel<<<1, 32, 0, st>>>(segA, segB, n_seg, tile_off_ws);
-  const int64_t cap = (int64_t)sm_count() * 16;
-  const int grid = (int)(n_tiles < cap ? (n_tiles < 1 ? 1 : n_tiles) : cap);
-  traj_viou_tile_kernel<<<grid, T2_THREADS, 0, st>>>(
-      reinterpret_cast<const float4*>(boxesA), offA, duraA, reinterpret_cast<const float4*>(boxesB), offB, duraB, segA, segB,
-      seg_out, tile_off_ws, n_seg, n_tiles, volA, volB, spans, mask, viou);
-  return check_launch("vsg_traj_viou_matrix_tiled", 2);
+  SegJobs* jobs = reinterpret_cast<SegJobs*>(jobs_ws);
+  seg_jobs_kernel<<<1, 32, 0, st>>>(segA, segB, seg_len, n_seg, jobs, njobs_ws);
+  if (viou) {
+    const int64_t cap = (int64_t)sm_count() * 6;
+    const int grid = (int)(n_jobs_bound < cap ? (n_jobs_bound < 1 ? 1 : n_jobs_bound) : cap);
+    traj_viou_tile_kernel<<<grid, T2_THREADS, 0, st>>>(reinterpret_cast<const float4*>(boxesA), offA, duraA,
+                                                       reinterpret_cast<const float4*>(boxesB), offB, duraB, segA, segB, jobs, n_seg,
+                                                       njobs_ws, part_ws);
+    ++launches;
+  }
+  traj_viou_tile_finalize_kernel<<<grid_for(n_pairs, 256, 8), 256, 0, st>>>(duraA, duraB, segA, segB, seg_out, jobs, n_seg, n_pairs, part_ws,
+                                                                           volA, volB, spans, mask, viou);
+  return check_launch("vsg_traj_viou_matrix_tiled", launches);
 }
 
 extern "C" int vsg_pair_labels(const float* viou, int n, int n_gt_traj, const int64_t* gt_so, int n_gt_pred, float th,

@@ -20,7 +20,7 @@ import torch
 from . import _cabi
 from ._cabi import check, lib, ptr, require_cuda, stream_ptr
 
-TILE = 32  # csrc/geometry.cu T2_TA / T2_TB
+TILE, CHUNK = 32, 256  # csrc/geometry.cu T2_TA / T2_TB, T2_CH
 
 
 # --------------------------------------------------------------------------------------------
@@ -28,8 +28,9 @@ class TrackTable(object):
     """Packed tracks of a batch of videos in HBM: boxes f32[sum L,4], off i64[n+1], dura i64[n,2] (closed),
     seg i32[V+1] (track range of each video)."""
 
-    def __init__(self, boxes, off, dura, seg, counts: List[int]):
+    def __init__(self, boxes, off, dura, seg, counts: List[int], seg_len: Optional[List[int]] = None):
         self.boxes, self.off, self.dura, self.seg, self.counts = boxes, off, dura, seg, counts
+        self.seg_len = seg_len      # frames on each video's absolute frame axis (video_len); needed by the tiled kernel
 
     @property
     def n_tracks(self):
@@ -38,8 +39,9 @@ class TrackTable(object):
     @classmethod
     def from_containers(cls, items: Sequence, device=None) -> "TrackTable":
         """``items``: TrajProposal / VideoGraph objects (packed ``bboxes``/``lengths``) of the batch."""
-        boxes_l, lens_l, dura_l, counts = [], [], [], []
+        boxes_l, lens_l, dura_l, counts, seg_len = [], [], [], [], []
         for it in items:
+            seg_len.append(int(getattr(it, "video_len", 0)))
             bx = it.bboxes
             du = it.traj_durations
             device = device or bx.device
@@ -55,7 +57,7 @@ class TrackTable(object):
         off[1:] = torch.cumsum(lens, 0)
         seg = torch.zeros(len(counts) + 1, dtype=torch.int32)
         seg[1:] = torch.cumsum(torch.tensor(counts, dtype=torch.int32), 0)
-        return cls(boxes, off.to(device), dura, seg.to(device), counts)
+        return cls(boxes, off.to(device), dura, seg.to(device), counts, seg_len if all(x > 0 for x in seg_len) else None)
 
     @classmethod
     def from_lists(cls, boxes_list: Sequence[torch.Tensor], dura: torch.Tensor) -> "TrackTable":
@@ -131,12 +133,24 @@ def traj_viou_batched(A: TrackTable, B: TrackTable, want_spans=True, want_mask=T
     volB = volA if same else torch.empty(max(B.n_tracks, 1), dtype=torch.float32, device=dev)
     if variant == 2:
         assert not want_inter
-        n_tiles = sum(((a + TILE - 1) // TILE) * ((b + TILE - 1) // TILE) for a, b in zip(A.counts, B.counts))
-        tile_ws = torch.empty(len(A.counts) + 1, dtype=torch.long, device=dev)
+        seg_len = A.seg_len or B.seg_len
+        if seg_len is None:      # no video_len known: one D2H read of the largest end frame
+            hi = 0
+            if A.n_tracks:
+                hi = max(hi, int(A.dura[:, 1].max().item()) + 1)
+            if B.n_tracks:
+                hi = max(hi, int(B.dura[:, 1].max().item()) + 1)
+            seg_len = [hi] * len(A.counts)
+        n_jobs = sum(((a + TILE - 1) // TILE) * ((b + TILE - 1) // TILE) * max(1, (l + CHUNK - 1) // CHUNK)
+                     for a, b, l in zip(A.counts, B.counts, seg_len))
+        seg_len_d = torch.tensor(seg_len, dtype=torch.long).to(dev)
+        jobs_ws = torch.empty((len(A.counts) + 1) * 3, dtype=torch.long, device=dev)
+        njobs_ws = torch.empty(1, dtype=torch.long, device=dev)
+        part_ws = torch.empty(max(n_jobs, 1) * TILE * TILE, dtype=torch.float32, device=dev)
         check(lib().vsg_traj_viou_matrix_tiled(
             ptr(A.boxes), ptr(A.off), ptr(A.dura), A.n_tracks, ptr(B.boxes), ptr(B.off), ptr(B.dura), B.n_tracks,
-            ptr(A.seg), ptr(B.seg), ptr(seg_out), len(A.counts), P, n_tiles, ptr(spans), ptr(mask), ptr(viou),
-            ptr(volA), ptr(volB), ptr(tile_ws), stream_ptr(dev)), "vsg_traj_viou_matrix_tiled")
+            ptr(A.seg), ptr(B.seg), ptr(seg_out), ptr(seg_len_d), len(A.counts), P, n_jobs, ptr(spans), ptr(mask), ptr(viou),
+            ptr(volA), ptr(volB), ptr(jobs_ws), ptr(njobs_ws), ptr(part_ws), stream_ptr(dev)), "vsg_traj_viou_matrix_tiled")
     else:
         check(lib().vsg_traj_viou_matrix(
             ptr(A.boxes), ptr(A.off), ptr(A.dura), A.n_tracks, ptr(B.boxes), ptr(B.off), ptr(B.dura), B.n_tracks,
