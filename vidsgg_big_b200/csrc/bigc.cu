@@ -459,6 +459,122 @@ role_attention_kernel(const float* __restrict__ p2a, const float* __restrict__ e
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Shared-memory staged role attention for E = 128 / 512 (the production dims).  Same maths as role_attention_kernel, but the
+// e2a / enco rows of the video are staged chunk-wise in shared memory once per CTA (8 queries) instead of being re-read
+// from L2 by every warp, and lanes own interleaved float4 columns (j*32 + lane) so every LDS.128 is conflict-free.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RA_CH = 16;  // tracks per staged chunk
+
+template <int E>
+__global__ void __launch_bounds__(256)
+role_attention_smem_kernel(const float* __restrict__ p2a, const float* __restrict__ e2a, const float* __restrict__ enco,
+                           const int32_t* __restrict__ seg, int Q, float inv_sqrt_d, float* __restrict__ values,
+                           float* __restrict__ att_out, int att_ld, int32_t* __restrict__ so_out) {
+  constexpr int NJ = E / 128;            // float4 columns per lane
+  constexpr int E4 = E / 4;
+  extern __shared__ __align__(16) float ra_smem[];
+  float4* sRows = reinterpret_cast<float4*>(ra_smem);                              // [RA_CH][E4]
+  float (*sL)[2][RA_MAX_TRACKS] = reinterpret_cast<float (*)[2][RA_MAX_TRACKS]>(ra_smem + RA_CH * E);
+  const int v = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int q = blockIdx.y * 8 + warp;
+  const bool active = q < Q;
+  const int t0 = seg[v], n = seg[v + 1] - t0;
+  const int64_t qrow = (int64_t)v * Q + (active ? q : 0);
+  float4 pq[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) pq[j] = reinterpret_cast<const float4*>(p2a + qrow * E)[j * 32 + lane];
+  // ---- pass 1: logits ----
+  for (int c0 = 0; c0 < n; c0 += RA_CH) {
+    const int cn = min(RA_CH, n - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * E4; i += 256)
+      sRows[i] = reinterpret_cast<const float4*>(e2a + (int64_t)(t0 + c0) * E)[i];
+    __syncthreads();
+    if (active) {
+      for (int e = 0; e < cn; ++e) {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float4 x = sRows[e * E4 + j * 32 + lane];
+          const float t = pq[j].x * x.x + pq[j].y * x.y + pq[j].z * x.z + pq[j].w * x.w;
+          const bool obj = (j * 32 + lane) * 4 >= E / 2;
+          d0 += obj ? 0.f : t;
+          d1 += obj ? t : 0.f;
+        }
+        d0 = warp_sum(d0); d1 = warp_sum(d1);
+        if (lane == 0) { sL[warp][0][c0 + e] = d0 * inv_sqrt_d; sL[warp][1][c0 + e] = d1 * inv_sqrt_d; }
+      }
+    }
+  }
+  __syncwarp();
+  float best[2] = {-INFINITY, -INFINITY};
+  int best_e[2] = {0x7fffffff, 0x7fffffff};
+  if (active) {
+    float mx[2] = {-INFINITY, -INFINITY};
+    for (int e = lane; e < n; e += 32) { mx[0] = fmaxf(mx[0], sL[warp][0][e]); mx[1] = fmaxf(mx[1], sL[warp][1][e]); }
+    mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
+    float sm[2] = {0.f, 0.f};
+    for (int e = lane; e < n; e += 32) { sm[0] += expf(sL[warp][0][e] - mx[0]); sm[1] += expf(sL[warp][1][e] - mx[1]); }
+    sm[0] = warp_sum(sm[0]); sm[1] = warp_sum(sm[1]);
+    for (int e = lane; e < n; e += 32) {
+      const float l0 = sL[warp][0][e], l1 = sL[warp][1][e];
+      const float m = fmaxf(l0, l1);
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      const float a0 = (expf(l0 - mx[0]) / sm[0]) * (e0 / (e0 + e1));
+      const float a1 = (expf(l1 - mx[1]) / sm[1]) * (e1 / (e0 + e1));
+      sL[warp][0][e] = a0; sL[warp][1][e] = a1;
+      if (a0 > best[0]) { best[0] = a0; best_e[0] = e; }
+      if (a1 > best[1]) { best[1] = a1; best_e[1] = e; }
+      if (att_out) { att_out[(qrow * 2 + 0) * att_ld + e] = a0; att_out[(qrow * 2 + 1) * att_ld + e] = a1; }
+    }
+    if (so_out) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best[r], o);
+          const int oe = __shfl_xor_sync(0xffffffffu, best_e[r], o);
+          if (ob > best[r] || (ob == best[r] && oe < best_e[r])) { best[r] = ob; best_e[r] = oe; }
+        }
+      }
+      if (lane == 0) { so_out[qrow * 2] = t0 + best_e[0]; so_out[qrow * 2 + 1] = t0 + best_e[1]; }
+    }
+  }
+  __syncwarp();
+  // ---- pass 2: values ----
+  float4 acc0[NJ], acc1[NJ];
+#pragma unroll
+  for (int j = 0; j < NJ; ++j) { acc0[j] = make_float4(0.f, 0.f, 0.f, 0.f); acc1[j] = acc0[j]; }
+  for (int c0 = 0; c0 < n; c0 += RA_CH) {
+    const int cn = min(RA_CH, n - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * E4; i += 256)
+      sRows[i] = reinterpret_cast<const float4*>(enco + (int64_t)(t0 + c0) * E)[i];
+    __syncthreads();
+    if (active) {
+      for (int e = 0; e < cn; ++e) {
+        const float a0 = sL[warp][0][c0 + e], a1 = sL[warp][1][c0 + e];
+#pragma unroll
+        for (int j = 0; j < NJ; ++j) {
+          const float4 x = sRows[e * E4 + j * 32 + lane];
+          acc0[j].x = fmaf(a0, x.x, acc0[j].x); acc0[j].y = fmaf(a0, x.y, acc0[j].y);
+          acc0[j].z = fmaf(a0, x.z, acc0[j].z); acc0[j].w = fmaf(a0, x.w, acc0[j].w);
+          acc1[j].x = fmaf(a1, x.x, acc1[j].x); acc1[j].y = fmaf(a1, x.y, acc1[j].y);
+          acc1[j].z = fmaf(a1, x.z, acc1[j].z); acc1[j].w = fmaf(a1, x.w, acc1[j].w);
+        }
+      }
+    }
+  }
+  if (active) {
+    float4* o0 = reinterpret_cast<float4*>(values + qrow * (2 * E));
+    float4* o1 = o0 + E4;
+#pragma unroll
+    for (int j = 0; j < NJ; ++j) { o0[j * 32 + lane] = acc0[j]; o1[j * 32 + lane] = acc1[j]; }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Head input: Z[row] = concat of up to 8 pieces, each a (possibly gathered) row of a source matrix
 // (prediction_head concat, model_0v10.py:501/503, model_0v7.py:506/508).  idx < 0 => identity row.
 // ---------------------------------------------------------------------------------------------------
@@ -751,9 +867,20 @@ extern "C" int vsg_role_attention(const float* p2a, const float* e2a, const floa
   VSG_REQUIRE(max_tracks <= RA_MAX_TRACKS, "vsg_role_attention: more than %d tracks in a video", RA_MAX_TRACKS);
   VSG_REQUIRE(aligned16(e2a) && aligned16(enco) && aligned16(values), "vsg_role_attention: misaligned pointer");
   dim3 grid(n_vid, (Q + 7) / 8);
-  if (E == 512) role_attention_kernel<512><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
+  VSG_REQUIRE(aligned16(p2a), "vsg_role_attention: misaligned p2a");
+  const size_t smem = (size_t)(RA_CH * E + 8 * 2 * RA_MAX_TRACKS) * sizeof(float);
+  if (E == 512) {
+    static bool attr_done = false;
+    if (!attr_done) {
+      if (cudaFuncSetAttribute(role_attention_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        set_error("vsg_role_attention: cannot raise dynamic shared memory to %zu", smem);
+        return VSG_E_LAUNCH;
+      }
+      attr_done = true;
+    }
+    role_attention_smem_kernel<512><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
+  } else if (E == 128) role_attention_smem_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
   else if (E == 64) role_attention_kernel<64><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
-  else if (E == 128) role_attention_kernel<128><<<grid, 256, 0, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
   else { set_error("vsg_role_attention: dim %d unsupported (64, 128, 512)", E); return VSG_E_UNSUPPORTED; }
   return check_launch("vsg_role_attention");
 }
