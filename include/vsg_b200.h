@@ -135,6 +135,14 @@ int vsg_rel_viou_match(const VsgRelTable* pred, const double* scores, const VsgR
                        double* vol_pred_ws /* [n_pred][2] */, double* vol_gt_ws /* [n_gt][2] */,
                        uint8_t* taken_ws /* [n_gt] */, void* stream);
 
+/* HOST function (CPU pointers): per-video records (video index, AP, n_gt, TP@det_n..., P@tag_n...) from the matcher's outputs,
+ * restating the numpy arithmetic of visual_relation_detection.py:28-33, :37-58, :82-93 and common.py:4-37 (voc_ap).
+ * hit_host f64[n_pred] rank order, order_host int32[n_pred], *_trip_host int64[n][3], *_off_host int64[n_vid+1],
+ * records_host f64[n_vid][3+n_det+n_tag].  Videos without GT are skipped; returns the number of records (<0 on error). */
+int vsg_eval_records_host(const double* hit_host, const int32_t* order_host, const int64_t* pred_trip_host, const int64_t* p_off_host,
+                          const int64_t* gt_trip_host, const int64_t* g_off_host, int n_vid, const int* det_n_host, int n_det,
+                          const int* tag_n_host, int n_tag, double* records_host);
+
 /* common.viou for a list of independent (traj_1, dur_1, traj_2, dur_2) problems, f64 boxes:
  * boxes1/boxes2 f64 [sum len][4], off1/off2 int64[n+1], dur1/dur2 int64[n][2] half-open;
  * out f64[n]. */

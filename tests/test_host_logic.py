@@ -122,3 +122,37 @@ def test_gather_records_gloo_world2():
     exp_rows = 3 + 6
     exp_sum = float(torch.arange(24, dtype=torch.float64).sum() + (torch.arange(48, dtype=torch.float64) + 1000).sum())
     assert all(r[1] == exp_rows and r[2] == exp_sum for r in res)
+
+
+def test_native_eval_records_equal_numpy_aggregation():
+    """csrc/evalhost.cu (host code of the library) restates the numpy per-video aggregation exactly."""
+    import ctypes as C
+    from vidsgg_big_b200 import evalapi, _cabi
+    rng = np.random.default_rng(0)
+    V, po, go, hits, orders, ptr_, gtr = 9, [0], [0], [], [], [], []
+    for v in range(V):
+        n = int(rng.integers(0, 160)); ng = int(rng.integers(0, 20)) if v != 3 else 0
+        sc = np.round(rng.uniform(0, 1, n), 2)
+        hits.append(np.where(rng.uniform(size=n) < 0.3, np.sort(sc)[::-1], -np.inf))
+        orders.append(rng.permutation(n).astype(np.int32))
+        ptr_.append(rng.integers(0, 4, size=(n, 3))); gtr.append(rng.integers(0, 4, size=(ng, 3)))
+        po.append(po[-1] + n); go.append(go[-1] + ng)
+    hit = np.ascontiguousarray(np.concatenate(hits)); order = np.ascontiguousarray(np.concatenate(orders))
+    ptrip = np.ascontiguousarray(np.concatenate(ptr_).astype(np.int64)); gtrip = np.ascontiguousarray(np.concatenate(gtr).astype(np.int64))
+    po, go = np.array(po, np.int64), np.array(go, np.int64)
+    det, tag = np.array([50, 100], np.int32), np.array([1, 5, 10], np.int32)
+    rec = np.zeros((V, 8))
+    hp = lambda a: C.c_void_p(a.ctypes.data)
+    n = _cabi.lib().vsg_eval_records_host(hp(hit), hp(order), hp(ptrip), hp(po), hp(gtrip), hp(go), V, hp(det), 2, hp(tag), 3, hp(rec))
+    vids, ngt, hh, tags = [], [], [], []
+    for v in range(V):
+        if go[v + 1] - go[v] == 0:
+            continue
+        o = order[po[v]:po[v + 1]]
+        trip = [tuple(t) for t in ptrip[po[v]:po[v + 1]][o].tolist()]
+        tags.append(evalapi._tagging_from_ids([tuple(t) for t in gtrip[go[v]:go[v + 1]].tolist()], trip, [1.0] * len(trip))[0])
+        vids.append(v); ngt.append(int(go[v + 1] - go[v])); hh.append(hit[po[v]:po[v + 1]])
+    ref = evalapi.per_video_records(vids, ngt, hh, tags)
+    assert n == ref.shape[0] == 8
+    assert np.array_equal(rec[:n, [0, 2, 3, 4, 5, 6, 7]], ref[:, [0, 2, 3, 4, 5, 6, 7]])
+    assert np.abs(rec[:n, 1] - ref[:, 1]).max() < 1e-14

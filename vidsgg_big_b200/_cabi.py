@@ -45,6 +45,7 @@ SIGNATURES = {
     "vsg_traj_viou_matrix_tiled": (i32, [p, p, p, i32, p, p, p, i32, p, p, p, p, i32, i64, i64, p, p, p, p, p, p, p, p, p]),
     "vsg_pair_labels": (i32, [p, i32, i32, p, i32, f32, p, p]),
     "vsg_rel_viou_match": (i32, [C.POINTER(VsgRelTable), p, C.POINTER(VsgRelTable), i32, p, f64, p, p, p, p, p, p, p, p]),
+    "vsg_eval_records_host": (i32, [p, p, p, p, p, p, i32, p, i32, p, i32, p]),
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),

@@ -367,6 +367,8 @@ def evaluate_packed(pred: PackedRelations, gt: PackedRelations, viou_threshold=0
                     tag_nreturns=(1, 5, 10), with_infos=False, want_records=False):
     """Packed fast path: same numbers as ``evaluate`` on the equivalent dicts, no dict materialisation."""
     m = match_relations(pred, gt, viou_threshold)
+    if want_records and not with_infos:
+        return _records_native(pred, gt, m, det_nreturns, tag_nreturns)
     hit = m.hit.cpu().numpy()
     order = m.order.cpu().numpy()
     g2d = m.gt2det.cpu().numpy().astype(int)
@@ -390,6 +392,27 @@ def evaluate_packed(pred: PackedRelations, gt: PackedRelations, viou_threshold=0
         return per_video_records(vids, ngt, hits, tags, det_nreturns, tag_nreturns)
     res = _aggregate(vids, ngt, hits, tags, list(det_nreturns), list(tag_nreturns))
     return res + (infos,) if with_infos else res
+
+
+def _records_native(pred: PackedRelations, gt: PackedRelations, m: MatchResult, det_nreturns, tag_nreturns) -> np.ndarray:
+    """Per-video records through the native host pass (csrc/evalhost.cu): three D2H reads, no Python loop over videos."""
+    hit = np.ascontiguousarray(m.hit.cpu().numpy())
+    order = np.ascontiguousarray(m.order.cpu().numpy())
+    ptrip = np.ascontiguousarray(pred.rel[:, :3].cpu().numpy())
+    if getattr(gt, "_trip_host", None) is None:
+        gt._trip_host = np.ascontiguousarray(gt.rel[:, :3].cpu().numpy())
+    gtrip = gt._trip_host
+    po = np.ascontiguousarray(pred.vid_off_host.astype(np.int64))
+    go = np.ascontiguousarray(gt.vid_off_host.astype(np.int64))
+    det = np.asarray(list(det_nreturns), dtype=np.int32)
+    tag = np.asarray(list(tag_nreturns), dtype=np.int32)
+    rec = np.zeros((gt.n_vid, 3 + det.size + tag.size), dtype=np.float64)
+    hp = lambda a: C.c_void_p(a.ctypes.data)
+    n = lib().vsg_eval_records_host(hp(hit), hp(order), hp(ptrip), hp(po), hp(gtrip), hp(go), gt.n_vid, hp(det), int(det.size),
+                                    hp(tag), int(tag.size), hp(rec))
+    if n < 0:
+        check(n, "vsg_eval_records_host")
+    return rec[:n]
 
 
 def eval_relation_with_gt(dataset_type, logger=None, prediction_results=None, json_results_path=None,
