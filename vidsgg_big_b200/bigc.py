@@ -51,24 +51,7 @@ class PackedVideos(object):
         tmax = torch.cat([torch.full((c,), int(l.max()), dtype=torch.int32) for c, l in zip(counts, lens)])
         track_vid = torch.cat([torch.full((c,), i, dtype=torch.int32) for i, c in enumerate(counts)])
         wh = torch.tensor([[float(p.video_wh[0]), float(p.video_wh[1])] for p in self.proposals], dtype=torch.float32)
-        def cat(xs):
-            """Concatenate along rows; zero-copy when the pieces are adjacent row views of one device buffer."""
-            if len(xs) == 1:
-                return xs[0].contiguous()
-            x0 = xs[0]
-            if x0.is_contiguous() and x0.dim() >= 1:
-                row = x0.stride(0) * x0.element_size() if x0.dim() > 1 else x0.element_size()
-                nxt, ok = x0.data_ptr(), True
-                for x in xs:
-                    if (not x.is_contiguous()) or x.data_ptr() != nxt or x.dtype != x0.dtype or x.shape[1:] != x0.shape[1:] \
-                            or x.untyped_storage().data_ptr() != x0.untyped_storage().data_ptr():
-                        ok = False
-                        break
-                    nxt += x.shape[0] * row
-                if ok:
-                    total = sum(int(x.shape[0]) for x in xs)
-                    return x0.as_strided((total,) + tuple(x0.shape[1:]), x0.stride())
-            return torch.cat(xs, 0)
+        from .geometry import cat_rows as cat
         self.boxes = cat([p.bboxes.to(device, torch.float32) for p in self.proposals])
         self.feats = cat([p.features.to(device, torch.float32) for p in self.proposals])
         self.dura = cat([p.traj_durations.to(device, torch.long) for p in self.proposals])

@@ -23,6 +23,26 @@ from ._cabi import check, lib, ptr, require_cuda, stream_ptr
 TILE, CHUNK = 32, 256  # csrc/geometry.cu T2_TA / T2_TB, T2_CH
 
 
+def cat_rows(xs):
+    """Concatenate along rows; zero-copy when the pieces are adjacent row views of one device buffer."""
+    if len(xs) == 1:
+        return xs[0].contiguous()
+    x0 = xs[0]
+    if x0.is_contiguous() and x0.dim() >= 1:
+        row = x0.stride(0) * x0.element_size() if x0.dim() > 1 else x0.element_size()
+        nxt, ok = x0.data_ptr(), True
+        for x in xs:
+            if (not x.is_contiguous()) or x.data_ptr() != nxt or x.dtype != x0.dtype or x.shape[1:] != x0.shape[1:] \
+                    or x.untyped_storage().data_ptr() != x0.untyped_storage().data_ptr():
+                ok = False
+                break
+            nxt += x.shape[0] * row
+        if ok:
+            total = sum(int(x.shape[0]) for x in xs)
+            return x0.as_strided((total,) + tuple(x0.shape[1:]), x0.stride())
+    return torch.cat(xs, 0)
+
+
 # --------------------------------------------------------------------------------------------
 class TrackTable(object):
     """Packed tracks of a batch of videos in HBM: boxes f32[sum L,4], off i64[n+1], dura i64[n,2] (closed),
@@ -50,8 +70,7 @@ class TrackTable(object):
             lens_l.append(it.lengths)
             counts.append(int(du.shape[0]))
         require_cuda(*boxes_l)
-        boxes = boxes_l[0].contiguous() if len(boxes_l) == 1 else torch.cat(boxes_l, 0)
-        dura = dura_l[0].contiguous() if len(dura_l) == 1 else torch.cat(dura_l, 0)
+        boxes, dura = cat_rows(boxes_l), cat_rows(dura_l)
         lens = torch.cat([torch.as_tensor(l, dtype=torch.long) for l in lens_l]) if lens_l else torch.zeros(0, dtype=torch.long)
         off = torch.zeros(lens.numel() + 1, dtype=torch.long)
         off[1:] = torch.cumsum(lens, 0)
