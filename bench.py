@@ -31,13 +31,14 @@ from vidsgg_big_b200 import synth  # noqa: E402
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--videos", type=int, default=200, help="videos per GPU per step (weak scaling)")
     ap.add_argument("--workload", default="vidvrd", choices=["vidvrd", "vidor"])
     ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32_simt"])
-    ap.add_argument("--cpu-sample", type=int, default=16, help="videos in the bounded CPU-baseline sample")
+    ap.add_argument("--cpu-sample", type=int, default=None,
+                    help="videos in the bounded CPU sample (default: 200 for cpu_baseline, 40 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -284,6 +285,8 @@ def run_reference(args, rank, world):
     if rank != 0:
         return
     cfg, wl = workload_cfg(args.workload)
+    if args.cpu_sample is None:
+        args.cpu_sample = 40 if args.workload == "vidvrd" else 2
     times = []
     for i in range(args.warmup + args.steps):
         v, dt = cpu_baseline(args.workload, args.cpu_sample)
@@ -325,6 +328,8 @@ def main():
     # CPU baseline first (rank 0, N=1 only), so it does not overlap the GPU timing
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        if args.cpu_sample is None:
+            args.cpu_sample = 200 if args.workload == "vidvrd" else 6
         v, dt = cpu_baseline(args.workload, args.cpu_sample)
         cpu = {"value": v, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
                "sample": "%d videos of the same workload (seeds 1000..), %.1f s of CPU work" % (args.cpu_sample, dt)}
