@@ -101,3 +101,31 @@ def test_eval_packed_path_equals_dict_path():
     for i, P in enumerate(props):
         h_ref, g_ref = ref[3][P.video_name]
         assert np.array_equal(infos[i][0], h_ref) and np.array_equal(infos[i][1], g_ref)
+
+
+def test_convertor_equals_oracle_and_driver_roundtrip():
+    """Product EvalFmtCvtor == oracle convertor (itself pinned to the reference's), and the batched VidVRD driver gives the
+    metrics of evaluating its own dict export through the dict path."""
+    from vidsgg_big_b200 import bigc, convert, driver
+    api = _api()
+    en, pn = oc.default_names("e", 64), oc.default_names("p", 200)
+    cv = convert.EvalFmtCvtor("vidvrd")
+    P = synth.make_proposal(500, 9, 120, 8, 36, with_features=False)
+    G = synth.make_gt_graph(500, P, 133)
+    T = synth.make_predictions(500, P, G, 133, m=40)
+    assert cv.to_eval_format_pr(P, T) == oc.to_eval_format_pr(P, T, en, pn)
+    assert cv.to_eval_format_gt(G) == oc.to_eval_format_gt(G, en, pn)
+    assert cv.to_eval_format_pr(P, None) == {P.video_name: []}
+    # driver on a tiny model
+    cfg = synth.tiny_vidvrd_config()
+    model = bigc.BIG_C_vidvrd(cfg, precision="3xtf32")
+    model.load_state_dict(synth.make_bigc_state(7, cfg)); model.cuda()
+    props, graphs, gts = [], [], {}
+    for sd in range(540, 546):
+        p = synth.make_proposal(sd, 8, 60, 136, cfg["num_enti_cats"])
+        g = synth.make_gt_graph(sd, p, cfg["num_pred_cats"], n_rel=(3, 10))
+        gts.update(cv.to_eval_format_gt(g))
+        props.append(p.to(DEV)); graphs.append(g.to(DEV))
+    m_ap, rec, mprec, dicts = driver.inference_then_eval(model, props, graphs, topk=5, want_dicts=True)
+    m2, r2, p2 = api.eval_visual_relation(gts, dicts)
+    assert abs(m_ap - m2) < 1e-12 and rec[50] == r2[50] and rec[100] == r2[100] and all(mprec[k] == p2[k] for k in (1, 5, 10))

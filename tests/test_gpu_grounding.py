@@ -118,3 +118,34 @@ def test_classify_then_ground_packed_equals_driver_expansion():
     assert torch.equal(A.rel, B.rel) and torch.equal(A.vid_off, B.vid_off)
     assert torch.allclose(A.scores, B.scores, rtol=1e-6)
     assert A.n_rel >= sum(t[0].shape[0] for t in per_video)          # at least one bin per query
+
+
+def test_vidor_combined_driver():
+    """evaluate_cls_stage / evaluate_combined (tools/eval_vidor.py) on a small VidOR-shaped set: runs end to end, the packed
+    metrics equal those of the dict path fed with the driver-style expansion."""
+    from vidsgg_big_b200 import bigc, convert, driver, evalapi, grounding
+    cfg = synth.vidor_config()
+    cls_model = bigc.BIG_C_vidor(cfg, precision="3xtf32")
+    cls_model.load_state_dict(synth.make_bigc_state(2, cfg)); cls_model.cuda()
+    grd = _model("3xtf32")
+    cv = convert.EvalFmtCvtor("vidvrd")
+    props, graphs, feats, gts = [], [], [], {}
+    for sd, n, vl in ((711, 8, 120), (712, 12, 200), (713, 6, 90)):
+        p = synth.make_proposal(sd, n, vl, 1324, 81, min_len=15)
+        g = synth.make_gt_graph(sd, p, 51, n_rel=(3, 10))
+        gts.update(cv.to_eval_format_gt(g))
+        props.append(p.to(DEV)); graphs.append(g.to(DEV)); feats.append(synth.make_video_feature(sd, vl).to(DEV))
+    (m0, r0, p0), save = driver.evaluate_cls_stage(cls_model, props, graphs, topk=3)
+    assert set(save) == {p.video_name for p in props} and all(v is None or len(v) == 4 for v in save.values())
+    m_ap, rec, mprec, infos = driver.evaluate_combined(grd, cls_model, props, feats, graphs, topk=3, **INF)
+    # reference-style: per video expansion -> dicts -> dict-path evaluation
+    prs = {}
+    with torch.no_grad():
+        res = cls_model(props, topk=3)
+    for p, f, r in zip(props, feats, res):
+        pooled, probs, mask = grd([f], [(r[0], r[2], p.video_len)], with_gt_data=False, **INF)
+        prs.update(cv.to_eval_format_pr(p, grounding.expand_after_grounding(r[0], r[1], pooled, probs, mask, p.video_len)))
+    m2, r2, p2, infos2 = evalapi.evaluate_v2(gts, prs)
+    assert abs(m_ap - m2) < 1e-12 and rec[50] == r2[50] and rec[100] == r2[100]
+    for v in infos2:
+        assert np.array_equal(infos[v][0], infos2[v][0]) and np.array_equal(infos[v][1], infos2[v][1])

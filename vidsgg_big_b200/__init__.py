@@ -11,9 +11,11 @@ from .evalapi import (eval_visual_relation, evaluate, evaluate_v2, eval_relation
                       PackedRelations, evaluate_packed)
 from .bigc import BIG_C, BIG_C_vidvrd, BIG_C_vidor                                       # noqa: F401
 from .grounding import DEBUG, expand_after_grounding                                     # noqa: F401
+from .convert import EvalFmtCvtor                                                        # noqa: F401
+from . import driver                                                                     # noqa: F401
 
 __all__ = ["TrajProposal", "VideoGraph", "dura_intersection_ts", "vIoU_ts", "trajid2pairid", "traj_viou_matrix",
            "traj_viou_batched", "enti_viou_align", "pair_labels", "TrackTable", "eval_visual_relation", "evaluate",
            "evaluate_v2", "eval_relation_with_gt", "eval_detection_scores", "eval_detection_scores_v2",
            "eval_tagging_scores", "viou", "voc_ap", "PackedRelations", "evaluate_packed", "BIG_C", "BIG_C_vidvrd",
-           "BIG_C_vidor", "DEBUG", "expand_after_grounding"]
+           "BIG_C_vidor", "DEBUG", "expand_after_grounding", "EvalFmtCvtor", "driver"]
