@@ -194,3 +194,39 @@ def test_forward_packed_equals_forward():
     A = evalapi.PackedRelations.from_packed_triplets(tt, packed)
     B = evalapi.PackedRelations.from_triplets(tt, [None if t is None else (t[0], t[1].mean(-1), t[2]) for t in ref])
     assert torch.equal(A.rel, B.rel) and torch.equal(A.vid_off, B.vid_off) and torch.allclose(A.scores, B.scores)
+
+
+def test_bigc_vidor_max_proposals_vs_oracle():
+    """VidOR upper end (180 proposals, tracks up to 600 frames, exp5 dims): device logits / attention vs the oracle run here,
+    and identical triplets up to near-ties.  Exercises the 180-track role attention and the long-stretch conv/pool path."""
+    cfg = synth.vidor_config()
+    st = synth.make_bigc_state(2, cfg)
+    model = _model(cfg, st, "3xtf32")
+    P = synth.make_proposal(4321, 180, 900, 1324, 81, min_len=15, max_len=600)
+    with torch.no_grad():
+        _, ref_logits, ref_att = ob.encode2decode(st, cfg, P)
+        ref = ob.construct_triplet(P, ref_logits, ref_att, 3)
+        P.to(DEV)
+        _, logits, att, so, _ = model.forward_debug(P)
+        ret = model([P], topk=3)[0]
+    same_so = (so.cpu() == torch.argmax(ref_att, -1).t()).all(1).numpy()
+    err = (logits.cpu() - ref_logits).abs().numpy()[same_so].max() / ref_logits.abs().max().item()
+    print("n=180: rel logit err %.2e, (s,o) agreement %d/%d" % (err, same_so.sum(), same_so.size))
+    assert same_so.mean() >= 0.97 and err <= 3e-4
+    assert (att.cpu() - ref_att).abs().max().item() <= 2e-4
+    mine = {tuple(r) for r in ret[0].cpu().tolist()}
+    theirs = {tuple(r) for r in ref[0].tolist()}
+    assert len(mine ^ theirs) <= max(2, len(theirs) // 20)
+
+
+def test_bigc_full_dims_batched_equals_single():
+    cfg = synth.vidvrd_config()
+    st = synth.make_bigc_state(1, cfg)
+    model = _model(cfg, st, "3xtf32")
+    props = [bigc_inputs(cfg, 960 + i, n, vl, 150).to(DEV) for i, (n, vl) in enumerate([(30, 300), (5, 90), (50, 700), (17, 240)])]
+    with torch.no_grad():
+        batched = model(props, topk=10)
+        single = [model([p], topk=10)[0] for p in props]
+    for b, s in zip(batched, single):
+        assert torch.equal(b[0], s[0]) and torch.equal(b[2], s[2]) and torch.equal(b[3], s[3])
+        assert torch.allclose(b[1], s[1], rtol=1e-5, atol=1e-7)
