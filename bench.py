@@ -200,6 +200,17 @@ class Pipeline(object):
         return (float(m_ap), float(r_at[50]), float(r_at[100])), int(PR.n_rel), viou
 
 
+def gt_from_predictions(pipe, props, cfg, kind, base_seed, device):
+    """One classification pass -> GT graphs built from its predictions (synth.make_gt_from_predictions), moved to the device."""
+    with torch.no_grad():
+        trips = pipe.model(props, topk=pipe.wl["topk"])
+    graphs = []
+    for i, (p, t) in enumerate(zip(props, trips)):
+        t3 = None if t is None else (t[0], t[1].mean(-1), t[2])
+        graphs.append(synth.make_gt_from_predictions(base_seed + i, p, t3, num_pred_cats=cfg["num_pred_cats"]).to(device))
+    return graphs
+
+
 class HostBatch(object):
     """One batch held the way a data loader would hand it over: pinned host buffers (features in one buffer, the small
     per-track fields concatenated per field) plus per-video metadata.  ``upload`` copies it into preallocated device
@@ -271,6 +282,13 @@ def cpu_baseline(kind, n_sample, repeats=1):
     cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu")
     st = synth.make_bigc_state(1, cfg)
     gst = synth.make_grounding_state(21, synth.grounding_config()) if kind == "vidor" else None
+    from oracle import bigc as ob
+    with torch.no_grad():                                                  # GT from the (oracle's) own predictions, untimed
+        graphs = []
+        for i, p in enumerate(props):
+            r = ob.forward(st, cfg, [p], wl["topk"])[0]
+            graphs.append(synth.make_gt_from_predictions(1000 + i, p, None if r is None else (r[0], r[1].mean(-1), r[2]),
+                                                         num_pred_cats=cfg["num_pred_cats"]))
     cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl, gst)                # warm-up
     best = None
     for _ in range(repeats):
@@ -350,6 +368,8 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # GT derived from the model's own predictions (first pass), so that the evaluation stage has real matches to find
+    graphs = gt_from_predictions(pipe, props, cfg, args.workload, 1000 + 100000 * rank, device)
     for _ in range(args.warmup):
         metrics, n_trip, _ = pipe.step(props, graphs)
     # ---- timed region: K steps, inputs resident in HBM (they exceed L2 by far: no flush needed) ----
@@ -404,8 +424,7 @@ def main():
         del props, feats
         torch.cuda.empty_cache()
         cfg, wl, hprops, hgraphs, hfeats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device, pinned=True)
-        for g in hgraphs:
-            g.to(device)
+        hgraphs = graphs                                          # same GT (resident), same videos
         hb = HostBatch(hprops, device)
         copy_stream = torch.cuda.Stream(device=device)
         copied = [torch.cuda.Event(), torch.cuda.Event()]

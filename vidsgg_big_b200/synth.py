@@ -219,6 +219,50 @@ def make_predictions(seed: int, proposal: TrajProposal, gt: VideoGraph, num_pred
     return (torch.tensor(rows, dtype=torch.long), torch.from_numpy(score), torch.tensor(spans, dtype=torch.long))
 
 
+def make_gt_from_predictions(seed: int, proposal: TrajProposal, triplets, n_rel=(5, 40), jitter_px: float = 3.0,
+                             p_wrong_pred: float = 0.3, num_pred_cats: int = 133) -> VideoGraph:
+    """GT graph whose relations are drawn from a model's own predictions (so the evaluation has real matches to find):
+    up to ``n_rel`` predicted (pred, subject track, object track) rows become GT relations on jittered + rounded copies of those
+    proposal tracks, with a random sub-interval of the s-o overlap as duration; a fraction gets a different predicate (misses).
+    ``triplets`` = (quintuples i64[m,5], scores, spans i64[m,2]) on any device, or None (-> falls back to ``make_gt_graph``)."""
+    if triplets is None or triplets[0].shape[0] == 0:
+        return make_gt_graph(seed, proposal, num_pred_cats)
+    rng = np.random.default_rng(seed + 99_000_000)
+    quint = triplets[0].cpu().numpy()
+    spans = triplets[2].cpu().numpy()
+    m = int(min(quint.shape[0], rng.integers(n_rel[0], n_rel[1] + 1)))
+    rows = np.sort(rng.choice(quint.shape[0], size=m, replace=False))
+    used = sorted(set(quint[rows, 3].tolist()) | set(quint[rows, 4].tolist()))
+    remap = {t: i for i, t in enumerate(used)}
+    lens = proposal.lengths.numpy()
+    offs = np.concatenate([[0], np.cumsum(lens)])
+    duras = proposal.traj_durations.cpu().numpy()
+    pb = proposal.bboxes.cpu().numpy()
+    cats = proposal.cat_ids.cpu().numpy()
+    g_boxes, g_duras, g_cats = [], [], []
+    for t in used:
+        b = np.rint(pb[offs[t]:offs[t + 1]] + rng.normal(0, jitter_px, (int(lens[t]), 4))).astype(np.float32)
+        b[:, 2] = np.maximum(b[:, 2], b[:, 0] + 1)
+        b[:, 3] = np.maximum(b[:, 3], b[:, 1] + 1)
+        g_boxes.append(b); g_duras.append(duras[t].tolist()); g_cats.append(int(cats[t]))
+    rel_c, rel_d = [], []
+    adj = np.zeros((2, m, len(used)), np.float32)
+    for i, r in enumerate(rows):
+        pc, _, _, st, ot = quint[r]
+        s, e = int(spans[r, 0]), int(spans[r, 1])
+        ln = int(rng.integers(max(1, (e - s + 1) // 2), e - s + 2))
+        b0 = int(s + rng.integers(0, e - s + 2 - ln))
+        if rng.uniform() < p_wrong_pred:
+            pc = int(1 + (pc + rng.integers(0, num_pred_cats - 2)) % (num_pred_cats - 1))
+        rel_c.append(int(pc)); rel_d.append([b0, b0 + ln - 1])
+        adj[0, i, remap[int(st)]] = 1.0
+        adj[1, i, remap[int(ot)]] = 1.0
+    g = VideoGraph(proposal.video_name, proposal.video_len, proposal.video_wh, g_cats, np.asarray(g_duras, np.int64).reshape(-1, 2),
+                   np.concatenate(g_boxes, 0), rel_c, np.asarray(rel_d, np.float32).reshape(-1, 2), adj, lengths=[b.shape[0] for b in g_boxes])
+    g.src_prop_ids = used
+    return g
+
+
 def vidvrd_video_shape(rng) -> Tuple[int, int]:
     """(video_len, n) of SURVEY §8d config 2."""
     return int(rng.integers(90, 1201)), int(rng.integers(5, 51))
