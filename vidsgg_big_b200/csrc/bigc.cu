@@ -220,8 +220,14 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
   if (q_base >= n) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hc = head * DH;
-  constexpr int OD = (DH + 31) / 32;
+  constexpr int OD = (DH + 31) / 32;   // output dims per lane
   constexpr int D4 = DH / 4;
+  // PV lane layout: for DH < 32 the warp is split into G = 32/DH groups, each owning QPL = 8/G of the warp's 8 queries,
+  // so that all 32 lanes stay busy (lane -> dim lane % DH of the queries of group lane / DH)
+  constexpr int G = DH < 32 ? 32 / DH : 1;
+  constexpr int QPL = 8 / G;
+  const int grp = DH < 32 ? lane / DH : 0;
+  const int dlane = DH < 32 ? lane % DH : lane;
   // queries of this block (zero rows beyond n)
   for (int i = threadIdx.x; i < MHA_QB * D4; i += 256) {
     const int q = i / D4, d4 = i % D4;
@@ -232,13 +238,13 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
     }
     reinterpret_cast<float4*>(Qs)[i] = v;
   }
-  float m_run[8], l_run[8], o_acc[8][OD];
+  float m_run[8], l_run[8], o_acc[QPL][OD];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    m_run[j] = -INFINITY; l_run[j] = 0.f;
+  for (int j = 0; j < 8; ++j) { m_run[j] = -INFINITY; l_run[j] = 0.f; }
+#pragma unroll
+  for (int j = 0; j < QPL; ++j)
 #pragma unroll
     for (int d = 0; d < OD; ++d) o_acc[j][d] = 0.f;
-  }
   const int kg = warp & 3, qh = warp >> 2;
   for (int k0 = 0; k0 < n; k0 += MHA_SK) {
     const int kc = min(MHA_SK, n - k0);
@@ -280,6 +286,7 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
     // ---- phase B: warp owns queries 8*warp .. 8*warp+7 ----
     if (q_base + 8 * warp < n) {    // warp-uniform
       const int nk_groups = (kc + 31) / 32;
+      float c8[8];
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int q = 8 * warp + j;
@@ -305,34 +312,54 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
         psum = warp_sum(psum);
         l_run[j] = l_run[j] * corr + psum;
         m_run[j] = m_new;
+        c8[j] = corr;
+      }
 #pragma unroll
-        for (int d = 0; d < OD; ++d) o_acc[j][d] *= corr;
+      for (int j = 0; j < QPL; ++j) {
+        float c = c8[j];
+#pragma unroll
+        for (int g = 1; g < G; ++g) c = (grp == g) ? c8[g * QPL + j] : c;
+#pragma unroll
+        for (int d = 0; d < OD; ++d) o_acc[j][d] *= c;
       }
       __syncwarp();
-      if (lane < DH) {
+      if (DH >= 32 ? (lane < DH) : true) {
+        const float* prow = St + 8 * warp + grp * QPL;
         for (int kr = 0; kr < kc; ++kr) {
-          const float4 p0 = *reinterpret_cast<const float4*>(St + kr * MHA_PITCH + 8 * warp);
-          const float4 p1 = *reinterpret_cast<const float4*>(St + kr * MHA_PITCH + 8 * warp + 4);
+          float pv[QPL];
+          if (QPL == 8) {
+            const float4 p0 = *reinterpret_cast<const float4*>(prow + kr * MHA_PITCH);
+            const float4 p1 = *reinterpret_cast<const float4*>(prow + kr * MHA_PITCH + 4);
+            pv[0] = p0.x; pv[1] = p0.y; pv[2] = p0.z; pv[3] = p0.w;
+            pv[4 % QPL] = p1.x; pv[5 % QPL] = p1.y; pv[6 % QPL] = p1.z; pv[7 % QPL] = p1.w;
+          } else if (QPL == 4) {
+            const float4 p0 = *reinterpret_cast<const float4*>(prow + kr * MHA_PITCH);
+            pv[0] = p0.x; pv[1] = p0.y; pv[2 % QPL] = p0.z; pv[3 % QPL] = p0.w;
+          } else {
+#pragma unroll
+            for (int j = 0; j < QPL; ++j) pv[j] = prow[kr * MHA_PITCH + j];
+          }
 #pragma unroll
           for (int d = 0; d < OD; ++d) {
-            const float v = Vs[kr * DH + lane + 32 * d];
-            o_acc[0][d] = fmaf(p0.x, v, o_acc[0][d]); o_acc[1][d] = fmaf(p0.y, v, o_acc[1][d]);
-            o_acc[2][d] = fmaf(p0.z, v, o_acc[2][d]); o_acc[3][d] = fmaf(p0.w, v, o_acc[3][d]);
-            o_acc[4][d] = fmaf(p1.x, v, o_acc[4][d]); o_acc[5][d] = fmaf(p1.y, v, o_acc[5][d]);
-            o_acc[6][d] = fmaf(p1.z, v, o_acc[6][d]); o_acc[7][d] = fmaf(p1.w, v, o_acc[7][d]);
+            const float v = Vs[kr * DH + dlane + 32 * d];
+#pragma unroll
+            for (int j = 0; j < QPL; ++j) o_acc[j][d] = fmaf(pv[j], v, o_acc[j][d]);
           }
         }
       }
     }
   }
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int q = q_base + 8 * warp + j;
+  for (int j = 0; j < QPL; ++j) {
+    const int q = q_base + 8 * warp + grp * QPL + j;
+    float l = l_run[j];
+#pragma unroll
+    for (int g = 1; g < G; ++g) l = (grp == g) ? l_run[g * QPL + j] : l;
     if (q >= n) continue;
 #pragma unroll
     for (int d = 0; d < OD; ++d) {
-      const int dd = lane + 32 * d;
-      if (dd < DH) Op[(row0 + q) * ldo + hc + dd] = o_acc[j][d] / l_run[j];
+      const int dd = dlane + 32 * d;
+      if (dd < DH) Op[(row0 + q) * ldo + hc + dd] = o_acc[j][d] / l;
     }
   }
 }
