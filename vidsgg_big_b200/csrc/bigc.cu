@@ -203,16 +203,21 @@ __global__ void broadcast_rows_kernel(const float* __restrict__ x, int period, i
 //            the 8 probabilities of a key fetched by two broadcast LDS.128 and V[key][lane(+32)] from smem:
 //            16 FMAs per 4 shared loads.
 // ---------------------------------------------------------------------------------------------------
-constexpr int MHA_QB = 64, MHA_SK = 128, MHA_PITCH = 68;
+constexpr int MHA_QB = 64, MHA_PITCH = 68;
+template <int DH> struct MhaCfg { static constexpr int SK = DH >= 64 ? 128 : 256; };   // keys per super-chunk
 
 template <int DH>
 __global__ void __launch_bounds__(256, 2)
 mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp, int ldv,
            const int64_t* __restrict__ seg_off, int fixed_len, int n_head, float scale, float* __restrict__ Op, int ldo) {
+  constexpr int MHA_SK = MhaCfg<DH>::SK;
+  constexpr int KG = MHA_SK / 32;               // key groups of 32 (one per warp in phase A)
+  constexpr int QH = 8 / KG;                    // query slices in phase A
+  constexpr int QPS = MHA_QB / QH;              // queries per slice
   extern __shared__ __align__(16) float mha_smem[];
   float* Qs = mha_smem;                         // [64][DH] pre-scaled
-  float* Vs = Qs + MHA_QB * DH;                 // [128][DH]
-  float* St = Vs + MHA_SK * DH;                 // [128][68] scores / probabilities, transposed (key-major)
+  float* Vs = Qs + MHA_QB * DH;                 // [SK][DH]
+  float* St = Vs + MHA_SK * DH;                 // [SK][68] scores / probabilities, transposed (key-major)
   const int seg = blockIdx.x, head = blockIdx.y;
   const int64_t row0 = seg_off ? seg_off[seg] : (int64_t)seg * fixed_len;
   const int n = seg_off ? (int)(seg_off[seg + 1] - row0) : fixed_len;
@@ -245,7 +250,7 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
   for (int j = 0; j < QPL; ++j)
 #pragma unroll
     for (int d = 0; d < OD; ++d) o_acc[j][d] = 0.f;
-  const int kg = warp & 3, qh = warp >> 2;
+  const int kg = warp % KG, qh = warp / KG;
   for (int k0 = 0; k0 < n; k0 += MHA_SK) {
     const int kc = min(MHA_SK, n - k0);
     __syncthreads();  // previous chunk fully consumed (and Qs visible on the first pass)
@@ -267,10 +272,10 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
           const float4 v = *reinterpret_cast<const float4*>(kp + 4 * d4);
           kreg[4 * d4] = v.x; kreg[4 * d4 + 1] = v.y; kreg[4 * d4 + 2] = v.z; kreg[4 * d4 + 3] = v.w;
         }
-        float* srow = St + key * MHA_PITCH + qh * 32;
+        float* srow = St + key * MHA_PITCH + qh * QPS;
 #pragma unroll 4
-        for (int q = 0; q < 32; ++q) {
-          const float4* qp = reinterpret_cast<const float4*>(Qs + (qh * 32 + q) * DH);
+        for (int q = 0; q < QPS; ++q) {
+          const float4* qp = reinterpret_cast<const float4*>(Qs + (qh * QPS + q) * DH);
           float acc = 0.f;
 #pragma unroll
           for (int d4 = 0; d4 < D4; ++d4) {
@@ -864,7 +869,8 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
   VSG_REQUIRE((ldq % 4) == 0 && (ldk % 4) == 0 && (ldv % 4) == 0 && aligned16(Q) && aligned16(K) && aligned16(V),
               "vsg_mha: Q/K/V must be 16-byte aligned with leading dimensions that are multiples of 4");
   dim3 grid(n_seg, n_head, (max_len + MHA_QB - 1) / MHA_QB);
-  const size_t smem = (size_t)(MHA_QB * head_dim + MHA_SK * head_dim + MHA_SK * MHA_PITCH) * sizeof(float);
+  const int sk = head_dim >= 64 ? 128 : 256;
+  const size_t smem = (size_t)(MHA_QB * head_dim + sk * head_dim + sk * MHA_PITCH) * sizeof(float);
 #define VSG_MHA_LAUNCH(DH_)                                                                                              \
   do {                                                                                                                   \
     static bool attr_done = false;                                                                                       \
