@@ -206,9 +206,12 @@ int vsg_add_layernorm(const float* x, int ldx, const float* a, int lda, const fl
 int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* out, void* stream);
 
 /* softmax(Q K^T / sqrt(head_dim)) V per segment and head on packed rows (the core of nn.MultiheadAttention,
- * model_0v10.py:109, :183; grd_model_v5.py:100-108).  Segments: seg_off int64[n_seg+1] or fixed_len rows each. */
+ * model_0v10.py:109, :183; grd_model_v5.py:100-108).  Segments: seg_off int64[n_seg+1] or fixed_len rows each.
+ * Optional work list for ragged segments (avoids empty CTAs): blk_seg / blk_q0 int32[n_blocks] = segment and first query of
+ * every 64-query block; NULL => a dense (n_seg x ceil(max_len/64)) grid. */
 int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
-            int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, void* stream);
+            int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, const int32_t* blk_seg,
+            const int32_t* blk_q0, int n_blocks, void* stream);
 
 /* Role attention (model_0v10.py:190-214): att = softmax_tracks * softmax_roles of <p2a, e2a>/sqrt(dim_enti),
  * values f32[V*Q][2E] = att[r] @ enco.  Optional: att_out f32[V*Q][2][att_ld], so_out int32[V*Q][2] = per-role

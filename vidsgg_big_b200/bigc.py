@@ -63,6 +63,7 @@ class PackedVideos(object):
         self.V, self.N, self.R = V, int(all_len.numel()), int(all_len.sum())
         self.max_tracks = max(counts) if counts else 0
         self.counts = counts
+        self.mha_blocks = linalg.mha_block_list(counts, device)     # ragged (video, 64-token block) work list of the encoder attention
 
 
 class PackedTriplets(object):
@@ -250,12 +251,13 @@ class BIG_C(object):
               "vsg_add_layernorm")
         return out
 
-    def _mha(self, qkv, d, seg_off, n_seg, fixed_len, max_len):
+    def _mha(self, qkv, d, seg_off, n_seg, fixed_len, max_len, blocks=None):
         out = torch.empty(qkv.shape[0], d, dtype=torch.float32, device=qkv.device)
         ld = qkv.stride(0)
+        bs, bq, nb = blocks if blocks is not None else (None, None, 0)
         check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * d), ld, C.c_void_p(qkv.data_ptr() + 8 * d), ld,
                             _raw(seg_off), n_seg, fixed_len, max_len, self.n_att_head, d // self.n_att_head, _raw(out), d,
-                            stream_ptr(qkv.device)), "vsg_mha")
+                            _raw(bs), _raw(bq), nb, stream_ptr(qkv.device)), "vsg_mha")
         return out
 
     def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
@@ -300,7 +302,7 @@ class BIG_C(object):
         x = enti2enco
         for lw in w["enc"]:
             qkv = gemm(m, x, lw["qkv"])
-            att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks)
+            att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks, pk.mha_blocks)
             x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"])
             x = self._add_ln(x, gemm(m, gemm(m, x, lw["l1"], relu=True), lw["l2"]), lw["n2"])
             if dbg is not None:

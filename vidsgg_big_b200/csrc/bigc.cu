@@ -209,7 +209,8 @@ template <int DH> struct MhaCfg { static constexpr int SK = DH >= 64 ? 128 : 256
 template <int DH>
 __global__ void __launch_bounds__(256, 2)
 mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, int ldk, const float* __restrict__ Vp, int ldv,
-           const int64_t* __restrict__ seg_off, int fixed_len, int n_head, float scale, float* __restrict__ Op, int ldo) {
+           const int64_t* __restrict__ seg_off, int fixed_len, int n_head, float scale, float* __restrict__ Op, int ldo,
+           const int32_t* __restrict__ blk_seg, const int32_t* __restrict__ blk_q0) {
   constexpr int MHA_SK = MhaCfg<DH>::SK;
   constexpr int KG = MHA_SK / 32;               // key groups of 32 (one per warp in phase A)
   constexpr int QH = 8 / KG;                    // query slices in phase A
@@ -218,10 +219,11 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
   float* Qs = mha_smem;                         // [64][DH] pre-scaled
   float* Vs = Qs + MHA_QB * DH;                 // [SK][DH]
   float* St = Vs + MHA_SK * DH;                 // [SK][68] scores / probabilities, transposed (key-major)
-  const int seg = blockIdx.x, head = blockIdx.y;
+  // work item = (segment, 64-query block): either listed explicitly (ragged segments: no empty CTAs) or grid (x, z)
+  const int seg = blk_seg ? blk_seg[blockIdx.x] : blockIdx.x, head = blockIdx.y;
   const int64_t row0 = seg_off ? seg_off[seg] : (int64_t)seg * fixed_len;
   const int n = seg_off ? (int)(seg_off[seg + 1] - row0) : fixed_len;
-  const int q_base = blockIdx.z * MHA_QB;
+  const int q_base = blk_seg ? blk_q0[blockIdx.x] : blockIdx.z * MHA_QB;
   if (q_base >= n) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int hc = head * DH;
@@ -860,7 +862,8 @@ extern "C" int vsg_broadcast_rows(const float* x, int period, int D, int64_t row
 }
 
 extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
-                       int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, void* stream) {
+                       int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, const int32_t* blk_seg,
+                       const int32_t* blk_q0, int n_blocks, void* stream) {
   VSG_REQUIRE(n_seg >= 0 && n_head > 0 && max_len >= 0, "vsg_mha: bad size");
   if (n_seg == 0 || max_len == 0) return VSG_OK;
   VSG_REQUIRE(Q && K && V && O, "vsg_mha: null pointer");
@@ -868,7 +871,9 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
   const float scale = 1.0f / sqrtf((float)head_dim);
   VSG_REQUIRE((ldq % 4) == 0 && (ldk % 4) == 0 && (ldv % 4) == 0 && aligned16(Q) && aligned16(K) && aligned16(V),
               "vsg_mha: Q/K/V must be 16-byte aligned with leading dimensions that are multiples of 4");
-  dim3 grid(n_seg, n_head, (max_len + MHA_QB - 1) / MHA_QB);
+  VSG_REQUIRE((blk_seg == nullptr) == (blk_q0 == nullptr), "vsg_mha: blk_seg and blk_q0 go together");
+  if (blk_seg && n_blocks == 0) return VSG_OK;
+  dim3 grid(blk_seg ? n_blocks : n_seg, n_head, blk_seg ? 1 : (max_len + MHA_QB - 1) / MHA_QB);
   const int sk = head_dim >= 64 ? 128 : 256;
   const size_t smem = (size_t)(MHA_QB * head_dim + sk * head_dim + sk * MHA_PITCH) * sizeof(float);
 #define VSG_MHA_LAUNCH(DH_)                                                                                              \
@@ -881,7 +886,7 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
       }                                                                                                                  \
       attr_done = true;                                                                                                  \
     }                                                                                                                    \
-    mha_kernel<DH_><<<grid, 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo); \
+    mha_kernel<DH_><<<grid, 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo, blk_seg, blk_q0); \
   } while (0)
   if (head_dim == 64) VSG_MHA_LAUNCH(64);
   else if (head_dim == 32) VSG_MHA_LAUNCH(32);

@@ -87,3 +87,14 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         ev1.record()
         _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, mode))
     return out
+
+
+def mha_block_list(lengths, device, qb: int = 64):
+    """(blk_seg int32[B], blk_q0 int32[B]) work list of csrc/bigc.cu mha_kernel for ragged segment lengths (host ints)."""
+    import numpy as np
+    lengths = np.asarray(lengths, dtype=np.int64)
+    nblk = (lengths + qb - 1) // qb
+    seg = np.repeat(np.arange(lengths.size, dtype=np.int32), nblk)
+    first = np.concatenate([[0], np.cumsum(nblk)])[:-1]
+    q0 = (np.arange(int(nblk.sum()), dtype=np.int64) - np.repeat(first, nblk)) * qb
+    return (torch.from_numpy(seg.astype(np.int32)).to(device), torch.from_numpy(q0.astype(np.int32)).to(device), int(nblk.sum()))
