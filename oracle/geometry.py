@@ -168,3 +168,25 @@ def pair_labels(viou: torch.Tensor, gt_so: torch.Tensor, th: float) -> torch.Ten
             s, o = pid[k].tolist()
             out[g, k] = bool(viou[s, gs] > th) and bool(viou[o, go] > th)
     return out
+
+
+def label_maps(viou: torch.Tensor, gt_5tuples: torch.Tensor, th: float, num_pred_cats: int):
+    """Base-C training labels of one video, as consumed by the trainer: the dict loop of tools/train_vidor.py:143-159
+    (pairs keyed in order of first hit: outer loop GT relation, inner loop pair order) followed by :242-256
+    (``pairid2trajids`` + multi-hot predicate matrix).  Returns None when nothing hits."""
+    n = viou.shape[0]
+    pid = pair_ids(n)
+    table = {}
+    for g in range(gt_5tuples.shape[0]):
+        gs, go = gt_5tuples[g, 3:].tolist()
+        for k in range(pid.shape[0]):
+            s, o = pid[k].tolist()
+            if bool(viou[s, gs] > th) and bool(viou[o, go] > th):
+                table.setdefault((s, o), []).append(int(gt_5tuples[g, 0]))
+    if not table:
+        return None
+    pairs = torch.tensor(list(table.keys()), dtype=torch.long)
+    multihot = torch.zeros(len(table), num_pred_cats)
+    for i, cats in enumerate(table.values()):
+        multihot[i, cats] = 1
+    return pairs, multihot

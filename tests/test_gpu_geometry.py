@@ -156,3 +156,30 @@ def test_errors_are_loud():
     from vidsgg_big_b200._cabi import VsgError
     with pytest.raises(VsgError):
         g.dura_intersection_ts(torch.zeros(2, 2, dtype=torch.long), torch.zeros(2, 2, dtype=torch.long))   # CPU tensors
+
+
+def test_prop_pair_to_gt_pred_dataset():
+    """Batched Base-C label assignment == the reference's dict loop restated in the oracle (order of pairs included)."""
+    g = _geo()
+    props, graphs = [], []
+    for sd, n in ((801, 14), (802, 9), (803, 1), (804, 20)):
+        P = synth.make_proposal(sd, n, 120, 8, 36, with_features=False)
+        props.append(P); graphs.append(synth.make_gt_graph(sd, P, 133, n_rel=(3, 12), jitter_px=1.5))
+    ref = {}
+    for P, G in zip(props, graphs):
+        viou, _, _ = og.traj_viou_matrix(P.bboxes_list, P.traj_durations, G.traj_bboxes, G.traj_durations)
+        so = torch.argmax(G.adj_matrix, dim=-1).t()
+        cats = G.traj_cat_ids[so]
+        gt5 = torch.cat([G.pred_cat_ids[:, None], cats, so], -1)
+        ref[G.video_name] = og.label_maps(viou, gt5, 0.5, 133) if P.num_proposals > 1 else None
+    out, stats = g.prop_pair_to_gt_pred([p.to(DEV) for p in props], [x.to(DEV) for x in graphs], 0.5, 133)
+    assert stats["gt_traj"] == sum(x.num_trajs for x in graphs) and stats["hit_gt_traj"] > 0
+    n_checked = 0
+    for name, r in ref.items():
+        if r is None:
+            assert out[name] is None
+            continue
+        assert torch.equal(out[name][0].cpu(), r[0]), name
+        assert torch.equal(out[name][1].cpu(), r[1]), name
+        n_checked += 1
+    assert n_checked >= 2

@@ -243,3 +243,52 @@ def enti_viou_align(gt_adj: torch.Tensor, proposal, gt_graph, positive_vIoU_th: 
     best_gt = torch.argmax(viou, dim=1)
     aligned = gt_adj.to(viou.device)[:, :, best_gt] * row_has[None, None, :].float()
     return aligned, viou
+
+
+def prop_pair_to_gt_pred(proposals: Sequence, gt_graphs: Sequence, positive_vIoU_th: float, num_pred_cats: int):
+    """Base-C training label assignment for a whole dataset (tools/train_vidor.py:80-170 "takes around 1.5 hours" + the
+    multi-hot construction of :242-256): ONE launch computes every video's proposal x GT-trajectory vIoU matrix, then a
+    label kernel per video marks the ordered proposal pairs (s, o) whose subject AND object exceed the threshold for a GT relation.
+
+    Returns ``(label_maps, stats)``: ``label_maps[video_name] = None | (pairid2trajids i64[num_pairs,2], multihot f32[num_pairs,P])``
+    with pairs in the reference's order (first hit: GT relation major, pair minor); ``stats`` = hit counters the reference prints.
+    GT ``traj_durations`` are closed spans.
+    """
+    live = [i for i, g in enumerate(gt_graphs) if g.num_trajs > 0 and g.num_preds > 0 and proposals[i].num_proposals > 0]
+    out = {g.video_name: None for g in gt_graphs}
+    stats = dict(hit_gt_traj=0, gt_traj=0, hit_gt_pred=0, gt_pred=0)
+    if not live:
+        return out, stats
+    lp, lg = [proposals[i] for i in live], [gt_graphs[i] for i in live]
+    A = TrackTable.from_containers(lp)
+    B = TrackTable.from_containers(lg, device=A.boxes.device)
+    viou, _, _, seg, _ = traj_viou_batched(A, B, want_spans=False, want_mask=False)
+    dev = viou.device
+    for k, (p, g) in enumerate(zip(lp, lg)):
+        n, ng = p.num_proposals, g.num_trajs
+        v = viou[seg[k]:seg[k + 1]].view(n, ng)
+        stats["gt_traj"] += ng
+        stats["hit_gt_traj"] += int((v > positive_vIoU_th).any(dim=0).sum())
+        so = torch.argmax(g.adj_matrix.to(dev), dim=-1).t().contiguous()
+        stats["gt_pred"] += g.num_preds
+        if n < 2:
+            continue
+        lab = pair_labels(v, so, positive_vIoU_th)                       # bool [n_gt_pred, n(n-1)]
+        gi, pi = lab.nonzero(as_tuple=True)                              # sorted by GT relation, then pair: the reference's loop order
+        stats["hit_gt_pred"] += int(torch.unique(gi).numel())
+        if gi.numel() == 0:
+            continue
+        uniq, inv = torch.unique(pi, return_inverse=True)               # sorted by pair id; re-order by first appearance
+        first = torch.full((uniq.numel(),), gi.numel(), dtype=torch.long, device=dev).scatter_reduce_(
+            0, inv, torch.arange(gi.numel(), device=dev), reduce="amin")
+        order = torch.argsort(first)
+        rank = torch.empty_like(order)
+        rank[order] = torch.arange(order.numel(), device=dev)
+        pair_ids_sorted = uniq[order]
+        s = pair_ids_sorted // (n - 1)
+        r = pair_ids_sorted % (n - 1)
+        o = r + (r >= s).long()
+        multihot = torch.zeros(uniq.numel(), num_pred_cats, device=dev)
+        multihot[rank[inv], g.pred_cat_ids.to(dev)[gi]] = 1
+        out[g.video_name] = (torch.stack([s, o], 1), multihot)
+    return out, stats
