@@ -91,30 +91,43 @@ __global__ void rank_kernel(const double* __restrict__ scores, const int64_t* __
 }
 
 // ---- 3. ov[p][g] for equal triplets ---------------------------------------------------------------
+// One warp per PREDICTION: lanes scan the video's GT relations (triplet compare + temporal overlap test, one GT per lane),
+// non-candidates are written directly (-1 / 0), candidates are collected with a ballot and then processed by the whole warp
+// (coalesced box loads over the overlap).  Most (pred, GT) pairs differ in their triplet, so this avoids spending a warp on each.
 template <typename TP, typename TG>
 __global__ void rel_ov_kernel(VsgRelTable pr, VsgRelTable gt, int n_vid, const int64_t* __restrict__ ov_off,
                               const double* __restrict__ vol_p, const double* __restrict__ vol_g, double* __restrict__ ov) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const int64_t total = ov_off[n_vid];
   const TP* pb = reinterpret_cast<const TP*>(pr.boxes);
   const TG* gb = reinterpret_cast<const TG*>(gt.boxes);
-  for (int64_t job = warp; job < total; job += n_warps) {
-    const int v = find_segment(ov_off, n_vid, job);
+  for (int64_t p = warp; p < pr.n_rel; p += n_warps) {
+    const int v = find_segment(pr.vid_off, n_vid, p);
     const int64_t g0 = gt.vid_off[v];
     const int ng = (int)(gt.vid_off[v + 1] - g0);
-    const int64_t local = job - ov_off[v];
-    const int64_t p = pr.vid_off[v] + local / ng;
-    const int64_t g = g0 + local % ng;
+    if (ng == 0) continue;
     const int64_t* rp = pr.rel + 7 * p;
-    const int64_t* rg = gt.rel + 7 * g;
-    double res = -1.0;
-    if (rp[0] == rg[0] && rp[1] == rg[1] && rp[2] == rg[2]) {
-      const int64_t s1 = rp[5], e1 = rp[6], s2 = rg[5], e2 = rg[6];
-      if (s1 >= e2 || e1 <= s2) {
-        res = 0.0;
-      } else {
+    const int64_t t0 = rp[0], t1 = rp[1], t2 = rp[2], s1 = rp[5], e1 = rp[6];
+    double* out = ov + ov_off[v] + (p - pr.vid_off[v]) * ng;
+    for (int gbase = 0; gbase < ng; gbase += 32) {
+      const int gi = gbase + lane;
+      bool cand = false;
+      if (gi < ng) {
+        const int64_t* rg = gt.rel + 7 * (g0 + gi);
+        if (rg[0] == t0 && rg[1] == t1 && rg[2] == t2) {
+          if (s1 >= rg[6] || e1 <= rg[5]) out[gi] = 0.0; else cand = true;
+        } else {
+          out[gi] = -1.0;
+        }
+      }
+      unsigned todo = __ballot_sync(0xffffffffu, cand);
+      while (todo) {
+        const int l = __ffs(todo) - 1;
+        todo &= todo - 1;
+        const int64_t g = g0 + gbase + l;
+        const int64_t* rg = gt.rel + 7 * g;
+        const int64_t s2 = rg[5], e2 = rg[6];
         const int64_t lo = s1 > s2 ? s1 : s2, hi = e1 < e2 ? e1 : e2;
         double role_iou[2];
 #pragma unroll
@@ -125,10 +138,9 @@ __global__ void rel_ov_kernel(VsgRelTable pr, VsgRelTable gt, int n_vid, const i
           const double o = warp_overlap<TP, TG>(pb, rowp, gb, rowg, hi - lo, lane);
           role_iou[role] = o / (vol_p[2 * p + role] + vol_g[2 * g + role] - o);
         }
-        res = fmin(role_iou[0], role_iou[1]);
+        if (lane == 0) out[gbase + l] = fmin(role_iou[0], role_iou[1]);
       }
     }
-    if (lane == 0) ov[job] = res;
   }
 }
 
@@ -229,8 +241,7 @@ extern "C" int vsg_rel_viou_match(const VsgRelTable* pred, const double* scores,
   }
   if (np > 0 && ng > 0) {
     VSG_REQUIRE(ov_ws, "vsg_rel_viou_match: null ov workspace");
-    // upper bound of jobs for the grid: np * ng is an over-estimate of sum_v np_v*ng_v; use it only to size the grid
-    const int g = grid_warps(np * (ng / (n_vid > 0 ? n_vid : 1) + 1), 8);
+    const int g = grid_warps(np, 8);   // one warp per prediction
     if (pred->box_f64 && gt->box_f64) rel_ov_kernel<double, double><<<g, 256, 0, st>>>(*pred, *gt, n_vid, ov_off, vol_pred_ws, vol_gt_ws, ov_ws);
     else if (pred->box_f64) rel_ov_kernel<double, float><<<g, 256, 0, st>>>(*pred, *gt, n_vid, ov_off, vol_pred_ws, vol_gt_ws, ov_ws);
     else if (gt->box_f64) rel_ov_kernel<float, double><<<g, 256, 0, st>>>(*pred, *gt, n_vid, ov_off, vol_pred_ws, vol_gt_ws, ov_ws);

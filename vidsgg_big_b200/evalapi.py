@@ -65,16 +65,22 @@ class PackedRelations(object):
 
     # ---- dict path ---------------------------------------------------------------------------
     @classmethod
-    def from_dicts(cls, per_video: Sequence[List[dict]], vocab: Dict[tuple, int], device, with_scores: bool):
+    def from_dicts(cls, per_video: Sequence[List[dict]], vocab: Dict[tuple, int], device, with_scores: bool,
+                   candidates: Optional[Sequence[set]] = None):
+        """``candidates[v]`` (optional): the triplets that occur in video v's ground truth.  A prediction with any other
+        triplet can never be matched (its vIoU is never evaluated by the reference either, visual_relation_detection.py:16-17),
+        so its box lists are not converted -- it keeps a zero-length track and only takes part in the ranking."""
         rows, boxes, lens, tstart, scores, vid_off = [], [], [], [], [], [0]
         trk = 0
-        for rels in per_video:
+        empty = np.zeros((0, 4), np.float64)
+        for v, rels in enumerate(per_video):
+            cand = None if candidates is None else candidates[v]
             for r in rels:
                 t = tuple(r["triplet"])
                 tid = vocab.setdefault(t, len(vocab))
                 s, e = int(r["duration"][0]), int(r["duration"][1])
                 for key in ("sub_traj", "obj_traj"):
-                    b = np.asarray(r[key], dtype=np.float64).reshape(-1, 4)
+                    b = np.array(r[key], dtype=np.float64).reshape(-1, 4) if (cand is None or t in cand) else empty
                     boxes.append(b)
                     lens.append(b.shape[0])
                     tstart.append(s)
@@ -250,7 +256,8 @@ def _match_dicts(gt_lists, pred_lists, thr):
     dev = _device()
     vocab: Dict[tuple, int] = {}
     g = PackedRelations.from_dicts(gt_lists, vocab, dev, with_scores=False)
-    p = PackedRelations.from_dicts(pred_lists, vocab, dev, with_scores=True)
+    cands = [set(tuple(r["triplet"]) for r in rels) for rels in gt_lists]
+    p = PackedRelations.from_dicts(pred_lists, vocab, dev, with_scores=True, candidates=cands)
     m = match_relations(p, g, thr)
     return m.hit.cpu().numpy(), m.gt2det.cpu().numpy().astype(int), p.vid_off_host, g.vid_off_host
 
