@@ -275,7 +275,7 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
           kreg[4 * d4] = v.x; kreg[4 * d4 + 1] = v.y; kreg[4 * d4 + 2] = v.z; kreg[4 * d4 + 3] = v.w;
         }
         float* srow = St + key * MHA_PITCH + qh * QPS;
-#pragma unroll 4
+#pragma unroll 8
         for (int q = 0; q < QPS; ++q) {
           const float4* qp = reinterpret_cast<const float4*>(Qs + (qh * QPS + q) * DH);
           float acc = 0.f;
@@ -332,6 +332,7 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
       __syncwarp();
       if (DH >= 32 ? (lane < DH) : true) {
         const float* prow = St + 8 * warp + grp * QPL;
+#pragma unroll 4
         for (int kr = 0; kr < kc; ++kr) {
           float pv[QPL];
           if (QPL == 8) {
