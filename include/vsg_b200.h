@@ -167,6 +167,28 @@ int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* 
              const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
              int accumulate, const float* residual, int ld_res, float* C, int ldc, void* stream);
 
+/* Full-option form of vsg_gemm.  Extras:
+ *   C_lo   optional second output: x - trunc_tf32(x) of every stored value (lets the NEXT 3xTF32 GEMM use this result as its
+ *          pre-split "W" operand, e.g. K and V^T of an attention layer);
+ *   batch  > 1: `batch` independent problems of extent M x N x K inside larger operands (attention QK^T / PV over (video, head)):
+ *          problem p -> outer = p / batch_inner, inner = p % batch_inner; A rows / cols, W rows / cols and the C pointer are offset
+ *          by outer * x_outer + inner * x_inner (rows, columns: elements; C: elements).  a_rows/a_cols/w_rows/w_cols = full operand
+ *          extents (TMA bounds).  Requires a tensor-core mode, K %% 32 == 0, no bias / residual. */
+typedef struct VsgGemmArgs {
+  int mode;
+  const float* A; int lda; int a_rows; int a_cols;
+  const float* W_hi; const float* W_lo; int ldw; int w_rows; int w_cols;
+  int M, N, K;
+  const float* bias; const float* rowbias; const int32_t* rb_index; int rb_period; int ld_rb; int relu; int accumulate;
+  const float* residual; int ld_res;
+  float* C; float* C_lo; int ldc;
+  int batch, batch_inner;
+  int a_row_outer, a_row_inner, a_col_outer, a_col_inner;
+  int b_row_outer, b_row_inner, b_col_outer, b_col_inner;
+  long long c_outer, c_inner;
+} VsgGemmArgs;
+int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
+
 /* Validation knob for VSG_GEMM_3XTF32: 1 = the in-kernel split also rewrites the A tile with its masked high part;
  * 0 (default) relies on tcgen05 kind::tf32 ignoring the low 13 mantissa bits (checked bit-exact by tests). Returns the old value. */
 int vsg_gemm_set_store_hi(int on);
@@ -212,6 +234,12 @@ int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* o
 int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
             int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, const int32_t* blk_seg,
             const int32_t* blk_q0, int n_blocks, void* stream);
+
+/* Glue of the tensor-core attention path (QK^T and PV are batched vsg_gemm_ex problems, one per (video, head)):
+ * in-place row softmax of scale*S over the first n (<= 256) columns, and the transpose of an activation block
+ * X[rows][cols] (ld) into T_hi[cols][rows] (ld_t) plus its tf32 low part T_lo (may be NULL). */
+int vsg_softmax_rows(float* S, int ld, int n, int64_t rows, float scale, void* stream);
+int vsg_transpose_split(const float* X, int ld, int64_t rows, int cols, float* T_hi, float* T_lo, int64_t ld_t, void* stream);
 
 /* Role attention (model_0v10.py:190-214): att = softmax_tracks * softmax_roles of <p2a, e2a>/sqrt(dim_enti),
  * values f32[V*Q][2E] = att[r] @ enco.  Optional: att_out f32[V*Q][2][att_ld], so_out int32[V*Q][2] = per-role

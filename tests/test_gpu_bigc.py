@@ -230,3 +230,28 @@ def test_bigc_full_dims_batched_equals_single():
     for b, s in zip(batched, single):
         assert torch.equal(b[0], s[0]) and torch.equal(b[2], s[2]) and torch.equal(b[3], s[3])
         assert torch.allclose(b[1], s[1], rtol=1e-5, atol=1e-7)
+
+
+@pytest.mark.parametrize("precision", ["3xtf32", "tf32"])
+def test_tensor_core_attention_equals_simt_attention(precision):
+    """Decoder self-attention as batched tcgen05 GEMMs (QK^T, PV) + softmax / transpose glue vs the fp32 SIMT kernel."""
+    cfg = synth.vidvrd_config()
+    st = synth.make_bigc_state(1, cfg)
+    model = _model(cfg, st, precision)
+    V, Q, d = 3, cfg["num_querys"], cfg["dim_pred"]
+    g = torch.Generator(device="cpu").manual_seed(3)
+    qkv = (torch.randn(V * Q, 3 * d, generator=g) * 0.7).to(DEV)
+    lo = torch.empty_like(qkv)
+    from vidsgg_big_b200._cabi import lib, check, ptr, stream_ptr
+    hi = torch.empty_like(qkv)
+    check(lib().vsg_split_tf32(ptr(qkv), ptr(hi), ptr(lo), qkv.numel(), stream_ptr(qkv.device)), "split")
+    ref = model._mha(qkv, d, None, V, Q, Q)
+    got = model._mha_tc(qkv, lo if precision == "3xtf32" else None, V, Q, d)
+    # fp64 reference
+    q, k, v = [t.double().view(V, Q, 8, d // 8).transpose(1, 2) for t in (qkv[:, :d], qkv[:, d:2 * d], qkv[:, 2 * d:])]
+    exact = (torch.softmax(q @ k.transpose(-1, -2) / (d // 8) ** 0.5, -1) @ v).transpose(1, 2).reshape(V * Q, d)
+    e_ref = (ref.double() - exact).abs().max().item()
+    e_got = (got.double() - exact).abs().max().item()
+    print("attention max err vs fp64: simt %.2e  tensor-core %s %.2e" % (e_ref, precision, e_got))
+    assert e_ref < 1e-5
+    assert e_got < (2e-5 if precision == "3xtf32" else 5e-3)

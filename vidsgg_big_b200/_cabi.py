@@ -26,6 +26,18 @@ class VsgRelTable(C.Structure):
                 ("vol_full_track", i32)]
 
 
+class VsgGemmArgs(C.Structure):
+    _fields_ = [("mode", i32), ("A", p), ("lda", i32), ("a_rows", i32), ("a_cols", i32),
+                ("W_hi", p), ("W_lo", p), ("ldw", i32), ("w_rows", i32), ("w_cols", i32),
+                ("M", i32), ("N", i32), ("K", i32),
+                ("bias", p), ("rowbias", p), ("rb_index", p), ("rb_period", i32), ("ld_rb", i32), ("relu", i32), ("accumulate", i32),
+                ("residual", p), ("ld_res", i32), ("C", p), ("C_lo", p), ("ldc", i32),
+                ("batch", i32), ("batch_inner", i32),
+                ("a_row_outer", i32), ("a_row_inner", i32), ("a_col_outer", i32), ("a_col_inner", i32),
+                ("b_row_outer", i32), ("b_row_inner", i32), ("b_col_outer", i32), ("b_col_inner", i32),
+                ("c_outer", C.c_longlong), ("c_inner", C.c_longlong)]
+
+
 class VsgError(RuntimeError):
     pass
 
@@ -48,7 +60,10 @@ SIGNATURES = {
     "vsg_eval_records_host": (i32, [p, p, p, p, p, p, i32, p, i32, p, i32, p]),
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
+    "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
+    "vsg_softmax_rows": (i32, [p, i32, i32, i64, f32, p]),
+    "vsg_transpose_split": (i32, [p, i32, i64, i32, p, p, i64, p]),
     "vsg_gemm_set_store_hi": (i32, [i32]),
     "vsg_gemm_force_bn": (i32, [i32]),
     "vsg_bbox_feat_mlp1": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p, p]),

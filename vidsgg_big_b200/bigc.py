@@ -115,6 +115,7 @@ class BIG_C(object):
             raise VsgError("attention kernel is instantiated for head_dim 16 / 32 / 64")
         self.precision = precision
         self.mode = linalg.MODES[precision]
+        self.attention = "tc"      # decoder self-attention: "tc" = batched tcgen05 GEMMs (+ glue), "simt" = fp32 SIMT kernel
         self.topk = 10
         self.device = None
         self._w = None
@@ -260,6 +261,29 @@ class BIG_C(object):
                             _raw(bs), _raw(bq), nb, stream_ptr(qkv.device)), "vsg_mha")
         return out
 
+    def _mha_tc(self, qkv, qkv_lo, n_seg, Q, d):
+        """Self-attention of ``n_seg`` fixed-length segments (the Q decoder queries of every video) on the tensor cores:
+        S = Q K^T and O = P V are batched tcgen05 GEMMs (one problem per (segment, head)), softmax / V^T are glue kernels."""
+        m, dev = self.mode, qkv.device
+        H = self.n_att_head
+        dh = d // H
+        rows = n_seg * Q
+        L = lib()
+        sp = stream_ptr(dev)
+        S = torch.empty(n_seg * H * Q, Q, dtype=torch.float32, device=dev)
+        linalg.gemm_batched(m, qkv[:, :d], qkv[:, d:2 * d], None if qkv_lo is None else qkv_lo[:, d:2 * d], Q, Q, dh, S, Q,
+                            n_seg * H, H, a_off=(Q, 0, 0, dh), b_off=(Q, 0, 0, dh), c_off=(H * Q * Q, Q * Q))
+        check(L.vsg_softmax_rows(_raw(S), Q, Q, S.shape[0], float(1.0 / math.sqrt(dh)), sp), "vsg_softmax_rows")
+        ldt = (rows + 3) // 4 * 4
+        vt_hi = torch.empty(d, ldt, dtype=torch.float32, device=dev)
+        vt_lo = torch.empty(d, ldt, dtype=torch.float32, device=dev) if m == linalg.X3TF32 else None
+        check(L.vsg_transpose_split(C.c_void_p(qkv.data_ptr() + 8 * d), qkv.stride(0), rows, d, _raw(vt_hi), _raw(vt_lo), ldt, sp),
+              "vsg_transpose_split")
+        att = torch.empty(rows, d, dtype=torch.float32, device=dev)
+        linalg.gemm_batched(m, S, vt_hi[:, :rows], None if vt_lo is None else vt_lo[:, :rows], Q, dh, Q, att, d, n_seg * H, H,
+                            a_off=(H * Q, Q, 0, 0), b_off=(0, dh, 0, Q), c_off=(Q * d, dh))
+        return att
+
     def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
         """model_0v10.py:434-475 for the whole batch.  Returns (logits [V*Q, P], so int32[V*Q,2], extras)."""
         w, m, dev = self._w, self.mode, self.device
@@ -328,8 +352,15 @@ class BIG_C(object):
             # fc_pred2att are video-independent -- computed once on Q rows, then broadcast
             x = w["query_init"] if li == 0 else query
             nv = 1 if li == 0 else V
-            qkv = gemm(m, x, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
-            att = self._mha(qkv, Pd, None, nv, Q, Q)
+            use_tc = self.attention == "tc" and m != linalg.SIMT and (Pd // self.n_att_head) % 32 == 0 and Q % 32 == 0
+            if use_tc:
+                qkv = torch.empty(x.shape[0], 3 * Pd, dtype=torch.float32, device=dev)
+                qkv_lo = torch.empty_like(qkv) if m == linalg.X3TF32 else None
+                gemm(m, x, lw["qkv"], out=qkv, rowbias=lw["posb"], rb_period=Q, out_lo=qkv_lo)
+                att = self._mha_tc(qkv, qkv_lo, nv, Q, Pd)
+            else:
+                qkv = gemm(m, x, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
+                att = self._mha(qkv, Pd, None, nv, Q, Q)
             x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"], post=w["pos"], period=Q)
             p2a = gemm(m, x, lw["p2a"])
             if li == 0:

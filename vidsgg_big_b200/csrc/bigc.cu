@@ -373,6 +373,69 @@ mha_kernel(const float* __restrict__ Qp, int ldq, const float* __restrict__ Kp, 
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Tensor-core attention helpers (fixed-length segments: the 192 decoder queries of every video).  QK^T and PV run as batched
+// tcgen05 GEMMs (csrc/gemm.cu, one problem per (video, head)); these two kernels are the glue:
+//   softmax_rows_kernel   P = softmax(scale * S) row-wise, in place; one warp per row, n <= 256 columns
+//   transpose_split_kernel  V part of the packed qkv buffer [rows][ld] -> VT_hi / VT_lo [cols][ld_t] (K-major B operand of the
+//                           PV GEMM + its tf32 low part), 32x32 smem tiles
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(float* __restrict__ S, int ld, int n, int64_t rows, float scale) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  for (int64_t r = warp; r < rows; r += n_warps) {
+    float* row = S + r * ld;
+    float x[8];
+    float mx = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < n ? row[c] * scale : -INFINITY;
+      mx = fmaxf(mx, x[i]);
+    }
+    mx = warp_max(mx);
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      x[i] = c < n ? expf(x[i] - mx) : 0.f;
+      sum += x[i];
+    }
+    sum = warp_sum(sum);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int c = lane + 32 * i;
+      if (c < n) row[c] = x[i] / sum;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ X, int ld, int64_t rows, int cols, float* __restrict__ Thi, float* __restrict__ Tlo,
+                       int64_t ld_t) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;   // 32 x 8
+  for (int i = ty; i < 32; i += 8) {
+    const int64_t r = r0 + i;
+    tile[i][tx] = (r < rows && c0 + tx < cols) ? X[r * ld + c0 + tx] : 0.f;
+  }
+  __syncthreads();
+  for (int i = ty; i < 32; i += 8) {
+    const int c = c0 + i;
+    const int64_t r = r0 + tx;
+    if (c < cols && r < rows) {
+      const float v = tile[tx][i];
+      const float h = __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+      Thi[(int64_t)c * ld_t + r] = v;
+      if (Tlo) Tlo[(int64_t)c * ld_t + r] = v - h;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Role attention of RoleAttnDecoderLayer (model_0v10.py:190-214) for every video:
 //   logits[r][q][e] = <p2a[q][r-half], e2a[e][r-half]> / sqrt(dim_enti)
 //   att = softmax_e(logits) * softmax_r(logits);   values[r][q] = sum_e att[r][q][e] * enco[e]
@@ -895,6 +958,23 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
   else { set_error("vsg_mha: head_dim %d unsupported (16, 32, 64)", head_dim); return VSG_E_UNSUPPORTED; }
 #undef VSG_MHA_LAUNCH
   return check_launch("vsg_mha");
+}
+
+extern "C" int vsg_softmax_rows(float* S, int ld, int n, int64_t rows, float scale, void* stream) {
+  VSG_REQUIRE(rows >= 0 && n >= 1 && n <= 256 && ld >= n, "vsg_softmax_rows: 1 <= n <= 256 <= ld required");
+  if (rows == 0) return VSG_OK;
+  VSG_REQUIRE(S != nullptr, "vsg_softmax_rows: null pointer");
+  softmax_rows_kernel<<<grid_cap((rows + 7) / 8, 8), 256, 0, (cudaStream_t)stream>>>(S, ld, n, rows, scale);
+  return check_launch("vsg_softmax_rows");
+}
+
+extern "C" int vsg_transpose_split(const float* X, int ld, int64_t rows, int cols, float* T_hi, float* T_lo, int64_t ld_t, void* stream) {
+  VSG_REQUIRE(rows >= 0 && cols >= 0 && ld >= cols && ld_t >= rows, "vsg_transpose_split: bad sizes");
+  if (rows == 0 || cols == 0) return VSG_OK;
+  VSG_REQUIRE(X && T_hi, "vsg_transpose_split: null pointer");
+  dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
+  transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, cols, T_hi, T_lo, ld_t);
+  return check_launch("vsg_transpose_split");
 }
 
 extern "C" int vsg_role_attention(const float* p2a, const float* e2a, const float* enco, const int32_t* seg, int n_vid, int Q, int E,

@@ -50,7 +50,30 @@ struct GemmEpilogue {
   int ldc;
   int M, N, K;
   int store_hi;             // 3xTF32: also write the masked high part back (0 = rely on the MMA ignoring the low 13 bits)
+  float* C_lo;              // optional: x - trunc_tf32(x) of every stored value (the B-side low part for a following 3xTF32 GEMM)
+  // batched problems: tile -> (problem p, m block, n block); p -> (outer = p / batch_inner, inner = p % batch_inner).
+  // TMA coordinates and the C pointer are offset per problem; M / N are per-problem extents (batch == 1: plain GEMM).
+  int batch, batch_inner;
+  int a_row_outer, a_row_inner, a_col_outer, a_col_inner;
+  int b_row_outer, b_row_inner, b_col_outer, b_col_inner;
+  long long c_outer, c_inner;
 };
+
+struct TileCoord { int m0, n0, a_row, a_col, b_row, b_col; long long c_off; };
+__device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile, int tiles_m, int tiles_n, int BN_) {
+  TileCoord t;
+  const int per = tiles_m * tiles_n;
+  const int p = tile / per, in = tile - p * per;
+  const int outer = p / ep.batch_inner, inner = p - outer * ep.batch_inner;
+  t.m0 = (in / tiles_n) * 128;
+  t.n0 = (in % tiles_n) * BN_;
+  t.a_row = t.m0 + outer * ep.a_row_outer + inner * ep.a_row_inner;
+  t.a_col = outer * ep.a_col_outer + inner * ep.a_col_inner;
+  t.b_row = t.n0 + outer * ep.b_row_outer + inner * ep.b_row_inner;
+  t.b_col = outer * ep.b_col_outer + inner * ep.b_col_inner;
+  t.c_off = outer * ep.c_outer + inner * ep.c_inner;
+  return t;
+}
 
 // ---------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -199,7 +222,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
-  const int n_tiles = tiles_m * tiles_n;
+  const int n_tiles = tiles_m * tiles_n * ep.batch;
   const int kblocks = (ep.K + BK - 1) / BK;
 
   if (warp == 0 && lane == 0) {
@@ -234,14 +257,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+        const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
         for (int kb = 0; kb < kblocks; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
           mbar_expect_tx(&full[stage], TILE_A + (MODE == 2 ? 2 : 1) * CF::TILE_B);
-          tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK, m0);
-          tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK, n0);
-          if (MODE == 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK, n0);
+          tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
+          tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
+          if (MODE == 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -288,7 +311,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const int m0 = (tile / tiles_n) * BM, n0 = (tile % tiles_n) * BN;
+      const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
+      const int m0 = tc.m0, n0 = tc.n0;
       const int row = m0 + row_in_tile;
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
@@ -299,7 +323,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int ri = ep.rb_index ? ep.rb_index[row] : (row % ep.rb_period);
         rb = ep.rowbias + (size_t)ri * ep.ld_rb;
       }
-      float* crow = ep.C + (size_t)(row_ok ? row : 0) * ep.ldc;
+      float* crow = ep.C + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc;
+      float* crow_lo = ep.C_lo ? ep.C_lo + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc : nullptr;
       const float* res = (row_ok && ep.residual) ? ep.residual + (size_t)row * ep.ld_res : nullptr;
       const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                           ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
@@ -329,6 +354,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
               *dst = v;
+              if (crow_lo) {
+                float4 l;
+                l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+                l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+                *reinterpret_cast<float4*>(crow_lo + col0 + j) = l;
+              }
             }
           } else {
 #pragma unroll
@@ -342,6 +373,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (ep.relu) v = fmaxf(v, 0.f);
                 if (res) v += res[col];
                 crow[col] = v;
+                if (crow_lo) crow_lo[col] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
               }
             }
           }
@@ -436,6 +468,7 @@ gemm_simt_kernel(const float* __restrict__ A, int lda, const float* __restrict__
       if (ep.relu) v = fmaxf(v, 0.f);
       if (ep.residual) v += ep.residual[(size_t)row * ep.ld_res + col];
       *dst = v;
+      if (ep.C_lo) ep.C_lo[(size_t)row * ep.ldc + col] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
     }
   }
 }
@@ -513,14 +546,15 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, int box
 }
 
 template <int MODE, int BN_>
-static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, int ldw, const GemmEpilogue& ep, cudaStream_t st) {
+static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const float* Wl, int ldw, int w_rows, int w_cols,
+                     const GemmEpilogue& ep, cudaStream_t st) {
   using CF = Cfg<MODE, BN_>;
   CUtensorMap mA, mBh, mBl;
-  int rc = get_tensor_map(A, ep.M, ep.K, lda, BM, CF::BK, &mA);
+  int rc = get_tensor_map(A, a_rows, a_cols, lda, BM, CF::BK, &mA);
   if (rc) return rc;
-  rc = get_tensor_map(Wh, ep.N, ep.K, ldw, BN_, CF::BK, &mBh);
+  rc = get_tensor_map(Wh, w_rows, w_cols, ldw, BN_, CF::BK, &mBh);
   if (rc) return rc;
-  if (MODE == 2) { rc = get_tensor_map(Wl, ep.N, ep.K, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
+  if (MODE == 2) { rc = get_tensor_map(Wl, w_rows, w_cols, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
@@ -530,8 +564,8 @@ static int launch_tc(const float* A, int lda, const float* Wh, const float* Wl, 
     }
     attr_set = true;
   }
-  const int tiles = ((ep.M + BM - 1) / BM) * ((ep.N + BN_ - 1) / BN_);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
+  const long long tiles = (long long)((ep.M + BM - 1) / BM) * ((ep.N + BN_ - 1) / BN_) * ep.batch;
+  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
   gemm_tc_kernel<MODE, BN_><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, ep);
   return check_launch("vsg_gemm(tcgen05)");
 }
@@ -560,31 +594,65 @@ extern "C" int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, v
   return check_launch("vsg_split_tf32");
 }
 
-extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
-                        const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
-                        int accumulate, const float* residual, int ld_res, float* C, int ldc, void* stream) {
+extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
+  VSG_REQUIRE(a != nullptr, "vsg_gemm_ex: null args");
+  const int M = a->M, N = a->N, K = a->K;
   VSG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vsg_gemm: negative size");
+  const int batch = a->batch > 0 ? a->batch : 1;
   if (M == 0 || N == 0) return VSG_OK;
-  VSG_REQUIRE(A && W_hi && C, "vsg_gemm: null matrix pointer");
-  VSG_REQUIRE(lda >= K && ldw >= K && ldc >= N, "vsg_gemm: leading dimension smaller than extent");
-  VSG_REQUIRE(rowbias == nullptr || rb_index != nullptr || rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
+  VSG_REQUIRE(a->A && a->W_hi && a->C, "vsg_gemm: null matrix pointer");
+  VSG_REQUIRE(a->lda >= K && a->ldw >= K && a->ldc >= N, "vsg_gemm: leading dimension smaller than extent");
+  VSG_REQUIRE(a->rowbias == nullptr || a->rb_index != nullptr || a->rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
   GemmEpilogue ep;
-  ep.bias = bias; ep.rowbias = rowbias; ep.rb_index = rb_index; ep.rb_period = rb_period; ep.ld_rb = ld_rb;
+  ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
   ep.store_hi = g_store_hi;
-  ep.relu = relu; ep.accumulate = accumulate; ep.residual = residual; ep.ld_res = ld_res; ep.C = C; ep.ldc = ldc; ep.M = M; ep.N = N; ep.K = K;
+  ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
+  ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
+  ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
+  ep.a_row_outer = a->a_row_outer; ep.a_row_inner = a->a_row_inner; ep.a_col_outer = a->a_col_outer; ep.a_col_inner = a->a_col_inner;
+  ep.b_row_outer = a->b_row_outer; ep.b_row_inner = a->b_row_inner; ep.b_col_outer = a->b_col_outer; ep.b_col_inner = a->b_col_inner;
+  ep.c_outer = a->c_outer; ep.c_inner = a->c_inner;
+  if (batch == 1) {
+    ep.a_row_outer = ep.a_row_inner = ep.a_col_outer = ep.a_col_inner = 0;
+    ep.b_row_outer = ep.b_row_inner = ep.b_col_outer = ep.b_col_inner = 0;
+    ep.c_outer = ep.c_inner = 0;
+  }
+  const int a_rows = batch > 1 ? a->a_rows : M, a_cols = batch > 1 ? a->a_cols : K;
+  const int w_rows = batch > 1 ? a->w_rows : N, w_cols = batch > 1 ? a->w_cols : K;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool tma_ok = (lda % 4 == 0) && (ldw % 4 == 0) && aligned16(A) && aligned16(W_hi) && K >= 1;
+  const bool tma_ok = (a->lda % 4 == 0) && (a->ldw % 4 == 0) && aligned16(a->A) && aligned16(a->W_hi) && K >= 1;
+  const int mode = a->mode;
+  if (batch > 1) {
+    VSG_REQUIRE(mode != 0 && tma_ok, "vsg_gemm_ex: batched problems need a tensor-core mode and TMA-compatible operands");
+    VSG_REQUIRE(K % 32 == 0, "vsg_gemm_ex: batched problems need K %% 32 == 0 (K blocks must not straddle problems)");
+    VSG_REQUIRE(a->a_rows > 0 && a->a_cols > 0 && a->w_rows > 0 && a->w_cols > 0, "vsg_gemm_ex: batched problems need the full operand extents");
+    VSG_REQUIRE(!a->bias && !a->rowbias && !a->residual && !a->accumulate, "vsg_gemm_ex: batched problems take no bias / residual / accumulate");
+  }
   if (mode == 0 || !tma_ok) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    gemm_simt_kernel<<<grid, 256, 0, st>>>(A, lda, W_hi, ldw, ep);
+    gemm_simt_kernel<<<grid, 256, 0, st>>>(a->A, a->lda, a->W_hi, a->ldw, ep);
     return check_launch("vsg_gemm(simt)");
   }
   const bool wide = use_bn256(N) && g_force_bn != 128;
-  if (mode == 1) return wide ? launch_tc<1, 256>(A, lda, W_hi, nullptr, ldw, ep, st) : launch_tc<1, 128>(A, lda, W_hi, nullptr, ldw, ep, st);
+  if (mode == 1)
+    return wide ? launch_tc<1, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st)
+                : launch_tc<1, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st);
   if (mode == 2) {
-    VSG_REQUIRE(W_lo && aligned16(W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
-    return wide ? launch_tc<2, 256>(A, lda, W_hi, W_lo, ldw, ep, st) : launch_tc<2, 128>(A, lda, W_hi, W_lo, ldw, ep, st);
+    VSG_REQUIRE(a->W_lo && aligned16(a->W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
+    return wide ? launch_tc<2, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st)
+                : launch_tc<2, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st);
   }
   set_error("vsg_gemm: unknown mode %d", mode);
   return VSG_E_UNSUPPORTED;
+}
+
+extern "C" int vsg_gemm(int mode, const float* A, int lda, const float* W_hi, const float* W_lo, int ldw, int M, int N, int K,
+                        const float* bias, const float* rowbias, const int32_t* rb_index, int rb_period, int ld_rb, int relu,
+                        int accumulate, const float* residual, int ld_res, float* C, int ldc, void* stream) {
+  VsgGemmArgs a;
+  memset(&a, 0, sizeof(a));
+  a.mode = mode; a.A = A; a.lda = lda; a.W_hi = W_hi; a.W_lo = W_lo; a.ldw = ldw; a.M = M; a.N = N; a.K = K;
+  a.bias = bias; a.rowbias = rowbias; a.rb_index = rb_index; a.rb_period = rb_period; a.ld_rb = ld_rb; a.relu = relu;
+  a.accumulate = accumulate; a.residual = residual; a.ld_res = ld_res; a.C = C; a.ldc = ldc; a.batch = 1; a.batch_inner = 1;
+  return vsg_gemm_ex(&a, stream);
 }

@@ -59,7 +59,7 @@ LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py'
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
          accumulate: bool = False, bias: bool = True, K: Optional[int] = None,
-         residual: Optional[torch.Tensor] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
     """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
     wider row-major buffers (their row stride is passed as the leading dimension)."""
     require_cuda(A)
@@ -79,13 +79,57 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
     if _Profile.enabled:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
-                         _raw(rb_index), int(rb_period), 0 if rowbias is None else rowbias.stride(0), 1 if relu else 0,
-                         1 if accumulate else 0, _raw(residual), 0 if residual is None else residual.stride(0),
-                         _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
+    if out_lo is not None:
+        from ._cabi import VsgGemmArgs
+        import ctypes as C
+        assert out_lo.shape == out.shape and out_lo.stride() == out.stride()
+        a = VsgGemmArgs()
+        a.mode = mode; a.A = A.data_ptr(); a.lda = lda; a.W_hi = w_hi.data_ptr(); a.W_lo = None if w_lo is None else w_lo.data_ptr()
+        a.ldw = W.w.stride(0); a.M, a.N, a.K = M, W.N, K
+        a.bias = None if b is None else b.data_ptr(); a.rowbias = None if rowbias is None else rowbias.data_ptr()
+        a.rb_index = None if rb_index is None else rb_index.data_ptr(); a.rb_period = int(rb_period)
+        a.ld_rb = 0 if rowbias is None else rowbias.stride(0); a.relu = 1 if relu else 0; a.accumulate = 1 if accumulate else 0
+        a.residual = None if residual is None else residual.data_ptr(); a.ld_res = 0 if residual is None else residual.stride(0)
+        a.C = out.data_ptr(); a.C_lo = out_lo.data_ptr(); a.ldc = ldc; a.batch = 1; a.batch_inner = 1
+        check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
+    else:
+        check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
+                             _raw(rb_index), int(rb_period), 0 if rowbias is None else rowbias.stride(0), 1 if relu else 0,
+                             1 if accumulate else 0, _raw(residual), 0 if residual is None else residual.stride(0),
+                             _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
     if _Profile.enabled:
         ev1.record()
         _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, mode))
+    return out
+
+
+def gemm_batched(mode: int, A: torch.Tensor, W_hi: torch.Tensor, W_lo: Optional[torch.Tensor], M: int, N: int, K: int,
+                 out: torch.Tensor, ldc: int, batch: int, batch_inner: int, a_off=(0, 0, 0, 0), b_off=(0, 0, 0, 0), c_off=(0, 0)):
+    """``batch`` independent M x N x K problems inside larger operands (vsg_gemm_ex batched form).  ``A`` / ``W_hi`` / ``W_lo`` are 2-D
+    views (row stride = leading dimension, shape = TMA bounds) of the full operands; problem p -> outer = p // batch_inner,
+    inner = p % batch_inner; ``a_off`` / ``b_off`` = (row_outer, row_inner, col_outer, col_inner) element offsets, ``c_off`` =
+    (outer, inner) element offsets into ``out``."""
+    from ._cabi import VsgGemmArgs
+    import ctypes as C
+    a = VsgGemmArgs()
+    a.mode = mode
+    a.A = A.data_ptr(); a.lda = A.stride(0); a.a_rows, a.a_cols = A.shape
+    a.W_hi = W_hi.data_ptr(); a.W_lo = None if W_lo is None else W_lo.data_ptr()
+    a.ldw = W_hi.stride(0); a.w_rows, a.w_cols = W_hi.shape
+    a.M, a.N, a.K = M, N, K
+    a.C = out.data_ptr(); a.C_lo = None; a.ldc = ldc
+    a.batch, a.batch_inner = batch, batch_inner
+    a.a_row_outer, a.a_row_inner, a.a_col_outer, a.a_col_inner = a_off
+    a.b_row_outer, a.b_row_inner, a.b_col_outer, a.b_col_inner = b_off
+    a.c_outer, a.c_inner = c_off
+    LAUNCHES[0] += 1
+    if _Profile.enabled:
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(out.device)), "vsg_gemm_ex")
+    if _Profile.enabled:
+        ev1.record()
+        _Profile.records.append((ev0, ev1, 2.0 * M * N * K * batch, mode))
     return out
 
 
