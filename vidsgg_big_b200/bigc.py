@@ -281,7 +281,7 @@ class BIG_C(object):
               "vsg_transpose_split")
         att = torch.empty(rows, d, dtype=torch.float32, device=dev)
         linalg.gemm_batched(m, S, vt_hi[:, :rows], None if vt_lo is None else vt_lo[:, :rows], Q, dh, Q, att, d, n_seg * H, H,
-                            a_off=(H * Q, Q, 0, 0), b_off=(0, dh, 0, Q), c_off=(Q * d, dh))
+                            a_off=(H * Q, Q, 0, 0), b_off=(0, dh, Q, 0), c_off=(Q * d, dh))
         return att
 
     def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
