@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--videos", type=int, default=200, help="videos per GPU per step (weak scaling)")
     ap.add_argument("--workload", default="vidvrd", choices=["vidvrd", "vidor"])
-    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32", "fp32_simt"])
+    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32+bf16x2", "tf32", "fp32_simt"])
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="videos in the bounded CPU sample (default: 200 for cpu_baseline, 40 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

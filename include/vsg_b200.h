@@ -155,6 +155,8 @@ int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t*
 #define VSG_GEMM_SIMT 0   /* fp32 FFMA tiles (comparator / shapes TMA cannot describe)          */
 #define VSG_GEMM_TF32 1   /* tcgen05.mma kind::tf32, fp32 accumulate in TMEM                     */
 #define VSG_GEMM_3XTF32 2 /* fp32-faithful 3xTF32 split on tcgen05 (needs W_lo from vsg_split_tf32) */
+#define VSG_GEMM_TF32_BF16X2 3 /* fp32-class: tf32 main product + the two correction products as bf16 MMAs (kind::f16);
+                                  needs W_b16 / W_lo16 from vsg_split_bf16; vsg_gemm_ex only, plain (non-batched) problems */
 
 /* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ) (+ residual[M][N]),
  * fp32 row-major; the residual is added after the activation (QANet blocks, models/grd_model_v5.py:118-135).
@@ -186,6 +188,8 @@ typedef struct VsgGemmArgs {
   int a_row_outer, a_row_inner, a_col_outer, a_col_inner;
   int b_row_outer, b_row_inner, b_col_outer, b_col_inner;
   long long c_outer, c_inner;
+  int lo_col_begin, lo_col_end;                       /* C_lo is written for columns in [begin, end) only (multiples of 4); 0, 0 = every column */
+  const void* W_b16; const void* W_lo16; int ldw16;   /* mode VSG_GEMM_TF32_BF16X2: bf16 [N][ldw16] copies of W (W_hi = the fp32 W) */
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 
@@ -194,9 +198,18 @@ int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 int vsg_gemm_set_store_hi(int on);
 /* Validation knob: 128 forces the 128x128-tile kernel for every shape, 0 (default) picks 128x256 tiles where N allows. */
 int vsg_gemm_force_bn(int bn);
+/* Validation knob: 0 = the epilogue writes C with per-row 16-byte stores only; 1 (default) = full 32x32 output slabs are staged in
+ * shared memory (128B swizzle) and leave through cp.async.bulk.tensor stores.  Both give bit-identical C.  Returns the old value. */
+int vsg_gemm_set_tma_store(int on);
+/* Timing probes for bottleneck analysis (the results become garbage): bit 0 skip the W loads, bit 1 skip the A split,
+ * bit 2 skip the MMAs, bit 3 skip the A loads; 0 (default) = normal operation.  Returns the old value. */
+int vsg_gemm_debug_flags(int flags);
 
 /* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
 int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
+/* bf16 operands of mode VSG_GEMM_TF32_BF16X2 for a weight w[rows][cols] (ldw): w16 = bf16_rn(w), lo16 = bf16_rn(w - trunc_tf32(w)),
+ * both [rows][ld16] (ld16 >= cols, a multiple of 8; the padding columns are written as zeros). */
+int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void* w16, void* lo16, int ld16, void* stream);
 
 /* ---- BIG-C classification stage, non-GEMM kernels -------------------------
  * Batch layout: rows = all box-frames of all tracks of all videos; off int64[N+1]; seg int32[V+1] track range

@@ -7,17 +7,23 @@ DEV = "cuda:0"
 
 SHAPES = [  # M, N, K
     (128, 128, 32), (128, 128, 64), (256, 128, 512), (300, 512, 2048), (37, 512, 512), (1000, 1536, 1024),
-    (192, 133, 3160), (4500, 512, 832), (1, 512, 2048), (129, 51, 512), (777, 128, 128), (20000, 512, 512),
+    (192, 133, 3160), (4500, 512, 832), (1, 512, 2048), (129, 51, 512), (777, 128, 128), (20000, 512, 512), (200, 256, 100),
 ]
 # 3xTF32: the tensor core accumulates with truncation, so the error grows ~K/8 * 2^-24 (1e-5 at K=2048)
-TOL = {0: 2e-6, 1: 2e-3, 2: 2e-5}
+# tf32 + 2 x bf16 corrections (mode 3): per-product error <= 2^-18 on top of the same accumulation error
+TOL = {0: 2e-6, 1: 2e-3, 2: 2e-5, 3: 3e-5}
+
+
+def _weight(mode, W, bias=None):
+    from vidsgg_big_b200 import linalg
+    return linalg.Weight(W, bias, split="bf16" if mode == 3 else True)
 
 
 def _ref(A, W, bias):
     return A.double() @ W.double().t() + (bias.double() if bias is not None else 0)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 @pytest.mark.parametrize("shape", SHAPES, ids=["%dx%dx%d" % s for s in SHAPES])
 def test_gemm_modes(mode, shape):
     from vidsgg_big_b200 import linalg
@@ -26,7 +32,7 @@ def test_gemm_modes(mode, shape):
     A = torch.randn(M, K, generator=g).to(DEV)
     W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
     bias = torch.randn(N, generator=g).to(DEV)
-    wt = linalg.Weight(W, bias)
+    wt = _weight(mode, W, bias)
     out = linalg.gemm(mode, A, wt)
     torch.cuda.synchronize()
     ref = _ref(A, W, bias)
@@ -35,7 +41,7 @@ def test_gemm_modes(mode, shape):
     assert err <= TOL[mode] * scale, "mode %d shape %s: max err %.3e (scale %.3e)" % (mode, shape, err, scale)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_gemm_epilogue_options(mode):
     from vidsgg_big_b200 import linalg
     g = torch.Generator(device="cpu").manual_seed(5)
@@ -45,7 +51,7 @@ def test_gemm_epilogue_options(mode):
     bias = torch.randn(N, generator=g).to(DEV)
     rowb = torch.randn(192, N, generator=g).to(DEV)
     idx = torch.randint(0, 192, (M,), generator=g).int().to(DEV)
-    wt = linalg.Weight(W, bias)
+    wt = _weight(mode, W, bias)
     tol = TOL[mode]
     base = _ref(A[:, 32:32 + K], W, bias)
     # periodic row bias + relu, written into the right half of a wider output
@@ -79,6 +85,23 @@ def test_gemm_3xtf32_is_fp32_class():
     assert e3x <= 40 * e32 + 1e-6 and e1x > 20 * e3x
 
 
+def test_gemm_tf32_bf16x2_is_fp32_class():
+    """Mode 3 (tf32 main product + two bf16 correction products): same error class as 3xTF32 (within 4x of it) and >20x better
+    than plain tf32, also when the operands span several orders of magnitude (the corrections are bf16, so no range is lost)."""
+    from vidsgg_big_b200 import linalg
+    g = torch.Generator(device="cpu").manual_seed(10)
+    for scale_spread in (0.0, 3.0):
+        A = torch.randn(2048, 2048, generator=g) * torch.exp(scale_spread * torch.randn(2048, 2048, generator=g))
+        W = torch.randn(512, 2048, generator=g) / 45.0 * torch.exp(scale_spread * torch.randn(512, 2048, generator=g))
+        A, W = A.to(DEV), W.to(DEV)
+        ref = A.double() @ W.double().t()
+        e3x = (linalg.gemm(2, A, linalg.Weight(W)).double() - ref).abs().max().item()
+        emix = (linalg.gemm(3, A, _weight(3, W)).double() - ref).abs().max().item()
+        e1x = (linalg.gemm(1, A, linalg.Weight(W)).double() - ref).abs().max().item()
+        print("spread %.0f: 3xtf32 err %.3e  tf32+bf16x2 err %.3e  tf32 err %.3e  (scale %.3e)" % (scale_spread, e3x, emix, e1x, ref.abs().max().item()))
+        assert emix <= 4 * e3x + 1e-7 * ref.abs().max().item() and e1x > 20 * emix
+
+
 def test_tf32_mma_ignores_low_mantissa_bits():
     """The 3xTF32 kernel leaves the raw fp32 A tile in shared memory as the 'high' operand.  That is only valid if
     tcgen05 kind::tf32 ignores the low 13 mantissa bits: the result must be BIT-IDENTICAL to the variant that masks them."""
@@ -98,7 +121,7 @@ def test_tf32_mma_ignores_low_mantissa_bits():
     assert torch.equal(masked, raw)
 
 
-@pytest.mark.parametrize("mode", [1, 2])
+@pytest.mark.parametrize("mode", [1, 2, 3])
 def test_wide_tiles_equal_narrow_tiles(mode):
     """The 128x256-tile kernel against the 128x128-tile kernel: bit-identical in tf32 mode (same accumulation order over K);
     in 3xTF32 mode the wide kernel walks K in blocks of 16 instead of 32, which reorders the three partial products."""
@@ -109,14 +132,51 @@ def test_wide_tiles_equal_narrow_tiles(mode):
         A = torch.randn(M, K, generator=g).to(DEV)
         W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
         b = torch.randn(N, generator=g).to(DEV)
-        wt = linalg.Weight(W, b)
+        wt = _weight(mode, W, b)
         wide = linalg.gemm(mode, A, wt, relu=True).clone()
         old = lib().vsg_gemm_force_bn(128)
         try:
             narrow = linalg.gemm(mode, A, wt, relu=True).clone()
         finally:
             lib().vsg_gemm_force_bn(old)
-        if mode == 1:
+        if mode in (1, 3):       # same K walk (mode 3 uses 16-column blocks for both tile widths)
             assert torch.equal(wide, narrow), (M, N, K)
         else:
             assert (wide - narrow).abs().max().item() <= 1e-5 * narrow.abs().max().item(), (M, N, K)
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_tma_store_epilogue_equals_direct_stores(mode):
+    """The TMA-store epilogue (32x32 slabs staged in shared memory) against the per-row store epilogue: bit-identical C, also
+    for ragged M / N (edge slabs fall back to direct stores), column-slice outputs and every epilogue option."""
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(17)
+    for (M, N, K) in ((1000, 512, 256), (333, 1536, 128), (4097, 200, 96), (95, 64, 64), (192, 133, 320), (38400, 512, 512)):
+        A = torch.randn(M, K, generator=g).to(DEV)
+        W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+        b = torch.randn(N, generator=g).to(DEV)
+        rowb = torch.randn(192, N, generator=g).to(DEV)
+        resid = torch.randn(M, N, generator=g).to(DEV)
+        wt = _weight(mode, W, b)
+        outs = []
+        for on in (1, 0):
+            old = lib().vsg_gemm_set_tma_store(on)
+            try:
+                o1 = torch.full((M, N + 8), -3.0, device=DEV)
+                linalg.gemm(mode, A, wt, out=o1[:, 4:4 + N] if N % 4 == 0 else o1[:, :N], relu=True, rowbias=rowb, rb_period=192)
+                o2 = torch.ones(M, N, device=DEV)
+                linalg.gemm(mode, A, wt, out=o2, accumulate=True, residual=resid)
+                lo = torch.zeros(M, N, device=DEV)
+                o3 = torch.empty(M, N, device=DEV)
+                linalg.gemm(mode, A, wt, out=o3, out_lo=lo, lo_cols=(N // 16 * 4, N // 8 * 4))
+                outs.append((o1.clone(), o2.clone(), o3.clone(), lo.clone()))
+            finally:
+                lib().vsg_gemm_set_tma_store(old)
+        for x, y in zip(*outs):
+            assert torch.equal(x, y), (mode, M, N, K)
+        o3, lo = outs[0][2], outs[0][3]
+        want = o3 - (o3.view(torch.int32) & -8192).view(torch.float32)
+        c0, c1 = N // 16 * 4, N // 8 * 4                                  # window bounds are multiples of 4 (float4 granularity)
+        assert torch.equal(lo[:, c0:c1], want[:, c0:c1])
+        assert bool((lo[:, :c0] == 0).all()) and bool((lo[:, c1:] == 0).all())

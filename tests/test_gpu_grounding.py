@@ -21,7 +21,7 @@ def _model(precision):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-4), ("3xtf32", 3e-4), ("tf32", 5e-2)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-4), ("3xtf32", 3e-4), ("tf32+bf16x2", 3e-4), ("tf32", 5e-2)])
 def test_grounding_network_vs_reference(golden, precision, tol):
     g = golden("grounding")
     model = _model(precision)
@@ -52,7 +52,7 @@ def test_grounding_post_exact_on_reference_outputs(golden):
         np.testing.assert_allclose(probs.cpu().numpy(), g[k + "_probs"], rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32", "tf32+bf16x2"])
 def test_grounding_forward_end_to_end(golden, precision):
     g = golden("grounding")
     model = _model(precision)

@@ -197,7 +197,7 @@ class BIG_C(object):
             raise VsgError("BIG_C runs on a CUDA device only (no CPU fallback)")
         st = {k: v.to(dev) for k, v in self._state.items()}
         E, Pd, Q = self.dim_enti, self.dim_pred, self.num_querys
-        split = self.mode == linalg.X3TF32
+        split = {linalg.X3TF32: "tf32", linalg.TF32_BF16X2: "bf16"}.get(self.mode, False)
         W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
         w = {}
         w["bbox1_w"], w["bbox1_b"] = st["fc_bbox2enti.0.weight"].contiguous(), st["fc_bbox2enti.0.bias"].contiguous()
@@ -264,7 +264,7 @@ class BIG_C(object):
     def _mha_tc(self, qkv, qkv_lo, n_seg, Q, d):
         """Self-attention of ``n_seg`` fixed-length segments (the Q decoder queries of every video) on the tensor cores:
         S = Q K^T and O = P V are batched tcgen05 GEMMs (one problem per (segment, head)), softmax / V^T are glue kernels."""
-        m, dev = self.mode, qkv.device
+        m, dev = linalg.attention_mode(self.mode), qkv.device
         H = self.n_att_head
         dh = d // H
         rows = n_seg * Q
@@ -355,8 +355,8 @@ class BIG_C(object):
             use_tc = self.attention == "tc" and m != linalg.SIMT and (Pd // self.n_att_head) % 32 == 0 and Q % 32 == 0
             if use_tc:
                 qkv = torch.empty(x.shape[0], 3 * Pd, dtype=torch.float32, device=dev)
-                qkv_lo = torch.empty_like(qkv) if m == linalg.X3TF32 else None
-                gemm(m, x, lw["qkv"], out=qkv, rowbias=lw["posb"], rb_period=Q, out_lo=qkv_lo)
+                qkv_lo = torch.empty_like(qkv) if linalg.attention_mode(m) == linalg.X3TF32 else None
+                gemm(m, x, lw["qkv"], out=qkv, rowbias=lw["posb"], rb_period=Q, out_lo=qkv_lo, lo_cols=(Pd, 2 * Pd))   # only K's low part is read
                 att = self._mha_tc(qkv, qkv_lo, nv, Q, Pd)
             else:
                 qkv = gemm(m, x, lw["qkv"], rowbias=lw["posb"], rb_period=Q)

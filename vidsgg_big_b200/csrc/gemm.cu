@@ -10,6 +10,11 @@
 //   VSG_GEMM_TF32   (1)  tcgen05.mma kind::tf32, operands read as fp32 straight from TMA-staged smem;
 //   VSG_GEMM_3XTF32 (2)  fp32-faithful: A = Ah + Al split on the fly in smem by 4 transform warps, W = Wh + Wl
 //                        pre-split in HBM; D += Al*Wh + Ah*Wl + Ah*Wh (error ~2^-21, like an fp32 GEMM).
+//   VSG_GEMM_TF32_BF16X2 (3)  fp32-class at 2/3 of the tensor time of (2): the two CORRECTION products only need ~8 significant
+//                        bits (they are 2^-11 of the result), so they run as kind::f16 bf16 MMAs (K=16 per instruction, i.e. half
+//                        the issue slots of tf32): D += bf16(Al)*bf16(W) + bf16(A)*bf16(Wl) + tf32(A)*tf32(W).  The split warps
+//                        write the two bf16 A tiles (SWIZZLE_32B rows of 16) next to the fp32 A tile; bf16(W), bf16(Wl) are
+//                        pre-computed in HBM (vsg_split_bf16).  Per-product error ~2^-18 worst case.
 //
 // tcgen05 kernel anatomy (one CTA per SM, persistent over 128x128 output tiles, BLOCK_K = 32 fp32 = one
 // 128-byte swizzle row):
@@ -20,6 +25,7 @@
 //   warps 8-11  (3xTF32 only) hi/lo split of the A stage in shared memory
 #include "common.cuh"
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -51,15 +57,18 @@ struct GemmEpilogue {
   int M, N, K;
   int store_hi;             // 3xTF32: also write the masked high part back (0 = rely on the MMA ignoring the low 13 bits)
   float* C_lo;              // optional: x - trunc_tf32(x) of every stored value (the B-side low part for a following 3xTF32 GEMM)
+  int lo_c0, lo_c1;         // C_lo is written for columns in [lo_c0, lo_c1) only
+  int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
   // batched problems: tile -> (problem p, m block, n block); p -> (outer = p / batch_inner, inner = p % batch_inner).
   // TMA coordinates and the C pointer are offset per problem; M / N are per-problem extents (batch == 1: plain GEMM).
+  int dbg;                  // probe flags (vsg_gemm_debug_flags): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads
   int batch, batch_inner;
   int a_row_outer, a_row_inner, a_col_outer, a_col_inner;
   int b_row_outer, b_row_inner, b_col_outer, b_col_inner;
   long long c_outer, c_inner;
 };
 
-struct TileCoord { int m0, n0, a_row, a_col, b_row, b_col; long long c_off; };
+struct TileCoord { int m0, n0, a_row, a_col, b_row, b_col; long long c_off; int c_row, c_col; };
 __device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile, int tiles_m, int tiles_n, int BN_) {
   TileCoord t;
   const int per = tiles_m * tiles_n;
@@ -72,6 +81,8 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile
   t.b_row = t.n0 + outer * ep.b_row_outer + inner * ep.b_row_inner;
   t.b_col = outer * ep.b_col_outer + inner * ep.b_col_inner;
   t.c_off = outer * ep.c_outer + inner * ep.c_inner;
+  t.c_row = (int)(t.c_off / ep.ldc);
+  t.c_col = (int)(t.c_off - (long long)t.c_row * ep.ldc);
   return t;
 }
 
@@ -116,6 +127,28 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
   }
 }
+__device__ __forceinline__ void mbar_spin(uint64_t* bar, uint32_t parity) {   // non-blocking test_wait poll (probe)
+  uint32_t ok = 0, spins = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (++spins > (1u << 28)) __trap();
+  }
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
@@ -125,6 +158,13 @@ __device__ __forceinline__ void tma_load_2d(uint32_t smem_dst, const CUtensorMap
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t smem_src, int c_inner, int c_outer) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(reinterpret_cast<uint64_t>(map)), "r"(smem_src), "r"(c_inner), "r"(c_outer) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -144,6 +184,14 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
       "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
       ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
       : "memory");
 }
@@ -178,28 +226,45 @@ __device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
   d |= (uint64_t)(BK_ == 32 ? 2 : 4) << 61;
   return d;
 }
+// K-major bf16 tile with 32-byte rows (16 bf16 = one K=16 MMA), SWIZZLE_32B: SBO = 8 rows * 32 B = 256 B, layout = 6
+__device__ __forceinline__ uint64_t make_smem_desc_b16(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(256 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)6 << 61;
+  return d;
+}
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
 template <int BN_> struct IDesc {
   static constexpr uint32_t tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  static constexpr uint32_t bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
 };
 
 // ---------------------------------------------------------------------------------------------------
 template <int MODE, int BN_> struct Cfg {
-  static constexpr int BK = (MODE == 2 && BN_ == 256) ? 16 : 32;
+  static constexpr int BK = ((MODE == 2 && BN_ == 256) || MODE == 3) ? 16 : 32;
   static constexpr int TILE_A = BM * BK * 4;
   static constexpr int TILE_B = BN_ * BK * 4;
-  static constexpr int STAGE_BYTES = (MODE == 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo])
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32)
-  static constexpr int THREADS = MODE == 2 ? 384 : 256;
-  static constexpr int OFF_BH = TILE_A, OFF_AL = TILE_A + TILE_B, OFF_BL = 2 * TILE_A + TILE_B;
+  static constexpr int STAGE_BYTES = (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16)
+  static constexpr int SPLIT_GROUPS = 2;                                         // groups of 4 split warps that alternate stages
+  static constexpr int THREADS = MODE >= 2 ? 256 + 128 * SPLIT_GROUPS : 256;
+  // MODE 2: [A | B_hi | A_lo | B_lo] fp32.   MODE 3: [A f32 | W f32 | bf16(A_lo) | bf16(A) | bf16(W) | bf16(W_lo)]
+  static constexpr int OFF_BH = TILE_A, OFF_AL = TILE_A + TILE_B;
+  static constexpr int OFF_A16 = OFF_AL + TILE_A / 2, OFF_B16 = OFF_AL + TILE_A;
+  static constexpr int OFF_BL = MODE == 3 ? OFF_B16 + TILE_B / 2 : 2 * TILE_A + TILE_B;
   static constexpr int TMEM_COLS = 2 * BN_;                                      // double-buffered fp32 accumulator
+  static constexpr int STAGING_BYTES = 4 * 2 * 32 * 128;                         // TMA-store staging of the epilogue warps
 };
 
-template <int MODE, int BN_>
+template <int MODE, int BN_, bool PROBE>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
-               const __grid_constant__ CUtensorMap mapBl, const GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
+               const __grid_constant__ CUtensorMap mapC, const GemmEpilogue ep) {
   using CF = Cfg<MODE, BN_>;
   constexpr int STAGES = CF::STAGES;
   constexpr int STAGE_BYTES = CF::STAGE_BYTES;
@@ -212,7 +277,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   // stage layout: [A | B_hi] (MODE 1) or [A(hi) | B_hi | A_lo | B_lo] (MODE 2)
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + STAGES * STAGE_BYTES);
+  uint8_t* staging = smem + STAGES * STAGE_BYTES;                     // 4 epilogue warps x 2 buffers x (32 rows x 128 B)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(staging + CF::STAGING_BYTES);
   uint64_t* full = bars;                   // TMA landed
   uint64_t* empty = bars + STAGES;         // MMAs that read the stage retired
   uint64_t* ready = bars + 2 * STAGES;     // (MODE 2) split done
@@ -228,13 +294,15 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
     tma_prefetch_desc(&mapBh);
-    if (MODE == 2) tma_prefetch_desc(&mapBl);
+    if (MODE >= 2) tma_prefetch_desc(&mapBl);
+    if (MODE == 3) tma_prefetch_desc(&mapB16);
+    if (ep.tma_store) tma_prefetch_desc(&mapC);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
-      mbar_init(&ready[s], 128);
+      mbar_init(&ready[s], 128);          // every thread of the split group that owns the stage (measured faster than one elected lane per warp)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -259,34 +327,68 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
         for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(&empty[stage], phase ^ 1);
+          if (PROBE && (ep.dbg & 32)) mbar_spin(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          mbar_expect_tx(&full[stage], TILE_A + (MODE == 2 ? 2 : 1) * CF::TILE_B);
+          if (PROBE && (ep.dbg & 9)) {   // timing probes only (results are garbage)
+            const bool la = !(ep.dbg & 8), lw = !(ep.dbg & 1);
+            if (!la && !lw) { mbar_arrive(&full[stage]); }
+            else {
+              mbar_expect_tx(&full[stage], (la ? TILE_A : 0) + (lw ? (MODE >= 2 ? 2 : 1) * CF::TILE_B : 0));
+              if (la) tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
+              if (lw) {
+                tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
+                if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
+                if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
+              }
+            }
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
+          mbar_expect_tx(&full[stage], TILE_A + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
           tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
           tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
-          if (MODE == 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
+          if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
+          if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    if (lane == 0) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+    // The WHOLE warp walks the (warp-uniform) loop and one elected lane issues: a lane-divergent `if (lane == 0)` loop makes the
+    // compiler rebuild every descriptor through ELECT / R2UR sequences (~160 SASS instructions per k-block, measured to take about
+    // as long as the MMAs themselves).  Descriptors are one 32-bit add on a per-kernel base.
+    int stage = 0;
+    uint32_t phase = 0;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    const uint32_t base16 = (smem_u32(smem) & 0x3FFFF) >> 4;                                 // stage 0 start address >> 4
+    constexpr uint32_t DESC_HI = (uint32_t)((8 * BK * 4) >> 4) | (1u << 14) | ((BK == 32 ? 2u : 4u) << 29);        // SBO | version | swizzle
+    constexpr uint32_t DESC_HI_B16 = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);                                // bf16 tiles, SWIZZLE_32B
+    constexpr uint32_t LBO = 1u << 16;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(&acc_empty[acc], acc_phase ^ 1);
+      tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if (PROBE && (ep.dbg & 32)) mbar_spin(MODE >= 2 ? &ready[stage] : &full[stage], phase);
+        else mbar_wait(MODE >= 2 ? &ready[stage] : &full[stage], phase);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
-        for (int kb = 0; kb < kblocks; ++kb) {
-          mbar_wait(MODE == 2 ? &ready[stage] : &full[stage], phase);
-          tc_fence_after();
-          const uint32_t st = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_hi = make_smem_desc<BK>(st), b_hi = make_smem_desc<BK>(st + CF::OFF_BH);
-          if (MODE == 2) {
-            const uint64_t a_lo = make_smem_desc<BK>(st + CF::OFF_AL), b_lo = make_smem_desc<BK>(st + CF::OFF_BL);
+        if (elect_one()) {
+          const uint32_t st16 = base16 + (uint32_t)stage * (STAGE_BYTES >> 4);
+          auto desc = [&](uint32_t off_bytes, uint32_t hi) -> uint64_t {
+            return ((uint64_t)hi << 32) | (uint64_t)((st16 + (off_bytes >> 4)) | LBO);
+          };
+          const uint64_t a_hi = desc(0, DESC_HI), b_hi = desc(CF::OFF_BH, DESC_HI);
+          if (PROBE && (ep.dbg & 4)) {
+          } else if (MODE == 3) {
+            // corrections first (bf16, one K=16 instruction each), then the tf32 main product
+            umma_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), IDesc<BN_>::bf16, kb ? 1u : 0u);
+            umma_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), IDesc<BN_>::bf16, 1u);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, 1u);
+          } else if (MODE == 2) {
+            const uint64_t a_lo = desc(CF::OFF_AL, DESC_HI), b_lo = desc(CF::OFF_BL, DESC_HI);
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
 #pragma unroll
@@ -297,19 +399,27 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
           }
-          umma_commit(&empty[stage]);
+          if (PROBE && (ep.dbg & 16)) mbar_arrive(&empty[stage]); else umma_commit(&empty[stage]);
           if (kb == kblocks - 1) umma_commit(&acc_full[acc]);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        __syncwarp();
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   } else if (warp >= 4 && warp < 8) {
     // ================= epilogue =================
+    // Per warp: 32 accumulator rows.  Each 32-column chunk is read from TMEM (one row per lane), gets bias / row-bias /
+    // accumulate / ReLU / residual, and leaves either (fast path, full 32x32 slab) through a 128B-swizzled staging buffer and a
+    // TMA store -- coalesced, asynchronous, two buffers in flight -- or (edges, unaligned C) through per-row 16-byte stores.
     const int quad = warp & 3;              // TMEM lane quadrant this warp may read
     const int row_in_tile = quad * 32 + lane;
-    int acc = 0;
+    uint8_t* stg = staging + quad * (2 * 4096);
+    int acc = 0, sbuf = 0;
     uint32_t acc_phase = 0;
+    const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
+                        ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+    const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
       const int m0 = tc.m0, n0 = tc.n0;
@@ -318,6 +428,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
       const bool row_ok = row < ep.M;
+      const bool slab_rows_ok = m0 + quad * 32 + 32 <= ep.M;                 // warp-uniform
       const float* rb = nullptr;
       if (row_ok && ep.rowbias) {
         const int ri = ep.rb_index ? ep.rb_index[row] : (row % ep.rb_period);
@@ -326,15 +437,56 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       float* crow = ep.C + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc;
       float* crow_lo = ep.C_lo ? ep.C_lo + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc : nullptr;
       const float* res = (row_ok && ep.residual) ? ep.residual + (size_t)row * ep.ld_res : nullptr;
-      const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
-                          ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
 #pragma unroll 1
       for (int c = 0; c < BN / 32; ++c) {
+        const int col0 = n0 + c * 32;
+        if (col0 >= ep.N) break;                                              // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        if (row_ok) {
-          const int col0 = n0 + c * 32;
+        const bool fast = ep.tma_store && vec_ok && slab_rows_ok && col0 + 32 <= ep.N;   // warp-uniform
+        if (fast) {
+          uint8_t* sb = stg + sbuf * 4096;
+          if (lane == 0) bulk_wait_read<1>();                                 // the store that last read this buffer is done
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (ep.bias) {
+              const float4 b = *reinterpret_cast<const float4*>(ep.bias + col0 + j);
+              v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+            }
+            if (rb) {
+              if (rb_vec) {
+                const float4 b = *reinterpret_cast<const float4*>(rb + col0 + j);
+                v.x += b.x; v.y += b.y; v.z += b.z; v.w += b.w;
+              } else {
+                v.x += rb[col0 + j]; v.y += rb[col0 + j + 1]; v.z += rb[col0 + j + 2]; v.w += rb[col0 + j + 3];
+              }
+            }
+            if (ep.accumulate) {
+              const float4 o = *reinterpret_cast<const float4*>(crow + col0 + j);
+              v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
+            }
+            if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+            if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+            // SWIZZLE_128B: 16-byte chunk q of row r sits at chunk q ^ (r & 7) (buffer is 1024-byte aligned)
+            *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+            if (crow_lo && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
+              float4 l;
+              l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+              l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(crow_lo + col0 + j) = l;
+            }
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapC, smem_u32(sb), tc.c_col + col0, tc.c_row + m0 + quad * 32);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+        } else if (row_ok) {
           if (col0 + 32 <= ep.N && vec_ok) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
@@ -354,7 +506,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
               *dst = v;
-              if (crow_lo) {
+              if (crow_lo && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
                 float4 l;
                 l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
                 l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
@@ -373,7 +525,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (ep.relu) v = fmaxf(v, 0.f);
                 if (res) v += res[col];
                 crow[col] = v;
-                if (crow_lo) crow_lo[col] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
+                if (crow_lo && col >= ep.lo_c0 && col < ep.lo_c1) crow_lo[col] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
               }
             }
           }
@@ -383,18 +535,59 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       mbar_arrive(&acc_empty[acc]);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else if (MODE == 2 && warp >= 8) {
-    // ================= A hi/lo split (element-wise, so it is oblivious to the 128B swizzle) =================
-    const int t = threadIdx.x - 256;  // 0..127
-    int stage = 0;
+    if (lane == 0) bulk_wait_all();                                           // staging reads AND global writes complete before exit
+  } else if (MODE == 3 && warp >= 8) {
+    // ================= bf16 correction operands of the A tile =================
+    // fp32 tile: 128 rows x 16 floats, 64-byte rows, SWIZZLE_64B: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3).
+    // bf16 tiles: 128 rows x 16 bf16, 32-byte rows, SWIZZLE_32B: 16-byte chunk m of row r sits at chunk m ^ ((r >> 2) & 1).
+    // two groups of 4 warps alternate stages, so that the split of stage s+1 overlaps the tail (fence + arrive) of stage s
+    const int t = (threadIdx.x - 256) & 127;  // 0..127
+    const int grp = (threadIdx.x - 256) >> 7;
+    int stage = 0, it = 0;
     uint32_t phase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kblocks; ++kb) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        if ((it % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+        mbar_wait(&full[stage], phase);
+        uint8_t* st = smem + stage * STAGE_BYTES;
+        const float4* src = reinterpret_cast<const float4*>(st);
+        uint8_t* lo16 = st + CF::OFF_AL;
+        uint8_t* a16 = st + CF::OFF_A16;
+#pragma unroll
+        for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : TILE_A / 16 / 128); ++i) {
+          const int idx = i * 128 + t;
+          const int r = idx >> 2, l = (idx & 3) ^ ((r >> 1) & 3);   // logical chunk l = columns 4l .. 4l+3 of row r
+          const float4 x = src[idx];
+          float4 lo;
+          lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
+          lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
+          lo.z = x.z - __uint_as_float(__float_as_uint(x.z) & 0xFFFFE000u);
+          lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
+          const __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
+          const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
+          const int dst = r * 32 + ((((l >> 1) ^ ((r >> 2) & 1))) << 4) + (l & 1) * 8;
+          *reinterpret_cast<uint2*>(lo16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+          *reinterpret_cast<uint2*>(a16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+        }
+        fence_proxy_async();
+        mbar_arrive(&ready[stage]);
+        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else if (MODE == 2 && warp >= 8) {
+    // ================= A hi/lo split (element-wise, so it is oblivious to the 128B swizzle) =================
+    const int t = (threadIdx.x - 256) & 127;  // 0..127
+    const int grp = (threadIdx.x - 256) >> 7;
+    int stage = 0, it = 0;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      for (int kb = 0; kb < kblocks; ++kb, ++it) {
+        if ((it % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
         mbar_wait(&full[stage], phase);
         float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + CF::OFF_AL);
 #pragma unroll
-        for (int i = 0; i < TILE_A / 16 / 128; ++i) {
+        for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : TILE_A / 16 / 128); ++i) {
           const int idx = i * 128 + t;
           const float4 x = hi[idx];
           float4 h, l;
@@ -482,6 +675,19 @@ __global__ void split_tf32_kernel(const float* __restrict__ w, float* __restrict
   }
 }
 
+// bf16 copies of a weight for mode 3: w16 = bf16_rn(w), lo16 = bf16_rn(w - trunc_tf32(w)); rows padded to ld16
+__global__ void split_bf16_kernel(const float* __restrict__ w, int ldw, int rows, int cols, __nv_bfloat16* __restrict__ w16,
+                                  __nv_bfloat16* __restrict__ lo16, int ld16) {
+  const int64_t n = (int64_t)rows * ld16;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int r = (int)(i / ld16), c = (int)(i - (int64_t)r * ld16);
+    const float x = c < cols ? w[(size_t)r * ldw + c] : 0.f;
+    const float h = __uint_as_float(__float_as_uint(x) & 0xFFFFE000u);
+    w16[i] = __float2bfloat16_rn(x);
+    lo16[i] = __float2bfloat16_rn(x - h);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------
@@ -502,23 +708,26 @@ static EncodeTiledFn get_encode() {
 }
 
 struct MapKey {
-  const void* ptr; int rows, cols, ld, box_rows, box_cols;
+  const void* ptr; int rows, cols, ld, box_rows, box_cols, esize;
   bool operator==(const MapKey& o) const {
-    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols;
+    return ptr == o.ptr && rows == o.rows && cols == o.cols && ld == o.ld && box_rows == o.box_rows && box_cols == o.box_cols &&
+           esize == o.esize;
   }
 };
 struct MapKeyHash {
   size_t operator()(const MapKey& k) const {
     return std::hash<const void*>()(k.ptr) ^ (std::hash<int>()(k.rows) * 31) ^ (std::hash<int>()(k.cols) * 131) ^ (std::hash<int>()(k.ld) * 1031) ^
-           (std::hash<int>()(k.box_rows) * 7919) ^ (std::hash<int>()(k.box_cols) * 104729);
+           (std::hash<int>()(k.box_rows) * 7919) ^ (std::hash<int>()(k.box_cols) * 104729) ^ (size_t)k.esize;
   }
 };
+static int g_tma_store = 1;
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
-// 2-D fp32 row-major [rows][cols] with leading dimension ld; box = BK x box_rows, SWIZZLE_128B, zero OOB fill
-static int get_tensor_map(const float* base, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out) {
-  MapKey key{base, rows, cols, ld, box_rows, box_cols};
+// 2-D row-major [rows][cols] (fp32, or bf16 when esize == 2) with leading dimension ld (elements); box = box_cols x box_rows,
+// swizzle span = the box row (128 / 64 / 32 bytes), zero OOB fill
+static int get_tensor_map(const void* base, int rows, int cols, int ld, int box_rows, int box_cols, CUtensorMap* out, int esize = 4) {
+  MapKey key{base, rows, cols, ld, box_rows, box_cols, esize};
   {
     std::lock_guard<std::mutex> g(g_map_mu);
     auto it = g_maps.find(key);
@@ -527,12 +736,14 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, int box
   EncodeTiledFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled is unavailable (driver entry point lookup failed)"); return VSG_E_LAUNCH; }
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
-  cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * esize};
   cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUtensorMap m;
-  CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+  const int row_bytes = box_cols * esize;
+  CUresult r = enc(&m, esize == 2 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void*>(base), dims,
+                   strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : row_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
                    CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d) for [%d x %d] ld %d", (int)r, rows, cols, ld); return VSG_E_LAUNCH; }
@@ -546,19 +757,45 @@ static int get_tensor_map(const float* base, int rows, int cols, int ld, int box
 }
 
 template <int MODE, int BN_>
-static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const float* Wl, int ldw, int w_rows, int w_cols,
-                     const GemmEpilogue& ep, cudaStream_t st) {
+static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
+                     const GemmEpilogue& ep_in, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
   using CF = Cfg<MODE, BN_>;
-  CUtensorMap mA, mBh, mBl;
+  CUtensorMap mA, mBh, mBl, mB16;
   int rc = get_tensor_map(A, a_rows, a_cols, lda, BM, CF::BK, &mA);
   if (rc) return rc;
   rc = get_tensor_map(Wh, w_rows, w_cols, ldw, BN_, CF::BK, &mBh);
   if (rc) return rc;
   if (MODE == 2) { rc = get_tensor_map(Wl, w_rows, w_cols, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
-  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  mB16 = mBh;
+  if (MODE == 3) {
+    rc = get_tensor_map(Wl, w_rows, w_cols, ldw16, BN_, CF::BK, &mBl, 2);
+    if (rc) return rc;
+    rc = get_tensor_map(W16, w_rows, w_cols, ldw16, BN_, CF::BK, &mB16, 2);
+    if (rc) return rc;
+  }
+  GemmEpilogue ep = ep_in;
+  CUtensorMap mC = mA;
+  ep.tma_store = 0;
+  if (g_tma_store && (ep.ldc & 3) == 0 && aligned16(ep.C)) {
+    // C as a 2-D tensor of 32x32 fp32 boxes (SWIZZLE_128B).  Batched problems address boxes inside the whole C buffer, whose row
+    // length is ldc; only slabs that lie fully inside a problem take this path, so the bounds are never relied on for clipping.
+    long long rows = ep.M, cols = ep.N;
+    if (ep.batch > 1) {
+      const long long last = (long long)((ep.batch - 1) / ep.batch_inner) * ep.c_outer + (long long)(ep.batch_inner - 1) * ep.c_inner;
+      rows = last / ep.ldc + ep.M + 1;
+      cols = ep.ldc;
+    }
+    if (rows < 0x7fffffffLL && ep.c_outer >= 0 && ep.c_inner >= 0) {
+      rc = get_tensor_map(ep.C, (int)rows, (int)cols, ep.ldc, 32, 32, &mC);
+      if (rc) return rc;
+      ep.tma_store = 1;
+    }
+  }
+  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
@@ -566,7 +803,8 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   }
   const long long tiles = (long long)((ep.M + BM - 1) / BM) * ((ep.N + BN_ - 1) / BN_) * ep.batch;
   const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tc_kernel<MODE, BN_><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, ep);
+  if (ep.dbg) gemm_tc_kernel<MODE, BN_, true><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, mB16, mC, ep);   // timing probes
+  else gemm_tc_kernel<MODE, BN_, false><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, mB16, mC, ep);
   return check_launch("vsg_gemm(tcgen05)");
 }
 
@@ -578,6 +816,11 @@ static inline bool use_bn256(int N) { return 2 * ((N + 255) / 256) <= (N + 127) 
 using namespace vsg;
 
 static int g_store_hi = 0;
+static int g_dbg = 0;
+/* timing probes (results become garbage): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads, 16 free stages by a plain arrive, 32 producer / issuer poll with test_wait; 0 = normal */
+/* validation knob: 0 = the epilogue writes C with per-row 16-byte stores only, 1 (default) = full 32x32 slabs leave through TMA stores */
+extern "C" int vsg_gemm_set_tma_store(int on) { int old = vsg::g_tma_store; vsg::g_tma_store = on ? 1 : 0; return old; }
+extern "C" int vsg_gemm_debug_flags(int f) { int old = g_dbg; g_dbg = f; return old; }
 static int g_force_bn = 0;
 /* debug/validation knob: 128 forces the N=128 tile kernel everywhere, 0 = automatic */
 extern "C" int vsg_gemm_force_bn(int bn) { int old = g_force_bn; g_force_bn = bn; return old; }
@@ -594,6 +837,16 @@ extern "C" int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, v
   return check_launch("vsg_split_tf32");
 }
 
+extern "C" int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void* w16, void* lo16, int ld16, void* stream) {
+  VSG_REQUIRE(rows >= 0 && cols >= 0 && ldw >= cols && ld16 >= cols, "vsg_split_bf16: bad extents");
+  if (rows == 0 || cols == 0) return VSG_OK;
+  VSG_REQUIRE(w && w16 && lo16, "vsg_split_bf16: null pointer");
+  int64_t blocks = ((int64_t)rows * ld16 + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  split_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, ldw, rows, cols, (__nv_bfloat16*)w16, (__nv_bfloat16*)lo16, ld16);
+  return check_launch("vsg_split_bf16");
+}
+
 extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   VSG_REQUIRE(a != nullptr, "vsg_gemm_ex: null args");
   const int M = a->M, N = a->N, K = a->K;
@@ -605,8 +858,10 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   VSG_REQUIRE(a->rowbias == nullptr || a->rb_index != nullptr || a->rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
   GemmEpilogue ep;
   ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
-  ep.store_hi = g_store_hi;
+  ep.store_hi = g_store_hi; ep.dbg = g_dbg;
   ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
+  ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0;
+  if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
   ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
   ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
   ep.a_row_outer = a->a_row_outer; ep.a_row_inner = a->a_row_inner; ep.a_col_outer = a->a_col_outer; ep.a_col_inner = a->a_col_inner;
@@ -641,6 +896,13 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
     VSG_REQUIRE(a->W_lo && aligned16(a->W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
     return wide ? launch_tc<2, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st)
                 : launch_tc<2, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st);
+  }
+  if (mode == 3) {
+    VSG_REQUIRE(batch == 1, "vsg_gemm_ex: mode 3 (tf32 + 2 x bf16) takes plain problems only; batched attention problems use mode 2");
+    VSG_REQUIRE(a->W_b16 && a->W_lo16 && aligned16(a->W_b16) && aligned16(a->W_lo16) && a->ldw16 >= K && a->ldw16 % 8 == 0,
+                "vsg_gemm_ex: mode 3 needs the bf16 copies of W from vsg_split_bf16 (16-byte aligned, ldw16 a multiple of 8)");
+    return wide ? launch_tc<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
+                : launch_tc<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
   }
   set_error("vsg_gemm: unknown mode %d", mode);
   return VSG_E_UNSUPPORTED;

@@ -8,20 +8,34 @@ import torch
 
 from ._cabi import check, lib, ptr, require_cuda, stream_ptr
 
-SIMT, TF32, X3TF32 = 0, 1, 2
-MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32}
+SIMT, TF32, X3TF32, TF32_BF16X2 = 0, 1, 2, 3
+MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2}
+
+
+def attention_mode(mode: int) -> int:
+    """Mode of the batched attention GEMMs (activation x activation): TF32_BF16X2 needs pre-computed bf16 copies of the "weight"
+    operand, which only exist for real weights -- those few problems stay on the 3xTF32 kernel."""
+    return X3TF32 if mode == TF32_BF16X2 else mode
 
 
 class Weight(object):
     """A [N,K] fp32 weight resident in HBM with its (optional) tf32 hi/lo split."""
 
-    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor] = None, split: bool = True):
+    def __init__(self, w: torch.Tensor, bias: Optional[torch.Tensor] = None, split=True):
+        """``split``: True / "tf32" -> fp32 hi/lo pair of the 3xTF32 mode; "bf16" -> the bf16 copies of the tf32+bf16x2 mode
+        (w16 = bf16(w), lo16 = bf16(w - trunc_tf32(w)), rows padded to a multiple of 8); False -> none."""
         require_cuda(w)
         self.w = w.detach().float().contiguous()
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.N, self.K = self.w.shape
-        self.hi = self.lo = None
-        if split:
+        self.hi = self.lo = self.w16 = self.lo16 = None
+        if split == "bf16":
+            self.ld16 = (self.K + 7) // 8 * 8
+            self.w16 = torch.empty(self.N, self.ld16, dtype=torch.bfloat16, device=self.w.device)
+            self.lo16 = torch.empty_like(self.w16)
+            check(lib().vsg_split_bf16(ptr(self.w), self.w.stride(0), self.N, self.K, ptr(self.w16), ptr(self.lo16), self.ld16,
+                                       stream_ptr(self.w.device)), "vsg_split_bf16")
+        elif split:
             self.hi = torch.empty_like(self.w)
             self.lo = torch.empty_like(self.w)
             check(lib().vsg_split_tf32(ptr(self.w), ptr(self.hi), ptr(self.lo), self.w.numel(), stream_ptr(self.w.device)),
@@ -59,9 +73,10 @@ LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py'
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
          accumulate: bool = False, bias: bool = True, K: Optional[int] = None,
-         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, lo_cols=None) -> torch.Tensor:
     """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
-    wider row-major buffers (their row stride is passed as the leading dimension)."""
+    wider row-major buffers (their row stride is passed as the leading dimension).  ``out_lo`` (same shape / strides as ``out``)
+    receives ``x - trunc_tf32(x)`` of the result, restricted to the column window ``lo_cols = (begin, end)`` if given."""
     require_cuda(A)
     assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32
     M = A.shape[0]
@@ -79,10 +94,12 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
     if _Profile.enabled:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if out_lo is not None:
+    if mode == TF32_BF16X2 and W.w16 is None:
+        raise ValueError("gemm: mode tf32+bf16x2 needs a Weight built with split='bf16'")
+    if out_lo is not None or mode == TF32_BF16X2:
         from ._cabi import VsgGemmArgs
         import ctypes as C
-        assert out_lo.shape == out.shape and out_lo.stride() == out.stride()
+        assert out_lo is None or (out_lo.shape == out.shape and out_lo.stride() == out.stride())
         a = VsgGemmArgs()
         a.mode = mode; a.A = A.data_ptr(); a.lda = lda; a.W_hi = w_hi.data_ptr(); a.W_lo = None if w_lo is None else w_lo.data_ptr()
         a.ldw = W.w.stride(0); a.M, a.N, a.K = M, W.N, K
@@ -90,7 +107,11 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         a.rb_index = None if rb_index is None else rb_index.data_ptr(); a.rb_period = int(rb_period)
         a.ld_rb = 0 if rowbias is None else rowbias.stride(0); a.relu = 1 if relu else 0; a.accumulate = 1 if accumulate else 0
         a.residual = None if residual is None else residual.data_ptr(); a.ld_res = 0 if residual is None else residual.stride(0)
-        a.C = out.data_ptr(); a.C_lo = out_lo.data_ptr(); a.ldc = ldc; a.batch = 1; a.batch_inner = 1
+        a.C = out.data_ptr(); a.C_lo = None if out_lo is None else out_lo.data_ptr(); a.ldc = ldc; a.batch = 1; a.batch_inner = 1
+        if lo_cols is not None:
+            a.lo_col_begin, a.lo_col_end = int(lo_cols[0]), int(lo_cols[1])
+        if mode == TF32_BF16X2:
+            a.W_b16, a.W_lo16, a.ldw16 = W.w16.data_ptr(), W.lo16.data_ptr(), W.ld16
         check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
     else:
         check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
