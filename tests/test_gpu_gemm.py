@@ -180,3 +180,52 @@ def test_tma_store_epilogue_equals_direct_stores(mode):
         c0, c1 = N // 16 * 4, N // 8 * 4                                  # window bounds are multiples of 4 (float4 granularity)
         assert torch.equal(lo[:, c0:c1], want[:, c0:c1])
         assert bool((lo[:, :c0] == 0).all()) and bool((lo[:, c1:] == 0).all())
+
+
+@pytest.mark.parametrize("mode", [1, 2, 3])
+def test_cta_pair_multicast_equals_single_cta(mode):
+    """CTA pairs (cluster of 2, W half-tiles multicast to both CTAs) against one CTA per tile: bit-identical C, including an odd
+    number of M tiles (the pair's second CTA runs a dummy tile), a single pair, ragged edges and wide / narrow N tiles."""
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(19)
+    for (M, N, K) in ((129, 512, 256), (256, 128, 64), (1000, 512, 1024), (4097, 1536, 512), (38400, 512, 512), (641, 133, 3160),
+                      (100000, 64, 96)):
+        A = torch.randn(M, K, generator=g).to(DEV)
+        W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+        b = torch.randn(N, generator=g).to(DEV)
+        wt = _weight(mode, W, b)
+        outs = []
+        for cl in (2, 1):
+            old = lib().vsg_gemm_set_cluster(cl)
+            try:
+                outs.append(linalg.gemm(mode, A, wt, relu=True).clone())
+            finally:
+                lib().vsg_gemm_set_cluster(old)
+        assert torch.equal(outs[0], outs[1]), (mode, M, N, K)
+        ref = torch.relu(_ref(A, W, b))
+        assert (outs[0].double() - ref).abs().max().item() <= TOL[mode] * ref.abs().max().item()
+
+
+def test_batched_odd_stage_count_is_race_free():
+    """The PV product of the tensor-core attention (N = 64 -> 128-wide tiles, 3 pipeline stages in 3xTF32 mode) repeated many times:
+    regression test for a parity-aliasing race between the two split-warp groups when stage ownership followed the iteration."""
+    from vidsgg_big_b200 import linalg
+    g = torch.Generator(device="cpu").manual_seed(23)
+    n_seg, H, Q, dh = 150, 8, 192, 64
+    d = H * dh
+    S = torch.rand(n_seg * H * Q, Q, generator=g).to(DEV)
+    vt = torch.randn(d, n_seg * Q, generator=g).to(DEV)
+    vt_hi = (vt.view(torch.int32) & -8192).view(torch.float32)
+    vt_lo = vt - vt_hi
+    ref = None
+    for it in range(30):
+        att = torch.empty(n_seg * Q, d, device=DEV)
+        linalg.gemm_batched(2, S, vt_hi, vt_lo, Q, dh, Q, att, d, n_seg * H, H, a_off=(H * Q, Q, 0, 0), b_off=(0, dh, Q, 0), c_off=(Q * d, dh))
+        torch.cuda.synchronize()
+        if ref is None:
+            ref = att.clone()
+            want = torch.einsum("shqk,shkd->sqhd", S.view(n_seg, H, Q, Q).double(), vt.double().view(H, dh, n_seg, Q).permute(2, 0, 3, 1)).reshape(n_seg * Q, d)
+            assert (att.double() - want).abs().max().item() <= 2e-5 * want.abs().max().item()
+        else:
+            assert torch.equal(att, ref), it

@@ -65,6 +65,7 @@ SIGNATURES = {
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
     "vsg_gemm_debug_flags": (i32, [i32]),
     "vsg_gemm_set_tma_store": (i32, [i32]),
+    "vsg_gemm_set_cluster": (i32, [i32]),
     "vsg_split_bf16": (i32, [p, i32, i32, i32, p, p, i32, p]),
     "vsg_softmax_rows": (i32, [p, i32, i32, i64, f32, p]),
     "vsg_transpose_split": (i32, [p, i32, i64, i32, p, p, i64, p]),

@@ -69,12 +69,12 @@ struct GemmEpilogue {
 };
 
 struct TileCoord { int m0, n0, a_row, a_col, b_row, b_col; long long c_off; int c_row, c_col; };
-__device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile, int tiles_m, int tiles_n, int BN_) {
+__device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile, int tiles_m, int tiles_n, int BN_, int m_mul = 1, int m_add = 0) {
   TileCoord t;
   const int per = tiles_m * tiles_n;
   const int p = tile / per, in = tile - p * per;
   const int outer = p / ep.batch_inner, inner = p - outer * ep.batch_inner;
-  t.m0 = (in / tiles_n) * 128;
+  t.m0 = ((in / tiles_n) * m_mul + m_add) * 128;     // cluster of 2: the pair owns M tiles 2i and 2i+1 of one N tile
   t.n0 = (in % tiles_n) * BN_;
   t.a_row = t.m0 + outer * ep.a_row_outer + inner * ep.a_row_inner;
   t.a_col = outer * ep.a_col_outer + inner * ep.a_col_inner;
@@ -165,6 +165,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sm
 __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 template <int N> __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory"); }
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// W half-tile multicast to both CTAs of a pair: lands at the same offset in each CTA and signals each CTA's own `full` barrier
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensorMap* map, uint64_t* bar, int c_inner, int c_outer, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+      ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(map)) : "memory");
 }
@@ -197,6 +208,10 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 }
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {   // arrives on the barrier at this offset in every CTA of mask
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -260,7 +275,9 @@ template <int MODE, int BN_> struct Cfg {
   static constexpr int STAGING_BYTES = 4 * 2 * 32 * 128;                         // TMA-store staging of the epilogue warps
 };
 
-template <int MODE, int BN_, bool PROBE>
+// CL = 2: CTA pairs (cluster of 2) share one N tile; each CTA loads half of the W tile and multicasts it to both, which
+// cuts the L2 -> SM operand traffic per SM from A + W to A + W/2 (W is 4/5 of it in the split modes).  MMA / TMEM stay per CTA.
+template <int MODE, int BN_, bool PROBE, int CL>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
@@ -287,9 +304,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tiles_m = (ep.M + BM - 1) / BM, tiles_n = (ep.N + BN - 1) / BN;
+  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int tiles_m_real = (ep.M + BM - 1) / BM;
+  const int tiles_m = CL == 2 ? (tiles_m_real + 1) / 2 : tiles_m_real;      // CL == 2: rows of tile PAIRS (an odd tail gets a dummy tile)
+  const int tiles_n = (ep.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n * ep.batch;
   const int kblocks = (ep.K + BK - 1) / BK;
+  const int tile0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -301,7 +322,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], CL);           // CL == 2: a stage is refilled by BOTH CTAs' multicasts, so both MMAs must have retired it
       mbar_init(&ready[s], 128);          // every thread of the split group that owns the stage (measured faster than one elected lane per warp)
     }
     for (int a = 0; a < 2; ++a) {
@@ -316,6 +337,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   }
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -324,8 +346,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
+      for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL, rank);
         for (int kb = 0; kb < kblocks; ++kb) {
           if (PROBE && (ep.dbg & 32)) mbar_spin(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
@@ -346,9 +368,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           mbar_expect_tx(&full[stage], TILE_A + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
           tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
-          tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
-          if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
-          if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
+          if (CL == 2) {
+            // this CTA's half of the W rows (maps have BN/2-row boxes), written into both CTAs of the pair
+            constexpr int HB = CF::TILE_B / 2;
+            const int brow = tc.b_row + rank * (BN / 2);
+            tma_load_2d_mc(smem_u32(st + CF::OFF_BH + rank * HB), &mapBh, &full[stage], kb * BK + tc.b_col, brow, 3);
+            if (MODE == 2) tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * HB), &mapBl, &full[stage], kb * BK + tc.b_col, brow, 3);
+            if (MODE == 3) {
+              tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * (HB / 2)), &mapBl, &full[stage], kb * BK + tc.b_col, brow, 3);
+              tma_load_2d_mc(smem_u32(st + CF::OFF_B16 + rank * (HB / 2)), &mapB16, &full[stage], kb * BK + tc.b_col, brow, 3);
+            }
+          } else {
+            tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
+            if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
+            if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -366,7 +400,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr uint32_t DESC_HI = (uint32_t)((8 * BK * 4) >> 4) | (1u << 14) | ((BK == 32 ? 2u : 4u) << 29);        // SBO | version | swizzle
     constexpr uint32_t DESC_HI_B16 = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);                                // bf16 tiles, SWIZZLE_32B
     constexpr uint32_t LBO = 1u << 16;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
@@ -399,7 +433,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
           }
-          if (PROBE && (ep.dbg & 16)) mbar_arrive(&empty[stage]); else umma_commit(&empty[stage]);
+          if (PROBE && (ep.dbg & 16)) mbar_arrive(&empty[stage]);
+          else if (CL == 2) umma_commit_mc(&empty[stage], 3);
+          else umma_commit(&empty[stage]);
           if (kb == kblocks - 1) umma_commit(&acc_full[acc]);
         }
         __syncwarp();
@@ -420,8 +456,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN);
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL, rank);
       const int m0 = tc.m0, n0 = tc.n0;
       const int row = m0 + row_in_tile;
       mbar_wait(&acc_full[acc], acc_phase);
@@ -540,14 +576,17 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ================= bf16 correction operands of the A tile =================
     // fp32 tile: 128 rows x 16 floats, 64-byte rows, SWIZZLE_64B: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3).
     // bf16 tiles: 128 rows x 16 bf16, 32-byte rows, SWIZZLE_32B: 16-byte chunk m of row r sits at chunk m ^ ((r >> 2) & 1).
-    // two groups of 4 warps alternate stages, so that the split of stage s+1 overlaps the tail (fence + arrive) of stage s
+    // two groups of 4 warps alternate stages, so that the split of stage s+1 overlaps the tail (fence + arrive) of stage s.
+    // Ownership is by STAGE INDEX (not by iteration): a barrier is then only ever waited on by the group that consumed its previous
+    // phase, so no waiter can run two phases ahead of `full[stage]` and alias its parity (with an odd stage count, ownership by
+    // iteration let group 0 poll a stage whose previous phase -- owned by group 1 -- had not landed yet)
     const int t = (threadIdx.x - 256) & 127;  // 0..127
     const int grp = (threadIdx.x - 256) >> 7;
-    int stage = 0, it = 0;
+    int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        if ((it % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if ((stage % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
         mbar_wait(&full[stage], phase);
         uint8_t* st = smem + stage * STAGE_BYTES;
         const float4* src = reinterpret_cast<const float4*>(st);
@@ -578,11 +617,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // ================= A hi/lo split (element-wise, so it is oblivious to the 128B swizzle) =================
     const int t = (threadIdx.x - 256) & 127;  // 0..127
     const int grp = (threadIdx.x - 256) >> 7;
-    int stage = 0, it = 0;
+    int stage = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-      for (int kb = 0; kb < kblocks; ++kb, ++it) {
-        if ((it % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
+    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      for (int kb = 0; kb < kblocks; ++kb) {
+        if ((stage % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
         mbar_wait(&full[stage], phase);
         float4* hi = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES);
         float4* lo = reinterpret_cast<float4*>(smem + stage * STAGE_BYTES + CF::OFF_AL);
@@ -607,6 +646,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
+  if (CL == 2) cluster_sync_all();        // no CTA exits while its peer can still multicast to it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -721,6 +761,7 @@ struct MapKeyHash {
   }
 };
 static int g_tma_store = 1;
+static int g_cluster = 2;
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
@@ -756,21 +797,22 @@ static int get_tensor_map(const void* base, int rows, int cols, int ld, int box_
   return VSG_OK;
 }
 
-template <int MODE, int BN_>
+template <int MODE, int BN_, int CL>
 static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                      const GemmEpilogue& ep_in, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
   using CF = Cfg<MODE, BN_>;
   CUtensorMap mA, mBh, mBl, mB16;
+  constexpr int WBOX = BN_ / CL;                  // CL == 2: each CTA of a pair loads (and multicasts) half of the W rows
   int rc = get_tensor_map(A, a_rows, a_cols, lda, BM, CF::BK, &mA);
   if (rc) return rc;
-  rc = get_tensor_map(Wh, w_rows, w_cols, ldw, BN_, CF::BK, &mBh);
+  rc = get_tensor_map(Wh, w_rows, w_cols, ldw, WBOX, CF::BK, &mBh);
   if (rc) return rc;
-  if (MODE == 2) { rc = get_tensor_map(Wl, w_rows, w_cols, ldw, BN_, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
+  if (MODE == 2) { rc = get_tensor_map(Wl, w_rows, w_cols, ldw, WBOX, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
   mB16 = mBh;
   if (MODE == 3) {
-    rc = get_tensor_map(Wl, w_rows, w_cols, ldw16, BN_, CF::BK, &mBl, 2);
+    rc = get_tensor_map(Wl, w_rows, w_cols, ldw16, WBOX, CF::BK, &mBl, 2);
     if (rc) return rc;
-    rc = get_tensor_map(W16, w_rows, w_cols, ldw16, BN_, CF::BK, &mB16, 2);
+    rc = get_tensor_map(W16, w_rows, w_cols, ldw16, WBOX, CF::BK, &mB16, 2);
     if (rc) return rc;
   }
   GemmEpilogue ep = ep_in;
@@ -794,18 +836,37 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
     attr_set = true;
   }
-  const long long tiles = (long long)((ep.M + BM - 1) / BM) * ((ep.N + BN_ - 1) / BN_) * ep.batch;
-  const int grid = (int)(tiles < sm_count() ? tiles : sm_count());
-  if (ep.dbg) gemm_tc_kernel<MODE, BN_, true><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, mB16, mC, ep);   // timing probes
-  else gemm_tc_kernel<MODE, BN_, false><<<grid, CF::THREADS, SMEM, st>>>(mA, mBh, mBl, mB16, mC, ep);
+  const long long tiles_m = (ep.M + BM - 1) / BM;
+  const long long work = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((ep.N + BN_ - 1) / BN_) * ep.batch;   // tiles, or tile pairs
+  const int slots = sm_count() / CL;
+  const int grid = (int)(work < slots ? work : slots) * CL;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CF::THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+  cudaError_t e = ep.dbg ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, true, CL>, mA, mBh, mBl, mB16, mC, ep)   // timing probes
+                         : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL>, mA, mBh, mBl, mB16, mC, ep);
+  if (e != cudaSuccess) { set_error("vsg_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VSG_E_LAUNCH; }
   return check_launch("vsg_gemm(tcgen05)");
+}
+
+template <int MODE, int BN_>
+static int launch_tc_auto(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
+                          const GemmEpilogue& ep, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
+  // CTA pairs with W multicast for plain problems with at least one full pair of M tiles
+  if (g_cluster == 2 && ep.batch == 1 && ep.M > BM)
+    return launch_tc<MODE, BN_, 2>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
+  return launch_tc<MODE, BN_, 1>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
 }
 
 // N=256 tiles whenever they do not add MMA work over N=128 tiles
@@ -820,6 +881,8 @@ static int g_dbg = 0;
 /* timing probes (results become garbage): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads, 16 free stages by a plain arrive, 32 producer / issuer poll with test_wait; 0 = normal */
 /* validation knob: 0 = the epilogue writes C with per-row 16-byte stores only, 1 (default) = full 32x32 slabs leave through TMA stores */
 extern "C" int vsg_gemm_set_tma_store(int on) { int old = vsg::g_tma_store; vsg::g_tma_store = on ? 1 : 0; return old; }
+/* validation knob: 1 = every GEMM runs one CTA per tile; 2 (default) = CTA pairs (cluster of 2) that multicast the W tile */
+extern "C" int vsg_gemm_set_cluster(int n) { int old = vsg::g_cluster; vsg::g_cluster = n == 1 ? 1 : 2; return old; }
 extern "C" int vsg_gemm_debug_flags(int f) { int old = g_dbg; g_dbg = f; return old; }
 static int g_force_bn = 0;
 /* debug/validation knob: 128 forces the N=128 tile kernel everywhere, 0 = automatic */
@@ -890,19 +953,19 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   }
   const bool wide = use_bn256(N) && g_force_bn != 128;
   if (mode == 1)
-    return wide ? launch_tc<1, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st)
-                : launch_tc<1, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st);
+    return wide ? launch_tc_auto<1, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st)
+                : launch_tc_auto<1, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st);
   if (mode == 2) {
     VSG_REQUIRE(a->W_lo && aligned16(a->W_lo), "vsg_gemm: mode 2 (3xTF32) needs the pre-split low part of W");
-    return wide ? launch_tc<2, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st)
-                : launch_tc<2, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st);
+    return wide ? launch_tc_auto<2, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st)
+                : launch_tc_auto<2, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo, a->ldw, w_rows, w_cols, ep, st);
   }
   if (mode == 3) {
     VSG_REQUIRE(batch == 1, "vsg_gemm_ex: mode 3 (tf32 + 2 x bf16) takes plain problems only; batched attention problems use mode 2");
     VSG_REQUIRE(a->W_b16 && a->W_lo16 && aligned16(a->W_b16) && aligned16(a->W_lo16) && a->ldw16 >= K && a->ldw16 % 8 == 0,
                 "vsg_gemm_ex: mode 3 needs the bf16 copies of W from vsg_split_bf16 (16-byte aligned, ldw16 a multiple of 8)");
-    return wide ? launch_tc<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
-                : launch_tc<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
+    return wide ? launch_tc_auto<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
+                : launch_tc_auto<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
   }
   set_error("vsg_gemm: unknown mode %d", mode);
   return VSG_E_UNSUPPORTED;
