@@ -409,8 +409,16 @@ def main():
     peak_src = "measured" if peaks else "fallback"
     gemm_tf = gemm_flops / (gemm_ms * 1e-3) / 1e12 if gemm_ms > 0 else 0.0
     geo_gbs = geo_bytes / (geo_ms * 1e-3) / 1e9 if geo_ms > 0 else 0.0
+    traffic, traffic_src = None, None
+    try:        # per-launch DRAM bytes of the step's GEMM launches from the committed ncu pass (same command, same workload)
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_v3.summary.json")))
+        if args.workload == "vidvrd" and args.videos == 200 and args.precision == "3xtf32":
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_gemm_traffic_v3.summary.json (dram read+write / launch, 82 launches)"
+    except Exception:
+        pass
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 %s)" % args.precision, "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak,
-                "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": None, "peak_source": peak_src + " bf16 dense sustained",
+                "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src + " bf16 dense sustained",
                 "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms_step,
                 "note": "achieved = useful 2MNK flops; 3xTF32 issues 3 tf32 MMAs per useful one and tf32 peak is half of bf16",
                 "also": {"kernel": "traj_viou_warp_kernel (+track volumes)", "bound": "hbm", "achieved": geo_gbs, "peak": hbm_peak,

@@ -184,3 +184,23 @@ def test_prop_pair_to_gt_pred_dataset():
         assert torch.equal(out[name][1].cpu(), r[1]), name
         n_checked += 1
     assert n_checked >= 2
+
+
+def test_row_block_sharding_reproduces_the_full_matrix():
+    """shard.traj_viou_row_sharded's per-rank work (rows [r0, r1) of one video against all of its tracks) for world = 3,
+    concatenated: bit-identical to the single-launch matrix (the N > 1 exchange itself is covered by the gloo CPU test)."""
+    from vidsgg_big_b200 import geometry, shard, synth
+    P = synth.make_proposal(77, 23, 400, 8, 36, min_len=30, max_len=300, with_features=False).to("cuda:0")
+    boxes, dura = P.bboxes_list, P.traj_durations
+    n = len(boxes)
+    T = geometry.TrackTable.from_lists(boxes, dura)
+    full_v, full_sp, full_m, _, _ = geometry.traj_viou_batched(T, T)
+    vs, sps, ms = [], [], []
+    for r in range(3):
+        r0, r1 = shard.row_block(n, r, 3)
+        A = geometry.TrackTable.from_lists(boxes[r0:r1], dura[r0:r1])
+        v, sp, m, _, _ = geometry.traj_viou_batched(A, T)
+        vs.append(v); sps.append(sp); ms.append(m)
+    assert torch.equal(torch.cat(vs), full_v) and torch.equal(torch.cat(sps), full_sp) and torch.equal(torch.cat(ms), full_m)
+    v1, sp1, m1 = shard.traj_viou_row_sharded(boxes, dura)            # world size 1: no collective
+    assert torch.equal(v1.reshape(-1), full_v) and torch.equal(sp1.reshape(-1, 2), full_sp)

@@ -124,6 +124,34 @@ def test_gather_records_gloo_world2():
     assert all(r[1] == exp_rows and r[2] == exp_sum for r in res)
 
 
+def _gloo_rows_worker(rank, world, port, q):
+    import torch.distributed as dist
+    from vidsgg_big_b200 import shard
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    n = 7                                                    # 7 rows over 2 ranks: blocks of 4 and 3
+    full = torch.arange(n * 5 * 2, dtype=torch.int64).reshape(n, 5, 2)
+    r0, r1 = shard.row_block(n, rank, world)
+    out = shard.gather_row_blocks(full[r0:r1].clone(), n)
+    q.put((rank, (r0, r1), bool(torch.equal(out, full))))
+    dist.destroy_process_group()
+
+
+def test_gather_row_blocks_gloo_world2():
+    """Row-block exchange of the single-video stress configuration (pair matrix split by rows over the ranks)."""
+    import torch.multiprocessing as mp
+    from vidsgg_big_b200 import shard
+    assert [shard.row_block(10, r, 4) for r in range(4)] == [(0, 3), (3, 6), (6, 8), (8, 10)]
+    assert [shard.row_block(2, r, 4) for r in range(4)] == [(0, 1), (1, 2), (2, 2), (2, 2)]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_gloo_rows_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted(q.get(timeout=120) for _ in range(2))
+    [p.join(timeout=60) for p in procs]
+    assert res == [(0, (0, 4), True), (1, (4, 7), True)]
+
+
 def test_native_eval_records_equal_numpy_aggregation():
     """csrc/evalhost.cu (host code of the library) restates the numpy per-video aggregation exactly."""
     import ctypes as C
