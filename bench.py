@@ -36,7 +36,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--videos", type=int, default=200, help="videos per GPU per step (weak scaling)")
     ap.add_argument("--workload", default="vidvrd", choices=["vidvrd", "vidor"])
-    ap.add_argument("--precision", default="3xtf32", choices=["3xtf32", "tf32+bf16x2", "tf32", "fp32_simt"])
+    ap.add_argument("--precision", default="tf32+bf16x2", choices=["3xtf32", "tf32+bf16x2", "tf32", "fp32_simt"])
     ap.add_argument("--cpu-sample", type=int, default=None,
                     help="videos in the bounded CPU sample (default: 200 for cpu_baseline, 40 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -57,8 +57,9 @@ def workload_cfg(kind):
                      topk=3, name="VidOR-val-shaped batch, BIG-C exp5 dims (RoI 1024 + classeme 300), 10-180 tracklets")
 
 
-def make_videos(kind, n_videos, base_seed, device, pinned=False):
-    """Proposals (boxes etc. from the seeded host generator) whose features are row views of ONE buffer, plus GT graphs."""
+def make_videos(kind, n_videos, base_seed, device, pinned=False, feats=None, i3d=None):
+    """Proposals (boxes etc. from the seeded host generator) whose features are row views of ONE buffer, plus GT graphs.
+    ``feats`` / ``i3d``: use these feature rows / per-video clip features instead of drawing new ones."""
     cfg, wl = workload_cfg(kind)
     props, graphs = [], []
     for i in range(n_videos):
@@ -71,7 +72,9 @@ def make_videos(kind, n_videos, base_seed, device, pinned=False):
         props.append(P)
     rows = sum(int(p.lengths.sum()) for p in props)
     g = torch.Generator(device=device).manual_seed(base_seed)
-    feats = torch.randn(rows, wl["feat_total"], generator=g, device=device, dtype=torch.float32) * 0.5
+    if feats is None:
+        feats = torch.randn(rows, wl["feat_total"], generator=g, device=device, dtype=torch.float32) * 0.5
+    assert feats.shape[0] == rows
     if pinned:
         host = torch.empty(rows, wl["feat_total"], dtype=torch.float32, pin_memory=True)
         host.copy_(feats)
@@ -83,9 +86,9 @@ def make_videos(kind, n_videos, base_seed, device, pinned=False):
         p.dim_feat = wl["feat_total"]
         r += L
     if kind == "vidor":      # I3D clip features for the grounding stage: f32[T, 1024] * 0.05, T = ceil(video_len / 8)
-        for p in props:
+        for k, p in enumerate(props):
             T = (p.video_len + 7) // 8
-            p.i3d = (torch.randn(T, 1024, generator=g, device=device, dtype=torch.float32) * 0.05)
+            p.i3d = i3d[k] if i3d is not None else (torch.randn(T, 1024, generator=g, device=device, dtype=torch.float32) * 0.05)
             if pinned:
                 p.i3d = p.i3d.cpu().pin_memory()
     return cfg, wl, props, graphs, feats
@@ -208,7 +211,7 @@ def gt_from_predictions(pipe, props, cfg, kind, base_seed, device):
     for i, (p, t) in enumerate(zip(props, trips)):
         t3 = None if t is None else (t[0], t[1].mean(-1), t[2])
         graphs.append(synth.make_gt_from_predictions(base_seed + i, p, t3, num_pred_cats=cfg["num_pred_cats"]).to(device))
-    return graphs
+    return graphs, trips
 
 
 class HostBatch(object):
@@ -277,26 +280,48 @@ def cpu_pass(kind, props, graphs, st, cfg, wl, gst=None):
     return oe.evaluate(gts, prs)
 
 
-def cpu_baseline(kind, n_sample, repeats=1):
+def cpu_baseline(kind, n_sample, repeats=1, feats_from=None):
+    """Times the oracle port on ``n_sample`` videos (seeds 1000..).  ``feats_from``: (features, i3d list) of the GPU arm's videos,
+    copied to the host so that both arms see bit-identical inputs (the CUDA and CPU generators differ).  Returns
+    (videos/s, seconds, metrics, per-video triplets of the oracle)."""
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu")
+    feats, i3d = feats_from if feats_from is not None else (None, None)
+    cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu", feats=feats, i3d=i3d)
     st = synth.make_bigc_state(1, cfg)
     gst = synth.make_grounding_state(21, synth.grounding_config()) if kind == "vidor" else None
     from oracle import bigc as ob
+    trips = []
     with torch.no_grad():                                                  # GT from the (oracle's) own predictions, untimed
         graphs = []
         for i, p in enumerate(props):
             r = ob.forward(st, cfg, [p], wl["topk"])[0]
+            trips.append(r)
             graphs.append(synth.make_gt_from_predictions(1000 + i, p, None if r is None else (r[0], r[1].mean(-1), r[2]),
                                                          num_pred_cats=cfg["num_pred_cats"]))
     cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl, gst)                # warm-up
-    best = None
+    best, metrics = None, None
     for _ in range(repeats):
         t0 = time.perf_counter()
-        cpu_pass(kind, props, graphs, st, cfg, wl, gst)
+        metrics = cpu_pass(kind, props, graphs, st, cfg, wl, gst)
         dt = time.perf_counter() - t0
         best = dt if best is None else min(best, dt)
-    return n_sample / best, best
+    return n_sample / best, best, metrics, trips
+
+
+def compare_triplets(gpu_trips, cpu_trips):
+    """Per-video identity of the classification output (quintuples + spans, as sets) between the CUDA path and the oracle."""
+    same = total = 0
+    for a, b in zip(gpu_trips, cpu_trips):
+        total += 1
+        if (a is None) != (b is None):
+            continue
+        if a is None:
+            same += 1
+            continue
+        sa = set(map(tuple, torch.cat([a[0].cpu(), a[2].cpu()], 1).tolist()))
+        sb = set(map(tuple, torch.cat([b[0], b[2]], 1).tolist()))
+        same += int(sa == sb)
+    return same, total
 
 
 def run_reference(args, rank, world):
@@ -307,7 +332,7 @@ def run_reference(args, rank, world):
         args.cpu_sample = 40 if args.workload == "vidvrd" else 2
     times = []
     for i in range(args.warmup + args.steps):
-        v, dt = cpu_baseline(args.workload, args.cpu_sample)
+        v, dt, _, _ = cpu_baseline(args.workload, args.cpu_sample)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -343,17 +368,21 @@ def main():
         dist.init_process_group("nccl", device_id=device)
     _cabi.lib()
 
-    # CPU baseline first (rank 0, N=1 only), so it does not overlap the GPU timing
-    cpu = None
+    pipe = Pipeline(args.workload, args.precision, device, rank)
+    cfg, wl, props, graphs, feats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device)
+
+    # CPU baseline (rank 0, N=1 only) before any GPU timing, on the SAME videos: their features are copied to the host, so the
+    # oracle's triplets / metrics can be compared with the CUDA path's at the benchmark's full size
+    cpu, cpu_metrics, cpu_trips = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         if args.cpu_sample is None:
             args.cpu_sample = 200 if args.workload == "vidvrd" else 6
-        v, dt = cpu_baseline(args.workload, args.cpu_sample)
+        args.cpu_sample = min(args.cpu_sample, args.videos)
+        rows = sum(int(p.lengths.sum()) for p in props[:args.cpu_sample])
+        i3d = [p.i3d.cpu() for p in props[:args.cpu_sample]] if args.workload == "vidor" else None
+        v, dt, cpu_metrics, cpu_trips = cpu_baseline(args.workload, args.cpu_sample, feats_from=(feats[:rows].cpu(), i3d))
         cpu = {"value": v, "unit": "videos/s", "cores": torch.get_num_threads(), "kind": "port",
-               "sample": "%d videos of the same workload (seeds 1000..), %.1f s of CPU work" % (args.cpu_sample, dt)}
-
-    pipe = Pipeline(args.workload, args.precision, device, rank)
-    cfg, wl, props, graphs, feats = make_videos(args.workload, args.videos, 1000 + 100000 * rank, device)
+               "sample": "the first %d videos of the same batch (same inputs, copied to the host), %.1f s of CPU work" % (args.cpu_sample, dt)}
     for g in graphs:
         g.to(device)
     for p in props:
@@ -369,7 +398,14 @@ def main():
         torch.cuda.synchronize()
 
     # GT derived from the model's own predictions (first pass), so that the evaluation stage has real matches to find
-    graphs = gt_from_predictions(pipe, props, cfg, args.workload, 1000 + 100000 * rank, device)
+    graphs, gpu_trips = gt_from_predictions(pipe, props, cfg, args.workload, 1000 + 100000 * rank, device)
+    parity = None
+    if cpu_trips is not None:
+        same, total = compare_triplets(gpu_trips[:len(cpu_trips)], cpu_trips)
+        parity = {"videos_with_identical_triplets": same, "videos_compared": total,
+                  "cpu_oracle_metrics": {"mAP": float(cpu_metrics[0]), "R@50": float(cpu_metrics[1][50]), "R@100": float(cpu_metrics[1][100])}
+                  if args.cpu_sample == args.videos and args.workload == "vidvrd" else None}
+    del gpu_trips
     for _ in range(args.warmup):
         metrics, n_trip, _ = pipe.step(props, graphs)
     # ---- timed region: K steps, inputs resident in HBM (they exceed L2 by far: no flush needed) ----
@@ -412,7 +448,7 @@ def main():
     traffic, traffic_src = None, None
     try:        # per-launch DRAM bytes of the step's GEMM launches from the committed ncu pass (same command, same workload)
         tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_v3.summary.json")))
-        if args.workload == "vidvrd" and args.videos == 200 and args.precision == "3xtf32":
+        if args.workload == "vidvrd" and args.videos == 200 and args.precision in ("3xtf32", "tf32+bf16x2"):
             traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_gemm_traffic_v3.summary.json (dram read+write / launch, 82 launches)"
     except Exception:
         pass
@@ -420,7 +456,8 @@ def main():
                 "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src + " bf16 dense sustained",
                 "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms_step,
-                "note": "achieved = useful 2MNK flops; 3xTF32 issues 3 tf32 MMAs per useful one and tf32 peak is half of bf16",
+                "note": "achieved = useful 2MNK flops of an fp32-class product: 3xtf32 issues 3 tf32 MMAs per useful one (6 bf16-equivalent "
+                        "tensor slots), tf32+bf16x2 issues 1 tf32 + 2 bf16 (4 slots); ncu: tensor pipe 91-93 % active on the large GEMMs",
                 "also": {"kernel": "traj_viou_warp_kernel (+track volumes)", "bound": "hbm", "achieved": geo_gbs, "peak": hbm_peak,
                          "unit": "GB/s", "frac": geo_gbs / hbm_peak, "ms": geo_ms, "algorithmic_bytes": geo_bytes}}
 
@@ -478,7 +515,7 @@ def main():
                        "grounding": "grd_model_v5 dims, 10 bins" if args.workload == "vidor" else "not in this workload (VidVRD has no grounding stage)",
                        "l2": "inputs (%.1f GB per GPU) exceed L2" % (in_bytes / 1e9),
                        "result": {"mAP": metrics[0], "R@50": metrics[1], "R@100": metrics[2], "triplets": n_trip}},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": n_launches,
+            "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu_oracle": parity, "e2e": e2e, "gpu_launches": n_launches,
             "clocks": clk,
         }
         print(json.dumps(out))

@@ -190,6 +190,8 @@ typedef struct VsgGemmArgs {
   long long c_outer, c_inner;
   int lo_col_begin, lo_col_end;                       /* C_lo is written for columns in [begin, end) only (multiples of 4); 0, 0 = every column */
   const void* W_b16; const void* W_lo16; int ldw16;   /* mode VSG_GEMM_TF32_BF16X2: bf16 [N][ldw16] copies of W (W_hi = the fp32 W) */
+  const void* W_img; int img_bn;                      /* optional (mode 3): pre-swizzled tile images from vsg_build_weight_image built for
+                                                         tile width img_bn; ignored unless img_bn == vsg_gemm_tile_n(N) */
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 
@@ -213,6 +215,15 @@ int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream
 /* bf16 operands of mode VSG_GEMM_TF32_BF16X2 for a weight w[rows][cols] (ldw): w16 = bf16_rn(w), lo16 = bf16_rn(w - trunc_tf32(w)),
  * both [rows][ld16] (ld16 >= cols, a multiple of 8; the padding columns are written as zeros). */
 int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void* w16, void* lo16, int ld16, void* stream);
+/* Weight-tile images of mode VSG_GEMM_TF32_BF16X2: for every (N tile of `bn` rows, 16-column k block) one contiguous block holding the
+ * shared-memory layout of the stage's three W operands (fp32 SWIZZLE_64B, bf16 and bf16-low SWIZZLE_32B; edges zero-padded), so that the
+ * kernel's producer fetches them with contiguous bulk copies instead of 32/64-byte-row tensor loads.  vsg_gemm_tile_n(N) = the tile
+ * width (128 / 256) vsg_gemm_ex will use for an N-column weight; vsg_weight_image_bytes = size of the image buffer (16-byte aligned). */
+int vsg_gemm_tile_n(int N);
+int64_t vsg_weight_image_bytes(int N, int K, int bn);
+int vsg_build_weight_image(const float* w, int ldw, int N, int K, int bn, void* img, void* stream);
+/* Validation knob: 0 = ignore W_img (tensor-map loads); 1 (default).  Bit-identical C.  Returns the old value. */
+int vsg_gemm_set_weight_image(int on);
 
 /* ---- BIG-C classification stage, non-GEMM kernels -------------------------
  * Batch layout: rows = all box-frames of all tracks of all videos; off int64[N+1]; seg int32[V+1] track range

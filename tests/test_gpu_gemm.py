@@ -229,3 +229,27 @@ def test_batched_odd_stage_count_is_race_free():
             assert (att.double() - want).abs().max().item() <= 2e-5 * want.abs().max().item()
         else:
             assert torch.equal(att, ref), it
+
+
+def test_weight_images_equal_tensor_map_loads():
+    """Mode 3 with the pre-swizzled weight-tile images (contiguous bulk loads) against the tensor-map loads of the same operands:
+    bit-identical C for wide / narrow tiles, ragged N and K, single CTAs and CTA pairs."""
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(29)
+    for (M, N, K) in ((1000, 512, 1024), (300, 1536, 512), (641, 133, 3160), (4097, 64, 96), (128, 128, 16), (777, 200, 100)):
+        A = torch.randn(M, K, generator=g).to(DEV)
+        W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+        b = torch.randn(N, generator=g).to(DEV)
+        wt = _weight(3, W, b)
+        assert wt.img is not None and wt.img_bn in (128, 256)
+        outs = []
+        for on, cl in ((1, 2), (0, 2), (1, 1)):
+            o1, o2 = lib().vsg_gemm_set_weight_image(on), lib().vsg_gemm_set_cluster(cl)
+            try:
+                outs.append(linalg.gemm(3, A, wt, relu=True).clone())
+            finally:
+                lib().vsg_gemm_set_weight_image(o1); lib().vsg_gemm_set_cluster(o2)
+        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (M, N, K)
+        ref = torch.relu(_ref(A, W, b))
+        assert (outs[0].double() - ref).abs().max().item() <= TOL[3] * ref.abs().max().item()

@@ -36,7 +36,8 @@ class VsgGemmArgs(C.Structure):
                 ("a_row_outer", i32), ("a_row_inner", i32), ("a_col_outer", i32), ("a_col_inner", i32),
                 ("b_row_outer", i32), ("b_row_inner", i32), ("b_col_outer", i32), ("b_col_inner", i32),
                 ("c_outer", C.c_longlong), ("c_inner", C.c_longlong),
-                ("lo_col_begin", i32), ("lo_col_end", i32), ("W_b16", p), ("W_lo16", p), ("ldw16", i32)]
+                ("lo_col_begin", i32), ("lo_col_end", i32), ("W_b16", p), ("W_lo16", p), ("ldw16", i32),
+                ("W_img", p), ("img_bn", i32)]
 
 
 class VsgError(RuntimeError):
@@ -66,6 +67,10 @@ SIGNATURES = {
     "vsg_gemm_debug_flags": (i32, [i32]),
     "vsg_gemm_set_tma_store": (i32, [i32]),
     "vsg_gemm_set_cluster": (i32, [i32]),
+    "vsg_gemm_tile_n": (i32, [i32]),
+    "vsg_weight_image_bytes": (i64, [i32, i32, i32]),
+    "vsg_build_weight_image": (i32, [p, i32, i32, i32, i32, p, p]),
+    "vsg_gemm_set_weight_image": (i32, [i32]),
     "vsg_split_bf16": (i32, [p, i32, i32, i32, p, p, i32, p]),
     "vsg_softmax_rows": (i32, [p, i32, i32, i64, f32, p]),
     "vsg_transpose_split": (i32, [p, i32, i64, i32, p, p, i64, p]),

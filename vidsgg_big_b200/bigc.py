@@ -95,7 +95,7 @@ class BIG_C(object):
 
     variant = "vidvrd"
 
-    def __init__(self, config: dict, is_train: bool = False, precision: str = "3xtf32"):
+    def __init__(self, config: dict, is_train: bool = False, precision: str = "tf32+bf16x2"):
         if is_train:
             raise NotImplementedError("vidsgg_big_b200.BIG_C covers the inference hot path only (is_train=False)")
         self.is_train = False

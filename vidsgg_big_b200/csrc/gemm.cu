@@ -59,6 +59,7 @@ struct GemmEpilogue {
   float* C_lo;              // optional: x - trunc_tf32(x) of every stored value (the B-side low part for a following 3xTF32 GEMM)
   int lo_c0, lo_c1;         // C_lo is written for columns in [lo_c0, lo_c1) only
   int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
+  const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null
   // batched problems: tile -> (problem p, m block, n block); p -> (outer = p / batch_inner, inner = p % batch_inner).
   // TMA coordinates and the C pointer are offset per problem; M / N are per-problem extents (batch == 1: plain GEMM).
   int dbg;                  // probe flags (vsg_gemm_debug_flags): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads
@@ -171,6 +172,15 @@ __device__ __forceinline__ void tma_load_2d_mc(uint32_t smem_dst, const CUtensor
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
       ::"r"(smem_dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(smem_u32(bar)), "r"(c_inner), "r"(c_outer), "h"(mask)
       : "memory");
+}
+// contiguous global -> shared copies of pre-swizzled weight-tile images (full 128-byte lines, unlike the 32 / 64-byte rows of the tensor loads)
+__device__ __forceinline__ void bulk_load(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_load_mc(uint32_t smem_dst, const void* src, uint32_t bytes, uint64_t* bar, uint16_t mask) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1], %2, [%3], %4;"
+               ::"r"(smem_dst), "l"(src), "r"(bytes), "r"(smem_u32(bar)), "h"(mask) : "memory");
 }
 __device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
 __device__ __forceinline__ void cluster_sync_all() {
@@ -368,7 +378,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           mbar_expect_tx(&full[stage], TILE_A + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
           tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
-          if (CL == 2) {
+          if (MODE == 3 && ep.w_img != nullptr) {
+            // W tiles as contiguous pre-swizzled images [W f32 | bf16(W) | bf16(W_lo)] per (N tile, k block)
+            constexpr int TB = CF::TILE_B;
+            const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(2 * TB);
+            if (CL == 2) {
+              bulk_load_mc(smem_u32(st + CF::OFF_BH + rank * (TB / 2)), img + rank * (TB / 2), TB / 2, &full[stage], 3);
+              bulk_load_mc(smem_u32(st + CF::OFF_B16 + rank * (TB / 4)), img + TB + rank * (TB / 4), TB / 4, &full[stage], 3);
+              bulk_load_mc(smem_u32(st + CF::OFF_BL + rank * (TB / 4)), img + TB + TB / 2 + rank * (TB / 4), TB / 4, &full[stage], 3);
+            } else {
+              bulk_load(smem_u32(st + CF::OFF_BH), img, TB, &full[stage]);
+              bulk_load(smem_u32(st + CF::OFF_B16), img + TB, TB, &full[stage]);      // bf16(W) and bf16(W_lo) are adjacent in the stage
+            }
+          } else if (CL == 2) {
             // this CTA's half of the W rows (maps have BN/2-row boxes), written into both CTAs of the pair
             constexpr int HB = CF::TILE_B / 2;
             const int brow = tc.b_row + rank * (BN / 2);
@@ -728,6 +750,35 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, int ldw, int rows
   }
 }
 
+// Pre-swizzled shared-memory images of the W tiles of mode 3 (BK = 16): for every (N tile, k block) one contiguous block
+//   [ W fp32: bn rows x 64 B, SWIZZLE_64B | bf16(W): bn rows x 32 B, SWIZZLE_32B | bf16(W - trunc_tf32(W)): same ]
+// so that the producer fetches a stage's W operands with plain contiguous bulk copies.  One thread per 16-byte fp32 chunk.
+__global__ void weight_image_kernel(const float* __restrict__ w, int ldw, int N, int K, int bn, uint8_t* __restrict__ img) {
+  const int kblocks = (K + 15) / 16, tiles_n = (N + bn - 1) / bn;
+  const int64_t total = (int64_t)tiles_n * kblocks * bn * 4;
+  const int tile_b = bn * 64;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 3);
+    const int r = (int)((i >> 2) % bn);
+    const int64_t blk = (i >> 2) / bn;                 // nt * kblocks + kb
+    const int kb = (int)(blk % kblocks), nt = (int)(blk / kblocks);
+    const int row = nt * bn + r, col = kb * 16 + c * 4;
+    float x[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) x[j] = (row < N && col + j < K) ? w[(size_t)row * ldw + col + j] : 0.f;
+    uint8_t* base = img + blk * (int64_t)(2 * tile_b);
+    *reinterpret_cast<float4*>(base + r * 64 + ((c ^ ((r >> 1) & 3)) << 4)) = make_float4(x[0], x[1], x[2], x[3]);
+    float lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) lo[j] = x[j] - __uint_as_float(__float_as_uint(x[j]) & 0xFFFFE000u);
+    const __nv_bfloat162 h0 = __floats2bfloat162_rn(x[0], x[1]), h1 = __floats2bfloat162_rn(x[2], x[3]);
+    const __nv_bfloat162 l0 = __floats2bfloat162_rn(lo[0], lo[1]), l1 = __floats2bfloat162_rn(lo[2], lo[3]);
+    const int dst = r * 32 + ((((c >> 1) ^ ((r >> 2) & 1))) << 4) + (c & 1) * 8;
+    *reinterpret_cast<uint2*>(base + tile_b + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+    *reinterpret_cast<uint2*>(base + tile_b + tile_b / 2 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------
 // host side: tensor maps
 // ---------------------------------------------------------------------------------------------------
@@ -761,6 +812,7 @@ struct MapKeyHash {
   }
 };
 static int g_tma_store = 1;
+static int g_w_image = 1;
 static int g_cluster = 2;
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
@@ -883,6 +935,8 @@ static int g_dbg = 0;
 extern "C" int vsg_gemm_set_tma_store(int on) { int old = vsg::g_tma_store; vsg::g_tma_store = on ? 1 : 0; return old; }
 /* validation knob: 1 = every GEMM runs one CTA per tile; 2 (default) = CTA pairs (cluster of 2) that multicast the W tile */
 extern "C" int vsg_gemm_set_cluster(int n) { int old = vsg::g_cluster; vsg::g_cluster = n == 1 ? 1 : 2; return old; }
+/* validation knob: 0 = mode 3 loads its W operands through tensor maps even when a weight image is supplied */
+extern "C" int vsg_gemm_set_weight_image(int on) { int old = vsg::g_w_image; vsg::g_w_image = on ? 1 : 0; return old; }
 extern "C" int vsg_gemm_debug_flags(int f) { int old = g_dbg; g_dbg = f; return old; }
 static int g_force_bn = 0;
 /* debug/validation knob: 128 forces the N=128 tile kernel everywhere, 0 = automatic */
@@ -910,6 +964,23 @@ extern "C" int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void*
   return check_launch("vsg_split_bf16");
 }
 
+extern "C" int vsg_gemm_tile_n(int N) { return (use_bn256(N) && g_force_bn != 128) ? 256 : 128; }
+
+extern "C" int64_t vsg_weight_image_bytes(int N, int K, int bn) {
+  if (N <= 0 || K <= 0 || (bn != 128 && bn != 256)) return 0;
+  return (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * (int64_t)(2 * bn * 64);
+}
+
+extern "C" int vsg_build_weight_image(const float* w, int ldw, int N, int K, int bn, void* img, void* stream) {
+  VSG_REQUIRE(N > 0 && K > 0 && ldw >= K && (bn == 128 || bn == 256), "vsg_build_weight_image: bad extents");
+  VSG_REQUIRE(w && img && aligned16(img), "vsg_build_weight_image: null or unaligned pointer");
+  const int64_t total = (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * bn * 4;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  weight_image_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, ldw, N, K, bn, (uint8_t*)img);
+  return check_launch("vsg_build_weight_image");
+}
+
 extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   VSG_REQUIRE(a != nullptr, "vsg_gemm_ex: null args");
   const int M = a->M, N = a->N, K = a->K;
@@ -923,7 +994,7 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
   ep.store_hi = g_store_hi; ep.dbg = g_dbg;
   ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
-  ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0;
+  ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.w_img = nullptr;
   if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
   ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
   ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
@@ -964,6 +1035,7 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
     VSG_REQUIRE(batch == 1, "vsg_gemm_ex: mode 3 (tf32 + 2 x bf16) takes plain problems only; batched attention problems use mode 2");
     VSG_REQUIRE(a->W_b16 && a->W_lo16 && aligned16(a->W_b16) && aligned16(a->W_lo16) && a->ldw16 >= K && a->ldw16 % 8 == 0,
                 "vsg_gemm_ex: mode 3 needs the bf16 copies of W from vsg_split_bf16 (16-byte aligned, ldw16 a multiple of 8)");
+    if (g_w_image && a->W_img && a->img_bn == (wide ? 256 : 128) && aligned16(a->W_img)) ep.w_img = (const uint8_t*)a->W_img;
     return wide ? launch_tc_auto<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
                 : launch_tc_auto<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
   }

@@ -39,7 +39,7 @@ def expand_after_grounding(quintuples, cls_scores3, pooled_se, bins_probs, bins_
 
 
 class DEBUG(object):
-    def __init__(self, config: dict, is_train: bool = False, precision: str = "3xtf32"):
+    def __init__(self, config: dict, is_train: bool = False, precision: str = "tf32+bf16x2"):
         if is_train:
             raise NotImplementedError("vidsgg_big_b200.DEBUG covers the inference hot path only (is_train=False)")
         self.is_train = False

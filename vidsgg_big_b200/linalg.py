@@ -28,13 +28,20 @@ class Weight(object):
         self.w = w.detach().float().contiguous()
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.N, self.K = self.w.shape
-        self.hi = self.lo = self.w16 = self.lo16 = None
+        self.hi = self.lo = self.w16 = self.lo16 = self.img = None
+        self.img_bn = 0
         if split == "bf16":
             self.ld16 = (self.K + 7) // 8 * 8
             self.w16 = torch.empty(self.N, self.ld16, dtype=torch.bfloat16, device=self.w.device)
             self.lo16 = torch.empty_like(self.w16)
             check(lib().vsg_split_bf16(ptr(self.w), self.w.stride(0), self.N, self.K, ptr(self.w16), ptr(self.lo16), self.ld16,
                                        stream_ptr(self.w.device)), "vsg_split_bf16")
+            # pre-swizzled tile images for the tile width the kernel will pick (contiguous bulk loads of the W operands)
+            self.img_bn = int(lib().vsg_gemm_tile_n(self.N))
+            nbytes = int(lib().vsg_weight_image_bytes(self.N, self.K, self.img_bn))
+            self.img = torch.empty(nbytes, dtype=torch.uint8, device=self.w.device)
+            check(lib().vsg_build_weight_image(ptr(self.w), self.w.stride(0), self.N, self.K, self.img_bn, ptr(self.img),
+                                               stream_ptr(self.w.device)), "vsg_build_weight_image")
         elif split:
             self.hi = torch.empty_like(self.w)
             self.lo = torch.empty_like(self.w)
@@ -112,6 +119,8 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
             a.lo_col_begin, a.lo_col_end = int(lo_cols[0]), int(lo_cols[1])
         if mode == TF32_BF16X2:
             a.W_b16, a.W_lo16, a.ldw16 = W.w16.data_ptr(), W.lo16.data_ptr(), W.ld16
+            if W.img is not None and K == W.K:           # the image's k blocks cover the whole of W.K
+                a.W_img, a.img_bn = W.img.data_ptr(), W.img_bn
         check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
     else:
         check(lib().vsg_gemm(mode, _raw(A), lda, _raw(w_hi), _raw(w_lo), W.w.stride(0), M, W.N, K, _raw(b), _raw(rowbias),
