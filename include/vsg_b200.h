@@ -203,8 +203,10 @@ int vsg_gemm_force_bn(int bn);
 /* Validation knob: 0 = the epilogue writes C with per-row 16-byte stores only; 1 (default) = full 32x32 output slabs are staged in
  * shared memory (128B swizzle) and leave through cp.async.bulk.tensor stores.  Both give bit-identical C.  Returns the old value. */
 int vsg_gemm_set_tma_store(int on);
-/* Validation knob: 1 = one CTA per output tile everywhere; 2 (default) = plain problems with M > 128 run as CTA pairs (thread-block
- * cluster of 2) that share an N tile and multicast each half of the W tile to both CTAs.  Bit-identical C.  Returns the old value. */
+/* Validation knob: 1 = one CTA per output tile everywhere; 2 = plain problems with M > 128 run as CTA pairs (thread-block cluster
+ * of 2) that share an N tile and multicast each half of the W tile to both CTAs; 3 (default) = as 2, but the fp32-class modes with
+ * 256-wide tiles issue ONE tcgen05.mma.cta_group::2 (M = 256) per pair, each CTA staging only its half of W (6 instead of 4 pipeline
+ * stages).  Bit-identical C across 1 / 2 / 3.  Returns the old value. */
 int vsg_gemm_set_cluster(int n);
 /* Timing probes for bottleneck analysis (the results become garbage): bit 0 skip the W loads, bit 1 skip the A split,
  * bit 2 skip the MMAs, bit 3 skip the A loads; 0 (default) = normal operation.  Returns the old value. */

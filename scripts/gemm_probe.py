@@ -20,7 +20,7 @@ if "--quick" in sys.argv:
     SHAPES = [SHAPES[0], SHAPES[3]]
 FLAGS = [(0, "normal"), (1, "no W loads"), (8, "no A loads"), (9, "no loads"), (2, "no split"), (4, "no MMA"), (6, "no split, no MMA"),
          (13, "no loads, no MMA")]
-CLUSTERS = (2, 1)
+CLUSTERS = (3, 2, 1)
 
 
 def time_gemm(mode, A, wt, out, reps=5):
@@ -49,7 +49,7 @@ def main():
                 for fl, fname in FLAGS:
                     if mode == 1 and (fl & 2):
                         continue
-                    if fl and (cl == 2 or "--normal" in sys.argv):      # the probe flags are only meaningful for the single-CTA kernel
+                    if fl and (cl >= 2 or "--normal" in sys.argv):      # the probe flags are only meaningful for the single-CTA kernel
                         continue
                     lib().vsg_gemm_debug_flags(fl)
                     try:
@@ -59,7 +59,7 @@ def main():
                     tf = 2.0 * M * N * K / (ms * 1e-3) / 1e12
                     res.append(dict(shape=name, M=M, N=N, K=K, mode=mname, cluster=cl, probe=fname, ms=ms, useful_tflops=tf))
                     print("%-8s %-12s cl%d %-18s %8.3f ms  %7.1f TF/s useful" % (name, mname, cl, fname, ms, tf), flush=True)
-            lib().vsg_gemm_set_cluster(2)
+            lib().vsg_gemm_set_cluster(3)
         del A, W, out
     if "--json" in sys.argv:
         json.dump(res, open(sys.argv[sys.argv.index("--json") + 1], "w"), indent=1)

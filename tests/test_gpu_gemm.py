@@ -184,7 +184,7 @@ def test_tma_store_epilogue_equals_direct_stores(mode):
 
 @pytest.mark.parametrize("mode", [1, 2, 3])
 def test_cta_pair_multicast_equals_single_cta(mode):
-    """CTA pairs (cluster of 2, W half-tiles multicast to both CTAs) against one CTA per tile: bit-identical C, including an odd
+    """CTA-pair MMAs (cta_group::2) and CTA pairs with W multicast against one CTA per tile: bit-identical C, including an odd
     number of M tiles (the pair's second CTA runs a dummy tile), a single pair, ragged edges and wide / narrow N tiles."""
     from vidsgg_big_b200 import linalg
     from vidsgg_big_b200._cabi import lib
@@ -196,13 +196,14 @@ def test_cta_pair_multicast_equals_single_cta(mode):
         b = torch.randn(N, generator=g).to(DEV)
         wt = _weight(mode, W, b)
         outs = []
-        for cl in (2, 1):
+        for cl in (3, 2, 1):
             old = lib().vsg_gemm_set_cluster(cl)
             try:
                 outs.append(linalg.gemm(mode, A, wt, relu=True).clone())
             finally:
                 lib().vsg_gemm_set_cluster(old)
-        assert torch.equal(outs[0], outs[1]), (mode, M, N, K)
+        assert torch.equal(outs[1], outs[2]), (mode, M, N, K)
+        assert torch.equal(outs[0], outs[1]), ("cta_group::2", mode, M, N, K)
         ref = torch.relu(_ref(A, W, b))
         assert (outs[0].double() - ref).abs().max().item() <= TOL[mode] * ref.abs().max().item()
 
@@ -244,12 +245,12 @@ def test_weight_images_equal_tensor_map_loads():
         wt = _weight(3, W, b)
         assert wt.img is not None and wt.img_bn in (128, 256)
         outs = []
-        for on, cl in ((1, 2), (0, 2), (1, 1)):
+        for on, cl in ((1, 3), (0, 3), (1, 2), (0, 2), (1, 1)):
             o1, o2 = lib().vsg_gemm_set_weight_image(on), lib().vsg_gemm_set_cluster(cl)
             try:
                 outs.append(linalg.gemm(3, A, wt, relu=True).clone())
             finally:
                 lib().vsg_gemm_set_weight_image(o1); lib().vsg_gemm_set_cluster(o2)
-        assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2]), (M, N, K)
+        assert all(torch.equal(outs[0], o) for o in outs[1:]), (M, N, K)
         ref = torch.relu(_ref(A, W, b))
         assert (outs[0].double() - ref).abs().max().item() <= TOL[3] * ref.abs().max().item()

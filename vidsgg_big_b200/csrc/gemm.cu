@@ -223,6 +223,62 @@ __device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {  
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
                ::"r"(smem_u32(bar)), "h"(mask) : "memory");
 }
+// ---- cta_group::2 (CTA-pair MMA) variants ----
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() { asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accum) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accum)
+      : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(smem_u32(bar)), "h"(mask) : "memory");
+}
+// arrive on the barrier at the same offset in CTA `cta` of the cluster.  Default semantics (release.cta), as CUTLASS's
+// ClusterBarrier::arrive(cta_id): the data it publishes was made visible to the async proxy by fence.proxy.async beforehand, and an
+// explicit .release.cluster compiles to MEMBAR.ALL.GPU + ERRBAR (measured: 15 % of all warp samples stalled there).
+__device__ __forceinline__ void mbar_arrive_cluster(uint64_t* bar, uint32_t cta) {
+  uint32_t raddr;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(bar)), "r"(cta));
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(raddr) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope (remote arrivals)
+  uint32_t spins = 0;
+  uint64_t t0 = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    if (ok) return;
+    if ((++spins & 0x3FF) == 0) {
+      const uint64_t now = global_ns();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > WATCHDOG_NS) __trap();
+    }
+  }
+}
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -263,16 +319,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_b16(uint32_t smem_addr) {
 }
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 (1<<4), a=b=TF32 (2<<7, 2<<10), K-major both,
 // n_dim = N>>3 at [17,23), m_dim = M>>4 at [24,29)
-template <int BN_> struct IDesc {
-  static constexpr uint32_t tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
-  static constexpr uint32_t bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+template <int BN_, int M_ = 128> struct IDesc {
+  static constexpr uint32_t tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+  static constexpr uint32_t bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
 };
 
 // ---------------------------------------------------------------------------------------------------
-template <int MODE, int BN_> struct Cfg {
+// PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 (M = 256) per k step; each CTA stages its 128 rows of A and only
+// HALF of the W tile (TILE_B below is the per-CTA part), so a stage shrinks from 48 to 32 KB and 6 stages fit instead of 4.
+template <int MODE, int BN_, bool PAIR = false> struct Cfg {
   static constexpr int BK = ((MODE == 2 && BN_ == 256) || MODE == 3) ? 16 : 32;
   static constexpr int TILE_A = BM * BK * 4;
-  static constexpr int TILE_B = BN_ * BK * 4;
+  static constexpr int TILE_B = (PAIR ? BN_ / 2 : BN_) * BK * 4;
   static constexpr int STAGE_BYTES = (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles)
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16)
   static constexpr int SPLIT_GROUPS = 2;                                         // groups of 4 split warps that alternate stages
@@ -287,12 +345,15 @@ template <int MODE, int BN_> struct Cfg {
 
 // CL = 2: CTA pairs (cluster of 2) share one N tile; each CTA loads half of the W tile and multicasts it to both, which
 // cuts the L2 -> SM operand traffic per SM from A + W to A + W/2 (W is 4/5 of it in the split modes).  MMA / TMEM stay per CTA.
+// CL = 3: CTA-pair MMA (cta_group::2, see Cfg<.., PAIR>): rank 0 issues M = 256 instructions over both CTAs' operands, each CTA
+// loads only its half of W (no multicast), the peer's split / epilogue warps signal the leader's barriers through DSMEM arrives.
 template <int MODE, int BN_, bool PROBE, int CL>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
                const __grid_constant__ CUtensorMap mapC, const GemmEpilogue ep) {
-  using CF = Cfg<MODE, BN_>;
+  constexpr bool PAIR = (CL == 3);
+  using CF = Cfg<MODE, BN_, PAIR>;
   constexpr int STAGES = CF::STAGES;
   constexpr int STAGE_BYTES = CF::STAGE_BYTES;
   constexpr int BN = BN_;
@@ -314,13 +375,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int rank = CL == 2 ? (int)cluster_ctarank() : 0;
+  const int rank = CL >= 2 ? (int)cluster_ctarank() : 0;
   const int tiles_m_real = (ep.M + BM - 1) / BM;
-  const int tiles_m = CL == 2 ? (tiles_m_real + 1) / 2 : tiles_m_real;      // CL == 2: rows of tile PAIRS (an odd tail gets a dummy tile)
+  const int tiles_m = CL >= 2 ? (tiles_m_real + 1) / 2 : tiles_m_real;      // clusters: rows of tile PAIRS (an odd tail gets a dummy tile)
   const int tiles_n = (ep.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n * ep.batch;
   const int kblocks = (ep.K + BK - 1) / BK;
-  const int tile0 = CL == 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CL == 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int tile0 = CL >= 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CL >= 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&mapA);
@@ -332,22 +393,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], CL);           // CL == 2: a stage is refilled by BOTH CTAs' multicasts, so both MMAs must have retired it
-      mbar_init(&ready[s], 128);          // every thread of the split group that owns the stage (measured faster than one elected lane per warp)
+      mbar_init(&empty[s], CL == 2 ? 2 : 1);   // CL == 2: a stage is refilled by BOTH CTAs' multicasts, so both MMAs must have retired it
+      mbar_init(&ready[s], PAIR ? 132 : 128);  // every thread of the split group that owns the stage (PAIR: + one DSMEM arrive per peer warp)
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
-      mbar_init(&acc_empty[a], 128);
+      mbar_init(&acc_empty[a], PAIR ? 132 : 128);
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if (PAIR) { tmem_alloc2(tmem_slot, TMEM_COLS); tmem_relinquish2(); }
+    else { tmem_alloc(tmem_slot, TMEM_COLS); tmem_relinquish(); }
   }
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to them
+  if (CL >= 2) cluster_sync_all();        // the peer's barriers are initialised before anything is multicast to / arrives on them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -357,7 +418,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0;
       uint32_t phase = 0;
       for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-        const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL, rank);
+        const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank);
         for (int kb = 0; kb < kblocks; ++kb) {
           if (PROBE && (ep.dbg & 32)) mbar_spin(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
@@ -378,7 +439,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
           mbar_expect_tx(&full[stage], TILE_A + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
           tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
-          if (MODE == 3 && ep.w_img != nullptr) {
+          if (PAIR) {
+            // this CTA's half of the W rows only; the pair's MMA reads the other half from the peer's shared memory
+            constexpr int TB = CF::TILE_B;                 // per-CTA W f32 bytes
+            if (MODE == 3 && ep.w_img != nullptr) {
+              const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(4 * TB);
+              bulk_load(smem_u32(st + CF::OFF_BH), img + rank * TB, TB, &full[stage]);
+              bulk_load(smem_u32(st + CF::OFF_B16), img + 2 * TB + rank * (TB / 2), TB / 2, &full[stage]);
+              bulk_load(smem_u32(st + CF::OFF_BL), img + 3 * TB + rank * (TB / 2), TB / 2, &full[stage]);
+            } else {
+              const int brow = tc.b_row + rank * (BN / 2);
+              tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, brow);
+              if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, brow);
+              if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, brow);
+            }
+          } else if (MODE == 3 && ep.w_img != nullptr) {
             // W tiles as contiguous pre-swizzled images [W f32 | bf16(W) | bf16(W_lo)] per (N tile, k block)
             constexpr int TB = CF::TILE_B;
             const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(2 * TB);
@@ -422,15 +497,42 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     constexpr uint32_t DESC_HI = (uint32_t)((8 * BK * 4) >> 4) | (1u << 14) | ((BK == 32 ? 2u : 4u) << 29);        // SBO | version | swizzle
     constexpr uint32_t DESC_HI_B16 = (uint32_t)(256 >> 4) | (1u << 14) | (6u << 29);                                // bf16 tiles, SWIZZLE_32B
     constexpr uint32_t LBO = 1u << 16;
-    for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+    for (int tile = tile0; tile < n_tiles && (!PAIR || rank == 0); tile += tile_step) {
       mbar_wait(&acc_empty[acc], acc_phase ^ 1);
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + acc * ACC_COLS;
       for (int kb = 0; kb < kblocks; ++kb) {
+        // (PAIR: the peer's arrives are release.cluster; like CUTLASS's 2-SM pipelines the wait itself is the default try_wait --
+        //  an acquire.cluster try_wait per k block was measured to cost ~1 us each)
         if (PROBE && (ep.dbg & 32)) mbar_spin(MODE >= 2 ? &ready[stage] : &full[stage], phase);
         else mbar_wait(MODE >= 2 ? &ready[stage] : &full[stage], phase);
         tc_fence_after();
-        if (elect_one()) {
+        if (PAIR) {
+          if (elect_one()) {
+            constexpr uint32_t ID_TF32 = IDesc<BN_, 256>::tf32, ID_BF16 = IDesc<BN_, 256>::bf16;
+            const uint32_t st16 = base16 + (uint32_t)stage * (STAGE_BYTES >> 4);
+            auto desc = [&](uint32_t off_bytes, uint32_t hi) -> uint64_t {
+              return ((uint64_t)hi << 32) | (uint64_t)((st16 + (off_bytes >> 4)) | LBO);
+            };
+            const uint64_t a_hi = desc(0, DESC_HI), b_hi = desc(CF::OFF_BH, DESC_HI);
+            if (MODE == 3) {
+              umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), ID_BF16, kb ? 1u : 0u);
+              umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), ID_BF16, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma2_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_TF32, 1u);
+            } else {
+              const uint64_t a_lo = desc(CF::OFF_AL, DESC_HI), b_lo = desc(CF::OFF_BL, DESC_HI);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma2_tf32(d_tmem, a_lo + 2 * k, b_hi + 2 * k, ID_TF32, (kb | k) ? 1u : 0u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma2_tf32(d_tmem, a_hi + 2 * k, b_lo + 2 * k, ID_TF32, 1u);
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) umma2_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_TF32, 1u);
+            }
+            umma2_commit_mc(&empty[stage], 3);                       // frees the stage in BOTH CTAs
+            if (kb == kblocks - 1) umma2_commit_mc(&acc_full[acc], 3);  // both epilogues read their own 128 accumulator rows
+          }
+        } else if (elect_one()) {
           const uint32_t st16 = base16 + (uint32_t)stage * (STAGE_BYTES >> 4);
           auto desc = [&](uint32_t off_bytes, uint32_t hi) -> uint64_t {
             return ((uint64_t)hi << 32) | (uint64_t)((st16 + (off_bytes >> 4)) | LBO);
@@ -479,7 +581,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
-      const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL, rank);
+      const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank);
       const int m0 = tc.m0, n0 = tc.n0;
       const int row = m0 + row_in_tile;
       mbar_wait(&acc_full[acc], acc_phase);
@@ -590,7 +692,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[acc]);
+      if (PAIR && rank != 0) {
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(&acc_empty[acc], 0);
+      } else {
+        mbar_arrive(&acc_empty[acc]);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();                                           // staging reads AND global writes complete before exit
@@ -631,7 +738,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           *reinterpret_cast<uint2*>(a16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
         }
         fence_proxy_async();
-        mbar_arrive(&ready[stage]);
+        if (PAIR && rank != 0) {            // peer CTA: one remote (DSMEM) arrive per warp on the leader's barrier
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&ready[stage], 0);
+        } else {
+          mbar_arrive(&ready[stage]);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -660,7 +772,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           lo[idx] = l;
         }
         fence_proxy_async();          // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&ready[stage]);
+        if (PAIR && rank != 0) {            // peer CTA: one remote (DSMEM) arrive per warp on the leader's barrier
+          __syncwarp();
+          if (lane == 0) mbar_arrive_cluster(&ready[stage], 0);
+        } else {
+          mbar_arrive(&ready[stage]);
+        }
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -668,10 +785,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   tc_fence_before();
   __syncthreads();
-  if (CL == 2) cluster_sync_all();        // no CTA exits while its peer can still multicast to it / arrive on its barriers
+  if (CL >= 2) cluster_sync_all();        // no CTA exits while its peer can still multicast to it / arrive on its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if (PAIR) tmem_dealloc2(tmem_base, TMEM_COLS); else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -813,7 +930,7 @@ struct MapKeyHash {
 };
 static int g_tma_store = 1;
 static int g_w_image = 1;
-static int g_cluster = 2;
+static int g_cluster = 3;
 static std::mutex g_map_mu;
 static std::unordered_map<MapKey, CUtensorMap, MapKeyHash> g_maps;
 
@@ -852,9 +969,10 @@ static int get_tensor_map(const void* base, int rows, int cols, int ld, int box_
 template <int MODE, int BN_, int CL>
 static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                      const GemmEpilogue& ep_in, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
-  using CF = Cfg<MODE, BN_>;
+  using CF = Cfg<MODE, BN_, CL == 3>;
+  constexpr int CLN = CL >= 2 ? 2 : 1;            // CTAs per cluster
   CUtensorMap mA, mBh, mBl, mB16;
-  constexpr int WBOX = BN_ / CL;                  // CL == 2: each CTA of a pair loads (and multicasts) half of the W rows
+  constexpr int WBOX = BN_ / CLN;                 // clusters: each CTA of a pair loads (CL == 2: and multicasts) half of the W rows
   int rc = get_tensor_map(A, a_rows, a_cols, lda, BM, CF::BK, &mA);
   if (rc) return rc;
   rc = get_tensor_map(Wh, w_rows, w_cols, ldw, WBOX, CF::BK, &mBh);
@@ -896,16 +1014,16 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
     attr_set = true;
   }
   const long long tiles_m = (ep.M + BM - 1) / BM;
-  const long long work = (CL == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((ep.N + BN_ - 1) / BN_) * ep.batch;   // tiles, or tile pairs
-  const int slots = sm_count() / CL;
-  const int grid = (int)(work < slots ? work : slots) * CL;
+  const long long work = (CLN == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((ep.N + BN_ - 1) / BN_) * ep.batch;   // tiles, or tile pairs
+  const int slots = sm_count() / CLN;
+  const int grid = (int)(work < slots ? work : slots) * CLN;
   cudaLaunchConfig_t cfg;
   memset(&cfg, 0, sizeof(cfg));
   cfg.gridDim = dim3(grid); cfg.blockDim = dim3(CF::THREADS); cfg.dynamicSmemBytes = SMEM; cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = CL > 1 ? 1 : 0;
+  attr[0].val.clusterDim.x = CLN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = CLN > 1 ? 1 : 0;
   cudaError_t e = ep.dbg ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, true, CL>, mA, mBh, mBl, mB16, mC, ep)   // timing probes
                          : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL>, mA, mBh, mBl, mB16, mC, ep);
   if (e != cudaSuccess) { set_error("vsg_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VSG_E_LAUNCH; }
@@ -915,8 +1033,11 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
 template <int MODE, int BN_>
 static int launch_tc_auto(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                           const GemmEpilogue& ep, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
-  // CTA pairs with W multicast for plain problems with at least one full pair of M tiles
-  if (g_cluster == 2 && ep.batch == 1 && ep.M > BM)
+  // plain problems with at least one full pair of M tiles run on CTA pairs: one cta_group::2 MMA per pair (split modes, 256-wide
+  // tiles), else two per-CTA MMAs with the W tile multicast
+  if (BN_ == 256 && MODE >= 2 && g_cluster == 3 && ep.batch == 1 && ep.M > BM && !ep.dbg)
+    return launch_tc<MODE, 256, 3>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
+  if (g_cluster >= 2 && ep.batch == 1 && ep.M > BM)
     return launch_tc<MODE, BN_, 2>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
   return launch_tc<MODE, BN_, 1>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
 }
@@ -933,8 +1054,9 @@ static int g_dbg = 0;
 /* timing probes (results become garbage): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads, 16 free stages by a plain arrive, 32 producer / issuer poll with test_wait; 0 = normal */
 /* validation knob: 0 = the epilogue writes C with per-row 16-byte stores only, 1 (default) = full 32x32 slabs leave through TMA stores */
 extern "C" int vsg_gemm_set_tma_store(int on) { int old = vsg::g_tma_store; vsg::g_tma_store = on ? 1 : 0; return old; }
-/* validation knob: 1 = every GEMM runs one CTA per tile; 2 (default) = CTA pairs (cluster of 2) that multicast the W tile */
-extern "C" int vsg_gemm_set_cluster(int n) { int old = vsg::g_cluster; vsg::g_cluster = n == 1 ? 1 : 2; return old; }
+/* validation knob: 1 = one CTA per tile; 2 = CTA pairs that multicast the W tile (per-CTA MMAs); 3 (default) = CTA-pair MMAs
+   (tcgen05 cta_group::2, M = 256) where available (split modes, 256-wide tiles), else as 2 */
+extern "C" int vsg_gemm_set_cluster(int n) { int old = vsg::g_cluster; vsg::g_cluster = (n >= 1 && n <= 3) ? n : 3; return old; }
 /* validation knob: 0 = mode 3 loads its W operands through tensor maps even when a weight image is supplied */
 extern "C" int vsg_gemm_set_weight_image(int on) { int old = vsg::g_w_image; vsg::g_w_image = on ? 1 : 0; return old; }
 extern "C" int vsg_gemm_debug_flags(int f) { int old = g_dbg; g_dbg = f; return old; }
