@@ -150,6 +150,20 @@ int vsg_viou_pairs_f64(const double* boxes1, const int64_t* off1, const int64_t*
                        const double* boxes2, const int64_t* off2, const int64_t* dur2,
                        int n, double* out, void* stream);
 
+/* tIoU / generalized_tIoU of closed 1-D spans (utils/utils_func.py:375-410; models/grd_model_v5.py:18-33):
+ * out f32[n1*n2] (broadcast) or f32[n1] (row-wise, n1 == n2) = (min(e1,e2) - max(s1,s2)) / (max(e1,e2) - min(s1,s2)); generalized = 0
+ * additionally zeroes pairs whose spans do not touch.  dtype 0: int64 spans (true-divided as float32, like torch), 1: float32. */
+int vsg_tiou(const void* d1, int n1, const void* d2, int n2, int broadcast, int generalized, int dtype, float* out, void* stream);
+
+/* The stretch of stack_with_repeat_2d (models/model_0v10.py:18-46): out f32[n_tracks][tmax][width]; frame i of an L-frame track
+ * (rows off[t] .. off[t+1] of src, leading dimension ld) is repeated ceil((tmax - i) / L) times.  The hot path never materialises
+ * this tensor; the entry point exists for callers of the reference helper. */
+int vsg_stretch_rows(const float* src, int ld, int width, const int64_t* off, int n_tracks, int tmax, float* out, void* stream);
+
+/* unique_with_idx_nd (utils/utils_func.py:330-345) for int64 rows[n][d], n <= 8192: order int32[n] = original row indices sorted by
+ * (row lexicographic, index); group int32[n] = id of the unique row of each sorted position; *n_groups = number of unique rows. */
+int vsg_unique_rows(const int64_t* rows, int n, int d, int32_t* order, int32_t* group, int32_t* n_groups, void* stream);
+
 /* ---- scoring: GEMM (kernels K4-K6) -------------------------------- */
 
 #define VSG_GEMM_SIMT 0   /* fp32 FFMA tiles (comparator / shapes TMA cannot describe)          */

@@ -320,7 +320,35 @@ def gen_grounding():
     save("grounding", **out)
 
 
+def gen_grounding_gt():
+    """DEBUG.forward(with_gt_data=True) in inference mode (grd_model_v5.py:198-221, 253-308): queries built from GT graphs."""
+    out = {}
+    cfg = synth.grounding_config()
+    state = synth.make_grounding_state(21, cfg)
+    tmp = tempfile.mkdtemp()
+    np.save(os.path.join(tmp, "e.npy"), state["EntiNameEmb"].numpy()); np.save(os.path.join(tmp, "p.npy"), state["PredNameEmb"].numpy())
+    rcfg = dict(cfg, EntiNameEmb_path=os.path.join(tmp, "e.npy"), PredNameEmb_path=os.path.join(tmp, "p.npy"))
+    model = DEBUG(rcfg, is_train=False)
+    model.load_state_dict(state, strict=True)
+    model.eval()
+    inf = synth.GROUNDING_INFERENCE
+    for sd, n, vl in ((611, 10, 200), (612, 16, 520)):
+        P = synth.make_proposal(sd, n, vl, 8, 81, min_len=15, with_features=False)
+        G = synth.make_gt_graph(sd, P, 51)
+        vf = synth.make_video_feature(sd, vl)
+        with torch.no_grad():
+            words, tinfo, target, index_map = model.prepare_gt_data(G)
+            pooled, probs, mask = model([vf], [G], with_gt_data=True, **inf)
+        k = "gt%d" % sd
+        out[k + "_tinfo"] = tinfo.numpy(); out[k + "_target"] = target.numpy()
+        out[k + "_index_map"] = torch.cat(index_map).numpy(); out[k + "_counts"] = np.array([len(x) for x in index_map])
+        out[k + "_pooled"] = pooled.numpy(); out[k + "_probs"] = probs.numpy(); out[k + "_mask"] = mask.numpy()
+        print("grounding (GT queries) golden", k, "n_uniq=%d of %d GT predicates" % (tinfo.shape[0], G.num_preds), "mask true=%d" % int(mask.sum()))
+    save("grounding_gt", **out)
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["geometry", "eval", "bigc", "align", "grounding"]
+    which = sys.argv[1:] or ["geometry", "eval", "bigc", "align", "grounding", "grounding_gt"]
     for w in which:
-        {"geometry": gen_geometry, "eval": gen_eval, "bigc": gen_bigc, "align": gen_align, "grounding": gen_grounding}[w]()
+        {"geometry": gen_geometry, "eval": gen_eval, "bigc": gen_bigc, "align": gen_align, "grounding": gen_grounding,
+         "grounding_gt": gen_grounding_gt}[w]()

@@ -204,3 +204,73 @@ def test_row_block_sharding_reproduces_the_full_matrix():
     assert torch.equal(torch.cat(vs), full_v) and torch.equal(torch.cat(sps), full_sp) and torch.equal(torch.cat(ms), full_m)
     v1, sp1, m1 = shard.traj_viou_row_sharded(boxes, dura)            # world size 1: no collective
     assert torch.equal(v1.reshape(-1), full_v) and torch.equal(sp1.reshape(-1, 2), full_sp)
+
+
+def test_tiou_and_generalized_tiou(golden):
+    """tIoU / generalized_tIoU (utils/utils_func.py:375-410) against the reference goldens (float spans) and the oracle (int64 spans,
+    row-wise mode)."""
+    from vidsgg_big_b200 import geometry
+    g = golden("geometry")
+    rng = np.random.default_rng(11)
+    s = rng.integers(0, 200, size=(23, 1)); d1 = np.concatenate([s, s + rng.integers(0, 120, size=(23, 1))], 1)
+    s = rng.integers(0, 200, size=(17, 1)); d2 = np.concatenate([s, s + rng.integers(0, 120, size=(17, 1))], 1)
+    t1, t2 = torch.from_numpy(d1), torch.from_numpy(d2)
+    f1, f2 = (t1.float() / 320).cuda(), (t2.float() / 320).cuda()
+    np.testing.assert_allclose(geometry.tIoU(f1, f2).cpu().numpy(), g["tiou"], rtol=1e-6, atol=0)
+    np.testing.assert_allclose(geometry.generalized_tIoU(f1, f2).cpu().numpy(), g["gtiou"], rtol=1e-6, atol=0)
+    # int64 spans (true division in float32) incl. the row-wise form
+    a, b = t1[:17].cuda(), t2.cuda()
+    for fn, ofn in ((geometry.tIoU, og.tiou), (geometry.generalized_tIoU, og.generalized_tiou)):
+        np.testing.assert_allclose(fn(a, b).cpu().numpy(), ofn(t1[:17], t2).numpy(), rtol=1e-6)
+        np.testing.assert_allclose(fn(a, b, broadcast=False).cpu().numpy(), ofn(t1[:17], t2, broadcast=False).numpy(), rtol=1e-6)
+    assert geometry.tIoU(a[:0], b).shape == (0, 17)
+
+
+def test_unique_with_idx_nd(golden):
+    """unique_with_idx_nd (utils/utils_func.py:330-345): SURVEY KAT, the reference golden, random rows vs the oracle, N-d rows."""
+    from vidsgg_big_b200 import geometry
+    g = golden("geometry")
+    kat = torch.tensor([[3, 1, 2, 0, 1], [1, 1, 2, 0, 1], [3, 1, 2, 0, 1], [1, 0, 2, 5, 1]])
+    u, groups = geometry.unique_with_idx_nd(kat.cuda())
+    assert u.cpu().tolist() == [[1, 0, 2, 5, 1], [1, 1, 2, 0, 1], [3, 1, 2, 0, 1]]
+    assert [x.cpu().tolist() for x in groups] == [[3], [1], [0, 2]]
+    rng = np.random.default_rng(11)
+    rng.integers(0, 200, size=(23, 1)); rng.integers(0, 120, size=(23, 1)); rng.integers(0, 200, size=(17, 1)); rng.integers(0, 120, size=(17, 1))
+    rnd = torch.from_numpy(rng.integers(0, 3, size=(60, 5)))
+    u, groups = geometry.unique_with_idx_nd(rnd.cuda())
+    assert np.array_equal(u.cpu().numpy(), g["uniq_rows"])
+    assert np.array_equal(np.array([int(x[0]) for x in groups]), g["uniq_first"])
+    assert np.array_equal(np.array([len(x) for x in groups]), g["uniq_counts"])
+    for n, d, hi in ((1, 3, 2), (777, 5, 3), (1920, 5, 4), (4097, 2, 50), (300, 1, 7)):
+        t = torch.from_numpy(np.random.default_rng(n).integers(-hi, hi, size=(n, d)))
+        u, groups = geometry.unique_with_idx_nd(t.cuda())
+        ou, ogr = og.unique_rows_with_groups(t)
+        assert torch.equal(u.cpu(), ou) and len(groups) == len(ogr)
+        assert all(torch.equal(a.cpu(), b) for a, b in zip(groups, ogr))
+    t3 = torch.from_numpy(np.random.default_rng(5).integers(0, 2, size=(40, 2, 2)))           # rows of shape (2, 2)
+    u, groups = geometry.unique_with_idx_nd(t3.cuda())
+    ou, ogr = og.unique_rows_with_groups(t3)
+    assert torch.equal(u.cpu(), ou) and all(torch.equal(a.cpu(), b) for a, b in zip(groups, ogr))
+    u, groups = geometry.unique_with_idx_nd(kat[:0].cuda())
+    assert u.shape[0] == 0 and groups == tuple()
+
+
+def test_stack_with_repeat_2d(golden):
+    """stack_with_repeat_2d (models/model_0v10.py:18-46): the stretch index maps of the reference goldens and both ragged axes."""
+    from vidsgg_big_b200 import geometry
+    g = golden("geometry")
+    for L, T in ((3, 7), (5, 5), (4, 13), (7, 8), (1, 6), (6, 29)):
+        out = geometry.stack_with_repeat_2d([torch.arange(L)[:, None].float().cuda(), torch.zeros(T, 1).cuda()], dim=0)
+        assert out.shape == (2, T, 1)
+        assert np.array_equal(out[0, :, 0].long().cpu().numpy(), g["stretch_%d_%d" % (L, T)])
+    rng = np.random.default_rng(3)
+    lens = [5, 17, 9, 17, 1]
+    ts = [torch.from_numpy(rng.standard_normal((l, 6)).astype(np.float32)) for l in lens]
+    want = torch.stack([t[torch.from_numpy(og.stretch_index_map(l, 17))] for t, l in zip(ts, lens)], 0)
+    got = geometry.stack_with_repeat_2d([t.cuda() for t in ts], dim=0)
+    assert torch.equal(got.cpu(), want)
+    got1 = geometry.stack_with_repeat_2d([t.cuda() for t in ts], dim=1)                       # stacked along dim 1
+    assert torch.equal(got1.cpu(), want.permute(1, 0, 2))
+    cols = [t.t().contiguous() for t in ts]                                                   # ragged axis = columns
+    gotc = geometry.stack_with_repeat_2d([t.cuda() for t in cols], dim=0)
+    assert torch.equal(gotc.cpu(), want.permute(0, 2, 1))

@@ -5,7 +5,8 @@ Importing this package never touches CUDA; the kernels live in libvsgb200.so and
 """
 from .containers import TrajProposal, VideoGraph                                         # noqa: F401
 from .geometry import (dura_intersection_ts, vIoU_ts, trajid2pairid, traj_viou_matrix,   # noqa: F401
-                       traj_viou_batched, enti_viou_align, pair_labels, TrackTable)
+                       traj_viou_batched, enti_viou_align, pair_labels, TrackTable,
+                       tIoU, generalized_tIoU, unique_with_idx_nd, stack_with_repeat_2d)
 from .evalapi import (eval_visual_relation, evaluate, evaluate_v2, eval_relation_with_gt,  # noqa: F401
                       eval_detection_scores, eval_detection_scores_v2, eval_tagging_scores, viou, voc_ap,
                       PackedRelations, evaluate_packed)
@@ -15,7 +16,8 @@ from .convert import EvalFmtCvtor                                               
 from . import driver                                                                     # noqa: F401
 
 __all__ = ["TrajProposal", "VideoGraph", "dura_intersection_ts", "vIoU_ts", "trajid2pairid", "traj_viou_matrix",
-           "traj_viou_batched", "enti_viou_align", "pair_labels", "TrackTable", "eval_visual_relation", "evaluate",
+           "traj_viou_batched", "enti_viou_align", "pair_labels", "TrackTable", "tIoU", "generalized_tIoU", "unique_with_idx_nd",
+           "stack_with_repeat_2d", "eval_visual_relation", "evaluate",
            "evaluate_v2", "eval_relation_with_gt", "eval_detection_scores", "eval_detection_scores_v2",
            "eval_tagging_scores", "viou", "voc_ap", "PackedRelations", "evaluate_packed", "BIG_C", "BIG_C_vidvrd",
            "BIG_C_vidor", "DEBUG", "expand_after_grounding", "EvalFmtCvtor", "driver"]

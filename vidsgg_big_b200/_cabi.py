@@ -63,6 +63,9 @@ SIGNATURES = {
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
+    "vsg_tiou": (i32, [p, i32, p, i32, i32, i32, i32, p, p]),
+    "vsg_stretch_rows": (i32, [p, i32, i32, p, i32, i32, p, p]),
+    "vsg_unique_rows": (i32, [p, i32, i32, p, p, p, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
     "vsg_gemm_debug_flags": (i32, [i32]),
     "vsg_gemm_set_tma_store": (i32, [i32]),

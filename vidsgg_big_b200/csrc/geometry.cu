@@ -465,3 +465,123 @@ extern "C" int vsg_pair_labels(const float* viou, int n, int n_gt_traj, const in
       viou, n, n_gt_traj, gt_so, n_gt_pred, th, out);
   return check_launch("vsg_pair_labels");
 }
+
+// ---------------------------------------------------------------------------------------------------
+// Remaining public helpers of utils/utils_func.py on the device: tIoU / generalized_tIoU (:375-410), the stretch of
+// stack_with_repeat_2d (models/model_0v10.py:18-46) and unique_with_idx_nd (utils_func.py:330-345)
+// ---------------------------------------------------------------------------------------------------
+namespace vsg {
+
+// (min(e1,e2) - max(s1,s2)) / (max(e1,e2) - min(s1,s2)) in fp32 (torch true-divides int64 spans as float32);
+// tIoU additionally zeroes pairs whose closed spans do not touch.  0/0 stays NaN like the reference.
+template <typename T>
+__global__ void tiou_kernel(const T* __restrict__ d1, int n1, const T* __restrict__ d2, int n2, int broadcast, int generalized,
+                            float* __restrict__ out) {
+  const int64_t total = broadcast ? (int64_t)n1 * n2 : n1;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int a = broadcast ? (int)(i / n2) : (int)i, b = broadcast ? (int)(i % n2) : (int)i;
+    const T s1 = d1[2 * a], e1 = d1[2 * a + 1], s2 = d2[2 * b], e2 = d2[2 * b + 1];
+    const T num = (e1 < e2 ? e1 : e2) - (s1 > s2 ? s1 : s2);
+    const T den = (e1 > e2 ? e1 : e2) - (s1 < s2 ? s1 : s2);
+    float v = (float)num / (float)den;
+    if (!generalized && !((e1 >= s2) && (e2 >= s1))) v = 0.f;
+    out[i] = v;
+  }
+}
+
+// out[t][j][:] = src[off[t] + map(j)][:], j < tmax: frame i of an L-frame track repeated ceil((tmax - i) / L) times
+__global__ void stretch_rows_kernel(const float* __restrict__ src, int ld, int width, const int64_t* __restrict__ off, int n_tracks,
+                                    int tmax, float* __restrict__ out) {
+  const int64_t rows = (int64_t)n_tracks * tmax;
+  for (int64_t r = blockIdx.x; r < rows; r += gridDim.x) {
+    const int t = (int)(r / tmax), j = (int)(r % tmax);
+    const int L = (int)(off[t + 1] - off[t]);
+    if (L <= 0) continue;
+    const int q = tmax / L, rem = tmax % L;
+    const int s = j < rem * (q + 1) ? j / (q + 1) : rem + (j - rem * (q + 1)) / max(q, 1);
+    const float* p = src + (off[t] + s) * (int64_t)ld;
+    float* o = out + r * (int64_t)width;
+    for (int c = threadIdx.x; c < width; c += blockDim.x) o[c] = p[c];
+  }
+}
+
+// One CTA: bitonic sort of the row indices by (row lexicographic, index), run heads, group id per sorted position.
+__device__ __forceinline__ int row_cmp(const int64_t* __restrict__ rows, int d, int a, int b) {
+  for (int c = 0; c < d; ++c) {
+    const int64_t x = rows[(int64_t)a * d + c], y = rows[(int64_t)b * d + c];
+    if (x != y) return x < y ? -1 : 1;
+  }
+  return 0;
+}
+__global__ void unique_rows_kernel(const int64_t* __restrict__ rows, int n, int d, int npow2, int32_t* __restrict__ order,
+                                   int32_t* __restrict__ group, int32_t* __restrict__ n_groups) {
+  extern __shared__ int32_t idx[];
+  for (int i = threadIdx.x; i < npow2; i += blockDim.x) idx[i] = i < n ? i : -1;      // -1 = +infinity padding
+  __syncthreads();
+  for (int k = 2; k <= npow2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int i = threadIdx.x; i < npow2; i += blockDim.x) {
+        const int p = i ^ j;
+        if (p > i) {
+          const int a = idx[i], b = idx[p];
+          bool a_gt_b;                                                                   // strict total order: padding last, ties by index
+          if (a < 0 || b < 0) a_gt_b = (a < 0) && (b >= 0);
+          else { const int c = row_cmp(rows, d, a, b); a_gt_b = c > 0 || (c == 0 && a > b); }
+          const bool up = (i & k) == 0;
+          if (a_gt_b == up) { idx[i] = b; idx[p] = a; }
+        }
+      }
+      __syncthreads();
+    }
+  }
+  // heads + inclusive scan of the head flags (single thread per chunk would do; n <= 4096, so a simple serial pass by thread 0)
+  if (threadIdx.x == 0) {
+    int g = -1;
+    for (int i = 0; i < n; ++i) {
+      if (i == 0 || row_cmp(rows, d, idx[i - 1], idx[i]) != 0) ++g;
+      order[i] = idx[i];
+      group[i] = g;
+    }
+    *n_groups = g + 1;
+  }
+}
+
+}  // namespace vsg
+
+extern "C" int vsg_tiou(const void* d1, int n1, const void* d2, int n2, int broadcast, int generalized, int dtype, float* out,
+                        void* stream) {
+  VSG_REQUIRE(n1 >= 0 && n2 >= 0, "vsg_tiou: negative size");
+  VSG_REQUIRE(broadcast || n1 == n2, "vsg_tiou: row-wise mode needs n1 == n2");
+  VSG_REQUIRE(dtype == 0 || dtype == 1, "vsg_tiou: dtype must be 0 (int64) or 1 (float32)");
+  if (n1 == 0 || n2 == 0) return VSG_OK;
+  VSG_REQUIRE(d1 && d2 && out, "vsg_tiou: null pointer");
+  const int g = grid_for(broadcast ? (int64_t)n1 * n2 : n1, 256, 8);
+  if (dtype == 0)
+    tiou_kernel<int64_t><<<g, 256, 0, (cudaStream_t)stream>>>((const int64_t*)d1, n1, (const int64_t*)d2, n2, broadcast, generalized, out);
+  else
+    tiou_kernel<float><<<g, 256, 0, (cudaStream_t)stream>>>((const float*)d1, n1, (const float*)d2, n2, broadcast, generalized, out);
+  return check_launch("vsg_tiou");
+}
+
+extern "C" int vsg_stretch_rows(const float* src, int ld, int width, const int64_t* off, int n_tracks, int tmax, float* out,
+                                void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && tmax >= 0 && width >= 0 && ld >= width, "vsg_stretch_rows: bad extents");
+  if (n_tracks == 0 || tmax == 0 || width == 0) return VSG_OK;
+  VSG_REQUIRE(src && off && out, "vsg_stretch_rows: null pointer");
+  int64_t rows = (int64_t)n_tracks * tmax;
+  const int grid = (int)(rows < (int64_t)sm_count() * 32 ? rows : (int64_t)sm_count() * 32);
+  stretch_rows_kernel<<<grid, width >= 256 ? 256 : 64, 0, (cudaStream_t)stream>>>(src, ld, width, off, n_tracks, tmax, out);
+  return check_launch("vsg_stretch_rows");
+}
+
+extern "C" int vsg_unique_rows(const int64_t* rows, int n, int d, int32_t* order, int32_t* group, int32_t* n_groups, void* stream) {
+  VSG_REQUIRE(n >= 0 && d >= 1, "vsg_unique_rows: bad extents");
+  VSG_REQUIRE(n <= 8192, "vsg_unique_rows: at most 8192 rows (one CTA sorts them in shared memory), got %d", n);
+  VSG_REQUIRE(n_groups != nullptr, "vsg_unique_rows: null n_groups");
+  if (n == 0) { cudaMemsetAsync(n_groups, 0, sizeof(int32_t), (cudaStream_t)stream); return VSG_OK; }
+  VSG_REQUIRE(rows && order && group, "vsg_unique_rows: null pointer");
+  int p2 = 1;
+  while (p2 < n) p2 <<= 1;
+  unique_rows_kernel<<<1, 1024, p2 * sizeof(int32_t), (cudaStream_t)stream>>>(rows, n, d, p2, order, group, n_groups);
+  return check_launch("vsg_unique_rows");
+}

@@ -5,6 +5,9 @@ Reference functions mirrored (same names, argument meaning and results):
   dura_intersection_ts   utils/utils_func.py:347-373
   vIoU_ts                utils/utils_func.py:437-471
   trajid2pairid          models/model_pairwise_baseline.py:104-111 / tools/train_vidor.py:73-78
+  tIoU, generalized_tIoU utils/utils_func.py:375-410 (models/grd_model_v5.py:18-33)
+  unique_with_idx_nd     utils/utils_func.py:330-345
+  stack_with_repeat_2d   models/model_0v10.py:18-46
 and the loops built on them:
   traj_viou_matrix       models/model_0v10.py:565-581, tools/train_vidor.py:107-122 (one launch for a batch of videos)
   enti_viou_align        models/model_0v10.py:559-604
@@ -112,6 +115,84 @@ def dura_intersection_ts(dura1: torch.Tensor, dura2: torch.Tensor, broadcast: bo
     check(lib().vsg_dura_intersection_ex(ptr(a), n1, ptr(b), n2, 1 if broadcast else 0, dt, ptr(inter), ptr(mask),
                                          stream_ptr(a.device)), "vsg_dura_intersection_ex")
     return inter, mask.bool()
+
+
+def _tiou(duras1, duras2, broadcast, generalized):
+    assert isinstance(duras1, torch.Tensor) and isinstance(duras2, torch.Tensor)
+    require_cuda(duras1, duras2)
+    n1, n2 = duras1.shape[0], duras2.shape[0]
+    if duras1.dtype == torch.long and duras2.dtype == torch.long:
+        dt, a, b = 0, duras1.contiguous(), duras2.contiguous()
+    else:
+        dt, a, b = 1, duras1.float().contiguous(), duras2.float().contiguous()
+    if not broadcast:
+        assert duras1.shape == duras2.shape
+    out = torch.empty((n1, n2) if broadcast else (n1,), dtype=torch.float32, device=a.device)
+    check(lib().vsg_tiou(ptr(a), n1, ptr(b), n2, 1 if broadcast else 0, 1 if generalized else 0, dt, ptr(out), stream_ptr(a.device)),
+          "vsg_tiou")
+    return out
+
+
+def tIoU(duras1: torch.Tensor, duras2: torch.Tensor, broadcast: bool = True) -> torch.Tensor:
+    """Temporal IoU of closed spans, zero where they do not touch (utils/utils_func.py:375-390)."""
+    return _tiou(duras1, duras2, broadcast, False)
+
+
+def generalized_tIoU(duras1: torch.Tensor, duras2: torch.Tensor, broadcast: bool = True) -> torch.Tensor:
+    """tIoU without the zeroing, in [-1, 1] (utils/utils_func.py:393-410, models/grd_model_v5.py:18-33)."""
+    return _tiou(duras1, duras2, broadcast, True)
+
+
+def unique_with_idx_nd(tensor: torch.Tensor):
+    """``(unique rows in lexicographic order, tuple of index tensors)`` -- utils/utils_func.py:330-345: ``torch.unique(dim=0)`` plus, per
+    unique row, the ascending original indices of its occurrences.  int64 input of shape (N, d1, ..., dk), N <= 8192; one D2H read of
+    the group count / sizes (the result is a Python tuple of ragged tensors)."""
+    require_cuda(tensor)
+    assert tensor.dtype == torch.long, "unique_with_idx_nd: int64 rows"
+    n = tensor.shape[0]
+    if n == 0:
+        return tensor[:0], tuple()
+    flat = tensor.reshape(n, -1).contiguous()
+    d = max(int(flat.shape[1]), 1)
+    dev = tensor.device
+    order = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    group = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    ng = torch.empty(1, dtype=torch.int32, device=dev)
+    check(lib().vsg_unique_rows(ptr(flat), n, d, ptr(order), ptr(group), ptr(ng), stream_ptr(dev)), "vsg_unique_rows")
+    if n == 0:
+        return tensor[:0], tuple()
+    order, group = order[:n].long(), group[:n].long()
+    counts = torch.bincount(group).tolist()                      # host sizes of the ragged result
+    index_map = torch.split(order, counts)
+    first = torch.cumsum(torch.tensor([0] + counts[:-1]), 0).to(dev)
+    return tensor[order[first]], tuple(index_map)
+
+
+def stack_with_repeat_2d(tensor_list: Sequence[torch.Tensor], dim: int) -> torch.Tensor:
+    """models/model_0v10.py:18-46: stretch every 2-D tensor to the longest one by repeating element i ``ceil((max_L - i) / L)`` times
+    along the ragged axis, then ``torch.stack(..., dim)``.  (The B200 hot path never builds this tensor -- its kernels apply the same
+    index map on the fly; this is the helper for code that calls the reference function.)"""
+    assert len(tensor_list) > 0 and tensor_list[0].dim() == 2
+    require_cuda(*tensor_list)
+    rows = [int(t.shape[0]) for t in tensor_list]
+    cols = [int(t.shape[1]) for t in tensor_list]
+    if all(r == rows[0] for r in rows):
+        repeat_dim = 1
+    elif all(c == cols[0] for c in cols):
+        repeat_dim = 0
+    else:
+        assert False
+    dev = tensor_list[0].device
+    srcs = [t.float() if repeat_dim == 0 else t.float().t() for t in tensor_list]        # ragged axis first
+    lens = [int(t.shape[0]) for t in srcs]
+    width, tmax, n = int(srcs[0].shape[1]), max(lens), len(srcs)
+    src = torch.cat([t.contiguous() for t in srcs], 0)
+    off = torch.zeros(n + 1, dtype=torch.long)
+    off[1:] = torch.cumsum(torch.tensor(lens), 0)
+    out = torch.empty(n, tmax, width, dtype=torch.float32, device=dev)
+    check(lib().vsg_stretch_rows(ptr(src), width, width, ptr(off.to(dev)), n, tmax, ptr(out), stream_ptr(dev)), "vsg_stretch_rows")
+    parts = list(out.unbind(0)) if repeat_dim == 0 else [o.t() for o in out.unbind(0)]
+    return torch.stack(parts, dim=dim).to(tensor_list[0].dtype)
 
 
 def trajid2pairid(num_prop: int, device="cuda") -> torch.Tensor:

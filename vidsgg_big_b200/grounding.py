@@ -270,11 +270,39 @@ class DEBUG(object):
         return self._post(f(regrs), f(conf_logits), f(cls_logits), comb_off, so_norm.to(dev, torch.float32).contiguous(), clip, vid_off,
                           q_vid, nq, [nq], th, regr_activated=True)[0]
 
+    def prepare_gt_data(self, gt_graph):
+        """grd_model_v5.py:253-308 in inference mode: the queries of a GT graph are its unique
+        ``[pred_cat, subj_cat, obj_cat, so_start, so_end]`` tags (``unique_with_idx_nd``), so_* = intersection of the subject / object
+        track spans.  Returns ``((tags5, spans, video_len), target, index_map)`` -- the first item is exactly a ``data_list`` entry of the
+        ``with_gt_data=False`` call (columns 3, 4 of ``tags5`` are not read by the network); ``target`` = normalised GT predicate spans
+        and ``index_map`` = per unique query the GT predicate ids it stands for (the inputs of the reference's ``eval_tiou``)."""
+        from . import geometry
+        if gt_graph.num_trajs == 0 or gt_graph.num_preds == 0:
+            return (None, None, int(gt_graph.video_len)), None, None
+        dev = self.device
+        video_len = int(gt_graph.video_len)
+        traj_cats = gt_graph.traj_cat_ids.to(dev)
+        traj_duras = gt_graph.traj_durations.to(dev)
+        pred_cats = gt_graph.pred_cat_ids.to(dev)
+        so_ids = torch.argmax(gt_graph.adj_matrix.to(dev), dim=-1).t()               # (n_pred, 2)
+        so_cats = traj_cats[so_ids]
+        inter, _ = geometry.dura_intersection_ts(traj_duras[so_ids[:, 0]], traj_duras[so_ids[:, 1]], broadcast=False)
+        tags = torch.cat([pred_cats[:, None], so_cats, inter], dim=-1)               # (n_pred, 5)
+        uniq, index_map = geometry.unique_with_idx_nd(tags)
+        target = gt_graph.pred_durations.to(dev).float() / video_len
+        return (uniq, uniq[:, 3:].contiguous(), video_len), target, index_map
+
     def forward(self, video_feature_list, data_list, score_th=0.5, tiou_th=0.5, bins_th=0.1, nms_th=0.5, with_gt_data=True,
                 max_rows: int = 1_500_000):
         if with_gt_data:
-            raise NotImplementedError("with_gt_data=True evaluates the grounding stage alone on GT queries (grd_model_v5.py:198-202); "
-                                      "only the inference path with_gt_data=False is on the hot path")
+            # grounding stage evaluated alone on the GT queries (grd_model_v5.py:198-202): data_list holds GT graphs
+            self.last_gt_targets = []
+            datas = []
+            for gt in data_list:
+                d, target, index_map = self.prepare_gt_data(gt)
+                self.last_gt_targets.append((target, index_map))
+                datas.append(d)
+            data_list = datas
         if self._w is None:
             raise VsgError("DEBUG has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
         assert len(video_feature_list) == len(data_list)
