@@ -307,6 +307,27 @@ int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int 
                           int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
                           void* stream);
 
+/* ---- Base-C pairwise baseline (models/model_pairwise_baseline.py) -----------------------------
+ * The per-track encoding and the pair MLP are the BIG-C kernels + vsg_gemm; these two entry points are what is specific to it. */
+
+/* trajid2pairid (:104-111) for every video of a batch: pair_off int64[V+1] = prefix of n_v (n_v - 1); so int32[n_pairs][2] receives
+ * GLOBAL track ids (seg[v] + local id), ordered like nonzero() of the off-diagonal mask; pair_vid int32[n_pairs] = video of each pair. */
+int vsg_pair_ids_batched(const int32_t* seg, int n_vid, const int64_t* pair_off, int64_t n_pairs, int32_t* so, int32_t* pair_vid,
+                         void* stream);
+
+/* construct_triplet (:314-395) for every video: softmax + top-k of each pair's logits, pairs whose closed spans do not overlap dropped,
+ * rows in lexicographic quintuple order [pred, scat, ocat, sid, oid] (sid / oid = LOCAL track ids), background (pred 0) removed; when
+ * rt_topk > 0 only the rt_topk best by mean(score3) (descending, ties in lexicographic order).  Video v owns output rows
+ * cand_off[v] .. cand_off[v] + n_out(v), cand_off[v] = topk * pair_off[v]; counts int32[V][2] = {#valid candidates, #background among
+ * them} -> n_out = counts[v][0] - counts[v][1] (min'ed with rt_topk), "None" in the reference when counts[v][0] == 0.
+ * chunk_off int32[V+1] = prefix of ceil(candidates_v / 256) (host-built work list), n_chunks = chunk_off[V].
+ * keys_ws u64[n_pairs*topk], score_ws f32[n_pairs*topk*3]: caller-owned workspace. */
+int vsg_pair_construct_triplet(const float* logits, int ld_logits, int P, int topk, const int32_t* so, const int32_t* pair_vid,
+                               int64_t n_pairs, const int32_t* seg, int n_vid, const int64_t* dura, const int64_t* cat_ids,
+                               const float* enti_scores, const int64_t* cand_off, const int32_t* chunk_off, int n_chunks, int rt_topk,
+                               unsigned long long* keys_ws, float* score_ws, int32_t* counts, int64_t* quint, float* scores,
+                               int64_t* spans, void* stream);
+
 /* ---- grounding stage, non-GEMM kernels (models/grd_model_v5.py) -----------
  * Row-major [rows][H] over ragged sequences seq_off int64[n_seq+1] (video clips / 3 query words / clips per query). */
 

@@ -36,7 +36,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, REF)
 
 from vidsgg_big_b200 import synth                                    # noqa: E402
-from oracle import geometry as og, evalapi as oe, bigc as ob, grounding as ogr, convert as oc   # noqa: E402
+from oracle import geometry as og, evalapi as oe, bigc as ob, grounding as ogr, convert as oc, basec as obc   # noqa: E402
 
 with contextlib.redirect_stdout(io.StringIO()):
     from utils import utils_func as R                                # noqa: E402  (reference)
@@ -254,6 +254,48 @@ def gen_bigc():
     save("bigc", **out)
 
 
+# ------------------------------------------------------------------ Base-C --------------
+BASEC_CASES = [   # tag, config factory name, overrides, [(seed, n, video_len, max_len)], weight seed, topk
+    ("tinybc", "tiny_basec_config", {}, [(701, 7, 40, None), (702, 12, 64, 30), (703, 1, 20, None), (704, 2, 30, 9)], 31, 3),
+    ("tinybc_rt", "tiny_basec_config", {"rt_triplets_topk": 25}, [(705, 10, 50, None)], 32, 3),
+    ("tinybc_emb", "tiny_basec_config", {"_force_entiemb": True, "EntiNameEmb_path": "x"}, [(706, 8, 45, None)], 33, 3),
+    ("bc", "basec_config", {"rt_triplets_topk": 200}, [(711, 40, 400, 200)], 3, 3),
+]
+
+
+def gen_basec():
+    """Base_C inference (models/model_pairwise_baseline.py:113-129, 170-273, 314-395)."""
+    out = {}
+    for tag, mk, over, shapes, wseed, topk in BASEC_CASES:
+        cfg = getattr(synth, mk)(**over)
+        state = synth.make_basec_state(wseed, cfg)
+        model = build_ref_bigc(cfg, state, Base_C)
+        feat_total = cfg["dim_feat"] + cfg["dim_clsme"]
+        for sd, n, vl, maxlen in shapes:
+            P = synth.make_proposal(sd, n, vl, feat_total, cfg["num_enti_cats"], max_len=maxlen)
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                pairs = model.trajid2pairid(n)
+                logits = model.forward_propagation(P, pairs)
+                ret = model([P], topk=topk)[0]
+                ologits = obc.forward_propagation(state, cfg, P, og.pair_ids(n))
+                oret = obc.forward(state, cfg, [P], topk)[0]
+            k = "%s_%d" % (tag, sd)
+            out[k + "_logits"] = logits.numpy()
+            if n > 1:
+                err = (ologits - logits).abs().max().item()
+                assert err < 2e-4 * max(1.0, logits.abs().max().item()), ("basec logits", k, err)
+            if ret is None:
+                out[k + "_none"] = np.array([1]); assert oret is None
+                print("basec golden", k, "-> None")
+                continue
+            q5, sc, sp, qi = ret
+            assert torch.equal(q5, oret[0]) and torch.equal(sp, oret[2]) and qi.shape == oret[3].shape, k
+            assert torch.allclose(sc, oret[1], atol=1e-5)
+            out[k + "_quint"] = q5.numpy(); out[k + "_scores"] = sc.numpy(); out[k + "_spans"] = sp.numpy()
+            print("basec golden", k, "n=%d pairs=%d triplets=%d" % (n, n * (n - 1), q5.shape[0]))
+    save("basec", **out)
+
+
 # ------------------------------------------------------------------ enti_viou_align ----
 def gen_align():
     out = {}
@@ -348,7 +390,7 @@ def gen_grounding_gt():
 
 
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["geometry", "eval", "bigc", "align", "grounding", "grounding_gt"]
+    which = sys.argv[1:] or ["geometry", "eval", "bigc", "align", "grounding", "grounding_gt", "basec"]
     for w in which:
         {"geometry": gen_geometry, "eval": gen_eval, "bigc": gen_bigc, "align": gen_align, "grounding": gen_grounding,
-         "grounding_gt": gen_grounding_gt}[w]()
+         "grounding_gt": gen_grounding_gt, "basec": gen_basec}[w]()

@@ -11,6 +11,7 @@ from .evalapi import (eval_visual_relation, evaluate, evaluate_v2, eval_relation
                       eval_detection_scores, eval_detection_scores_v2, eval_tagging_scores, viou, voc_ap,
                       PackedRelations, evaluate_packed)
 from .bigc import BIG_C, BIG_C_vidvrd, BIG_C_vidor                                       # noqa: F401
+from .basec import Base_C                                                                # noqa: F401
 from .grounding import DEBUG, expand_after_grounding                                     # noqa: F401
 from .convert import EvalFmtCvtor                                                        # noqa: F401
 from . import driver                                                                     # noqa: F401
@@ -20,4 +21,4 @@ __all__ = ["TrajProposal", "VideoGraph", "dura_intersection_ts", "vIoU_ts", "tra
            "stack_with_repeat_2d", "eval_visual_relation", "evaluate",
            "evaluate_v2", "eval_relation_with_gt", "eval_detection_scores", "eval_detection_scores_v2",
            "eval_tagging_scores", "viou", "voc_ap", "PackedRelations", "evaluate_packed", "BIG_C", "BIG_C_vidvrd",
-           "BIG_C_vidor", "DEBUG", "expand_after_grounding", "EvalFmtCvtor", "driver"]
+           "BIG_C_vidor", "Base_C", "DEBUG", "expand_after_grounding", "EvalFmtCvtor", "driver"]

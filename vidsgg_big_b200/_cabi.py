@@ -63,6 +63,8 @@ SIGNATURES = {
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
+    "vsg_pair_ids_batched": (i32, [p, i32, p, i64, p, p, p]),
+    "vsg_pair_construct_triplet": (i32, [p, i32, i32, i32, p, p, i64, p, i32, p, p, p, p, p, i32, i32, p, p, p, p, p, p, p]),
     "vsg_tiou": (i32, [p, i32, p, i32, i32, i32, i32, p, p]),
     "vsg_stretch_rows": (i32, [p, i32, i32, p, i32, i32, p, p]),
     "vsg_unique_rows": (i32, [p, i32, i32, p, p, p, p]),

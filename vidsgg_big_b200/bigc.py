@@ -284,11 +284,14 @@ class BIG_C(object):
                             a_off=(H * Q, Q, 0, 0), b_off=(0, dh, Q, 0), c_off=(Q * d, dh))
         return att
 
-    def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
-        """model_0v10.py:434-475 for the whole batch.  Returns (logits [V*Q, P], so int32[V*Q,2], extras)."""
+    def _track_encoding(self, pk: PackedVideos):
+        """Per-track encoding shared by BIG-C and Base-C (model_0v10.py:446-458 / model_pairwise_baseline.py:170-185): per-frame MLPs
+        on the unique frames, stretched conv / max-pool, fc_enti2enco; plus the stretched time-mean of the extra feature columns.
+        Needs ``self._w`` (bbox1_w, bbox1_b, bbox2, feat1, feat2, conv, conv_b, enco1, enco2), ``mode``, ``dim_enti``, ``dim_feat``,
+        ``extra_width``, ``enco_pool_len``, ``device``.  Returns (enti2enco [N, E], extra [N, extra_width] or None)."""
         w, m, dev = self._w, self.mode, self.device
-        E, Pd, Q, F_in = self.dim_enti, self.dim_pred, self.num_querys, self.dim_feat
-        R, N, V = pk.R, pk.N, pk.V
+        E, F_in = self.dim_enti, self.dim_feat
+        R, N = pk.R, pk.N
         sp = stream_ptr(dev)
         L = lib()
         if pk.feats.shape[1] < F_in + self.extra_width:
@@ -322,6 +325,17 @@ class BIG_C(object):
             extra = torch.empty(N, self.extra_width, dtype=torch.float32, device=dev)
             check(L.vsg_stretched_mean(_raw(pk.feats), pk.feats.stride(0), F_in, self.extra_width, _raw(pk.off), _raw(pk.tmax), N,
                                        _raw(extra), self.extra_width, sp), "vsg_stretched_mean")
+        return enti2enco, extra
+
+    def _encode2decode(self, pk: PackedVideos, want_att: bool = False):
+        """model_0v10.py:434-475 for the whole batch.  Returns (logits [V*Q, P], so int32[V*Q,2], extras)."""
+        w, m, dev = self._w, self.mode, self.device
+        E, Pd, Q, F_in = self.dim_enti, self.dim_pred, self.num_querys, self.dim_feat
+        R, N, V = pk.R, pk.N, pk.V
+        sp = stream_ptr(dev)
+        L = lib()
+        dbg = getattr(self, "_dbg", None)
+        enti2enco, extra = self._track_encoding(pk)
         # --- encoder (post-norm, tokens = tracks of a video)
         x = enti2enco
         for lw in w["enc"]:

@@ -54,6 +54,38 @@ def vidor_config(**over) -> dict:
     return cfg
 
 
+def basec_config(**over) -> dict:
+    """Base-C pairwise baseline, experiments/exp6/config_.py:1-17 (``rt_triplets_topk`` -1 = return all, 200 in config_rt200.py)."""
+    cfg = dict(dataset_type="VidOR", num_enti_cats=81, num_pred_cats=51, dim_ffn=512, dim_enti=512, dim_pred=512, dim_att=512,
+               dim_feat=1024, dim_clsme=300, enco_pool_len=4, positive_vIoU_th=0.5, rt_triplets_topk=-1,
+               EntiNameEmb_path=None, use_clsme=True, bias_matrix_path=None)
+    cfg.update(over)
+    return cfg
+
+
+def tiny_basec_config(**over) -> dict:
+    cfg = basec_config(num_enti_cats=9, num_pred_cats=17, dim_ffn=64, dim_enti=64, dim_feat=96, dim_clsme=20)
+    cfg.update(over)
+    return cfg
+
+
+def make_basec_state(seed: int, cfg: dict) -> "OrderedDict[str, torch.Tensor]":
+    """Random-but-healthy Base-C weights with the reference's state_dict keys (models/model_pairwise_baseline.py:27-76)."""
+    w = _W(seed)
+    E, C, NP = cfg["dim_enti"], cfg["num_enti_cats"], cfg["num_pred_cats"]
+    if cfg.get("EntiNameEmb_path") is not None or cfg.get("_force_entiemb", False):
+        w.sd["EntiNameEmb"] = torch.from_numpy(w.rng.standard_normal((C, cfg["dim_clsme"]), dtype=np.float32) * np.float32(0.4))
+    dirich = w.rng.dirichlet(np.ones(NP), size=(C, C)).astype(np.float32)
+    w.sd["bias_matrix"] = torch.from_numpy(np.log(dirich + np.float32(1e-3)).astype(np.float32))
+    w.linear("fc_feat2enti.0", E, cfg["dim_feat"]); w.linear("fc_feat2enti.2", E, E)
+    w.linear("fc_bbox2enti.0", E, 8); w.linear("fc_bbox2enti.2", E, E)
+    w.mat("conv_feat2enti.weight", E, 2 * E, 3); w.vec("conv_feat2enti.bias", E)
+    w.linear("fc_enti2enco.0", E, E * cfg["enco_pool_len"]); w.linear("fc_enti2enco.2", E, E)
+    dz = 2 * E + 2 * cfg["dim_clsme"]        # the reference sizes this layer for the classeme input regardless of use_clsme (:63-67)
+    w.linear("fc_pred2logits.0", cfg["dim_ffn"], dz, gain=2.0); w.linear("fc_pred2logits.2", NP, cfg["dim_ffn"], gain=2.0)
+    return w.sd
+
+
 def grounding_config(**over) -> dict:
     cfg = dict(dim_feat=1024, dim_clsme=300, dim_hidden=128, num_bins=10,
                EntiNameEmb_path=None, PredNameEmb_path=None,
