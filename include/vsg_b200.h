@@ -206,6 +206,11 @@ typedef struct VsgGemmArgs {
   const void* W_b16; const void* W_lo16; int ldw16;   /* mode VSG_GEMM_TF32_BF16X2: bf16 [N][ldw16] copies of W (W_hi = the fp32 W) */
   const void* W_img; int img_bn;                      /* optional (mode 3): pre-swizzled tile images from vsg_build_weight_image built for
                                                          tile width img_bn; ignored unless img_bn == vsg_gemm_tile_n(N) */
+  /* optional (mode 3, N <= 128): A is replaced by dwconv(A) computed inside the kernel -- DepthWiseSeparableConv1d.depth_wise of
+   * models/grd_model_v5.py:36-56 followed by its point-wise conv as ONE launch: dwconv(A)[r][c] = dw_b[c] + sum_j dw_w[c][j] *
+   * A[r + j - dw_k/2][c] with zero padding at the ends of the row's sequence (seq_pos[r] rows before r, seq_rem[r] rows after r in its
+   * sequence).  Bit-identical to vsg_dwconv followed by vsg_gemm. */
+  const float* dw_w; const float* dw_b; const int32_t* seq_pos; const int32_t* seq_rem; int dw_k;
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 

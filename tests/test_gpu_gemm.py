@@ -1,4 +1,5 @@
 """GPU: the GEMM kernels (SIMT comparator, tcgen05 tf32, tcgen05 3xTF32) against an fp64 product."""
+import numpy as np
 import pytest
 import torch
 
@@ -254,3 +255,40 @@ def test_weight_images_equal_tensor_map_loads():
         assert all(torch.equal(outs[0], o) for o in outs[1:]), (M, N, K)
         ref = torch.relu(_ref(A, W, b))
         assert (outs[0].double() - ref).abs().max().item() <= TOL[3] * ref.abs().max().item()
+
+
+def test_fused_dwconv_gemm_equals_dwconv_then_gemm():
+    """The CONV variant (depthwise conv computed by the split warps from a raw X tile with halo rows) against vsg_dwconv followed by the
+    plain mode-3 GEMM: bit-identical, for k = 7 / 3, ragged sequences (incl. length-1 / length-2 ones and sequences that straddle
+    tile boundaries), M not a multiple of 128, ReLU + residual epilogues, N = 128 and narrower."""
+    import ctypes as C
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import check, lib, stream_ptr
+    g = torch.Generator(device="cpu").manual_seed(31)
+    H = 128
+    for lens, N, k in (([130, 1, 2, 77, 300, 5, 128, 129], 128, 7), ([40] * 3 + [3], 128, 3), ([257, 255], 40, 7), ([1000], 20, 3)):
+        M = sum(lens)
+        off = np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)
+        pos = torch.from_numpy(np.concatenate([np.arange(l) for l in lens]).astype(np.int32)).to(DEV)
+        rem = torch.from_numpy(np.concatenate([np.arange(l)[::-1] for l in lens]).astype(np.int32)).to(DEV)
+        x = torch.randn(M, H, generator=g).to(DEV)
+        dw_w = (torch.randn(H, k, generator=g) * 0.4).to(DEV).contiguous()
+        dw_b = (torch.randn(H, generator=g) * 0.1).to(DEV).contiguous()
+        W = torch.randn(N, H, generator=g).to(DEV) / H ** 0.5
+        b = torch.randn(N, generator=g).to(DEV)
+        res = torch.randn(M, N, generator=g).to(DEV)
+        wt = _weight(3, W, b)
+        assert linalg.can_fuse_dwconv(3, wt, k=k)
+        t = torch.empty_like(x)
+        check(lib().vsg_dwconv(C.c_void_p(x.data_ptr()), C.c_void_p(pos.data_ptr()), C.c_void_p(rem.data_ptr()), C.c_void_p(dw_w.data_ptr()),
+                               C.c_void_p(dw_b.data_ptr()), k, M, H, C.c_void_p(t.data_ptr()), stream_ptr(x.device)), "vsg_dwconv")
+        for relu, rs in ((False, None), (True, res)):
+            want = linalg.gemm(3, t, wt, relu=relu, residual=rs)
+            got = linalg.gemm(3, x, wt, relu=relu, residual=rs, dwconv=(dw_w, dw_b, k, pos, rem))
+            assert torch.equal(got, want), (lens, N, k, relu)
+        # and the conv itself against a plain torch restatement (zero padding inside each sequence)
+        ref = torch.zeros_like(x)
+        for s0, s1 in zip(off[:-1], off[1:]):
+            seq = x[s0:s1].t()[None]                                   # [1, H, L]
+            ref[s0:s1] = torch.nn.functional.conv1d(seq, dw_w[:, None, :], dw_b, padding=k // 2, groups=H)[0].t()
+        assert (t - ref).abs().max().item() <= 1e-5

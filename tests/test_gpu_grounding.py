@@ -103,6 +103,23 @@ def test_grounding_on_gt_queries(golden, precision):
         assert bad.mean() <= 0.03
 
 
+def test_fused_dwconv_path_equals_separate_dwconv_launches(golden):
+    """grounding.DEBUG with the depthwise convs fused into the point-wise GEMMs (default) vs separate vsg_dwconv launches: the whole
+    network output is bit-identical (the fused operand is computed in the same operation order)."""
+    g = golden("grounding")
+    sd, n, vl, m = CASES[1]
+    k = "g%d" % sd
+    f = synth.make_video_feature(sd, vl).to(DEV)
+    d = (torch.from_numpy(g[k + "_quint"]).to(DEV), torch.from_numpy(g[k + "_spans"]).to(DEV), vl)
+    model = _model("tf32+bf16x2")
+    assert model.fuse_dwconv
+    fused = model([f], [d], with_gt_data=False, **INF)
+    model.fuse_dwconv = False
+    plain = model([f], [d], with_gt_data=False, **INF)
+    for a, b in zip(fused, plain):
+        assert torch.equal(a, b)
+
+
 def test_grounding_api_errors():
     from vidsgg_big_b200 import grounding
     cfg = synth.grounding_config()

@@ -37,7 +37,8 @@ class VsgGemmArgs(C.Structure):
                 ("b_row_outer", i32), ("b_row_inner", i32), ("b_col_outer", i32), ("b_col_inner", i32),
                 ("c_outer", C.c_longlong), ("c_inner", C.c_longlong),
                 ("lo_col_begin", i32), ("lo_col_end", i32), ("W_b16", p), ("W_lo16", p), ("ldw16", i32),
-                ("W_img", p), ("img_bn", i32)]
+                ("W_img", p), ("img_bn", i32),
+                ("dw_w", p), ("dw_b", p), ("seq_pos", p), ("seq_rem", p), ("dw_k", i32)]
 
 
 class VsgError(RuntimeError):

@@ -44,15 +44,32 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and os.path.exists(LIB) and os.path.exists(STAMP) and open(STAMP).read().strip() == dig:
         return LIB
     # no -lcuda: the one driver symbol needed (cuTensorMapEncodeTiled) is resolved at run time through
-    # cudaGetDriverEntryPoint, so the library also loads on a CPU-only box (symbol-export test)
-    cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + _sources()
-    if verbose:
-        print(" ".join(cmd))
+    # cudaGetDriverEntryPoint, so the library also loads on a CPU-only box (symbol-export test).
+    # Every .cu is compiled to an object in parallel (gemm.cu with its template instantiations dominates), then linked.
+    import tempfile
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = tempfile.mkdtemp(prefix="vsgb200_obj_")
+    compile_flags = [f for f in NVCC_FLAGS if f != "-shared"]
+
+    def compile_one(src):
+        obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+        cmd = [nvcc_path()] + compile_flags + (["-Xptxas", "-v"] if verbose else []) + ["-c", "-o", obj, src]
+        res = subprocess.run(cmd, capture_output=True, text=True)
+        return obj, cmd, res
+    with ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
+        results = list(ex.map(compile_one, _sources()))
+    for obj, cmd, res in results:
+        if verbose:
+            print(" ".join(cmd))
+            print(res.stderr)
+        if res.returncode != 0:
+            raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+    cmd = [nvcc_path(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB] + [r[0] for r in results]
     res = subprocess.run(cmd, capture_output=True, text=True)
-    if verbose:
-        print(res.stderr)
     if res.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
+        raise RuntimeError("nvcc link failed:\n" + res.stdout + res.stderr)
+    import shutil
+    shutil.rmtree(objdir, ignore_errors=True)
     with open(STAMP, "w") as fh:
         fh.write(dig)
     return LIB

@@ -60,6 +60,11 @@ struct GemmEpilogue {
   int lo_c0, lo_c1;         // C_lo is written for columns in [lo_c0, lo_c1) only
   int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
   const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null
+  const float* dw_w;        // CONV: depthwise weights [K][dw_k], bias dw_b [K], per-row position in / rows remaining of its sequence
+  const float* dw_b;
+  const int32_t* seq_pos;
+  const int32_t* seq_rem;
+  int dw_k;
   // batched problems: tile -> (problem p, m block, n block); p -> (outer = p / batch_inner, inner = p % batch_inner).
   // TMA coordinates and the C pointer are offset per problem; M / N are per-problem extents (batch == 1: plain GEMM).
   int dbg;                  // probe flags (vsg_gemm_debug_flags): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads
@@ -327,12 +332,19 @@ template <int BN_, int M_ = 128> struct IDesc {
 // ---------------------------------------------------------------------------------------------------
 // PAIR: the two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 (M = 256) per k step; each CTA stages its 128 rows of A and only
 // HALF of the W tile (TILE_B below is the per-CTA part), so a stage shrinks from 48 to 32 KB and 6 stages fit instead of 4.
-template <int MODE, int BN_, bool PAIR = false> struct Cfg {
+// CONV: the A operand is dwconv(X) (depthwise conv over the row axis, DepthWiseSeparableConv1d of grd_model_v5.py:36-56) computed by the
+// split warps from a raw X tile with a 3-row halo on each side, so the separate dwconv pass (one HBM round trip) disappears.
+template <int MODE, int BN_, bool PAIR = false, bool CONV = false> struct Cfg {
   static constexpr int BK = ((MODE == 2 && BN_ == 256) || MODE == 3) ? 16 : 32;
   static constexpr int TILE_A = BM * BK * 4;
   static constexpr int TILE_B = (PAIR ? BN_ / 2 : BN_) * BK * 4;
-  static constexpr int STAGE_BYTES = (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles)
+  static constexpr int RAW_ROWS = BM + 8;                                        // 3-row halo each side, rounded to the 8-row swizzle atom
+  static constexpr int RAW_TX = RAW_ROWS * BK * 4;                               // bytes the raw-tile TMA delivers
+  static constexpr int RAW_BYTES = CONV ? ((RAW_TX + 1023) / 1024) * 1024 : 0;
+  static constexpr int OFF_RAW = (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);
+  static constexpr int STAGE_BYTES = OFF_RAW + RAW_BYTES;                        // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles) (+ raw X)
   static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16)
+  static constexpr int DW_BYTES = CONV ? 8 * 1024 : 0;                           // depthwise weights [K][k] + bias [K] (K <= 224 channels, k <= 7)
   static constexpr int SPLIT_GROUPS = 2;                                         // groups of 4 split warps that alternate stages
   static constexpr int THREADS = MODE >= 2 ? 256 + 128 * SPLIT_GROUPS : 256;
   // MODE 2: [A | B_hi | A_lo | B_lo] fp32.   MODE 3: [A f32 | W f32 | bf16(A_lo) | bf16(A) | bf16(W) | bf16(W_lo)]
@@ -347,13 +359,13 @@ template <int MODE, int BN_, bool PAIR = false> struct Cfg {
 // cuts the L2 -> SM operand traffic per SM from A + W to A + W/2 (W is 4/5 of it in the split modes).  MMA / TMEM stay per CTA.
 // CL = 3: CTA-pair MMA (cta_group::2, see Cfg<.., PAIR>): rank 0 issues M = 256 instructions over both CTAs' operands, each CTA
 // loads only its half of W (no multicast), the peer's split / epilogue warps signal the leader's barriers through DSMEM arrives.
-template <int MODE, int BN_, bool PROBE, int CL>
+template <int MODE, int BN_, bool PROBE, int CL, bool CONV = false>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
                const __grid_constant__ CUtensorMap mapC, const GemmEpilogue ep) {
   constexpr bool PAIR = (CL == 3);
-  using CF = Cfg<MODE, BN_, PAIR>;
+  using CF = Cfg<MODE, BN_, PAIR, CONV>;
   constexpr int STAGES = CF::STAGES;
   constexpr int STAGE_BYTES = CF::STAGE_BYTES;
   constexpr int BN = BN_;
@@ -373,6 +385,11 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* acc_full = bars + 3 * STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  float* sdw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // CONV: [K][dw_k] weights, then [K] bias
+  if (CONV) {
+    for (int i = threadIdx.x; i < ep.K * ep.dw_k; i += blockDim.x) sdw[i] = ep.dw_w[i];
+    for (int i = threadIdx.x; i < ep.K; i += blockDim.x) sdw[ep.K * ep.dw_k + i] = ep.dw_b[i];
+  }
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rank = CL >= 2 ? (int)cluster_ctarank() : 0;
@@ -437,8 +454,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(&full[stage], TILE_A + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
-          tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
+          mbar_expect_tx(&full[stage], (CONV ? CF::RAW_TX : TILE_A) + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
+          if (CONV) tma_load_2d(smem_u32(st + CF::OFF_RAW), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row - 3);   // rows m0-3 .. m0+132 (OOB = 0)
+          else tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
           if (PAIR) {
             // this CTA's half of the W rows only; the pair's MMA reads the other half from the peer's shared memory
             constexpr int TB = CF::TILE_B;                 // per-CTA W f32 bytes
@@ -721,11 +739,37 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float4* src = reinterpret_cast<const float4*>(st);
         uint8_t* lo16 = st + CF::OFF_AL;
         uint8_t* a16 = st + CF::OFF_A16;
+        const int m0c = CONV ? tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank).m0 : 0;
 #pragma unroll
         for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : TILE_A / 16 / 128); ++i) {
           const int idx = i * 128 + t;
           const int r = idx >> 2, l = (idx & 3) ^ ((r >> 1) & 3);   // logical chunk l = columns 4l .. 4l+3 of row r
-          const float4 x = src[idx];
+          float4 x;
+          if (CONV) {
+            // x = dwconv(X)[m0 + r][kb*16 + 4l .. +3] = b + sum_j w[c][j] * X[row + j - k/2][c] inside the row's sequence (same operation
+            // order as dwconv_kernel, so the fused product is bit-identical to dwconv followed by the plain GEMM); written to the A tile
+            const int grow = m0c + r, k = ep.dw_k, c = kb * BK + 4 * l;
+            x = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (grow < ep.M) {
+              const int p = ep.seq_pos[grow], q = ep.seq_rem[grow];
+              const float* wv = sdw + c * k;
+              x = *reinterpret_cast<const float4*>(sdw + ep.K * k + c);
+              const uint8_t* raw = st + CF::OFF_RAW;
+              for (int j = 0; j < k; ++j) {
+                const int d = j - k / 2;
+                if (d < -p || d > q) continue;
+                const int rr = r + 3 + d;
+                const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
+                x.x = fmaf(wv[j], xin.x, x.x);
+                x.y = fmaf(wv[k + j], xin.y, x.y);
+                x.z = fmaf(wv[2 * k + j], xin.z, x.z);
+                x.w = fmaf(wv[3 * k + j], xin.w, x.w);
+              }
+            }
+            reinterpret_cast<float4*>(st)[idx] = x;
+          } else {
+            x = src[idx];
+          }
           float4 lo;
           lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
           lo.y = x.y - __uint_as_float(__float_as_uint(x.y) & 0xFFFFE000u);
@@ -966,14 +1010,14 @@ static int get_tensor_map(const void* base, int rows, int cols, int ld, int box_
   return VSG_OK;
 }
 
-template <int MODE, int BN_, int CL>
+template <int MODE, int BN_, int CL, bool CONV = false>
 static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                      const GemmEpilogue& ep_in, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
-  using CF = Cfg<MODE, BN_, CL == 3>;
+  using CF = Cfg<MODE, BN_, CL == 3, CONV>;
   constexpr int CLN = CL >= 2 ? 2 : 1;            // CTAs per cluster
   CUtensorMap mA, mBh, mBl, mB16;
   constexpr int WBOX = BN_ / CLN;                 // clusters: each CTA of a pair loads (CL == 2: and multicasts) half of the W rows
-  int rc = get_tensor_map(A, a_rows, a_cols, lda, BM, CF::BK, &mA);
+  int rc = get_tensor_map(A, a_rows, a_cols, lda, CONV ? CF::RAW_ROWS : BM, CF::BK, &mA);      // CONV: raw X tile with its halo rows
   if (rc) return rc;
   rc = get_tensor_map(Wh, w_rows, w_cols, ldw, WBOX, CF::BK, &mBh);
   if (rc) return rc;
@@ -1003,11 +1047,12 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
       ep.tma_store = 1;
     }
   }
-  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CF::DW_BYTES;
+  constexpr bool HAS_PROBE = (CL == 1) && !CONV;           // the timing probes exist for the single-CTA kernel only (compile time)
   static bool attr_set = false;
   if (!attr_set) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, true, CL>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
@@ -1024,8 +1069,8 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CLN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = CLN > 1 ? 1 : 0;
-  cudaError_t e = ep.dbg ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, true, CL>, mA, mBh, mBl, mB16, mC, ep)   // timing probes
-                         : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL>, mA, mBh, mBl, mB16, mC, ep);
+  cudaError_t e = (ep.dbg && HAS_PROBE) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, mA, mBh, mBl, mB16, mC, ep)   // timing probes
+                                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL, CONV>, mA, mBh, mBl, mB16, mC, ep);
   if (e != cudaSuccess) { set_error("vsg_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VSG_E_LAUNCH; }
   return check_launch("vsg_gemm(tcgen05)");
 }
@@ -1037,7 +1082,7 @@ static int launch_tc_auto(const float* A, int lda, int a_rows, int a_cols, const
   // tiles), else two per-CTA MMAs with the W tile multicast
   if (BN_ == 256 && MODE >= 2 && g_cluster == 3 && ep.batch == 1 && ep.M > BM && !ep.dbg)
     return launch_tc<MODE, 256, 3>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
-  if (g_cluster >= 2 && ep.batch == 1 && ep.M > BM)
+  if (g_cluster >= 2 && ep.batch == 1 && ep.M > BM && !ep.dbg)
     return launch_tc<MODE, BN_, 2>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
   return launch_tc<MODE, BN_, 1>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
 }
@@ -1117,6 +1162,8 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.store_hi = g_store_hi; ep.dbg = g_dbg;
   ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
   ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.w_img = nullptr;
+  ep.dw_w = nullptr; ep.dw_b = nullptr; ep.seq_pos = nullptr; ep.seq_rem = nullptr; ep.dw_k = 0;
+  VSG_REQUIRE(a->dw_w == nullptr || (a->mode == 3 && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for mode 3, plain problems");
   if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
   ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
   ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
@@ -1158,6 +1205,15 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
     VSG_REQUIRE(a->W_b16 && a->W_lo16 && aligned16(a->W_b16) && aligned16(a->W_lo16) && a->ldw16 >= K && a->ldw16 % 8 == 0,
                 "vsg_gemm_ex: mode 3 needs the bf16 copies of W from vsg_split_bf16 (16-byte aligned, ldw16 a multiple of 8)");
     if (g_w_image && a->W_img && a->img_bn == (wide ? 256 : 128) && aligned16(a->W_img)) ep.w_img = (const uint8_t*)a->W_img;
+    if (a->dw_w) {
+      // A = dwconv(X) computed inside the kernel (grounding conv blocks: depthwise k in {3, 7} over K = 128 channels, then the 1x1 conv)
+      VSG_REQUIRE(!wide && N <= 128, "vsg_gemm_ex: the fused depthwise conv needs N <= 128 (128-wide tiles)");
+      VSG_REQUIRE(a->dw_b && a->seq_pos && a->seq_rem && aligned16(a->dw_b), "vsg_gemm_ex: fused depthwise conv needs dw_b, seq_pos, seq_rem");
+      VSG_REQUIRE(a->dw_k >= 1 && a->dw_k <= 7 && (a->dw_k & 1) && K % 4 == 0 && K * (a->dw_k + 1) <= 2048,
+                  "vsg_gemm_ex: fused depthwise conv supports odd k <= 7 and K * (k + 1) <= 2048 (got k %d, K %d)", a->dw_k, K);
+      ep.dw_w = a->dw_w; ep.dw_b = a->dw_b; ep.seq_pos = a->seq_pos; ep.seq_rem = a->seq_rem; ep.dw_k = a->dw_k;
+      return launch_tc<3, 128, 1, true>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
+    }
     return wide ? launch_tc_auto<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
                 : launch_tc_auto<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
   }

@@ -160,6 +160,14 @@ class DEBUG(object):
                                _raw(out), stream_ptr(x.device)), "vsg_dwconv")
         return out
 
+    fuse_dwconv = True       # depthwise conv inside the point-wise GEMM's operand pipeline (False: separate vsg_dwconv launch)
+
+    def _dw_pw(self, x, cw, sq, relu=False, residual=None):
+        """DepthWiseSeparableConv1d (:36-56): depthwise conv over the sequence axis, then the 1x1 conv (+ ReLU, + residual)."""
+        if self.fuse_dwconv and linalg.can_fuse_dwconv(self.mode, cw["pw"], k=cw["k"]):
+            return gemm(self.mode, x, cw["pw"], relu=relu, residual=residual, dwconv=(cw["dw_w"], cw["dw_b"], cw["k"], sq["pos"], sq["rem"]))
+        return gemm(self.mode, self._dwconv(x, cw, sq["pos"], sq["rem"]), cw["pw"], relu=relu, residual=residual)
+
     def _seq(self, seq_off_host: np.ndarray):
         dev = self.device
         seq_off = torch.from_numpy(np.ascontiguousarray(seq_off_host.astype(np.int64))).to(dev)
@@ -179,8 +187,7 @@ class DEBUG(object):
         check(lib().vsg_pos_add_ln(_raw(x), _raw(sq["pos"]), _raw(w["freq"]), _raw(w["phase"]), _raw(ew["normb"][0]), _raw(ew["normb"][1]),
                                    x.shape[0], H, _raw(res), _raw(out), stream_ptr(x.device)), "vsg_pos_add_ln")
         for i in range(4):
-            t = self._dwconv(out, ew["convs"][i], sq["pos"], sq["rem"])
-            res = gemm(m, t, ew["convs"][i]["pw"], relu=True, residual=res)          # relu(conv) + res  (:120-122)
+            res = self._dw_pw(out, ew["convs"][i], sq, relu=True, residual=res)      # relu(conv) + res  (:120-122)
             out = self._ln(res, ew["norm_seq"][i])
         qkv = gemm(m, out, ew["qkv"])
         att = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
@@ -195,8 +202,8 @@ class DEBUG(object):
     def _head(self, hw, x, sq):
         y = x
         for c in range(4):
-            y = gemm(self.mode, self._dwconv(y, hw[c], sq["pos"], sq["rem"]), hw[c]["pw"], relu=True)
-        return gemm(self.mode, self._dwconv(y, hw[4], sq["pos"], sq["rem"]), hw[4]["pw"])
+            y = self._dw_pw(y, hw[c], sq, relu=True)
+        return self._dw_pw(y, hw[4], sq)
 
     # ---- batched forward ----------------------------------------------------------------------------------
     def _forward_videos(self, feats: Sequence[torch.Tensor], datas: Sequence[tuple], th, want_net: bool = False):

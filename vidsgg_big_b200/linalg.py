@@ -12,6 +12,12 @@ SIMT, TF32, X3TF32, TF32_BF16X2 = 0, 1, 2, 3
 MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2}
 
 
+def can_fuse_dwconv(mode: int, W: "Weight", K: Optional[int] = None, k: int = 7) -> bool:
+    """The depthwise conv can run inside the GEMM's operand pipeline (csrc/gemm.cu, CONV variant)."""
+    K = W.K if K is None else K
+    return mode == TF32_BF16X2 and W.w16 is not None and W.N <= 128 and K % 4 == 0 and K * (k + 1) <= 2048 and k % 2 == 1 and k <= 7
+
+
 def attention_mode(mode: int) -> int:
     """Mode of the batched attention GEMMs (activation x activation): TF32_BF16X2 needs pre-computed bf16 copies of the "weight"
     operand, which only exist for real weights -- those few problems stay on the 3xTF32 kernel."""
@@ -80,10 +86,12 @@ LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py'
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
          accumulate: bool = False, bias: bool = True, K: Optional[int] = None,
-         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, lo_cols=None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, lo_cols=None, dwconv=None) -> torch.Tensor:
     """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
     wider row-major buffers (their row stride is passed as the leading dimension).  ``out_lo`` (same shape / strides as ``out``)
-    receives ``x - trunc_tf32(x)`` of the result, restricted to the column window ``lo_cols = (begin, end)`` if given."""
+    receives ``x - trunc_tf32(x)`` of the result, restricted to the column window ``lo_cols = (begin, end)`` if given.
+    ``dwconv = (dw_w [K,k], dw_b [K], k, seq_pos i32[M], seq_rem i32[M])``: A is replaced by its depthwise conv over the row axis inside
+    the kernel (mode tf32+bf16x2, N <= 128; see ``can_fuse_dwconv``)."""
     require_cuda(A)
     assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32
     M = A.shape[0]
@@ -103,6 +111,7 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         ev0.record()
     if mode == TF32_BF16X2 and W.w16 is None:
         raise ValueError("gemm: mode tf32+bf16x2 needs a Weight built with split='bf16'")
+    assert dwconv is None or can_fuse_dwconv(mode, W, K)
     if out_lo is not None or mode == TF32_BF16X2:
         from ._cabi import VsgGemmArgs
         import ctypes as C
@@ -119,6 +128,9 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
             a.lo_col_begin, a.lo_col_end = int(lo_cols[0]), int(lo_cols[1])
         if mode == TF32_BF16X2:
             a.W_b16, a.W_lo16, a.ldw16 = W.w16.data_ptr(), W.lo16.data_ptr(), W.ld16
+            if dwconv is not None:
+                dw_w, dw_b, dw_k, seq_pos, seq_rem = dwconv
+                a.dw_w, a.dw_b, a.dw_k, a.seq_pos, a.seq_rem = dw_w.data_ptr(), dw_b.data_ptr(), int(dw_k), seq_pos.data_ptr(), seq_rem.data_ptr()
             if W.img is not None and K == W.K:           # the image's k blocks cover the whole of W.K
                 a.W_img, a.img_bn = W.img.data_ptr(), W.img_bn
         check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
