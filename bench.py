@@ -447,13 +447,16 @@ def main():
     geo_gbs = geo_bytes / (geo_ms * 1e-3) / 1e9 if geo_ms > 0 else 0.0
     traffic, traffic_src = None, None
     try:        # per-launch DRAM bytes of the step's GEMM launches from the committed ncu pass (same command, same workload)
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_v3.summary.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r01_gemm_traffic_v4.summary.json")))
         if args.workload == "vidvrd" and args.videos == 200 and args.precision in ("3xtf32", "tf32+bf16x2"):
-            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_gemm_traffic_v3.summary.json (dram read+write / launch, 82 launches)"
+            traffic, traffic_src = tj["dram_bytes_per_launch"], "profiles/r01_gemm_traffic_v4.summary.json (dram read+write / launch, 82 launches)"
     except Exception:
         pass
+    slots = {"tf32+bf16x2": 4.0, "3xtf32": 6.0, "tf32": 2.0}.get(args.precision)      # bf16-equivalent tensor slots issued per useful MAC
     roofline = {"kernel": "gemm_tc_kernel (tcgen05 %s)" % args.precision, "bound": "tensor", "achieved": gemm_tf, "peak": tc_peak,
                 "unit": "TFLOP/s", "frac": gemm_tf / tc_peak, "traffic": traffic, "traffic_source": traffic_src,
+                "issued_bf16_equiv": None if slots is None else gemm_tf * slots,
+                "frac_issued": None if slots is None else gemm_tf * slots / tc_peak,
                 "peak_source": peak_src + " bf16 dense sustained",
                 "launches_per_step": n_gemm, "share_of_step": gemm_ms / ms_step,
                 "note": "achieved = useful 2MNK flops of an fp32-class product: 3xtf32 issues 3 tf32 MMAs per useful one (6 bf16-equivalent "

@@ -167,12 +167,13 @@ add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restri
     for (int i = 0; i < MAXPL; ++i)
       if (i < per) { const float d = v[i] - mean; q += d * d; }
     const float rstd = rsqrtf(warp_sum(q) / (float)D + 1e-5f);
+    const float* prow = post ? post + (r % post_period) * (int64_t)D : nullptr;      // one 64-bit modulo per row, not per element
 #pragma unroll
     for (int i = 0; i < MAXPL; ++i) {
       if (i < per) {
         const int c = lane + 32 * i;
         float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-        if (post) y += post[(r % post_period) * (int64_t)D + c];
+        if (prow) y += prow[c];
         out[r * ldo + c] = y;
       }
     }
