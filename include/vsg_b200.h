@@ -271,6 +271,11 @@ int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, const int64
  * the "+ pos" of :189 is the post term).  a, post may be NULL.  D % 32 == 0, D <= 1024. */
 int vsg_add_layernorm(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
                       const float* post, int post_period, int64_t rows, int D, float* out, int ldo, void* stream);
+/* Dual form: out = LayerNorm(x + a), out2 = out + post[row % post_period] -- the decoder's last norm of a layer also emits the next layer's
+ * q / k input (query + pos, models/model_0v10.py:181) so that the q/k projection needs no row-periodic bias in its epilogue. */
+int vsg_add_layernorm_dual(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
+                           const float* post, int post_period, int64_t rows, int D, float* out, int ldo, float* out2, int ldo2,
+                           void* stream);
 
 /* out[r] = x[r % period]  (pred_query_init for every video, model_0v10.py:465). */
 int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* out, void* stream);

@@ -86,6 +86,7 @@ SIGNATURES = {
     "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
     "vsg_conv_pool": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
     "vsg_add_layernorm": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p]),
+    "vsg_add_layernorm_dual": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p, i32, p]),
     "vsg_broadcast_rows": (i32, [p, i32, i32, i64, p, p]),
     "vsg_mha": (i32, [p, i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, p, i32, p, p, i32, p]),
     "vsg_role_attention": (i32, [p, p, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),

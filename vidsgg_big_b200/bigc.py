@@ -218,17 +218,19 @@ class BIG_C(object):
                 n2=(st[p + "norm2.weight"].contiguous(), st[p + "norm2.bias"].contiguous())))
         pos = st["pos_embedding"].contiguous()
         w["pos"], w["query_init"] = pos, st["pred_query_init"].contiguous()
+        w["qk_init"] = (w["query_init"] + pos).contiguous()
         w["dec"] = []
         for i in range(self.n_deco_layers):
             p = "decoder_layers.%d." % i
-            qkv = Weight(st[p + "self_attn.in_proj_weight"], st[p + "self_attn.in_proj_bias"], split=split)
-            # q = k = (query + pos) W^T  ==  query W^T + (pos W^T): the pos term becomes a row-periodic bias (period Q)
-            posb = gemm(self.mode, pos, qkv, bias=False)
-            posb[:, 2 * Pd:] = 0.0
+            # q = k = (query + pos) W_qk^T, v = query W_v^T (model_0v10.py:181-183): two GEMMs on two inputs; `query + pos` comes out of
+            # the previous layer's last LayerNorm as a second output (a row-periodic bias in ONE qkv GEMM made its epilogue the bottleneck)
+            ipw, ipb = st[p + "self_attn.in_proj_weight"], st[p + "self_attn.in_proj_bias"]
+            qk = Weight(ipw[:2 * Pd].contiguous(), ipb[:2 * Pd].contiguous(), split=split)
+            vw = Weight(ipw[2 * Pd:].contiguous(), ipb[2 * Pd:].contiguous(), split=split)
             r2 = Weight(torch.cat([st[p + "fc_rolewise.0.2.weight"], st[p + "fc_rolewise.1.2.weight"]], 1).contiguous(),
                         st[p + "fc_rolewise.0.2.bias"] + st[p + "fc_rolewise.1.2.bias"], split=split)
             w["dec"].append(dict(
-                qkv=qkv, posb=posb.contiguous(), out=W(p + "self_attn.out_proj"),
+                qk=qk, v=vw, out=W(p + "self_attn.out_proj"),
                 p2a=W(p + "fc_pred2att"), e2a=W(p + "fc_enti2att"),
                 r1=(W(p + "fc_rolewise.0.0"), W(p + "fc_rolewise.1.0")), r2=r2,
                 f1=W(p + "fc2.0"), f2=W(p + "fc2.3"),
@@ -245,8 +247,14 @@ class BIG_C(object):
         self._w = w
 
     # ---- kernels ------------------------------------------------------------------------------------
-    def _add_ln(self, x, a, norm, post=None, period=0):
+    def _add_ln(self, x, a, norm, post=None, period=0, dual=False):
         out = torch.empty_like(x)
+        if dual:        # -> (LN(x + a), LN(x + a) + post)
+            out2 = torch.empty_like(x)
+            check(lib().vsg_add_layernorm_dual(_raw(x), x.stride(0), _raw(a), 0 if a is None else a.stride(0), _raw(norm[0]), _raw(norm[1]),
+                                               _raw(post), period, x.shape[0], x.shape[1], _raw(out), out.stride(0), _raw(out2),
+                                               out2.stride(0), stream_ptr(x.device)), "vsg_add_layernorm_dual")
+            return out, out2
         check(lib().vsg_add_layernorm(_raw(x), x.stride(0), _raw(a), 0 if a is None else a.stride(0), _raw(norm[0]), _raw(norm[1]),
                                       _raw(post), period, x.shape[0], x.shape[1], _raw(out), out.stride(0), stream_ptr(x.device)),
               "vsg_add_layernorm")
@@ -359,21 +367,25 @@ class BIG_C(object):
             check(L.vsg_broadcast_rows(_raw(x), Q, x.shape[1], VQ, _raw(out), sp), "vsg_broadcast_rows")
             return out
 
-        query = None
+        query = query_pos = None
         for li, lw in enumerate(w["dec"]):
             last = li == n_dec - 1
             # layer 0: the queries of every video are still pred_query_init, so its self-attention block and
             # fc_pred2att are video-independent -- computed once on Q rows, then broadcast
             x = w["query_init"] if li == 0 else query
+            x_qk = w["qk_init"] if li == 0 else query_pos
             nv = 1 if li == 0 else V
             use_tc = self.attention == "tc" and m != linalg.SIMT and (Pd // self.n_att_head) % 32 == 0 and Q % 32 == 0
+            qkv = torch.empty(x.shape[0], 3 * Pd, dtype=torch.float32, device=dev)
             if use_tc:
-                qkv = torch.empty(x.shape[0], 3 * Pd, dtype=torch.float32, device=dev)
                 qkv_lo = torch.empty_like(qkv) if linalg.attention_mode(m) == linalg.X3TF32 else None
-                gemm(m, x, lw["qkv"], out=qkv, rowbias=lw["posb"], rb_period=Q, out_lo=qkv_lo, lo_cols=(Pd, 2 * Pd))   # only K's low part is read
+                gemm(m, x_qk, lw["qk"], out=qkv[:, :2 * Pd], out_lo=None if qkv_lo is None else qkv_lo[:, :2 * Pd],
+                     lo_cols=(Pd, 2 * Pd))                                              # only K's low part is read
+                gemm(m, x, lw["v"], out=qkv[:, 2 * Pd:])
                 att = self._mha_tc(qkv, qkv_lo, nv, Q, Pd)
             else:
-                qkv = gemm(m, x, lw["qkv"], rowbias=lw["posb"], rb_period=Q)
+                gemm(m, x_qk, lw["qk"], out=qkv[:, :2 * Pd])
+                gemm(m, x, lw["v"], out=qkv[:, 2 * Pd:])
                 att = self._mha(qkv, Pd, None, nv, Q, Q)
             x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"], post=w["pos"], period=Q)
             p2a = gemm(m, x, lw["p2a"])
@@ -389,7 +401,11 @@ class BIG_C(object):
             gemm(m, values[:, :E], lw["r1"][0], out=hid[:, :Pd], relu=True)
             gemm(m, values[:, E:], lw["r1"][1], out=hid[:, Pd:], relu=True)
             query = self._add_ln(query, gemm(m, hid, lw["r2"]), lw["n2"])
-            query = self._add_ln(query, gemm(m, gemm(m, query, lw["f1"], relu=True), lw["f2"]), lw["n3"])
+            ffn = gemm(m, gemm(m, query, lw["f1"], relu=True), lw["f2"])
+            if last:
+                query = self._add_ln(query, ffn, lw["n3"])
+            else:                                                                       # also emit query + pos for the next layer's q / k
+                query, query_pos = self._add_ln(query, ffn, lw["n3"], post=w["pos"], period=Q, dual=True)
             if dbg is not None:
                 dbg.setdefault("dec_layers", []).append(query.clone())
         logits = self._prediction_head(pk, query, so, enti2enco, extra)

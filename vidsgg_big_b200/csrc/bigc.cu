@@ -143,7 +143,7 @@ template <int MAXPL>
 __global__ void __launch_bounds__(256)
 add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restrict__ a, int lda, const float* __restrict__ gamma,
                      const float* __restrict__ beta, const float* __restrict__ post, int post_period, int64_t rows, int D,
-                     float* __restrict__ out, int ldo) {
+                     float* __restrict__ out, int ldo, float* __restrict__ out2, int ldo2) {
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
@@ -173,8 +173,13 @@ add_layernorm_kernel(const float* __restrict__ x, int ldx, const float* __restri
       if (i < per) {
         const int c = lane + 32 * i;
         float y = (v[i] - mean) * rstd * gamma[c] + beta[c];
-        if (prow) y += prow[c];
-        out[r * ldo + c] = y;
+        if (out2) {                       // dual form: out = LN(.), out2 = LN(.) + post   (the next layer's q/k input, model_0v10.py:181)
+          out[r * ldo + c] = y;
+          out2[r * ldo2 + c] = y + prow[c];
+        } else {
+          if (prow) y += prow[c];
+          out[r * ldo + c] = y;
+        }
       }
     }
   }
@@ -902,19 +907,34 @@ extern "C" int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, 
   return check_launch("vsg_conv_pool");
 }
 
+static int add_layernorm_impl(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta, const float* post,
+                              int post_period, int64_t rows, int D, float* out, int ldo, float* out2, int ldo2, void* stream);
+
 extern "C" int vsg_add_layernorm(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
                                  const float* post, int post_period, int64_t rows, int D, float* out, int ldo, void* stream) {
+  return add_layernorm_impl(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo, nullptr, 0, stream);
+}
+
+extern "C" int vsg_add_layernorm_dual(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta,
+                                      const float* post, int post_period, int64_t rows, int D, float* out, int ldo, float* out2, int ldo2,
+                                      void* stream) {
+  VSG_REQUIRE(rows == 0 || (post && out2), "vsg_add_layernorm_dual: post and out2 are required");
+  return add_layernorm_impl(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo, out2, ldo2, stream);
+}
+
+static int add_layernorm_impl(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta, const float* post,
+                              int post_period, int64_t rows, int D, float* out, int ldo, float* out2, int ldo2, void* stream) {
   VSG_REQUIRE(rows >= 0 && D > 0 && D % 32 == 0 && D <= 1024, "vsg_add_layernorm: D must be a multiple of 32, <= 1024");
   if (rows == 0) return VSG_OK;
   VSG_REQUIRE(x && gamma && beta && out, "vsg_add_layernorm: null pointer");
   VSG_REQUIRE(post == nullptr || post_period > 0, "vsg_add_layernorm: post needs a period");
   const int g = grid_cap((rows + 7) / 8, 8);
   if (D <= 128)
-    add_layernorm_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+    add_layernorm_kernel<4><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo, out2, ldo2);
   else if (D <= 512)
-    add_layernorm_kernel<16><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+    add_layernorm_kernel<16><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo, out2, ldo2);
   else
-    add_layernorm_kernel<32><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo);
+    add_layernorm_kernel<32><<<g, 256, 0, (cudaStream_t)stream>>>(x, ldx, a, lda, gamma, beta, post, post_period, rows, D, out, ldo, out2, ldo2);
   return check_launch("vsg_add_layernorm");
 }
 

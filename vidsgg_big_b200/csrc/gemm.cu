@@ -59,6 +59,7 @@ struct GemmEpilogue {
   float* C_lo;              // optional: x - trunc_tf32(x) of every stored value (the B-side low part for a following 3xTF32 GEMM)
   int lo_c0, lo_c1;         // C_lo is written for columns in [lo_c0, lo_c1) only
   int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
+  int lo_tma;               // 1: C_lo slabs that lie fully inside the column window leave the same way (mapClo is valid)
   const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null
   const float* dw_w;        // CONV: depthwise weights [K][dw_k], bias dw_b [K], per-row position in / rows remaining of its sequence
   const float* dw_b;
@@ -363,7 +364,7 @@ template <int MODE, int BN_, bool PROBE, int CL, bool CONV = false>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
-               const __grid_constant__ CUtensorMap mapC, const GemmEpilogue ep) {
+               const __grid_constant__ CUtensorMap mapC, const __grid_constant__ CUtensorMap mapClo, const GemmEpilogue ep) {
   constexpr bool PAIR = (CL == 3);
   using CF = Cfg<MODE, BN_, PAIR, CONV>;
   constexpr int STAGES = CF::STAGES;
@@ -406,6 +407,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (MODE >= 2) tma_prefetch_desc(&mapBl);
     if (MODE == 3) tma_prefetch_desc(&mapB16);
     if (ep.tma_store) tma_prefetch_desc(&mapC);
+    if (ep.lo_tma) tma_prefetch_desc(&mapClo);
   }
   if (warp == 1 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) {
@@ -625,6 +627,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const bool fast = ep.tma_store && vec_ok && slab_rows_ok && col0 + 32 <= ep.N;   // warp-uniform
         if (fast) {
           uint8_t* sb = stg + sbuf * 4096;
+          const bool lo_slab = ep.lo_tma && col0 >= ep.lo_c0 && col0 + 32 <= ep.lo_c1;   // warp-uniform: the low parts leave by TMA too
           if (lane == 0) bulk_wait_read<1>();                                 // the store that last read this buffer is done
           __syncwarp();
 #pragma unroll
@@ -650,7 +653,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
             // SWIZZLE_128B: 16-byte chunk q of row r sits at chunk q ^ (r & 7) (buffer is 1024-byte aligned)
             *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
-            if (crow_lo && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
+            if (crow_lo && !lo_slab && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
               float4 l;
               l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
               l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
@@ -664,6 +667,28 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             bulk_commit();
           }
           sbuf ^= 1;
+          if (lo_slab) {
+            // x - trunc_tf32(x) of the slab just staged, built in the other buffer from the staged values
+            uint8_t* sb2 = stg + sbuf * 4096;
+            if (lane == 0) bulk_wait_read<1>();                               // all but this chunk's own store: sb2's last reader is done
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const int o = lane * 128 + (((j >> 2) ^ (lane & 7)) << 4);
+              const float4 v = *reinterpret_cast<const float4*>(sb + o);
+              float4 l;
+              l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
+              l.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xFFFFE000u); l.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xFFFFE000u);
+              *reinterpret_cast<float4*>(sb2 + o) = l;
+            }
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+              tma_store_2d(&mapClo, smem_u32(sb2), tc.c_col + col0, tc.c_row + m0 + quad * 32);
+              bulk_commit();
+            }
+            sbuf ^= 1;
+          }
         } else if (row_ok) {
           if (col0 + 32 <= ep.N && vec_ok) {
 #pragma unroll
@@ -1030,8 +1055,8 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
     if (rc) return rc;
   }
   GemmEpilogue ep = ep_in;
-  CUtensorMap mC = mA;
-  ep.tma_store = 0;
+  CUtensorMap mC = mA, mClo = mA;
+  ep.tma_store = 0; ep.lo_tma = 0;
   if (g_tma_store && (ep.ldc & 3) == 0 && aligned16(ep.C)) {
     // C as a 2-D tensor of 32x32 fp32 boxes (SWIZZLE_128B).  Batched problems address boxes inside the whole C buffer, whose row
     // length is ldc; only slabs that lie fully inside a problem take this path, so the bounds are never relied on for clipping.
@@ -1045,6 +1070,11 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
       rc = get_tensor_map(ep.C, (int)rows, (int)cols, ep.ldc, 32, 32, &mC);
       if (rc) return rc;
       ep.tma_store = 1;
+      if (ep.C_lo && aligned16(ep.C_lo)) {
+        rc = get_tensor_map(ep.C_lo, (int)rows, (int)cols, ep.ldc, 32, 32, &mClo);
+        if (rc) return rc;
+        ep.lo_tma = 1;
+      }
     }
   }
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CF::DW_BYTES;
@@ -1069,8 +1099,8 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CLN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = CLN > 1 ? 1 : 0;
-  cudaError_t e = (ep.dbg && HAS_PROBE) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, mA, mBh, mBl, mB16, mC, ep)   // timing probes
-                                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL, CONV>, mA, mBh, mBl, mB16, mC, ep);
+  cudaError_t e = (ep.dbg && HAS_PROBE) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, mA, mBh, mBl, mB16, mC, mClo, ep)   // timing probes
+                                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL, CONV>, mA, mBh, mBl, mB16, mC, mClo, ep);
   if (e != cudaSuccess) { set_error("vsg_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VSG_E_LAUNCH; }
   return check_launch("vsg_gemm(tcgen05)");
 }
@@ -1161,7 +1191,7 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
   ep.store_hi = g_store_hi; ep.dbg = g_dbg;
   ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
-  ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.w_img = nullptr;
+  ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.lo_tma = 0; ep.w_img = nullptr;
   ep.dw_w = nullptr; ep.dw_b = nullptr; ep.seq_pos = nullptr; ep.seq_rem = nullptr; ep.dw_k = 0;
   VSG_REQUIRE(a->dw_w == nullptr || (a->mode == 3 && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for mode 3, plain problems");
   if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
