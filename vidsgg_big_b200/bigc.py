@@ -69,8 +69,17 @@ class PackedVideos(object):
 class PackedTriplets(object):
     """Triplets of a batch of videos as written by the kernel: video v owns rows [v*cap, v*cap + counts[v,0])."""
 
-    def __init__(self, quint, scores, spans, qids, counts_host, cap):
-        self.quint, self.scores, self.spans, self.qids, self.counts, self.cap = quint, scores, spans, qids, counts_host, cap
+    def __init__(self, quint, scores, spans, qids, counts_host, cap, counts_dev=None):
+        self.quint, self.scores, self.spans, self.qids, self._counts, self.cap = quint, scores, spans, qids, counts_host, cap
+        self._counts_dev = counts_dev
+
+    @property
+    def counts(self):
+        """Per-video (rows written, positive pairs) on the host.  With ``forward_packed(..., sync=False)`` the D2H read is deferred to
+        the first access, so that the caller can enqueue more GPU work (or switch streams) before blocking on it."""
+        if self._counts is None:
+            self._counts = self._counts_dev.cpu().numpy()
+        return self._counts
 
     def compact(self):
         """Dense rows of all videos (video-major) + host offsets: 4 gathers for the whole batch."""
@@ -450,7 +459,7 @@ class BIG_C(object):
         Z = self._concat(pieces, VQ, ldz)
         return gemm(m, Z, w["log"], rowbias=w["bias_matrix"], rb_index=pair_index, K=self.dim_z)
 
-    def _construct_triplets(self, pk, logits, so, topk, packed=False):
+    def _construct_triplets(self, pk, logits, so, topk, packed=False, sync=True):
         """model_0v10.py:707-785 for every video; one D2H read of the per-video counts."""
         V, Q = pk.V, self.num_querys
         cap = Q * topk
@@ -464,7 +473,7 @@ class BIG_C(object):
                                           _raw(pk.dura), _raw(pk.cat_ids), _raw(pk.scores), _raw(quint), _raw(scores), _raw(spans),
                                           _raw(qids), _raw(counts), cap, stream_ptr(dev)), "vsg_construct_triplet")
         if packed:
-            return PackedTriplets(quint, scores, spans, qids, counts.cpu().numpy(), cap)
+            return PackedTriplets(quint, scores, spans, qids, counts.cpu().numpy() if sync else None, cap, counts_dev=counts)
         cnt = counts.cpu().tolist()
         out = []
         for v in range(V):
@@ -511,7 +520,7 @@ class BIG_C(object):
         """Index arrays / packed views of a batch (reusable across calls while the batch is resident in HBM)."""
         return PackedVideos(proposal_list, self.device)
 
-    def forward_packed(self, proposal_list, topk=None, packed_videos=None):
+    def forward_packed(self, proposal_list, topk=None, packed_videos=None, sync=True):
         """Same computation as ``forward`` for a batch of non-empty videos, but the result stays packed on the device
         (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``."""
         if self._w is None:
@@ -520,7 +529,7 @@ class BIG_C(object):
         assert all(p.num_proposals > 0 for p in proposal_list)
         pk = packed_videos if packed_videos is not None else PackedVideos(proposal_list, self.device)
         logits, so, _ = self._encode2decode(pk)
-        return self._construct_triplets(pk, logits, so, self.topk, packed=True)
+        return self._construct_triplets(pk, logits, so, self.topk, packed=True, sync=sync)
 
     def forward_debug(self, proposal):
         """(pred_queries, pred_logits [Q,P], att_matrx [2,Q,n]) of one video, like ``encode2decode`` (:434-475)."""

@@ -219,12 +219,20 @@ def traj_viou_batched(A: TrackTable, B: TrackTable, want_spans=True, want_mask=T
     assert len(A.counts) == len(B.counts)
     same = A is B
     dev = A.boxes.device
-    sizes = [a * b for a, b in zip(A.counts, B.counts)]
-    seg_out_h = [0]
-    for s in sizes:
-        seg_out_h.append(seg_out_h[-1] + s)
+    # per-video output offsets: cached on A for a given B (a resident batch is evaluated many times; the upload is a blocking H2D copy)
+    cache = A.__dict__.setdefault("_seg_out_cache", {})
+    hit = cache.get(id(B))
+    if hit is not None and hit[0] is B:
+        _, seg_out_h, seg_out = hit
+    else:
+        sizes = [a * b for a, b in zip(A.counts, B.counts)]
+        seg_out_h = [0]
+        for s in sizes:
+            seg_out_h.append(seg_out_h[-1] + s)
+        seg_out = torch.tensor(seg_out_h, dtype=torch.long).to(dev)
+        cache.clear()
+        cache[id(B)] = (B, seg_out_h, seg_out)
     P = seg_out_h[-1]
-    seg_out = torch.tensor(seg_out_h, dtype=torch.long).to(dev)
     spans = torch.empty(P, 2, dtype=torch.long, device=dev) if want_spans else None
     mask = torch.empty(P, dtype=torch.uint8, device=dev) if want_mask else None
     viou = torch.empty(P, dtype=torch.float32, device=dev) if want_viou else None
