@@ -404,7 +404,20 @@ def main():
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
     if world > 1:
-        dist.init_process_group("nccl", device_id=device)
+        # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout while the communicator is created: point fd 1 at stderr for
+        # that moment so that stdout carries the ONE JSON line only
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=device)
+            warm = torch.zeros(1, device=device)
+            dist.all_reduce(warm)
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     _cabi.lib()
 
     pipe = Pipeline(args.workload, args.precision, device, rank)
