@@ -129,3 +129,25 @@ def test_convertor_equals_oracle_and_driver_roundtrip():
     m_ap, rec, mprec, dicts = driver.inference_then_eval(model, props, graphs, topk=5, want_dicts=True)
     m2, r2, p2 = api.eval_visual_relation(gts, dicts)
     assert abs(m_ap - m2) < 1e-12 and rec[50] == r2[50] and rec[100] == r2[100] and all(mprec[k] == p2[k] for k in (1, 5, 10))
+
+
+def test_eval_idempotence_at_vidvrd_test_size():
+    """Size-independent property at the VidVRD-test size (200 videos): evaluating the GT relations against themselves (as
+    predictions with distinct scores) gives AP = 1 for every video, recall@100 = 1 and recall@50 = (sum of min(n_gt, 50)) / n_gt_total;
+    dropping every prediction gives zeros."""
+    from vidsgg_big_b200 import evalapi, geometry
+    graphs = []
+    for i in range(200):
+        rng = np.random.default_rng(5000 + i)
+        P = synth.make_proposal(5000 + i, int(rng.integers(5, 40)), int(rng.integers(90, 600)), 8, 36, with_features=False)
+        graphs.append(synth.make_gt_graph(5000 + i, P, 133, n_rel=(5, 60)).to(DEV))
+    gt_t = geometry.TrackTable.from_containers(graphs, device=DEV)
+    GT = evalapi.PackedRelations.from_gt_graphs(gt_t, graphs)
+    n = GT.rel.shape[0]
+    scores = torch.linspace(1.0, 0.5, n, dtype=torch.float64, device=DEV)
+    PR = evalapi.PackedRelations(GT.boxes, GT.off, GT.tstart, GT.rel.clone(), GT.vid_off.clone(), scores, vol_full_track=GT.vol_full_track)
+    m_ap, rec, mprec = evalapi.evaluate_packed(PR, GT)
+    per_vid = np.diff(GT.vid_off.cpu().numpy())
+    assert abs(m_ap - 1.0) < 1e-12
+    assert abs(float(rec[100]) - np.minimum(per_vid, 100).sum() / per_vid.sum()) < 1e-6
+    assert abs(float(rec[50]) - np.minimum(per_vid, 50).sum() / per_vid.sum()) < 1e-6

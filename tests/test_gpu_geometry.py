@@ -274,3 +274,30 @@ def test_stack_with_repeat_2d(golden):
     cols = [t.t().contiguous() for t in ts]                                                   # ragged axis = columns
     gotc = geometry.stack_with_repeat_2d([t.cuda() for t in cols], dim=0)
     assert torch.equal(gotc.cpu(), want.permute(0, 2, 1))
+
+
+def test_viou_properties_full_stress_size():
+    """BASELINE.json configs[4] at FULL size (256 tracklets, 10k frames, ~270 M frame pairs): symmetry, unit diagonal, range, span
+    symmetry / validity, agreement of the warp-per-pair and the tiled kernels, and sampled rows against the numpy oracle."""
+    g = _geo()
+    P = synth.make_proposal(4242, 256, 10000, 8, 36, min_len=2000, max_len=10000, with_features=False).to(DEV)
+    T = g.TrackTable.from_containers([P])
+    viou, spans, mask, seg, _ = g.traj_viou_batched(T, T, variant=1)
+    n = 256
+    V, S, M = viou.view(n, n), spans.view(n, n, 2), mask.view(n, n).bool()
+    assert torch.allclose(V, V.t(), rtol=2e-6, atol=0)
+    assert torch.allclose(torch.diagonal(V), torch.ones(n, device=DEV), rtol=2e-6)
+    assert bool((V >= 0).all()) and bool((V <= 1 + 1e-6).all())
+    assert torch.equal(S, S.transpose(0, 1)) and torch.equal(M, M.t())
+    d = P.traj_durations
+    assert torch.equal(S[..., 0], torch.maximum(d[:, None, 0], d[None, :, 0])) and torch.equal(S[..., 1], torch.minimum(d[:, None, 1], d[None, :, 1]))
+    assert torch.equal(M, S[..., 0] <= S[..., 1]) and bool((V[~M] == 0).all()) and bool((V[M] > 0).any())
+    tiled, _, _, _, _ = g.traj_viou_batched(T, T, variant=2)
+    assert torch.allclose(viou, tiled, rtol=3e-6, atol=1e-9)
+    bx = P.bboxes.cpu().numpy(); du = d.cpu().numpy()
+    off = np.concatenate([[0], np.cumsum(P.lengths.numpy())])
+    rows = [3, 200]
+    sub_off = np.concatenate([[0], np.cumsum([off[r + 1] - off[r] for r in rows])])
+    sub_bx = np.concatenate([bx[off[r]:off[r + 1]] for r in rows], 0)
+    ref = og.traj_viou_matrix_np(sub_bx, sub_off, du[rows], bx, off, du)
+    np.testing.assert_allclose(V[rows].cpu().numpy(), ref, rtol=1e-5, atol=1e-7)
