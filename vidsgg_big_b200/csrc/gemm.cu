@@ -16,13 +16,18 @@
 //                        write the two bf16 A tiles (SWIZZLE_32B rows of 16) next to the fp32 A tile; bf16(W), bf16(Wl) are
 //                        pre-computed in HBM (vsg_split_bf16).  Per-product error ~2^-18 worst case.
 //
-// tcgen05 kernel anatomy (one CTA per SM, persistent over 128x128 output tiles, BLOCK_K = 32 fp32 = one
-// 128-byte swizzle row):
-//   warp 0      TMA producer (cp.async.bulk.tensor.2d, SWIZZLE_128B, mbarrier complete_tx)
-//   warp 1      MMA issuer (one elected lane; tcgen05.mma cta_group::1, M=128 N=128 K=8; tcgen05.commit frees stages)
-//   warp 2      TMEM allocator (256 columns = two 128-column fp32 accumulators, double buffered)
-//   warps 4-7   epilogue: tcgen05.ld 32x32b.x32 -> bias / row-bias / ReLU -> global stores
-//   warps 8-11  (3xTF32 only) hi/lo split of the A stage in shared memory
+// tcgen05 kernel anatomy (persistent, one CTA per SM; 128 x BN output tiles per CTA, BN = 256 where N allows, else 128):
+//   warp 0       TMA producer: A tiles by cp.async.bulk.tensor.2d (mbarrier complete_tx), W tiles by tensor loads or -- mode 3 -- by
+//                contiguous cp.async.bulk copies of pre-swizzled weight-tile images (vsg_build_weight_image)
+//   warp 1       MMA issuer: the whole warp walks the uniform loop, one elected lane issues tcgen05.mma + tcgen05.commit
+//   warp 2       TMEM allocator (2 x BN columns: the fp32 accumulator is double buffered, epilogue(i) overlaps mainloop(i+1))
+//   warps 4-7    epilogue: tcgen05.ld 32x32b.x32 -> bias / row-bias / accumulate / ReLU / residual -> 128B-swizzled staging ->
+//                cp.async.bulk.tensor store (edge slabs: 16-byte stores)
+//   warps 8-15   (split modes) two groups of 4 warps that own alternate stages and build the low-order A operands in shared memory
+//                (mode 2: A_lo fp32; mode 3: bf16(A_lo), bf16(A); CONV variant: also the depthwise conv of the raw X tile)
+// Cluster variants (template CL): 1 = single CTA; 2 = CTA pairs sharing an N tile, W half-tiles TMA-multicast; 3 = CTA-pair MMA
+// (tcgen05.mma.cta_group::2, M = 256 per pair): each CTA stages its 128 A rows and half of W -> 32 KB stages, 6 deep.
+// Stage depth: 192 KB of stages per CTA (+ 32 KB store staging).  History of how it got here: profiles/README.md.
 #include "common.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
