@@ -205,7 +205,7 @@ typedef struct VsgGemmArgs {
   int lo_col_begin, lo_col_end;                       /* C_lo is written for columns in [begin, end) only (multiples of 4); 0, 0 = every column */
   const void* W_b16; const void* W_lo16; int ldw16;   /* mode VSG_GEMM_TF32_BF16X2: bf16 [N][ldw16] copies of W (W_hi = the fp32 W) */
   const void* W_img; int img_bn;                      /* optional (mode 3): pre-swizzled tile images from vsg_build_weight_image built for
-                                                         tile width img_bn; ignored unless img_bn == vsg_gemm_tile_n(N) */
+                                                         tile width img_bn over exactly this N and K (same k-block count); ignored unless img_bn == vsg_gemm_tile_n(N) */
   /* optional (mode 3, N <= 128): A is replaced by dwconv(A) computed inside the kernel -- DepthWiseSeparableConv1d.depth_wise of
    * models/grd_model_v5.py:36-56 followed by its point-wise conv as ONE launch: dwconv(A)[r][c] = dw_b[c] + sum_j dw_w[c][j] *
    * A[r + j - dw_k/2][c] with zero padding at the ends of the row's sequence (seq_pos[r] rows before r, seq_rem[r] rows after r in its

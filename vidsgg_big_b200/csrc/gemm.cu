@@ -1244,8 +1244,8 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
       // A = dwconv(X) computed inside the kernel (grounding conv blocks: depthwise k in {3, 7} over K = 128 channels, then the 1x1 conv)
       VSG_REQUIRE(!wide && N <= 128, "vsg_gemm_ex: the fused depthwise conv needs N <= 128 (128-wide tiles)");
       VSG_REQUIRE(a->dw_b && a->seq_pos && a->seq_rem && aligned16(a->dw_b), "vsg_gemm_ex: fused depthwise conv needs dw_b, seq_pos, seq_rem");
-      VSG_REQUIRE(a->dw_k >= 1 && a->dw_k <= 7 && (a->dw_k & 1) && K % 4 == 0 && K * (a->dw_k + 1) <= 2048,
-                  "vsg_gemm_ex: fused depthwise conv supports odd k <= 7 and K * (k + 1) <= 2048 (got k %d, K %d)", a->dw_k, K);
+      VSG_REQUIRE(a->dw_k >= 1 && a->dw_k <= 7 && (a->dw_k & 1) && K % 16 == 0 && K * (a->dw_k + 1) <= 2048,
+                  "vsg_gemm_ex: fused depthwise conv supports odd k <= 7, K %% 16 == 0 and K * (k + 1) <= 2048 (got k %d, K %d)", a->dw_k, K);
       ep.dw_w = a->dw_w; ep.dw_b = a->dw_b; ep.seq_pos = a->seq_pos; ep.seq_rem = a->seq_rem; ep.dw_k = a->dw_k;
       return launch_tc<3, 128, 1, true>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
     }

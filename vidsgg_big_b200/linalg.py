@@ -15,7 +15,7 @@ MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_
 def can_fuse_dwconv(mode: int, W: "Weight", K: Optional[int] = None, k: int = 7) -> bool:
     """The depthwise conv can run inside the GEMM's operand pipeline (csrc/gemm.cu, CONV variant)."""
     K = W.K if K is None else K
-    return mode == TF32_BF16X2 and W.w16 is not None and W.N <= 128 and K % 4 == 0 and K * (k + 1) <= 2048 and k % 2 == 1 and k <= 7
+    return mode == TF32_BF16X2 and W.w16 is not None and W.N <= 128 and K % 16 == 0 and K * (k + 1) <= 2048 and k % 2 == 1 and k <= 7
 
 
 def attention_mode(mode: int) -> int:
