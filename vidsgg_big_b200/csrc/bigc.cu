@@ -41,6 +41,7 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const bool vec4 = (E % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const int t = find_track(off, n_tracks, r);
     const bool last = (r + 1 == off[t + 1]);
@@ -59,11 +60,24 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
     f[6] = bh; f[7] = last ? 0.f : bh2 - bh;
     if (feat8_out && lane < 8) feat8_out[r * 8 + lane] = f[lane];
     float* o = out + r * (int64_t)ldo;
-    for (int c = lane; c < E; c += 32) {
-      float acc = sw[8 * E + c];
+    if (vec4) {
+      // 4 channels per lane and LDS.128: the scalar form issues 9 shared loads per output and is LDS-bound (same fmaf order per channel)
+      for (int c = lane * 4; c < E; c += 128) {
+        float4 acc = *reinterpret_cast<const float4*>(sw + 8 * E + c);
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc = fmaf(f[k], sw[k * E + c], acc);
-      o[c] = fmaxf(acc, 0.f);
+        for (int k = 0; k < 8; ++k) {
+          const float4 wv = *reinterpret_cast<const float4*>(sw + k * E + c);
+          acc.x = fmaf(f[k], wv.x, acc.x); acc.y = fmaf(f[k], wv.y, acc.y); acc.z = fmaf(f[k], wv.z, acc.z); acc.w = fmaf(f[k], wv.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(o + c) = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+      }
+    } else {
+      for (int c = lane; c < E; c += 32) {
+        float acc = sw[8 * E + c];
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc = fmaf(f[k], sw[k * E + c], acc);
+        o[c] = fmaxf(acc, 0.f);
+      }
     }
   }
 }
