@@ -184,3 +184,55 @@ def test_native_eval_records_equal_numpy_aggregation():
     assert n == ref.shape[0] == 8
     assert np.array_equal(rec[:n, [0, 2, 3, 4, 5, 6, 7]], ref[:, [0, 2, 3, 4, 5, 6, 7]])
     assert np.abs(rec[:n, 1] - ref[:, 1]).max() < 1e-14
+
+
+def test_basec_host_surface_without_gpu():
+    """Base_C mirrors the reference constructor contract on the host: training mode and the reference's unrunnable use_clsme=False
+    configuration are rejected, a checkpoint with wrong keys fails strict loading, and nothing runs without a CUDA device."""
+    from vidsgg_big_b200 import Base_C, synth
+    from vidsgg_big_b200._cabi import VsgError
+    cfg = synth.tiny_basec_config()
+    with pytest.raises(NotImplementedError):
+        Base_C(cfg, is_train=True)
+    with pytest.raises(VsgError):
+        Base_C(synth.tiny_basec_config(use_clsme=False))
+    m = Base_C(cfg)
+    st = synth.make_basec_state(1, cfg)
+    assert sorted(st.keys()) == sorted(m._expected_keys_static())
+    with pytest.raises(RuntimeError):
+        m.load_state_dict({k: v for k, v in st.items() if k != "bias_matrix"})
+    m.load_state_dict(st)
+    with pytest.raises(VsgError):
+        m.to("cpu")                                            # weights are staged in HBM only (no CPU fallback)
+    with pytest.raises(VsgError):
+        Base_C(cfg)([synth.make_proposal(1, 3, 20, cfg["dim_feat"] + cfg["dim_clsme"], cfg["num_enti_cats"])])
+
+
+def test_bench_triplet_comparison_helper():
+    """bench.py's parity_vs_cpu_oracle counts videos whose (quintuple, span) SETS agree, independent of row order."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(ROOT, "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    q = torch.tensor([[1, 2, 3, 0, 1], [4, 2, 3, 1, 0]])
+    sp = torch.tensor([[0, 9], [3, 7]])
+    a = (q, torch.zeros(2, 3), sp, torch.zeros(2))
+    b = (q.flip(0), torch.zeros(2, 3), sp.flip(0), torch.zeros(2))
+    c = (q, torch.zeros(2, 3), sp + 1, torch.zeros(2))
+    assert bench.compare_triplets([a, None, a, a], [b, None, c, None]) == (2, 4)
+
+
+def test_fused_dwconv_predicate():
+    from vidsgg_big_b200 import linalg
+
+    class W(object):
+        def __init__(self, n, k, has16=True):
+            self.N, self.K, self.w16 = n, k, object() if has16 else None
+    assert linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 128), k=7)
+    assert linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(20, 128), k=3)
+    assert not linalg.can_fuse_dwconv(linalg.X3TF32, W(128, 128), k=7)          # only the default split mode has the CONV variant
+    assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(256, 128), k=7)     # 128-wide tiles only
+    assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 120), k=7)     # K must be a multiple of 16
+    assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 128), k=4)     # odd taps only
+    assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 512), k=7)     # depthwise weights must fit the kernel's table
+    assert linalg.attention_mode(linalg.TF32_BF16X2) == linalg.X3TF32 and linalg.attention_mode(linalg.TF32) == linalg.TF32
