@@ -39,7 +39,7 @@ def parse():
     ap.add_argument("--workload", default="vidvrd", choices=["vidvrd", "vidor"])
     ap.add_argument("--precision", default="tf32+bf16x2", choices=["3xtf32", "tf32+bf16x2", "tf32", "fp32_simt"])
     ap.add_argument("--cpu-sample", type=int, default=None,
-                    help="videos in the bounded CPU sample (default: 200 for cpu_baseline, 40 per step for --impl reference)")
+                    help="videos in the bounded CPU sample (default: 200 for cpu_baseline, 100 per step for --impl reference)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run the K timed steps strictly one after another (no overlap of step i-1's "
@@ -301,32 +301,38 @@ def cpu_pass(kind, props, graphs, st, cfg, wl, gst=None):
     return oe.evaluate(gts, prs)
 
 
-def cpu_baseline(kind, n_sample, repeats=1, feats_from=None):
-    """Times the oracle port on ``n_sample`` videos (seeds 1000..).  ``feats_from``: (features, i3d list) of the GPU arm's videos,
-    copied to the host so that both arms see bit-identical inputs (the CUDA and CPU generators differ).  Returns
-    (videos/s, seconds, metrics, per-video triplets of the oracle)."""
+def cpu_prepare(kind, n_sample, feats_from=None):
+    """Inputs of the CPU arm: ``n_sample`` videos (seeds 1000..), oracle weights, and GT graphs derived from the oracle's own predictions
+    (untimed).  ``feats_from``: (features, i3d list) of the GPU arm's videos, copied to the host so that both arms see bit-identical inputs
+    (the CUDA and CPU generators differ)."""
     torch.set_num_threads(os.cpu_count() or 1)
     feats, i3d = feats_from if feats_from is not None else (None, None)
     cfg, wl, props, graphs, _ = make_videos(kind, n_sample, 1000, "cpu", feats=feats, i3d=i3d)
     st = synth.make_bigc_state(1, cfg)
     gst = synth.make_grounding_state(21, synth.grounding_config()) if kind == "vidor" else None
     from oracle import bigc as ob
-    trips = []
-    with torch.no_grad():                                                  # GT from the (oracle's) own predictions, untimed
-        graphs = []
+    trips, graphs = [], []
+    with torch.no_grad():
         for i, p in enumerate(props):
             r = ob.forward(st, cfg, [p], wl["topk"])[0]
             trips.append(r)
             graphs.append(synth.make_gt_from_predictions(1000 + i, p, None if r is None else (r[0], r[1].mean(-1), r[2]),
                                                          num_pred_cats=cfg["num_pred_cats"]))
     cpu_pass(kind, props[:1], graphs[:1], st, cfg, wl, gst)                # warm-up
-    best, metrics = None, None
-    for _ in range(repeats):
-        t0 = time.perf_counter()
-        metrics = cpu_pass(kind, props, graphs, st, cfg, wl, gst)
-        dt = time.perf_counter() - t0
-        best = dt if best is None else min(best, dt)
-    return n_sample / best, best, metrics, trips
+    return dict(kind=kind, props=props, graphs=graphs, st=st, cfg=cfg, wl=wl, gst=gst, trips=trips)
+
+
+def cpu_timed_pass(prep):
+    t0 = time.perf_counter()
+    metrics = cpu_pass(prep["kind"], prep["props"], prep["graphs"], prep["st"], prep["cfg"], prep["wl"], prep["gst"])
+    return time.perf_counter() - t0, metrics
+
+
+def cpu_baseline(kind, n_sample, feats_from=None):
+    """Times one pass of the oracle port over ``n_sample`` videos.  Returns (videos/s, seconds, metrics, per-video triplets)."""
+    prep = cpu_prepare(kind, n_sample, feats_from)
+    dt, metrics = cpu_timed_pass(prep)
+    return n_sample / dt, dt, metrics, prep["trips"]
 
 
 def compare_triplets(gpu_trips, cpu_trips):
@@ -350,10 +356,11 @@ def run_reference(args, rank, world):
         return
     cfg, wl = workload_cfg(args.workload)
     if args.cpu_sample is None:
-        args.cpu_sample = 40 if args.workload == "vidvrd" else 2
+        args.cpu_sample = 100 if args.workload == "vidvrd" else 2       # ~8 s / ~4 s of CPU work per step: K=20, W=3 ends within ~3.5 minutes
+    prep = cpu_prepare(args.workload, args.cpu_sample)                  # inputs, weights and GT once; every step is one full CPU pass over them
     times = []
     for i in range(args.warmup + args.steps):
-        v, dt, _, _ = cpu_baseline(args.workload, args.cpu_sample)
+        dt, _ = cpu_timed_pass(prep)
         if i >= args.warmup:
             times.append(dt)
     ms = 1e3 * float(np.mean(times))
@@ -364,7 +371,8 @@ def run_reference(args, rank, world):
         "impl": "reference", "metric": "videos/sec (classify+ground+vIoU)", "value": value, "unit": "videos/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": wl["name"], "stages": ["pair_geometry", "bigc_classify", "triplets", "viou_eval"], "videos_per_step": args.cpu_sample},
+        "config": {"workload": wl["name"], "videos_per_step": args.cpu_sample,
+                   "stages": ["pair_geometry", "bigc_classify", "triplets"] + (["grounding"] if args.workload == "vidor" else []) + ["viou_eval"]},
         "cpu_baseline": {"value": value, "unit": "videos/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
