@@ -133,7 +133,7 @@ int vsg_rel_viou_match(const VsgRelTable* pred, const double* scores, const VsgR
                        const int64_t* ov_off, double thr,
                        int32_t* order_out, double* ov_ws, double* hit_out, int32_t* gt2det_out,
                        double* vol_pred_ws /* [n_pred][2] */, double* vol_gt_ws /* [n_gt][2] */,
-                       uint8_t* taken_ws /* [n_gt] */, void* stream);
+                       uint8_t* taken_ws /* [n_gt + n_pred]: GT-taken flags, then per-prediction candidate flags */, void* stream);
 
 /* HOST function (CPU pointers): per-video records (video index, AP, n_gt, TP@det_n..., P@tag_n...) from the matcher's outputs,
  * restating the numpy arithmetic of visual_relation_detection.py:28-33, :37-58, :82-93 and common.py:4-37 (voc_ap).

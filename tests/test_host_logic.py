@@ -236,3 +236,16 @@ def test_fused_dwconv_predicate():
     assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 128), k=4)     # odd taps only
     assert not linalg.can_fuse_dwconv(linalg.TF32_BF16X2, W(128, 512), k=7)     # depthwise weights must fit the kernel's table
     assert linalg.attention_mode(linalg.TF32_BF16X2) == linalg.X3TF32 and linalg.attention_mode(linalg.TF32) == linalg.TF32
+
+
+def test_packed_relations_spread_keeps_empty_videos():
+    """Videos without predictions stay in the evaluation as empty prediction segments (driver.py; tools/eval_vidor.py:100-103)."""
+    from vidsgg_big_b200 import evalapi
+    z = lambda *s, dt=torch.long: torch.zeros(*s, dtype=dt)
+    rel = torch.arange(5 * 7).reshape(5, 7)
+    pr = evalapi.PackedRelations(z(0, 4, dt=torch.float32), z(1), z(0), rel, torch.tensor([0, 2, 5]), torch.ones(5, dtype=torch.float64))
+    sp = pr.spread([1, 4], 6)
+    assert sp.n_vid == 6 and sp.vid_off.tolist() == [0, 0, 2, 2, 2, 5, 5] and sp.rel is pr.rel and sp.n_rel == 5
+    assert pr.spread([0, 1], 2) is pr
+    with pytest.raises(AssertionError):
+        pr.spread([3, 1], 6)

@@ -34,6 +34,8 @@ class Base_C(BIG_C):
         self.is_train = False
         self.config = dict(config)
         self.num_pred_cats, self.num_enti_cats = c["num_pred_cats"], c["num_enti_cats"]
+        if self.num_enti_cats > 4096 or self.num_pred_cats > 256:      # 12-bit category / track fields of the sort key (csrc/basec.cu)
+            raise VsgError("triplet sort key: num_enti_cats <= 4096 and num_pred_cats <= 256")
         self.dim_feat, self.dim_clsme, self.dim_enti, self.dim_ffn = c["dim_feat"], c["dim_clsme"], c["dim_enti"], c["dim_ffn"]
         self.enco_pool_len = c["enco_pool_len"]
         self.use_clsme = c["use_clsme"]

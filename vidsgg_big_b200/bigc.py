@@ -63,6 +63,11 @@ class PackedVideos(object):
         self.V, self.N, self.R = V, int(all_len.numel()), int(all_len.sum())
         self.max_tracks = max(counts) if counts else 0
         self.counts = counts
+        # the triplet kernels pack (pred | s_cat | o_cat | s_id | o_id) into one 64-bit sort key with 12 bits per category / track id
+        # (csrc/bigc.cu construct_triplet_kernel, csrc/basec.cu): larger values would alias keys silently
+        if self.max_tracks > 4096:
+            raise VsgError("a video has %d tracks; the triplet sort key holds track ids < 4096" % self.max_tracks)
+
         self.mha_blocks = linalg.mha_block_list(counts, device)     # ragged (video, 64-token block) work list of the encoder attention
 
 
@@ -116,6 +121,8 @@ class BIG_C(object):
         self.enco_pool_len, self.n_enco_layers, self.n_deco_layers = c["enco_pool_len"], c["n_enco_layers"], c["n_deco_layers"]
         self.n_att_head, self.num_querys = c["n_att_head"], c["num_querys"]
         self.num_anchors = self.num_querys
+        if self.num_enti_cats > 4096 or self.num_pred_cats > 256:
+            raise VsgError("triplet sort key: num_enti_cats <= 4096 and num_pred_cats <= 256 (category ids index tables of that size)")
         if not (self.dim_enti == self.dim_pred == self.dim_att):
             raise VsgError("kernels assume dim_enti == dim_pred == dim_att (true for every reference config)")
         if self.dim_enti not in (64, 128, 512):

@@ -977,13 +977,14 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
   const size_t smem = (size_t)(MHA_QB * head_dim + sk * head_dim + sk * MHA_PITCH) * sizeof(float);
 #define VSG_MHA_LAUNCH(DH_)                                                                                              \
   do {                                                                                                                   \
-    static bool attr_done = false;                                                                                       \
-    if (!attr_done) {                                                                                                    \
+    static PerDeviceFlag attr_done;                                                                                      \
+    const int dev_ = current_device();                                                                                   \
+    if (!attr_done.is_set(dev_)) {                                                                                       \
       if (cudaFuncSetAttribute(mha_kernel<DH_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {  \
         set_error("vsg_mha: cannot raise dynamic shared memory to %zu", smem);                                           \
         return VSG_E_LAUNCH;                                                                                             \
       }                                                                                                                  \
-      attr_done = true;                                                                                                  \
+      attr_done.set(dev_);                                                                                               \
     }                                                                                                                    \
     mha_kernel<DH_><<<grid, 256, smem, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, n_head, scale, O, ldo, blk_seg, blk_q0); \
   } while (0)
@@ -1024,13 +1025,14 @@ extern "C" int vsg_role_attention(const float* p2a, const float* e2a, const floa
   VSG_REQUIRE(aligned16(p2a), "vsg_role_attention: misaligned p2a");
   const size_t smem = (size_t)(RA_CH * E + 8 * 2 * RA_MAX_TRACKS) * sizeof(float);
   if (E == 512) {
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceFlag attr_done;
+    const int dev_ = current_device();
+    if (!attr_done.is_set(dev_)) {
       if (cudaFuncSetAttribute(role_attention_smem_kernel<512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         set_error("vsg_role_attention: cannot raise dynamic shared memory to %zu", smem);
         return VSG_E_LAUNCH;
       }
-      attr_done = true;
+      attr_done.set(dev_);
     }
     role_attention_smem_kernel<512><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);
   } else if (E == 128) role_attention_smem_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, enco, seg, Q, inv_sqrt_d, values, att_out, att_ld, so_out);

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <stdarg.h>
+#include <atomic>
 
 #include "../../include/vsg_b200.h"
 
@@ -34,6 +35,15 @@ inline int check_launch(const char* what, int n_kernels = 1) {
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
 int sm_count();
+
+// cudaFuncSetAttribute is per device (context), so a process-wide `static bool` would leave a second GPU of the same process without
+// the raised shared-memory limit: one bit per device ordinal, set after the attribute call succeeded there (thread-safe).
+struct PerDeviceFlag {
+  std::atomic<unsigned long long> done{0};
+  bool is_set(int dev) const { return (done.load(std::memory_order_acquire) >> (dev & 63)) & 1ull; }
+  void set(int dev) { done.fetch_or(1ull << (dev & 63), std::memory_order_release); }
+};
+inline int current_device() { int d = 0; cudaGetDevice(&d); return d; }
 
 // ---- device helpers ---------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {

@@ -1084,14 +1084,15 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   }
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CF::DW_BYTES;
   constexpr bool HAS_PROBE = (CL == 1) && !CONV;           // the timing probes exist for the single-CTA kernel only (compile time)
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceFlag attr_set;
+  const int dev_ = current_device();
+  if (!attr_set.is_set(dev_)) {
     if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
         cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
-    attr_set = true;
+    attr_set.set(dev_);
   }
   const long long tiles_m = (ep.M + BM - 1) / BM;
   const long long work = (CLN == 2 ? (tiles_m + 1) / 2 : tiles_m) * ((ep.N + BN_ - 1) / BN_) * ep.batch;   // tiles, or tile pairs

@@ -54,6 +54,22 @@ class PackedRelations(object):
             self._vid_off_h = self.vid_off.cpu().numpy()
         return self._vid_off_h
 
+    def spread(self, video_ids: Sequence[int], n_videos: int) -> "PackedRelations":
+        """The same relations as segments of a LARGER video list: segment k of this table becomes video ``video_ids[k]``
+        (ascending) of ``n_videos``; every other video gets an empty segment.  This is how videos without predictions stay in
+        the evaluation with their ground truth (the reference only skips their predictions, tools/eval_vidor.py:100-103)."""
+        ids = np.asarray(list(video_ids), dtype=np.int64)
+        assert ids.size == self.n_vid and (ids.size == 0 or (np.all(np.diff(ids) > 0) and ids[0] >= 0 and ids[-1] < n_videos))
+        if ids.size == n_videos:
+            return self
+        per = np.zeros(n_videos, np.int64)
+        per[ids] = np.diff(self.vid_off_host)
+        off = np.concatenate([[0], np.cumsum(per)]).astype(np.int64)
+        out = PackedRelations(self.boxes, self.off, self.tstart, self.rel, torch.from_numpy(off).to(self.rel.device), self.scores,
+                              self.vol_full_track, self.triplets_host)
+        out._vid_off_h = off
+        return out
+
     def table(self) -> VsgRelTable:
         t = VsgRelTable()
         t.boxes, t.off, t.tstart = self.boxes.data_ptr(), self.off.data_ptr(), self.tstart.data_ptr()
@@ -81,6 +97,10 @@ class PackedRelations(object):
                 s, e = int(r["duration"][0]), int(r["duration"][1])
                 for key in ("sub_traj", "obj_traj"):
                     b = np.array(r[key], dtype=np.float64).reshape(-1, 4) if (cand is None or t in cand) else empty
+                    if b is not empty and b.shape[0] < e - s:
+                        # the kernels address rows by duration alone; the reference fails here too (common.py:88-90)
+                        raise IndexError("relation %s of video %d: %s has %d boxes for a duration of %d frames"
+                                         % (t, v, key, b.shape[0], e - s))
                     boxes.append(b)
                     lens.append(b.shape[0])
                     tstart.append(s)
@@ -197,7 +217,7 @@ def match_relations(pred: PackedRelations, gt: PackedRelations, viou_threshold: 
     ov = torch.empty(max(int(ov_off_h[-1]), 1), dtype=torch.float64, device=dev)
     vol_p = torch.empty(max(2 * npred, 1), dtype=torch.float64, device=dev)
     vol_g = torch.empty(max(2 * ngt, 1), dtype=torch.float64, device=dev)
-    taken = torch.empty(max(ngt, 1), dtype=torch.uint8, device=dev)
+    taken = torch.empty(max(ngt + npred, 1), dtype=torch.uint8, device=dev)     # GT-taken flags + per-prediction candidate flags
     scores = pred.scores if pred.scores is not None else torch.zeros(max(npred, 1), dtype=torch.float64, device=dev)
     tp, tg = pred.table(), gt.table()
     check(lib().vsg_rel_viou_match(C.byref(tp), ptr(scores), C.byref(tg), V, ptr(ov_off), float(viou_threshold),
