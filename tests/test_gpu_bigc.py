@@ -255,3 +255,36 @@ def test_tensor_core_attention_equals_simt_attention(precision):
     print("attention max err vs fp64: simt %.2e  tensor-core %s %.2e" % (e_ref, precision, e_got))
     assert e_ref < 1e-5
     assert e_got < (2e-5 if precision == "3xtf32" else 5e-3)
+
+
+def test_vidvrd_test_size_batch_identical_triplets_and_recall():
+    """The benchmark's parity claim as a test: BASELINE configs[1] at full size (200 VidVRD-shaped videos, exp2 dims, default precision)
+    through the batched CUDA path vs the CPU oracle video by video on the SAME inputs: identical triplets (quintuples + spans) for every
+    video and identical R@50 / R@100 of the packed evaluation vs the oracle's dict evaluation (north_star parity gate)."""
+    import bench
+    from oracle import convert as oc, evalapi as oe
+    n_videos = 200
+    seeds = [1000 + i for i in range(n_videos)]
+    pipe = bench.Pipeline("vidvrd", "tf32+bf16x2", torch.device(DEV))
+    cfg, wl, props, _, feats = bench.make_videos("vidvrd", seeds, DEV, seeds[0], with_gt=False)
+    prep = bench.cpu_prepare("vidvrd", seeds, seeds[0], feats_from=(feats.cpu(), None))      # oracle triplets + GT from them
+    for p in props:
+        f = p.features
+        p.to(DEV)
+        p.features = f
+    with torch.no_grad():
+        trips = pipe.model(props, topk=wl["topk"])
+    same, total = bench.compare_triplets(trips, prep["trips"])
+    assert total == n_videos and same == n_videos, "%d of %d videos have identical triplets" % (same, total)
+    # evaluation: packed CUDA path on our triplets vs the oracle's dict evaluation on its own triplets, same GT
+    import copy
+    graphs = [copy.copy(g).to(DEV) for g in prep["graphs"]]
+    (m_ap, r50, r100), n_rel, _ = pipe.step(props, graphs)
+    en, pn = oc.default_names("e", 256), oc.default_names("p", 256)
+    gts, prs = {}, {}
+    for p, g, r in zip(prep["props"], prep["graphs"], prep["trips"]):
+        prs.update(oc.to_eval_format_pr(p, None if r is None else (r[0], r[1].mean(-1), r[2]), en, pn))
+        gts.update(oc.to_eval_format_gt(g, en, pn))
+    ref = oe.evaluate(gts, prs)
+    assert r50 == float(ref[1][50]) and r100 == float(ref[1][100])
+    assert abs(m_ap - ref[0]) < 5e-5      # AP integrates over score ORDER: scores equal to 1e-6 can swap two near-tied predictions

@@ -220,9 +220,11 @@ def match_relations(pred: PackedRelations, gt: PackedRelations, viou_threshold: 
     taken = torch.empty(max(ngt + npred, 1), dtype=torch.uint8, device=dev)     # GT-taken flags + per-prediction candidate flags
     scores = pred.scores if pred.scores is not None else torch.zeros(max(npred, 1), dtype=torch.float64, device=dev)
     tp, tg = pred.table(), gt.table()
-    check(lib().vsg_rel_viou_match(C.byref(tp), ptr(scores), C.byref(tg), V, ptr(ov_off), float(viou_threshold),
-                                   ptr(order), ptr(ov), ptr(hit), ptr(gt2det), ptr(vol_p), ptr(vol_g), ptr(taken),
-                                   stream_ptr(dev)), "vsg_rel_viou_match")
+    from .linalg import _Profile
+    with _Profile.span("rel_match"):
+        check(lib().vsg_rel_viou_match(C.byref(tp), ptr(scores), C.byref(tg), V, ptr(ov_off), float(viou_threshold),
+                                       ptr(order), ptr(ov), ptr(hit), ptr(gt2det), ptr(vol_p), ptr(vol_g), ptr(taken),
+                                       stream_ptr(dev)), "vsg_rel_viou_match")
     return MatchResult(order[:npred], hit[:npred], gt2det[:ngt], ov if keep_ov else None, ov_off_h)
 
 

@@ -177,7 +177,8 @@ class DEBUG(object):
         check(lib().vsg_seq_positions(_raw(seq_off), len(seq_off_host) - 1, rows, _raw(pos), _raw(rem), stream_ptr(dev)), "vsg_seq_positions")
         lens = np.diff(seq_off_host)
         return dict(off=seq_off, n=len(seq_off_host) - 1, rows=rows, pos=pos, rem=rem, max_len=int(lens.max()) if lens.size else 0,
-                    blocks=linalg.mha_block_list(lens, dev))
+                    blocks=linalg.mha_block_list(lens, dev),
+                    att_flops=4.0 * self.dim_hidden * float((lens.astype(np.float64) ** 2).sum()))     # QK^T + PV over all heads
 
     def _qanet(self, ew, x, sq):
         """QANetEncoderLayer.forward (:110-137) on rows [rows, H] of ragged sequences."""
@@ -192,9 +193,10 @@ class DEBUG(object):
         qkv = gemm(m, out, ew["qkv"])
         att = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
         ld = qkv.stride(0)
-        check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld, _raw(sq["off"]),
-                            sq["n"], 0, sq["max_len"], 8, H // 8, _raw(att), H, _raw(sq["blocks"][0]), _raw(sq["blocks"][1]), sq["blocks"][2],
-                            stream_ptr(x.device)), "vsg_mha")
+        with linalg._Profile.span("mha", sq["att_flops"]):
+            check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld, _raw(sq["off"]),
+                                sq["n"], 0, sq["max_len"], 8, H // 8, _raw(att), H, _raw(sq["blocks"][0]), _raw(sq["blocks"][1]), sq["blocks"][2],
+                                stream_ptr(x.device)), "vsg_mha")
         res = gemm(m, att, ew["out"], residual=res)                                 # attn + res (:129-130)
         out = self._ln(res, ew["norme"])
         return gemm(m, out, ew["fc"], relu=True, residual=res)                      # relu(fc(LN)) + res (:133-136)

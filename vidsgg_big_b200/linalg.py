@@ -60,24 +60,45 @@ def _raw(t):
 
 
 class _Profile(object):
-    """Optional per-launch CUDA-event timing of the GEMM kernel (bench.py's roofline leg)."""
+    """Optional per-launch CUDA-event timing (bench.py's roofline legs): every GEMM launch, plus any kernel a caller brackets
+    with ``span``.  ``stage`` is a free-form label set by the caller (e.g. "bigc" / "grounding") and stored with each record."""
     enabled = False
-    records = []          # (start_event, end_event, useful_flops, mode)
+    stage = ""
+    records = []          # (start_event, end_event, useful_flops, kind, stage)
 
     @classmethod
     def begin(cls):
-        cls.enabled, cls.records = True, []
+        cls.enabled, cls.records, cls.stage = True, [], ""
 
     @classmethod
-    def end(cls):
-        """-> (n_launches, useful_flops, kernel_ms) after synchronising."""
+    def span(cls, kind, flops=0.0):
+        """Context manager: brackets the enclosed launches with events on the current stream (no-op unless enabled)."""
+        import contextlib
+
+        @contextlib.contextmanager
+        def cm():
+            if not cls.enabled:
+                yield
+                return
+            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev0.record()
+            yield
+            ev1.record()
+            cls.records.append((ev0, ev1, float(flops), kind, cls.stage))
+        return cm()
+
+    @classmethod
+    def end(cls, kind="gemm", stage=None):
+        """-> (n_launches, useful_flops, kernel_ms) of the records of ``kind`` (and ``stage``, if given) after synchronising."""
         cls.enabled = False
         torch.cuda.synchronize()
-        ms = sum(s.elapsed_time(e) for s, e, _, _ in cls.records)
-        fl = sum(f for _, _, f, _ in cls.records)
-        n = len(cls.records)
-        cls.records = []
-        return n, fl, ms
+        out = cls.summary(kind, stage)
+        return out
+
+    @classmethod
+    def summary(cls, kind="gemm", stage=None):
+        sel = [r for r in cls.records if r[3] == kind and (stage is None or r[4] == stage)]
+        return len(sel), sum(r[2] for r in sel), sum(r[0].elapsed_time(r[1]) for r in sel)
 
 
 LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py's gpu_launches)
@@ -141,7 +162,7 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
                              _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
     if _Profile.enabled:
         ev1.record()
-        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, mode))
+        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage))
     return out
 
 
@@ -171,7 +192,7 @@ def gemm_batched(mode: int, A: torch.Tensor, W_hi: torch.Tensor, W_lo: Optional[
     check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(out.device)), "vsg_gemm_ex")
     if _Profile.enabled:
         ev1.record()
-        _Profile.records.append((ev0, ev1, 2.0 * M * N * K * batch, mode))
+        _Profile.records.append((ev0, ev1, 2.0 * M * N * K * batch, "gemm", _Profile.stage))
     return out
 
 

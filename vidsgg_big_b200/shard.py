@@ -20,6 +20,40 @@ def video_cost(proposal, dim_feat: int) -> float:
     return float(proposal.num_proposals) * float(int(proposal.lengths.max())) * float(dim_feat)
 
 
+def flops_bigc(sum_len: float, n: int, t_max: int, dim_feat: int, E: int = 512, Q: int = 192, n_enc: int = 6, n_dec: int = 4,
+               head: float = 2.0 * 192 * (2136 * 512 + 512 * 51)) -> float:
+    """Useful flops of the BIG-C forward of one video (SURVEY.md 8d, K4/K5 formula with R = sum of track lengths)."""
+    tc = (t_max - 1) // 2 + 1
+    f = 2.0 * sum_len * (8 * E + E * E) + 2.0 * sum_len * (dim_feat * E + E * E)
+    f += 2.0 * n * tc * 6 * E * E + 2.0 * n * 5 * E * E
+    f += n_enc * (2.0 * n * 6 * E * E + 4.0 * n * n * E)
+    f += n_dec * (2.0 * Q * 11 * E * E + 2.0 * n * E * E + 4.0 * Q * Q * E + 6.0 * Q * n * E)
+    return f + head
+
+
+def flops_grd(T: int, nq: int, H: int = 128, B: int = 10) -> float:
+    """Useful flops of the grounding forward of one video (SURVEY.md 8d, K6 formula, re-associated context-query product)."""
+    enc = lambda rows, seqs, L, k: rows * (4 * (2 * k * H + 2 * H * H) + 10 * H * H) + seqs * 4.0 * L * L * H
+    f = 2.0 * T * 1024 * H + 2.0 * nq * 3 * 300 * H + 2.0 * nq * 2 * H
+    f += enc(T, 1, T, 7) + enc(3 * nq, nq, 3, 3) + enc(nq * T, nq, T, 7)
+    f += 2.0 * T * H * H + 2.0 * nq * T * H * 3 + 2.0 * nq * 3 * T * H + 2.0 * nq * T * 3 * H + 2.0 * nq * T * 3 * H + 2.0 * nq * T * 4 * H * H
+    for out in (B, B, 2 * B):
+        f += nq * T * (4 * (2 * 3 * H + 2 * H * H) + 2 * 3 * H + 2 * H * out)
+    return f
+
+
+def video_cost_flops(lengths, video_len: int, dim_feat: int, grounding: bool = True, nq_estimate: int = 450) -> float:
+    """Scheduling cost of one video in useful flops: BIG-C over the RAGGED rows (the per-frame stage never stretches tracks here,
+    so it scales with sum L, not n * Tmax) plus the grounding stage on ~``nq_estimate`` queries x ceil(video_len / 8) clips."""
+    n = int(len(lengths))
+    if n == 0:
+        return 0.0
+    c = flops_bigc(float(sum(int(x) for x in lengths)), n, int(max(lengths)), dim_feat)
+    if grounding:
+        c += flops_grd((int(video_len) + 7) // 8, nq_estimate)
+    return c
+
+
 def assign_lpt(costs: Sequence[float], world: int) -> List[List[int]]:
     """Longest-processing-time-first greedy: VidOR video costs spread ~100x, so round-robin is not enough."""
     order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))

@@ -134,6 +134,15 @@ def _random_walk_boxes(rng, L, w, h):
     return np.stack([x1, y1, x2, y2], 1).astype(np.float32)
 
 
+def proposal_lengths(seed: int, n: int, video_len: int, min_len: int = 5, max_len: Optional[int] = None) -> np.ndarray:
+    """Track lengths ``make_proposal`` will draw for this seed (its first draw), without building the boxes: lets a scheduler
+    cost a video (``shard.video_cost``) before anything is generated."""
+    rng = np.random.default_rng(seed)
+    max_len = min(max_len or video_len, video_len)
+    min_len = min(min_len, max_len)
+    return rng.integers(min_len, max_len + 1, size=n)
+
+
 def make_proposal(seed: int, n: int, video_len: int, dim_feat_total: int, num_enti_cats: int,
                   min_len: int = 5, max_len: Optional[int] = None, wh=(1280, 720),
                   with_features: bool = True, feat_scale: float = 0.5, name: Optional[str] = None) -> TrajProposal:
