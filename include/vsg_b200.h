@@ -171,6 +171,7 @@ int vsg_unique_rows(const int64_t* rows, int n, int d, int32_t* order, int32_t* 
 #define VSG_GEMM_3XTF32 2 /* fp32-faithful 3xTF32 split on tcgen05 (needs W_lo from vsg_split_tf32) */
 #define VSG_GEMM_TF32_BF16X2 3 /* fp32-class: tf32 main product + the two correction products as bf16 MMAs (kind::f16);
                                   needs W_b16 / W_lo16 from vsg_split_bf16; vsg_gemm_ex only, plain (non-batched) problems */
+#define VSG_GEMM_BF16 4   /* reduced precision: bf16 operands (A16, W_b16), ONE kind::f16 pass, fp32 accumulate; outputs fp32 C and / or bf16 C16 */
 
 /* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ) (+ residual[M][N]),
  * fp32 row-major; the residual is added after the activation (QANet blocks, models/grd_model_v5.py:118-135).
@@ -211,6 +212,11 @@ typedef struct VsgGemmArgs {
    * A[r + j - dw_k/2][c] with zero padding at the ends of the row's sequence (seq_pos[r] rows before r, seq_rem[r] rows after r in its
    * sequence).  Bit-identical to vsg_dwconv followed by vsg_gemm. */
   const float* dw_w; const float* dw_b; const int32_t* seq_pos; const int32_t* seq_rem; int dw_k;
+  /* mode VSG_GEMM_BF16 (4): the A operand as bf16 [M][lda16] (lda16 a multiple of 8; written by a previous launch's C16 or by
+   * vsg_cast_bf16) -- A / W_hi are not read; W_b16 [N][ldw16] is the weight.  C16 (any tensor-core mode of a plain problem): optional
+   * bf16 copy [M][ldc16] of the stored values; in mode 4, C may then be NULL (bf16 output only). */
+  const void* A16; int lda16;
+  void* C16; int ldc16;
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 
@@ -233,6 +239,9 @@ int vsg_gemm_debug_flags(int flags);
 
 /* hi = w with the low 13 mantissa bits cleared (exactly representable in tf32), lo = w - hi. */
 int vsg_split_tf32(const float* w, float* hi, float* lo, int64_t n, void* stream);
+/* out[r][c] = bf16_rn(x[r][c]) for c < cols, 0 for cols <= c < ldo (ldo a multiple of 8, out 16-byte aligned): the A operand of
+ * VSG_GEMM_BF16 when its producer wrote fp32 (reference counterpart: none -- models/model_0v10.py computes in fp32 throughout). */
+int vsg_cast_bf16(const float* x, int64_t ldx, int64_t rows, int cols, void* out, int64_t ldo, void* stream);
 /* bf16 operands of mode VSG_GEMM_TF32_BF16X2 for a weight w[rows][cols] (ldw): w16 = bf16_rn(w), lo16 = bf16_rn(w - trunc_tf32(w)),
  * both [rows][ld16] (ld16 >= cols, a multiple of 8; the padding columns are written as zeros). */
 int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void* w16, void* lo16, int ld16, void* stream);
@@ -256,6 +265,9 @@ int vsg_gemm_set_weight_image(int on);
 int vsg_bbox_feat_mlp1(const float* boxes, const int64_t* off, int n_tracks, int64_t n_rows, const int32_t* track_vid,
                        const float* wh, const float* W1, const float* b1, int E, float* out, int ldo, float* feat8_out,
                        void* stream);
+/* Same, written as bf16 [R][ldo] (the A operand of the following VSG_GEMM_BF16 launch; models/model_0v10.py:296-298 in reduced precision). */
+int vsg_bbox_feat_mlp1_bf16(const float* boxes, const int64_t* off, int n_tracks, int64_t n_rows, const int32_t* track_vid,
+                            const float* wh, const float* W1, const float* b1, int E, void* out16, int ldo, void* stream);
 
 /* Time-mean over the STRETCHED sequence of feature columns [col0, col0+width) (model_0v10.py:470,
  * model_0v7.py:473; stretch = stack_with_repeat_2d :18-46): out f32[N][ldo]. */
@@ -266,6 +278,9 @@ int vsg_stretched_mean(const float* feat, int ldf, int col0, int width, const in
  * products Y f32[R][3E] (tap-major); out f32[N][E*pool] flattened channel-major (c*pool+p). */
 int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,
                   int n_tracks, int pool, float* out, void* stream);
+/* Same with the tap products Y stored as bf16 [R][ldy] (written by a VSG_GEMM_BF16 launch's C16; model_0v10.py:450-457). */
+int vsg_conv_pool_bf16(const void* Y16, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,
+                       int n_tracks, int pool, float* out, void* stream);
 
 /* out = LayerNorm(x + a)*gamma + beta (+ post[row % post_period])  (norm1/2/3 of model_0v10.py:111-115, :186-223;
  * the "+ pos" of :189 is the post term).  a, post may be NULL.  D % 32 == 0, D <= 1024. */

@@ -10,7 +10,13 @@ from test_oracle_golden import BIGC_CASES, bigc_inputs
 pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 # max |dlogit| / max |logit| allowed per precision mode
-LOGIT_TOL = {"fp32_simt": 3e-4, "3xtf32": 3e-4, "tf32+bf16x2": 3e-4, "tf32": 6e-2}
+# measured on B200 (profiles/r02_parity_errors.txt): fp32_simt <= 1.1e-6, 3xtf32 <= 1.2e-5, tf32+bf16x2 <= 8.9e-6, tf32 <= 3.2e-3
+LOGIT_TOL = {"fp32_simt": 5e-6, "3xtf32": 4e-5, "tf32+bf16x2": 4e-5, "tf32": 1e-2, "bf16": 6e-2}
+
+
+# reduced-precision modes are REPORTED, not used for parity claims: (min share of queries keeping the (s,o) arg-max, max att error,
+# min share of reference triplets reproduced)
+REDUCED = {"tf32": (0.85, 5e-2, 0.7), "bf16": (0.6, 2e-1, 0.4)}
 
 
 def _model(cfg, state, precision):
@@ -36,7 +42,7 @@ def _unstable_queries(logits, att, topk, tau=2e-3):
     return set((tie_k | tie_a).nonzero().flatten().tolist())
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32", "tf32+bf16x2", "tf32"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32", "tf32+bf16x2", "tf32", "bf16"])
 @pytest.mark.parametrize("case", BIGC_CASES, ids=[c[0] for c in BIGC_CASES])
 def test_bigc_forward_vs_reference(golden, case, precision):
     g = golden("bigc")
@@ -56,31 +62,31 @@ def test_bigc_forward_vs_reference(golden, case, precision):
         scale = np.abs(ref_logits).max()
         ref_so = np.argmax(ref_att, axis=-1).T                       # [Q, 2]
         same_so = (so.cpu().numpy() == ref_so).all(axis=1)
-        if precision == "tf32":
+        if precision in REDUCED:
             # a flipped subject/object arg-max changes a query's logits wholesale: compare the agreeing queries only
-            print("   tf32: %d of %d queries keep the reference (s,o) arg-max" % (same_so.sum(), same_so.size))
-            assert same_so.mean() >= 0.85
+            print("   %s: %d of %d queries keep the reference (s,o) arg-max" % (precision, same_so.sum(), same_so.size))
+            assert same_so.mean() >= REDUCED[precision][0]
         else:
-            assert same_so.mean() >= 0.97
+            assert same_so.mean() >= 0.99
         err = np.abs(lg - ref_logits)[same_so].max() / scale
         att_err = np.abs(att.cpu().numpy() - ref_att).max()
         print("%s %s: rel logit err %.2e, att err %.2e" % (k, precision, err, att_err))
         assert err <= LOGIT_TOL[precision], (k, precision, err)
-        assert att_err <= (5e-2 if precision == "tf32" else 2e-4)
+        assert att_err <= (REDUCED[precision][1] if precision in REDUCED else 1e-4)      # measured: <= 2.9e-5 (fp32-class), <= 1.5e-2 (tf32)
         if (k + "_none") in g:
             assert ret is None
             continue
         assert ret is not None
-        unstable = _unstable_queries(ref_logits, ref_att, topk, tau=(5e-2 if precision == "tf32" else 2e-3))
+        unstable = _unstable_queries(ref_logits, ref_att, topk, tau=(5e-2 if precision in REDUCED else 2e-3))
         ref_rows = {tuple(r): (s, sp, q) for r, s, sp, q in zip(g[k + "_quint"].tolist(), g[k + "_scores"].tolist(),
                                                                   g[k + "_spans"].tolist(), g[k + "_qids"].tolist())}
         my_rows = {tuple(r): (s, sp, q) for r, s, sp, q in zip(ret[0].cpu().tolist(), ret[1].cpu().tolist(),
                                                                  ret[2].cpu().tolist(), ret[3].cpu().tolist())}
-        if precision == "tf32":
+        if precision in REDUCED:
             # reduced precision: report the overlap only (near-ties flip, dedup winners change)
             common = len(set(ref_rows) & set(my_rows))
-            print("   tf32: %d of %d reference triplets reproduced (%d emitted)" % (common, len(ref_rows), len(my_rows)))
-            assert common >= 0.7 * len(ref_rows)
+            print("   %s: %d of %d reference triplets reproduced (%d emitted)" % (precision, common, len(ref_rows), len(my_rows)))
+            assert common >= REDUCED[precision][2] * len(ref_rows)
             continue
         n_flip = 0
         for key in set(ref_rows) ^ set(my_rows):
@@ -94,8 +100,8 @@ def test_bigc_forward_vs_reference(golden, case, precision):
             if mq == rq or (mq not in unstable and rq not in unstable):
                 assert abs(rs[0] - ms[0]) <= 5e-4 * max(rs[0], 1e-3) + 1e-6
             assert rs[1:] == ms[1:]                                     # detector scores copied exactly
-        if precision != "tf32":
-            assert n_flip <= max(2, len(ref_rows) // 20), "too many near-tie flips: %d of %d" % (n_flip, len(ref_rows))
+        if precision not in REDUCED:
+            assert n_flip <= max(1, len(ref_rows) // 100), "too many near-tie flips: %d of %d" % (n_flip, len(ref_rows))     # measured: 0
             # emitted order is the lexicographic key order of torch.unique
             keys = [tuple(r) for r in ret[0].cpu().tolist()]
             assert keys == sorted(keys)

@@ -292,3 +292,68 @@ def test_fused_dwconv_gemm_equals_dwconv_then_gemm():
             seq = x[s0:s1].t()[None]                                   # [1, H, L]
             ref[s0:s1] = torch.nn.functional.conv1d(seq, dw_w[:, None, :], dw_b, padding=k // 2, groups=H)[0].t()
         assert (t - ref).abs().max().item() <= 1e-5
+
+
+# ---- mode 4: bf16 operands, one kind::f16 pass ------------------------------------------------------------------------
+def _bf16_round(x):
+    return x.to(torch.bfloat16).double()
+
+
+@pytest.mark.parametrize("shape", SHAPES + [(481, 1536, 1024), (38400, 512, 512), (5000, 133, 3160)], ids=lambda s: "%dx%dx%d" % s)
+def test_gemm_bf16_mode(shape):
+    """The bf16 mode against the fp64 product of the bf16-ROUNDED operands (what the tensor core multiplies: only the fp32 accumulation
+    differs), and loosely against the unrounded product (the precision the mode actually offers: ~2^-8 per operand)."""
+    from vidsgg_big_b200 import linalg
+    M, N, K = shape
+    g = torch.Generator(device="cpu").manual_seed(M * 7 + N * 3 + K)
+    A = torch.randn(M, K, generator=g).to(DEV)
+    W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+    bias = torch.randn(N, generator=g).to(DEV)
+    wt = linalg.Weight(W, bias, split="bf16w")
+    out = linalg.gemm(linalg.BF16, A, wt)
+    ref16 = _bf16_round(A) @ _bf16_round(W).t() + bias.double()
+    scale = ref16.abs().max().item()
+    assert (out.double() - ref16).abs().max().item() <= 2e-5 * scale, shape
+    assert (out.double() - _ref(A, W, bias)).abs().max().item() <= 3e-2 * scale
+    # A already bf16 (no cast launch) + bf16-only output: identical values, rounded once
+    A16 = linalg.cast_bf16(A)
+    assert torch.equal(A16[:, :K], A.to(torch.bfloat16))
+    o16 = linalg.gemm(linalg.BF16, A16, wt, f32_out=False, K=K)
+    assert o16.dtype == torch.bfloat16 and torch.equal(o16[:, :N], out.to(torch.bfloat16))
+
+
+def test_gemm_bf16_epilogue_and_cluster_variants():
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import lib
+    g = torch.Generator(device="cpu").manual_seed(41)
+    for (M, N, K) in ((384, 256, 320), (1000, 512, 1024), (4097, 1536, 512), (641, 133, 3160), (129, 64, 72)):
+        A = torch.randn(M, K + 64, generator=g).to(DEV)
+        W = torch.randn(N, K, generator=g).to(DEV) / K ** 0.5
+        bias = torch.randn(N, generator=g).to(DEV)
+        rowb = torch.randn(192, N, generator=g).to(DEV)
+        idx = torch.randint(0, 192, (M,), generator=g).int().to(DEV)
+        res = torch.randn(M, N, generator=g).to(DEV)
+        wt = linalg.Weight(W, bias, split="bf16w")
+        a = A[:, 32:32 + K]
+        base = _bf16_round(a) @ _bf16_round(W).t()
+        outs = []
+        for cl in (3, 2, 1):
+            old = lib().vsg_gemm_set_cluster(cl)
+            try:
+                out = torch.full((M, 2 * N), -7.0, device=DEV)
+                o16 = torch.full((M, 2 * ((N + 7) // 8 * 8)), -7.0, device=DEV, dtype=torch.bfloat16)
+                linalg.gemm(linalg.BF16, a, wt, out=out[:, N:], relu=True, rowbias=rowb, rb_period=192, residual=res, out16=o16[:, :N])
+                outs.append((out.clone(), o16.clone()))
+            finally:
+                lib().vsg_gemm_set_cluster(old)
+        assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[1][0], outs[2][0]), (M, N, K)
+        out, o16 = outs[0]
+        ref = torch.relu(base + bias.double() + rowb.double()[torch.arange(M, device=DEV) % 192]) + res.double()
+        assert (out[:, N:].double() - ref).abs().max().item() <= 2e-5 * ref.abs().max().item(), (M, N, K)
+        assert bool((out[:, :N] == -7.0).all())
+        assert torch.equal(o16[:, :N], out[:, N:].to(torch.bfloat16)) and bool((o16[:, N:] == -7.0).all())
+        # indexed row bias + accumulate, no bias
+        out2 = torch.ones(M, N, device=DEV)
+        linalg.gemm(linalg.BF16, a, wt, out=out2, rowbias=rowb, rb_index=idx, accumulate=True, bias=False)
+        ref2 = base + rowb.double()[idx.long()] + 1.0
+        assert (out2.double() - ref2).abs().max().item() <= 2e-5 * ref2.abs().max().item()

@@ -21,7 +21,8 @@ def _model(precision):
     return m.cuda().eval()
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-4), ("3xtf32", 3e-4), ("tf32+bf16x2", 3e-4), ("tf32", 5e-2)])
+# measured on B200 (profiles/r02_parity_errors.txt): fp32_simt <= 5.1e-7, 3xtf32 <= 2.0e-6, tf32+bf16x2 <= 2.2e-6, tf32 <= 9.2e-4
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5), ("tf32", 5e-3)])
 def test_grounding_network_vs_reference(golden, precision, tol):
     g = golden("grounding")
     model = _model(precision)
@@ -70,7 +71,7 @@ def test_grounding_forward_end_to_end(golden, precision):
         np.testing.assert_allclose(probs.cpu().numpy(), ref_probs, atol=5e-4)
         bad_bins = (np.abs(pooled.cpu().numpy() - ref_pooled) > 1e-4).any(-1) | (mask.cpu().numpy() != ref_mask)
         print(k, precision, "bins differing from the reference (near-tie flips): %d of %d" % (bad_bins.sum(), bad_bins.size))
-        assert bad_bins.mean() <= 0.03
+        assert bad_bins.mean() <= 0.01
     # expansion used by the eval driver (tools/eval_vidor.py:245-253)
     from vidsgg_big_b200.grounding import expand_after_grounding
     q, s, sp = expand_after_grounding(datas[0][0], torch.rand(datas[0][0].shape[0], 3, device=DEV), *model([feats[0]], [datas[0]], with_gt_data=False, **INF), CASES[0][2])
@@ -100,7 +101,7 @@ def test_grounding_on_gt_queries(golden, precision):
         np.testing.assert_allclose(probs.cpu().numpy(), g[k + "_probs"], atol=5e-4)
         bad = (np.abs(pooled.cpu().numpy() - g[k + "_pooled"]) > 1e-4).any(-1) | (mask.cpu().numpy() != g[k + "_mask"])
         print(k, precision, "bins differing from the reference (near-tie flips): %d of %d" % (bad.sum(), bad.size))
-        assert bad.mean() <= 0.03
+        assert bad.mean() <= 0.01
 
 
 def test_fused_dwconv_path_equals_separate_dwconv_launches(golden):
@@ -223,7 +224,7 @@ def _large_reference():
     return _LARGE_REF
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 2e-4), ("3xtf32", 3e-4), ("tf32+bf16x2", 3e-4)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5)])
 def test_grounding_vidor_size_vs_oracle(precision, tol):
     """Grounding parity at VidOR size (T = 613 clips >= 600, nq >= 500 queries, 10 bins): network outputs against the oracle's, the
     post-processing pinned EXACTLY on the oracle's network outputs, and the end-to-end outputs up to near-tie flips."""
@@ -248,7 +249,7 @@ def test_grounding_vidor_size_vs_oracle(precision, tol):
     np.testing.assert_allclose(probs.cpu().numpy(), r["probs"].numpy(), atol=5e-4)
     bad = ((pooled.cpu() - r["pooled"]).abs() > 1e-4).any(-1) | (mask.cpu() != r["mask"])
     print(precision, "bins differing from the oracle (near-tie flips): %d of %d" % (int(bad.sum()), bad.numel()))
-    assert bad.float().mean().item() <= 0.03
+    assert bad.float().mean().item() <= 0.01
     # frame spans the driver rounds to (tools/eval_vidor.py:248-253) on the bins both keep
     both = mask.cpu() & r["mask"]
     a, b = torch.round(pooled.cpu() * r["vl"])[both], torch.round(r["pooled"] * r["vl"])[both]

@@ -38,7 +38,8 @@ class VsgGemmArgs(C.Structure):
                 ("c_outer", C.c_longlong), ("c_inner", C.c_longlong),
                 ("lo_col_begin", i32), ("lo_col_end", i32), ("W_b16", p), ("W_lo16", p), ("ldw16", i32),
                 ("W_img", p), ("img_bn", i32),
-                ("dw_w", p), ("dw_b", p), ("seq_pos", p), ("seq_rem", p), ("dw_k", i32)]
+                ("dw_w", p), ("dw_b", p), ("seq_pos", p), ("seq_rem", p), ("dw_k", i32),
+                ("A16", p), ("lda16", i32), ("C16", p), ("ldc16", i32)]
 
 
 class VsgError(RuntimeError):
@@ -70,6 +71,7 @@ SIGNATURES = {
     "vsg_stretch_rows": (i32, [p, i32, i32, p, i32, i32, p, p]),
     "vsg_unique_rows": (i32, [p, i32, i32, p, p, p, p]),
     "vsg_split_tf32": (i32, [p, p, p, i64, p]),
+    "vsg_cast_bf16": (i32, [p, i64, i64, i32, p, i64, p]),
     "vsg_gemm_debug_flags": (i32, [i32]),
     "vsg_gemm_set_tma_store": (i32, [i32]),
     "vsg_gemm_set_cluster": (i32, [i32]),
@@ -83,6 +85,8 @@ SIGNATURES = {
     "vsg_gemm_set_store_hi": (i32, [i32]),
     "vsg_gemm_force_bn": (i32, [i32]),
     "vsg_bbox_feat_mlp1": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p, p]),
+    "vsg_bbox_feat_mlp1_bf16": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p]),
+    "vsg_conv_pool_bf16": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
     "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
     "vsg_conv_pool": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
     "vsg_add_layernorm": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p]),

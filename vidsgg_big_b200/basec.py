@@ -69,7 +69,7 @@ class Base_C(BIG_C):
             raise VsgError("Base_C runs on a CUDA device only (no CPU fallback)")
         st = {k: v.to(dev) for k, v in self._state.items()}
         E = self.dim_enti
-        split = {linalg.X3TF32: "tf32", linalg.TF32_BF16X2: "bf16"}.get(self.mode, False)
+        split = linalg.SPLITS.get(self.mode, False)
         W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
         w = {}
         w["bbox1_w"], w["bbox1_b"] = st["fc_bbox2enti.0.weight"].contiguous(), st["fc_bbox2enti.0.bias"].contiguous()

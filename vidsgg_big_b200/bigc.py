@@ -213,7 +213,7 @@ class BIG_C(object):
             raise VsgError("BIG_C runs on a CUDA device only (no CPU fallback)")
         st = {k: v.to(dev) for k, v in self._state.items()}
         E, Pd, Q = self.dim_enti, self.dim_pred, self.num_querys
-        split = {linalg.X3TF32: "tf32", linalg.TF32_BF16X2: "bf16"}.get(self.mode, False)
+        split = linalg.SPLITS.get(self.mode, False)
         W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
         w = {}
         w["bbox1_w"], w["bbox1_b"] = st["fc_bbox2enti.0.weight"].contiguous(), st["fc_bbox2enti.0.bias"].contiguous()
@@ -320,6 +320,8 @@ class BIG_C(object):
         L = lib()
         if pk.feats.shape[1] < F_in + self.extra_width:
             raise VsgError("features have %d columns, model needs %d" % (pk.feats.shape[1], F_in + self.extra_width))
+        if m == linalg.BF16:
+            return self._track_encoding_bf16(pk)
         # --- per-frame MLPs on the unique frames, written into the two halves of X [R, 2E]
         X = torch.empty(R, 2 * E, dtype=torch.float32, device=dev)
         h = torch.empty(R, E, dtype=torch.float32, device=dev)
@@ -344,6 +346,38 @@ class BIG_C(object):
             dbg["pooled"] = pooled.clone()
         enti2enco = gemm(m, gemm(m, pooled, w["enco1"], relu=True), w["enco2"], relu=True)
         # --- stretched time-mean of the extra columns (I3D / classeme)
+        extra = None
+        if self.extra_width:
+            extra = torch.empty(N, self.extra_width, dtype=torch.float32, device=dev)
+            check(L.vsg_stretched_mean(_raw(pk.feats), pk.feats.stride(0), F_in, self.extra_width, _raw(pk.off), _raw(pk.tmax), N,
+                                       _raw(extra), self.extra_width, sp), "vsg_stretched_mean")
+        return enti2enco, extra
+
+    def _track_encoding_bf16(self, pk: PackedVideos):
+        """``_track_encoding`` in the bf16 mode: the R-row chain (h, X, Y: ~12 KB of fp32 per box-frame in the fp32-class modes) lives in
+        HBM as bf16 -- every GEMM's epilogue writes the bf16 operand of the next one, the raw fp32 features are cast once."""
+        w, m, dev = self._w, self.mode, self.device
+        E, F_in = self.dim_enti, self.dim_feat
+        R, N = pk.R, pk.N
+        sp = stream_ptr(dev)
+        L = lib()
+        bf = torch.bfloat16
+        X16 = torch.empty(R, 2 * E, dtype=bf, device=dev)
+        h16 = torch.empty(R, E, dtype=bf, device=dev)
+        check(L.vsg_bbox_feat_mlp1_bf16(_raw(pk.boxes), _raw(pk.off), N, R, _raw(pk.track_vid), _raw(pk.wh), _raw(w["bbox1_w"]),
+                                        _raw(w["bbox1_b"]), E, _raw(h16), E, sp), "vsg_bbox_feat_mlp1_bf16")
+        gemm(m, h16, w["bbox2"], out16=X16[:, :E], relu=True, f32_out=False)
+        F16 = linalg.cast_bf16(pk.feats, K=F_in)
+        gemm(m, F16, w["feat1"], out16=h16, relu=True, f32_out=False, K=F_in)
+        del F16
+        gemm(m, h16, w["feat2"], out16=X16[:, E:], relu=True, f32_out=False)
+        Y16 = gemm(m, X16, w["conv"], bias=False, f32_out=False)
+        del X16, h16
+        pooled = torch.empty(N, E * self.enco_pool_len, dtype=torch.float32, device=dev)
+        check(L.vsg_conv_pool_bf16(_raw(Y16), Y16.stride(0), E, _raw(w["conv_b"]), _raw(pk.off), _raw(pk.tmax), N, self.enco_pool_len,
+                                   _raw(pooled), sp), "vsg_conv_pool_bf16")
+        del Y16
+        enti2enco = gemm(m, gemm(m, pooled, w["enco1"], relu=True), w["enco2"], relu=True)
         extra = None
         if self.extra_width:
             extra = torch.empty(N, self.extra_width, dtype=torch.float32, device=dev)

@@ -10,6 +10,7 @@
 // and stretched position j maps to   src(j) = j / (q+1)                     if j < rem*(q+1)
 //                                            rem + (j - rem*(q+1)) / q      otherwise.
 #include "common.cuh"
+#include <cuda_bf16.h>
 #include <float.h>
 
 namespace vsg {
@@ -33,7 +34,8 @@ __global__ void __launch_bounds__(256)
 bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restrict__ off, int n_tracks, int64_t n_rows,
                       const int32_t* __restrict__ track_vid, const float* __restrict__ wh,  // wh[V][2]
                       const float* __restrict__ W1, const float* __restrict__ b1, int E,    // W1 [E][8]
-                      float* __restrict__ out, int ldo, float* __restrict__ feat8_out /* optional [R][8] */) {
+                      float* __restrict__ out, int ldo, float* __restrict__ feat8_out /* optional [R][8] */,
+                      __nv_bfloat16* __restrict__ out16 = nullptr /* bf16 output instead of `out` (row stride ldo) */) {
   extern __shared__ float sw[];  // W1 transposed [8][E] + b1[E]
   for (int i = threadIdx.x; i < E * 8; i += blockDim.x) sw[(i % 8) * E + i / 8] = W1[i];
   for (int i = threadIdx.x; i < E; i += blockDim.x) sw[8 * E + i] = b1[i];
@@ -41,7 +43,7 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
   const int lane = threadIdx.x & 31;
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
-  const bool vec4 = (E % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const bool vec4 = (E % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out16) & 7) == 0);
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const int t = find_track(off, n_tracks, r);
     const bool last = (r + 1 == off[t + 1]);
@@ -69,14 +71,19 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
           const float4 wv = *reinterpret_cast<const float4*>(sw + k * E + c);
           acc.x = fmaf(f[k], wv.x, acc.x); acc.y = fmaf(f[k], wv.y, acc.y); acc.z = fmaf(f[k], wv.z, acc.z); acc.w = fmaf(f[k], wv.w, acc.w);
         }
-        *reinterpret_cast<float4*>(o + c) = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+        if (out16) {
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f)), p1 = __floats2bfloat162_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+          *reinterpret_cast<uint2*>(out16 + r * (int64_t)ldo + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        } else {
+          *reinterpret_cast<float4*>(o + c) = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+        }
       }
     } else {
       for (int c = lane; c < E; c += 32) {
         float acc = sw[8 * E + c];
 #pragma unroll
         for (int k = 0; k < 8; ++k) acc = fmaf(f[k], sw[k * E + c], acc);
-        o[c] = fmaxf(acc, 0.f);
+        if (out16) out16[r * (int64_t)ldo + c] = __float2bfloat16_rn(fmaxf(acc, 0.f)); else o[c] = fmaxf(acc, 0.f);
       }
     }
   }
@@ -108,8 +115,16 @@ stretched_mean_kernel(const float* __restrict__ feat, int ldf, int col0, int wid
 // One CTA per (track, pool bin); threads own 4 channels; consecutive positions that gather the same three
 // source frames are skipped, so a track costs O(L) loads however far it is stretched.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float4 load4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ float4 load4(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.x)), b = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+
+template <typename TY>
 __global__ void __launch_bounds__(128)
-conv_pool_kernel(const float* __restrict__ Y, int ldy, int E, const float* __restrict__ bias, const int64_t* __restrict__ off,
+conv_pool_kernel(const TY* __restrict__ Y, int ldy, int E, const float* __restrict__ bias, const int64_t* __restrict__ off,
                  const int32_t* __restrict__ tmax, int pool, float* __restrict__ out /* [N][E*pool] channel-major */) {
   const int t = blockIdx.x / pool, p = blockIdx.x % pool;
   const int64_t r0 = off[t];
@@ -129,13 +144,13 @@ conv_pool_kernel(const float* __restrict__ Y, int ldy, int E, const float* __res
       const int c = jc < Tmax ? st.src(jc) : -1;
       if (a == pa && b == pb && c == pc) continue;
       pa = a; pb = b; pc = c;
-      float4 v = *reinterpret_cast<const float4*>(Y + (r0 + b) * (int64_t)ldy + E + 4 * c4);
+      float4 v = load4(Y + (r0 + b) * (int64_t)ldy + E + 4 * c4);
       if (a >= 0) {
-        const float4 x = *reinterpret_cast<const float4*>(Y + (r0 + a) * (int64_t)ldy + 4 * c4);
+        const float4 x = load4(Y + (r0 + a) * (int64_t)ldy + 4 * c4);
         v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
       }
       if (c >= 0) {
-        const float4 x = *reinterpret_cast<const float4*>(Y + (r0 + c) * (int64_t)ldy + 2 * E + 4 * c4);
+        const float4 x = load4(Y + (r0 + c) * (int64_t)ldy + 2 * E + 4 * c4);
         v.x += x.x; v.y += x.y; v.z += x.z; v.w += x.w;
       }
       best.x = fmaxf(best.x, v.x); best.y = fmaxf(best.y, v.y); best.z = fmaxf(best.z, v.z); best.w = fmaxf(best.w, v.w);
@@ -917,8 +932,29 @@ extern "C" int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, 
   VSG_REQUIRE(n_tracks >= 0 && pool > 0 && E > 0 && E % 4 == 0 && ldy % 4 == 0, "vsg_conv_pool: bad size");
   if (n_tracks == 0) return VSG_OK;
   VSG_REQUIRE(Y && bias && off && tmax && out && aligned16(Y) && aligned16(bias), "vsg_conv_pool: null/misaligned pointer");
-  conv_pool_kernel<<<n_tracks * pool, 128, 0, (cudaStream_t)stream>>>(Y, ldy, E, bias, off, tmax, pool, out);
+  conv_pool_kernel<float><<<n_tracks * pool, 128, 0, (cudaStream_t)stream>>>(Y, ldy, E, bias, off, tmax, pool, out);
   return check_launch("vsg_conv_pool");
+}
+
+extern "C" int vsg_conv_pool_bf16(const void* Y16, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,
+                                  int n_tracks, int pool, float* out, void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && pool > 0 && E > 0 && E % 4 == 0 && ldy % 4 == 0, "vsg_conv_pool_bf16: bad size");
+  if (n_tracks == 0) return VSG_OK;
+  VSG_REQUIRE(Y16 && bias && off && tmax && out && (reinterpret_cast<uintptr_t>(Y16) & 7) == 0 && aligned16(bias), "vsg_conv_pool_bf16: null/misaligned pointer");
+  conv_pool_kernel<__nv_bfloat16><<<n_tracks * pool, 128, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)Y16, ldy, E, bias, off, tmax, pool, out);
+  return check_launch("vsg_conv_pool_bf16");
+}
+
+extern "C" int vsg_bbox_feat_mlp1_bf16(const float* boxes, const int64_t* off, int n_tracks, int64_t n_rows, const int32_t* track_vid,
+                                       const float* wh, const float* W1, const float* b1, int E, void* out16, int ldo, void* stream) {
+  VSG_REQUIRE(n_rows >= 0 && n_tracks >= 0 && E > 0 && ldo >= E, "vsg_bbox_feat_mlp1_bf16: bad size");
+  if (n_rows == 0) return VSG_OK;
+  VSG_REQUIRE(boxes && off && track_vid && wh && W1 && b1 && out16 && aligned16(boxes), "vsg_bbox_feat_mlp1_bf16: null/misaligned pointer");
+  const size_t smem = (size_t)9 * E * sizeof(float);
+  VSG_REQUIRE(smem <= 48 * 1024, "vsg_bbox_feat_mlp1_bf16: E too large");
+  bbox_feat_mlp1_kernel<<<grid_cap((n_rows + 7) / 8, 8), 256, smem, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float4*>(boxes), off, n_tracks, n_rows, track_vid, wh, W1, b1, E, nullptr, ldo, nullptr, (__nv_bfloat16*)out16);
+  return check_launch("vsg_bbox_feat_mlp1_bf16");
 }
 
 static int add_layernorm_impl(const float* x, int ldx, const float* a, int lda, const float* gamma, const float* beta, const float* post,

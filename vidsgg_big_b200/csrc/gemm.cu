@@ -16,6 +16,10 @@
 //                        write the two bf16 A tiles (SWIZZLE_32B rows of 16) next to the fp32 A tile; bf16(W), bf16(Wl) are
 //                        pre-computed in HBM (vsg_split_bf16).  Per-product error ~2^-18 worst case.
 //
+//   VSG_GEMM_BF16   (4)  reduced precision, ONE kind::f16 pass: A and W are bf16 in HBM (A written as bf16 by the producing kernel /
+//                        epilogue or by vsg_cast_bf16), fp32 accumulate, C as fp32 and / or bf16.  Runs as the single-pass kernel
+//                        (MODE 1 geometry: 128-byte stage rows = 64 bf16) with B16 = true; CTA pairs use cta_group::2 MMAs.
+//
 // tcgen05 kernel anatomy (persistent, one CTA per SM; 128 x BN output tiles per CTA, BN = 256 where N allows, else 128):
 //   warp 0       TMA producer: A tiles by cp.async.bulk.tensor.2d (mbarrier complete_tx), W tiles by tensor loads or -- mode 3 -- by
 //                contiguous cp.async.bulk copies of pre-swizzled weight-tile images (vsg_build_weight_image)
@@ -57,8 +61,10 @@ struct GemmEpilogue {
   int accumulate;           // C += result (before activation)
   const float* residual;    // [M][ld_res] added AFTER the activation, or null
   int ld_res;
-  float* C;
+  float* C;                 // may be null when only the bf16 copy is wanted
   int ldc;
+  __nv_bfloat16* C16;       // optional bf16 copy of the stored values ([M][ldc16]); the A operand of a following bf16 GEMM
+  int ldc16;
   int M, N, K;
   int store_hi;             // 3xTF32: also write the masked high part back (0 = rely on the MMA ignoring the low 13 bits)
   float* C_lo;              // optional: x - trunc_tf32(x) of every stored value (the B-side low part for a following 3xTF32 GEMM)
@@ -365,7 +371,8 @@ template <int MODE, int BN_, bool PAIR = false, bool CONV = false> struct Cfg {
 // cuts the L2 -> SM operand traffic per SM from A + W to A + W/2 (W is 4/5 of it in the split modes).  MMA / TMEM stay per CTA.
 // CL = 3: CTA-pair MMA (cta_group::2, see Cfg<.., PAIR>): rank 0 issues M = 256 instructions over both CTAs' operands, each CTA
 // loads only its half of W (no multicast), the peer's split / epilogue warps signal the leader's barriers through DSMEM arrives.
-template <int MODE, int BN_, bool PROBE, int CL, bool CONV = false>
+// B16 (MODE 1 only): operands are bf16 (64 elements per 128-byte stage row), one kind::f16 MMA per 16 columns.
+template <int MODE, int BN_, bool PROBE, int CL, bool CONV = false, bool B16 = false>
 __global__ void __launch_bounds__(Cfg<MODE, BN_>::THREADS, 1)
 gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
                const __grid_constant__ CUtensorMap mapBl, const __grid_constant__ CUtensorMap mapB16,
@@ -376,6 +383,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr int STAGE_BYTES = CF::STAGE_BYTES;
   constexpr int BN = BN_;
   constexpr int BK = CF::BK;
+  constexpr int BKE = B16 ? 2 * CF::BK : CF::BK;          // elements of K per stage (bf16: 64 per 128-byte row)
   constexpr int TILE_A = CF::TILE_A;
   constexpr int ACC_COLS = BN_;
   constexpr int TMEM_COLS = CF::TMEM_COLS;
@@ -403,7 +411,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   const int tiles_m = CL >= 2 ? (tiles_m_real + 1) / 2 : tiles_m_real;      // clusters: rows of tile PAIRS (an odd tail gets a dummy tile)
   const int tiles_n = (ep.N + BN - 1) / BN;
   const int n_tiles = tiles_m * tiles_n * ep.batch;
-  const int kblocks = (ep.K + BK - 1) / BK;
+  const int kblocks = (ep.K + BKE - 1) / BKE;
   const int tile0 = CL >= 2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x, tile_step = CL >= 2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
@@ -418,7 +426,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], CL == 2 ? 2 : 1);   // CL == 2: a stage is refilled by BOTH CTAs' multicasts, so both MMAs must have retired it
-      mbar_init(&ready[s], PAIR ? 132 : 128);  // every thread of the split group that owns the stage (PAIR: + one DSMEM arrive per peer warp)
+      // split modes: every thread of the split group that owns the stage (PAIR: + one DSMEM arrive per peer warp);
+      // single-pass PAIR: one relay arrive per CTA of the pair (warp 3) once that CTA's TMA data has landed
+      mbar_init(&ready[s], MODE >= 2 ? (PAIR ? 132 : 128) : 2);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&acc_full[a], 1);
@@ -451,19 +461,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (!la && !lw) { mbar_arrive(&full[stage]); }
             else {
               mbar_expect_tx(&full[stage], (la ? TILE_A : 0) + (lw ? (MODE >= 2 ? 2 : 1) * CF::TILE_B : 0));
-              if (la) tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
+              if (la) tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row);
               if (lw) {
-                tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
-                if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
-                if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
+                tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BKE + tc.b_col, tc.b_row);
+                if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BKE + tc.b_col, tc.b_row);
+                if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BKE + tc.b_col, tc.b_row);
               }
             }
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
           mbar_expect_tx(&full[stage], (CONV ? CF::RAW_TX : TILE_A) + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
-          if (CONV) tma_load_2d(smem_u32(st + CF::OFF_RAW), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row - 3);   // rows m0-3 .. m0+132 (OOB = 0)
-          else tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BK + tc.a_col, tc.a_row);
+          if (CONV) tma_load_2d(smem_u32(st + CF::OFF_RAW), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row - 3);   // rows m0-3 .. m0+132 (OOB = 0)
+          else tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row);
           if (PAIR) {
             // this CTA's half of the W rows only; the pair's MMA reads the other half from the peer's shared memory
             constexpr int TB = CF::TILE_B;                 // per-CTA W f32 bytes
@@ -474,9 +484,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               bulk_load(smem_u32(st + CF::OFF_BL), img + 3 * TB + rank * (TB / 2), TB / 2, &full[stage]);
             } else {
               const int brow = tc.b_row + rank * (BN / 2);
-              tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, brow);
-              if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, brow);
-              if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, brow);
+              tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BKE + tc.b_col, brow);
+              if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BKE + tc.b_col, brow);
+              if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BKE + tc.b_col, brow);
             }
           } else if (MODE == 3 && ep.w_img != nullptr) {
             // W tiles as contiguous pre-swizzled images [W f32 | bf16(W) | bf16(W_lo)] per (N tile, k block)
@@ -494,16 +504,16 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             // this CTA's half of the W rows (maps have BN/2-row boxes), written into both CTAs of the pair
             constexpr int HB = CF::TILE_B / 2;
             const int brow = tc.b_row + rank * (BN / 2);
-            tma_load_2d_mc(smem_u32(st + CF::OFF_BH + rank * HB), &mapBh, &full[stage], kb * BK + tc.b_col, brow, 3);
-            if (MODE == 2) tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * HB), &mapBl, &full[stage], kb * BK + tc.b_col, brow, 3);
+            tma_load_2d_mc(smem_u32(st + CF::OFF_BH + rank * HB), &mapBh, &full[stage], kb * BKE + tc.b_col, brow, 3);
+            if (MODE == 2) tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * HB), &mapBl, &full[stage], kb * BKE + tc.b_col, brow, 3);
             if (MODE == 3) {
-              tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * (HB / 2)), &mapBl, &full[stage], kb * BK + tc.b_col, brow, 3);
-              tma_load_2d_mc(smem_u32(st + CF::OFF_B16 + rank * (HB / 2)), &mapB16, &full[stage], kb * BK + tc.b_col, brow, 3);
+              tma_load_2d_mc(smem_u32(st + CF::OFF_BL + rank * (HB / 2)), &mapBl, &full[stage], kb * BKE + tc.b_col, brow, 3);
+              tma_load_2d_mc(smem_u32(st + CF::OFF_B16 + rank * (HB / 2)), &mapB16, &full[stage], kb * BKE + tc.b_col, brow, 3);
             }
           } else {
-            tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BK + tc.b_col, tc.b_row);
-            if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BK + tc.b_col, tc.b_row);
-            if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BK + tc.b_col, tc.b_row);
+            tma_load_2d(smem_u32(st + CF::OFF_BH), &mapBh, &full[stage], kb * BKE + tc.b_col, tc.b_row);
+            if (MODE >= 2) tma_load_2d(smem_u32(st + CF::OFF_BL), &mapBl, &full[stage], kb * BKE + tc.b_col, tc.b_row);
+            if (MODE == 3) tma_load_2d(smem_u32(st + CF::OFF_B16), &mapB16, &full[stage], kb * BKE + tc.b_col, tc.b_row);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -530,7 +540,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         // (PAIR: the peer's arrives are release.cluster; like CUTLASS's 2-SM pipelines the wait itself is the default try_wait --
         //  an acquire.cluster try_wait per k block was measured to cost ~1 us each)
         if (PROBE && (ep.dbg & 32)) mbar_spin(MODE >= 2 ? &ready[stage] : &full[stage], phase);
-        else mbar_wait(MODE >= 2 ? &ready[stage] : &full[stage], phase);
+        else mbar_wait((MODE >= 2 || PAIR) ? &ready[stage] : &full[stage], phase);
         tc_fence_after();
         if (PAIR) {
           if (elect_one()) {
@@ -540,7 +550,13 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               return ((uint64_t)hi << 32) | (uint64_t)((st16 + (off_bytes >> 4)) | LBO);
             };
             const uint64_t a_hi = desc(0, DESC_HI), b_hi = desc(CF::OFF_BH, DESC_HI);
-            if (MODE == 3) {
+            if (MODE < 2) {
+#pragma unroll
+              for (int k = 0; k < BK / UMMA_K; ++k) {
+                if (B16) umma2_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_BF16, (kb | k) ? 1u : 0u);
+                else umma2_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_TF32, (kb | k) ? 1u : 0u);
+              }
+            } else if (MODE == 3) {
               umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), ID_BF16, kb ? 1u : 0u);
               umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), ID_BF16, 1u);
 #pragma unroll
@@ -580,7 +596,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, 1u);
           } else {
 #pragma unroll
-            for (int k = 0; k < BK / UMMA_K; ++k) umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              if (B16) umma_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDesc<BN_>::bf16, (kb | k) ? 1u : 0u);
+              else umma_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, IDESC_TF32, (kb | k) ? 1u : 0u);
+            }
           }
           if (PROBE && (ep.dbg & 16)) mbar_arrive(&empty[stage]);
           else if (CL == 2) umma_commit_mc(&empty[stage], 3);
@@ -591,6 +610,21 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else if (warp == 3 && PAIR && MODE < 2) {
+    // ================= single-pass CTA pairs: stage relay =================
+    // the leader's cta_group::2 MMA reads BOTH CTAs' stage; each CTA's relay lane waits for its own TMA data and arrives on the
+    // leader's `ready` barrier (count 2) -- the peer through a DSMEM arrive, like the split warps of the fp32-class modes
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+        for (int kb = 0; kb < kblocks; ++kb) {
+          mbar_wait(&full[stage], phase);
+          if (rank != 0) mbar_arrive_cluster(&ready[stage], 0); else mbar_arrive(&ready[stage]);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
     }
   } else if (warp >= 4 && warp < 8) {
     // ================= epilogue =================
@@ -604,6 +638,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     uint32_t acc_phase = 0;
     const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
+    const bool bias_vec = (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0;
+    const bool c16_vec = ((ep.ldc16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C16) & 7) == 0);
     const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank);
@@ -619,7 +655,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int ri = ep.rb_index ? ep.rb_index[row] : (row % ep.rb_period);
         rb = ep.rowbias + (size_t)ri * ep.ld_rb;
       }
-      float* crow = ep.C + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc;
+      float* crow = ep.C ? ep.C + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc : nullptr;
+      __nv_bfloat16* crow16 = (ep.C16 && row_ok) ? ep.C16 + (size_t)row * ep.ldc16 : nullptr;   // plain problems only (no batch offset)
       float* crow_lo = ep.C_lo ? ep.C_lo + tc.c_off + (size_t)(row_ok ? row : 0) * ep.ldc : nullptr;
       const float* res = (row_ok && ep.residual) ? ep.residual + (size_t)row * ep.ld_res : nullptr;
 #pragma unroll 1
@@ -629,7 +666,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
         tmem_ld_wait();
-        const bool fast = ep.tma_store && vec_ok && slab_rows_ok && col0 + 32 <= ep.N;   // warp-uniform
+        const bool fast = ep.C && ep.tma_store && vec_ok && slab_rows_ok && col0 + 32 <= ep.N;   // warp-uniform
         if (fast) {
           uint8_t* sb = stg + sbuf * 4096;
           const bool lo_slab = ep.lo_tma && col0 >= ep.lo_c0 && col0 + 32 <= ep.lo_c1;   // warp-uniform: the low parts leave by TMA too
@@ -658,6 +695,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
             // SWIZZLE_128B: 16-byte chunk q of row r sits at chunk q ^ (r & 7) (buffer is 1024-byte aligned)
             *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+            if (crow16) {
+              const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+              *reinterpret_cast<uint2*>(crow16 + col0 + j) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+            }
             if (crow_lo && !lo_slab && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
               float4 l;
               l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -695,7 +736,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             sbuf ^= 1;
           }
         } else if (row_ok) {
-          if (col0 + 32 <= ep.N && vec_ok) {
+          if (col0 + 32 <= ep.N && (vec_ok || (!ep.C && bias_vec))) {
 #pragma unroll
             for (int j = 0; j < 32; j += 4) {
               float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
@@ -713,7 +754,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
               if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
               if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
-              *dst = v;
+              if (crow) *dst = v;
+              if (crow16 && c16_vec) {
+                const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
+                *reinterpret_cast<uint2*>(crow16 + col0 + j) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+              } else if (crow16) {
+                crow16[col0 + j] = __float2bfloat16_rn(v.x); crow16[col0 + j + 1] = __float2bfloat16_rn(v.y);
+                crow16[col0 + j + 2] = __float2bfloat16_rn(v.z); crow16[col0 + j + 3] = __float2bfloat16_rn(v.w);
+              }
               if (crow_lo && col0 + j >= ep.lo_c0 && col0 + j < ep.lo_c1) {
                 float4 l;
                 l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u); l.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xFFFFE000u);
@@ -732,7 +780,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (ep.accumulate) v += crow[col];
                 if (ep.relu) v = fmaxf(v, 0.f);
                 if (res) v += res[col];
-                crow[col] = v;
+                if (crow) crow[col] = v;
+                if (crow16) crow16[col] = __float2bfloat16_rn(v);
                 if (crow_lo && col >= ep.lo_c0 && col < ep.lo_c1) crow_lo[col] = v - __uint_as_float(__float_as_uint(v) & 0xFFFFE000u);
               }
             }
@@ -941,6 +990,31 @@ __global__ void split_bf16_kernel(const float* __restrict__ w, int ldw, int rows
   }
 }
 
+// fp32 -> bf16 (round to nearest even) copy of a row-major matrix: the A operand of the bf16 mode when its producer wrote fp32.
+// One thread per 8 columns (two 16-byte loads, one 16-byte store); the padding columns [cols, ldo) are written as zeros.
+__global__ void cast_bf16_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int cols, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  const int chunks = (int)(ldo >> 3);
+  const int64_t total = rows * chunks;
+  const bool vec = ((ldx & 3) == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / chunks;
+    const int c = (int)(i - r * chunks) * 8;
+    float v[8];
+    const float* src = x + r * ldx + c;
+    if (vec && c + 8 <= cols) {
+      const float4 a = ldg_stream(reinterpret_cast<const float4*>(src)), b = ldg_stream(reinterpret_cast<const float4*>(src) + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? src[j] : 0.f;
+    }
+    __nv_bfloat162 p[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) p[j] = __floats2bfloat162_rn(v[2 * j], v[2 * j + 1]);
+    *reinterpret_cast<uint4*>(out + r * ldo + c) = *reinterpret_cast<const uint4*>(p);
+  }
+}
+
 // Pre-swizzled shared-memory images of the W tiles of mode 3 (BK = 16): for every (N tile, k block) one contiguous block
 //   [ W fp32: bn rows x 64 B, SWIZZLE_64B | bf16(W): bn rows x 32 B, SWIZZLE_32B | bf16(W - trunc_tf32(W)): same ]
 // so that the producer fetches a stage's W operands with plain contiguous bulk copies.  One thread per 16-byte fp32 chunk.
@@ -1040,16 +1114,18 @@ static int get_tensor_map(const void* base, int rows, int cols, int ld, int box_
   return VSG_OK;
 }
 
-template <int MODE, int BN_, int CL, bool CONV = false>
+// B16 (MODE 1): `A` / `Wh` point to bf16 operands ([rows][lda] / [N][ldw] bf16 elements)
+template <int MODE, int BN_, int CL, bool CONV = false, bool B16 = false>
 static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                      const GemmEpilogue& ep_in, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
   using CF = Cfg<MODE, BN_, CL == 3, CONV>;
   constexpr int CLN = CL >= 2 ? 2 : 1;            // CTAs per cluster
   CUtensorMap mA, mBh, mBl, mB16;
   constexpr int WBOX = BN_ / CLN;                 // clusters: each CTA of a pair loads (CL == 2: and multicasts) half of the W rows
-  int rc = get_tensor_map(A, a_rows, a_cols, lda, CONV ? CF::RAW_ROWS : BM, CF::BK, &mA);      // CONV: raw X tile with its halo rows
+  constexpr int ES = B16 ? 2 : 4, BKE = B16 ? 2 * CF::BK : CF::BK;
+  int rc = get_tensor_map(A, a_rows, a_cols, lda, CONV ? CF::RAW_ROWS : BM, BKE, &mA, ES);      // CONV: raw X tile with its halo rows
   if (rc) return rc;
-  rc = get_tensor_map(Wh, w_rows, w_cols, ldw, WBOX, CF::BK, &mBh);
+  rc = get_tensor_map(Wh, w_rows, w_cols, ldw, WBOX, BKE, &mBh, ES);
   if (rc) return rc;
   if (MODE == 2) { rc = get_tensor_map(Wl, w_rows, w_cols, ldw, WBOX, CF::BK, &mBl); if (rc) return rc; } else mBl = mBh;
   mB16 = mBh;
@@ -1062,7 +1138,7 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   GemmEpilogue ep = ep_in;
   CUtensorMap mC = mA, mClo = mA;
   ep.tma_store = 0; ep.lo_tma = 0;
-  if (g_tma_store && (ep.ldc & 3) == 0 && aligned16(ep.C)) {
+  if (g_tma_store && ep.C && (ep.ldc & 3) == 0 && aligned16(ep.C)) {
     // C as a 2-D tensor of 32x32 fp32 boxes (SWIZZLE_128B).  Batched problems address boxes inside the whole C buffer, whose row
     // length is ldc; only slabs that lie fully inside a problem take this path, so the bounds are never relied on for clipping.
     long long rows = ep.M, cols = ep.N;
@@ -1083,12 +1159,12 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
     }
   }
   constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CF::DW_BYTES;
-  constexpr bool HAS_PROBE = (CL == 1) && !CONV;           // the timing probes exist for the single-CTA kernel only (compile time)
+  constexpr bool HAS_PROBE = (CL == 1) && !CONV && !B16;   // the timing probes exist for the single-CTA kernel only (compile time)
   static PerDeviceFlag attr_set;
   const int dev_ = current_device();
   if (!attr_set.is_set(dev_)) {
-    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
-        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, false, CL, CONV, B16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV, B16>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("cudaFuncSetAttribute(max dynamic smem %d) failed: %s", SMEM, cudaGetErrorString(cudaGetLastError()));
       return VSG_E_LAUNCH;
     }
@@ -1105,22 +1181,22 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CLN; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = CLN > 1 ? 1 : 0;
-  cudaError_t e = (ep.dbg && HAS_PROBE) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV>, mA, mBh, mBl, mB16, mC, mClo, ep)   // timing probes
-                                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL, CONV>, mA, mBh, mBl, mB16, mC, mClo, ep);
+  cudaError_t e = (ep.dbg && HAS_PROBE) ? cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, HAS_PROBE, CL, CONV, B16>, mA, mBh, mBl, mB16, mC, mClo, ep)   // timing probes
+                                        : cudaLaunchKernelEx(&cfg, gemm_tc_kernel<MODE, BN_, false, CL, CONV, B16>, mA, mBh, mBl, mB16, mC, mClo, ep);
   if (e != cudaSuccess) { set_error("vsg_gemm(tcgen05): launch failed: %s", cudaGetErrorString(e)); cudaGetLastError(); return VSG_E_LAUNCH; }
   return check_launch("vsg_gemm(tcgen05)");
 }
 
-template <int MODE, int BN_>
+template <int MODE, int BN_, bool B16 = false>
 static int launch_tc_auto(const float* A, int lda, int a_rows, int a_cols, const float* Wh, const void* Wl, int ldw, int w_rows, int w_cols,
                           const GemmEpilogue& ep, cudaStream_t st, const void* W16 = nullptr, int ldw16 = 0) {
-  // plain problems with at least one full pair of M tiles run on CTA pairs: one cta_group::2 MMA per pair (split modes, 256-wide
-  // tiles), else two per-CTA MMAs with the W tile multicast
-  if (BN_ == 256 && MODE >= 2 && g_cluster == 3 && ep.batch == 1 && ep.M > BM && !ep.dbg)
-    return launch_tc<MODE, 256, 3>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
+  // plain problems with at least one full pair of M tiles run on CTA pairs: one cta_group::2 MMA per pair (split modes and the bf16
+  // mode, 256-wide tiles), else two per-CTA MMAs with the W tile multicast
+  if (BN_ == 256 && (MODE >= 2 || B16) && g_cluster == 3 && ep.batch == 1 && ep.M > BM && !ep.dbg)
+    return launch_tc<MODE, 256, 3, false, B16>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
   if (g_cluster >= 2 && ep.batch == 1 && ep.M > BM && !ep.dbg)
-    return launch_tc<MODE, BN_, 2>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
-  return launch_tc<MODE, BN_, 1>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
+    return launch_tc<MODE, BN_, 2, false, B16>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
+  return launch_tc<MODE, BN_, 1, false, B16>(A, lda, a_rows, a_cols, Wh, Wl, ldw, w_rows, w_cols, ep, st, W16, ldw16);
 }
 
 // N=256 tiles whenever they do not add MMA work over N=128 tiles
@@ -1167,6 +1243,17 @@ extern "C" int vsg_split_bf16(const float* w, int ldw, int rows, int cols, void*
   return check_launch("vsg_split_bf16");
 }
 
+extern "C" int vsg_cast_bf16(const float* x, int64_t ldx, int64_t rows, int cols, void* out, int64_t ldo, void* stream) {
+  VSG_REQUIRE(rows >= 0 && cols >= 0 && ldx >= cols && ldo >= cols && ldo % 8 == 0, "vsg_cast_bf16: bad extents (ldo must be a multiple of 8)");
+  if (rows == 0 || cols == 0) return VSG_OK;
+  VSG_REQUIRE(x && out && aligned16(out), "vsg_cast_bf16: null or unaligned pointer");
+  const int64_t total = rows * (ldo / 8);
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 32) blocks = (int64_t)sm_count() * 32;
+  cast_bf16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(x, ldx, rows, cols, (__nv_bfloat16*)out, ldo);
+  return check_launch("vsg_cast_bf16");
+}
+
 extern "C" int vsg_gemm_tile_n(int N) { return (use_bn256(N) && g_force_bn != 128) ? 256 : 128; }
 
 extern "C" int64_t vsg_weight_image_bytes(int N, int K, int bn) {
@@ -1190,6 +1277,29 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   VSG_REQUIRE(M >= 0 && N >= 0 && K >= 0, "vsg_gemm: negative size");
   const int batch = a->batch > 0 ? a->batch : 1;
   if (M == 0 || N == 0) return VSG_OK;
+  if (a->mode == 4) {
+    // bf16 operands (A16 [M][lda16], W_b16 [N][ldw16]), fp32 accumulate, C as fp32 and / or bf16
+    VSG_REQUIRE(batch == 1, "vsg_gemm_ex: mode 4 (bf16) takes plain problems only");
+    VSG_REQUIRE(a->A16 && a->W_b16 && (a->C || a->C16), "vsg_gemm_ex: mode 4 needs A16, W_b16 and C and / or C16");
+    VSG_REQUIRE(aligned16(a->A16) && aligned16(a->W_b16) && a->lda16 >= K && a->ldw16 >= K && a->lda16 % 8 == 0 && a->ldw16 % 8 == 0,
+                "vsg_gemm_ex: mode 4 operands must be 16-byte aligned with leading dimensions that are multiples of 8 and >= K");
+    VSG_REQUIRE(!a->C || a->ldc >= N, "vsg_gemm_ex: ldc < N");
+    VSG_REQUIRE(!a->C16 || (a->ldc16 >= N && (reinterpret_cast<uintptr_t>(a->C16) & 1) == 0), "vsg_gemm_ex: bad C16");
+    VSG_REQUIRE(!a->accumulate || a->C, "vsg_gemm_ex: accumulate needs C");
+    VSG_REQUIRE(!a->C_lo && !a->dw_w, "vsg_gemm_ex: mode 4 has no C_lo / fused depthwise conv");
+    VSG_REQUIRE(a->rowbias == nullptr || a->rb_index != nullptr || a->rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
+    GemmEpilogue ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
+    ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res;
+    ep.C = a->C; ep.ldc = a->C ? a->ldc : N; ep.C16 = (__nv_bfloat16*)a->C16; ep.ldc16 = a->ldc16;
+    ep.M = M; ep.N = N; ep.K = K; ep.lo_c1 = N; ep.batch = 1; ep.batch_inner = 1;
+    const float* A16 = reinterpret_cast<const float*>(a->A16);
+    const float* W16f = reinterpret_cast<const float*>(a->W_b16);
+    const bool wide4 = use_bn256(N) && g_force_bn != 128;
+    return wide4 ? launch_tc_auto<1, 256, true>(A16, a->lda16, M, K, W16f, nullptr, a->ldw16, N, K, ep, (cudaStream_t)stream)
+                 : launch_tc_auto<1, 128, true>(A16, a->lda16, M, K, W16f, nullptr, a->ldw16, N, K, ep, (cudaStream_t)stream);
+  }
   VSG_REQUIRE(a->A && a->W_hi && a->C, "vsg_gemm: null matrix pointer");
   VSG_REQUIRE(a->lda >= K && a->ldw >= K && a->ldc >= N, "vsg_gemm: leading dimension smaller than extent");
   VSG_REQUIRE(a->rowbias == nullptr || a->rb_index != nullptr || a->rb_period > 0, "vsg_gemm: rowbias needs rb_index or rb_period");
@@ -1197,6 +1307,7 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.bias = a->bias; ep.rowbias = a->rowbias; ep.rb_index = a->rb_index; ep.rb_period = a->rb_period; ep.ld_rb = a->ld_rb;
   ep.store_hi = g_store_hi; ep.dbg = g_dbg;
   ep.relu = a->relu; ep.accumulate = a->accumulate; ep.residual = a->residual; ep.ld_res = a->ld_res; ep.C = a->C; ep.C_lo = a->C_lo;
+  ep.C16 = (__nv_bfloat16*)a->C16; ep.ldc16 = a->ldc16;
   ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.lo_tma = 0; ep.w_img = nullptr;
   ep.dw_w = nullptr; ep.dw_b = nullptr; ep.seq_pos = nullptr; ep.seq_rem = nullptr; ep.dw_k = 0;
   VSG_REQUIRE(a->dw_w == nullptr || (a->mode == 3 && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for mode 3, plain problems");

@@ -338,7 +338,9 @@ def _aggregate(vids, n_gt_per_vid, hits, tag_precs, det_nreturns, tag_nreturns):
         sc = np.concatenate(pool_sc[k])
         tp = np.concatenate(pool_tp[k])[np.argsort(sc)[::-1]]
         ctp = np.cumsum(tp).astype(np.float32)
-        rec_at[k] = (ctp / np.maximum(total_gt, F32_EPS))[-1]
+        # no prediction in ANY video: the reference indexes an empty array here (IndexError, visual_relation_detection.py:105);
+        # a batched driver that keeps prediction-less videos reports the recall that situation means
+        rec_at[k] = (ctp / np.maximum(total_gt, F32_EPS))[-1] if ctp.size else np.float32(0.0)
     return mean_ap, rec_at, {k: np.mean(p_at[k]) for k in tag_nreturns}
 
 

@@ -115,7 +115,7 @@ class DEBUG(object):
             raise VsgError("DEBUG runs on a CUDA device only (no CPU fallback)")
         st = {k: v.to(dev) for k, v in self._state.items()}
         H = self.dim_hidden
-        split = {linalg.X3TF32: "tf32", linalg.TF32_BF16X2: "bf16"}.get(self.mode, False)
+        split = linalg.SPLITS.get(self.mode, False)
         W = lambda name: Weight(st[name + ".weight"], st[name + ".bias"], split=split)
         w = {"video_fc": W("video_fc"), "vq_fc": W("vq_fc")}
         qfc = W("query_fc")

@@ -8,8 +8,9 @@ import torch
 
 from ._cabi import check, lib, ptr, require_cuda, stream_ptr
 
-SIMT, TF32, X3TF32, TF32_BF16X2 = 0, 1, 2, 3
-MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2}
+SIMT, TF32, X3TF32, TF32_BF16X2, BF16 = 0, 1, 2, 3, 4
+MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2, "bf16": BF16}
+SPLITS = {X3TF32: "tf32", TF32_BF16X2: "bf16", BF16: "bf16w"}      # mode -> what ``Weight`` must precompute (default: nothing)
 
 
 def can_fuse_dwconv(mode: int, W: "Weight", K: Optional[int] = None, k: int = 7) -> bool:
@@ -21,6 +22,8 @@ def can_fuse_dwconv(mode: int, W: "Weight", K: Optional[int] = None, k: int = 7)
 def attention_mode(mode: int) -> int:
     """Mode of the batched attention GEMMs (activation x activation): TF32_BF16X2 needs pre-computed bf16 copies of the "weight"
     operand, which only exist for real weights -- those few problems stay on the 3xTF32 kernel."""
+    if mode == BF16:
+        return TF32             # reduced-precision mode: single-pass tf32 attention products
     return X3TF32 if mode == TF32_BF16X2 else mode
 
 
@@ -36,12 +39,15 @@ class Weight(object):
         self.N, self.K = self.w.shape
         self.hi = self.lo = self.w16 = self.lo16 = self.img = None
         self.img_bn = 0
-        if split == "bf16":
+        if split in ("bf16", "bf16w"):
             self.ld16 = (self.K + 7) // 8 * 8
             self.w16 = torch.empty(self.N, self.ld16, dtype=torch.bfloat16, device=self.w.device)
             self.lo16 = torch.empty_like(self.w16)
             check(lib().vsg_split_bf16(ptr(self.w), self.w.stride(0), self.N, self.K, ptr(self.w16), ptr(self.lo16), self.ld16,
                                        stream_ptr(self.w.device)), "vsg_split_bf16")
+            if split == "bf16w":          # bf16 mode: only bf16(W) is read
+                self.lo16 = None
+                return
             # pre-swizzled tile images for the tile width the kernel will pick (contiguous bulk loads of the W operands)
             self.img_bn = int(lib().vsg_gemm_tile_n(self.N))
             nbytes = int(lib().vsg_weight_image_bytes(self.N, self.K, self.img_bn))
@@ -104,20 +110,43 @@ class _Profile(object):
 LAUNCHES = [0]            # GEMM launches issued through this wrapper (bench.py's gpu_launches)
 
 
+def cast_bf16(x: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """bf16 copy ``[rows, ceil8(K)]`` of the first K columns of an fp32 row-major matrix (zero padding columns): the A operand of
+    the bf16 mode when the producer wrote fp32."""
+    require_cuda(x)
+    assert x.dim() == 2 and x.stride(1) == 1 and x.dtype == torch.float32
+    K = x.shape[1] if K is None else K
+    ld = (K + 7) // 8 * 8
+    if out is None:
+        out = torch.empty(x.shape[0], ld, dtype=torch.bfloat16, device=x.device)
+    assert out.dtype == torch.bfloat16 and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.shape[1] >= K
+    LAUNCHES[0] += 1
+    with _Profile.span("cast"):
+        check(lib().vsg_cast_bf16(_raw(x), x.stride(0) if x.shape[0] > 1 else max(x.stride(0), K), x.shape[0], K, _raw(out),
+                                  out.stride(0) if x.shape[0] > 1 else max(out.stride(0), ld), stream_ptr(x.device)), "vsg_cast_bf16")
+    return out
+
+
 def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = None, relu: bool = False,
          rowbias: Optional[torch.Tensor] = None, rb_index: Optional[torch.Tensor] = None, rb_period: int = 0,
          accumulate: bool = False, bias: bool = True, K: Optional[int] = None,
-         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, lo_cols=None, dwconv=None) -> torch.Tensor:
+         residual: Optional[torch.Tensor] = None, out_lo: Optional[torch.Tensor] = None, lo_cols=None, dwconv=None,
+         out16: Optional[torch.Tensor] = None, f32_out: bool = True) -> torch.Tensor:
     """``out[:, :N] = act(A[:, :K] @ W.w.T + bias (+ rowbias) (+ out))``.  ``A`` / ``out`` may be column slices of
     wider row-major buffers (their row stride is passed as the leading dimension).  ``out_lo`` (same shape / strides as ``out``)
     receives ``x - trunc_tf32(x)`` of the result, restricted to the column window ``lo_cols = (begin, end)`` if given.
     ``dwconv = (dw_w [K,k], dw_b [K], k, seq_pos i32[M], seq_rem i32[M])``: A is replaced by its depthwise conv over the row axis inside
-    the kernel (mode tf32+bf16x2, N <= 128; see ``can_fuse_dwconv``)."""
+    the kernel (mode tf32+bf16x2, N <= 128; see ``can_fuse_dwconv``).
+    Mode ``BF16``: ``A`` may be fp32 (cast by ``cast_bf16`` first) or already bf16; ``out16`` (bf16 ``[M, >= N]``, row stride a
+    multiple of 4) also receives the result as bf16; ``f32_out=False`` skips the fp32 output and returns ``out16``."""
     require_cuda(A)
-    assert A.dim() == 2 and A.stride(1) == 1 and A.dtype == torch.float32
+    assert A.dim() == 2 and A.stride(1) == 1
     M = A.shape[0]
     K = W.K if K is None else K
     assert A.shape[1] >= K
+    if mode == BF16:
+        return _gemm_bf16(A, W, out, relu, rowbias, rb_index, rb_period, accumulate, bias, K, residual, out16, f32_out)
+    assert A.dtype == torch.float32 and out16 is None and f32_out
     if out is None:
         out = torch.empty(M, W.N, dtype=torch.float32, device=A.device)
     assert out.dim() == 2 and out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= W.N
@@ -130,7 +159,7 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
     if _Profile.enabled:
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         ev0.record()
-    if mode == TF32_BF16X2 and W.w16 is None:
+    if mode == TF32_BF16X2 and (W.w16 is None or W.lo16 is None):
         raise ValueError("gemm: mode tf32+bf16x2 needs a Weight built with split='bf16'")
     assert dwconv is None or can_fuse_dwconv(mode, W, K)
     if out_lo is not None or mode == TF32_BF16X2:
@@ -164,6 +193,43 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         ev1.record()
         _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage))
     return out
+
+
+def _gemm_bf16(A, W, out, relu, rowbias, rb_index, rb_period, accumulate, bias, K, residual, out16, f32_out):
+    """Mode BF16 (csrc/gemm.cu, B16 kernel): bf16 operands, one kind::f16 pass, fp32 accumulate."""
+    from ._cabi import VsgGemmArgs
+    import ctypes as C
+    if W.w16 is None:
+        raise ValueError("gemm: mode bf16 needs a Weight built with split='bf16w' (or 'bf16')")
+    M = A.shape[0]
+    if M == 0:
+        return out if f32_out else out16
+    A16 = A if A.dtype == torch.bfloat16 else cast_bf16(A, K)
+    assert A16.stride(1) == 1 and (A16.stride(0) % 8 == 0 or M == 1) and A16.data_ptr() % 16 == 0
+    if f32_out and out is None:
+        out = torch.empty(M, W.N, dtype=torch.float32, device=A.device)
+    if not f32_out and out16 is None:
+        out16 = torch.empty(M, (W.N + 7) // 8 * 8, dtype=torch.bfloat16, device=A.device)
+    a = VsgGemmArgs()
+    a.mode = BF16; a.M, a.N, a.K = M, W.N, K
+    a.A16 = A16.data_ptr(); a.lda16 = A16.stride(0) if M > 1 else max(A16.stride(0), (K + 7) // 8 * 8)
+    a.W_b16 = W.w16.data_ptr(); a.ldw16 = W.ld16
+    b = W.bias if bias else None
+    a.bias = None if b is None else b.data_ptr(); a.rowbias = None if rowbias is None else rowbias.data_ptr()
+    a.rb_index = None if rb_index is None else rb_index.data_ptr(); a.rb_period = int(rb_period)
+    a.ld_rb = 0 if rowbias is None else rowbias.stride(0); a.relu = 1 if relu else 0; a.accumulate = 1 if accumulate else 0
+    a.residual = None if residual is None else residual.data_ptr(); a.ld_res = 0 if residual is None else residual.stride(0)
+    if f32_out:
+        assert out.dim() == 2 and out.stride(1) == 1 and out.shape[0] == M and out.shape[1] >= W.N and out.dtype == torch.float32
+        a.C = out.data_ptr(); a.ldc = out.stride(0) if M > 1 else max(out.stride(0), W.N)
+    if out16 is not None:
+        assert out16.dtype == torch.bfloat16 and out16.stride(1) == 1 and out16.shape[0] == M and out16.shape[1] >= W.N
+        a.C16 = out16.data_ptr(); a.ldc16 = out16.stride(0) if M > 1 else max(out16.stride(0), W.N)
+    a.batch = 1; a.batch_inner = 1
+    LAUNCHES[0] += 1
+    with _Profile.span("gemm", 2.0 * M * W.N * K):
+        check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
+    return out if f32_out else out16
 
 
 def gemm_batched(mode: int, A: torch.Tensor, W_hi: torch.Tensor, W_lo: Optional[torch.Tensor], M: int, N: int, K: int,
