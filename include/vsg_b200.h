@@ -302,6 +302,14 @@ int vsg_broadcast_rows(const float* x, int period, int D, int64_t rows, float* o
 int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
             int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, const int32_t* blk_seg,
             const int32_t* blk_q0, int n_blocks, void* stream);
+/* The same attention for head_dim == 16 on the tensor cores (tcgen05.mma kind::tf32 + TMEM; csrc/attn_tc.cu): the grounding
+ * network's nn.MultiheadAttention(128, 8) of models/grd_model_v5.py:90, :100-108, :128-130.  Work list as for vsg_mha but with blocks of
+ * 128 queries: blk_seg[b] = sequence, blk_q0[b] = first query of block b; sequences are rows [seg_off[s], seg_off[s+1]) of Q / K / V / O.
+ * products = 3: every product as lo*hi + hi*lo + hi*hi of tf32 splits (fp32-class, like VSG_GEMM_3XTF32); 1: single tf32 pass.
+ * Softmax scale 1/sqrt(16); exact two-pass softmax(s - max). */
+int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off,
+                 int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
+                 void* stream);
 
 /* Glue of the tensor-core attention path (QK^T and PV are batched vsg_gemm_ex problems, one per (video, head)):
  * in-place row softmax of scale*S over the first n (<= 256) columns, and the transpose of an activation block

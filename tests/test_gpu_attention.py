@@ -1,0 +1,73 @@
+"""GPU: the tcgen05 attention kernel for head_dim 16 (csrc/attn_tc.cu, the grounding network's mh_attn) against an fp64 softmax
+attention and against the fp32 SIMT kernel it replaces."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _run(qkv, lens, products=None):
+    from vidsgg_big_b200 import linalg
+    from vidsgg_big_b200._cabi import check, lib, stream_ptr
+    H = 128
+    off = torch.from_numpy(np.concatenate([[0], np.cumsum(lens)]).astype(np.int64)).to(DEV)
+    out = torch.full((qkv.shape[0], H), float("nan"), device=DEV)
+    ld = qkv.stride(0)
+    raw = lambda t: C.c_void_p(t.data_ptr())
+    q, k, v = raw(qkv), C.c_void_p(qkv.data_ptr() + 4 * H), C.c_void_p(qkv.data_ptr() + 8 * H)
+    if products is None:       # SIMT comparator
+        bs, bq, nb = linalg.mha_block_list(lens, DEV)
+        check(lib().vsg_mha(q, ld, k, ld, v, ld, raw(off), len(lens), 0, int(max(lens)), 8, 16, raw(out), H, raw(bs), raw(bq), nb, stream_ptr(DEV)), "vsg_mha")
+    else:
+        bs, bq, nb = linalg.mha_block_list(lens, DEV, qb=128)
+        check(lib().vsg_mha_tc16(q, ld, k, ld, v, ld, raw(off), 8, raw(out), H, raw(bs), raw(bq), nb, products, stream_ptr(DEV)), "vsg_mha_tc16")
+    torch.cuda.synchronize()
+    return out
+
+
+def _ref(qkv, lens):
+    H, dh = 128, 16
+    outs, r = [], 0
+    for L in lens:
+        x = qkv[r:r + L].double()
+        q, k, v = [t.view(L, 8, dh).transpose(0, 1) for t in (x[:, :H], x[:, H:2 * H], x[:, 2 * H:])]
+        outs.append((torch.softmax(q @ k.transpose(-1, -2) / dh ** 0.5, -1) @ v).transpose(0, 1).reshape(L, H))
+        r += L
+    return torch.cat(outs, 0)
+
+
+@pytest.mark.parametrize("lens", [[1], [17, 64, 65], [130, 3, 128, 129, 300], [675, 16, 613], [63] * 40 + [200] * 9],
+                         ids=["one", "small", "mixed", "vidor-max", "many"])
+def test_mha_tc16_vs_fp64(lens):
+    g = torch.Generator(device="cpu").manual_seed(sum(lens))
+    rows = sum(lens)
+    # scores with a spread of a few units (post-LayerNorm activations through in_proj), so that the softmax is far from uniform
+    qkv = (torch.randn(rows, 384, generator=g) * torch.tensor([2.0] * 128 + [2.0] * 128 + [1.0] * 128)).to(DEV)
+    ref = _ref(qkv, lens)
+    scale = ref.abs().max().item()
+    simt = _run(qkv, lens)
+    tc3 = _run(qkv, lens, 3)
+    tc1 = _run(qkv, lens, 1)
+    e_simt = (simt.double() - ref).abs().max().item() / scale
+    e3 = (tc3.double() - ref).abs().max().item() / scale
+    e1 = (tc1.double() - ref).abs().max().item() / scale
+    print("attention rel err vs fp64: simt %.2e  tcgen05 3xtf32 %.2e  tcgen05 tf32 %.2e" % (e_simt, e3, e1))
+    assert not torch.isnan(tc3).any() and not torch.isnan(tc1).any()
+    assert e_simt < 1e-5
+    assert e3 < 1e-5, "3xTF32 attention is fp32-class"
+    assert e1 < 2e-2
+
+
+def test_mha_tc16_in_column_slices_of_a_wider_buffer():
+    """Q / K / V / O strides: the kernel is called on column slices (row stride 384) exactly like grounding._qanet does."""
+    lens = [90, 200]
+    g = torch.Generator(device="cpu").manual_seed(5)
+    qkv = torch.randn(sum(lens), 384, generator=g).to(DEV)
+    a = _run(qkv, lens, 3)
+    b = _run(qkv.clone(), lens, 3)
+    assert torch.equal(a, b)                                          # deterministic
+    assert (a.double() - _ref(qkv, lens)).abs().max().item() < 1e-5

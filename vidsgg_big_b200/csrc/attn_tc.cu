@@ -1,0 +1,264 @@
+// Multi-head attention with head_dim 16 on the 5th-generation tensor cores (tcgen05 + TMEM).
+//
+// The grounding network's three QANet encoders run nn.MultiheadAttention(128, 8 heads) (models/grd_model_v5.py:90, :100-108, :128-130)
+// over ragged sequences: the video encoder (one sequence of T clips), the query encoder (nq sequences of 3 words) and the combined
+// encoder (nq sequences of T clips) -- the last one is 4 T^2 128 flops per query, the largest non-GEMM kernel of the VidOR step.
+//
+// One CTA = (sequence, block of 128 queries, head).  Per block of 64 keys:
+//   S  = Q K^T      tcgen05.mma kind::tf32, M = 128, N = 64, K = 16: Q / K tiles staged by the CTA's threads as K-major SWIZZLE_64B
+//                   tiles (64-byte rows = the 16 floats of one head), accumulator in TMEM columns [0, 64)
+//   P  = exp(...)   the 128 threads read their own row of S with tcgen05.ld (one TMEM lane each), exponentiate and write P as the
+//                   A operand of the second product: two K-major SWIZZLE_128B panels of 32 keys
+//   O += P V        tcgen05.mma M = 128, N = 16, K = 64 against V^T (staged transposed: 16 rows x 32 keys per panel), accumulator in
+//                   TMEM columns [64, 80)
+// Softmax is two-pass (pass 1: row maxima over all key blocks, pass 2: exp / sum / PV), i.e. exactly softmax(s - max) of the reference;
+// recomputing S costs six MMAs per key block, nothing next to the exponentials.
+// fp32-class precision (`products` = 3, the default of the fp32-class GEMM modes): every operand is split into hi = trunc_tf32(x) (the raw
+// fp32 value -- the MMA ignores the low 13 mantissa bits) and lo = x - hi, and each product is lo*hi + hi*lo + hi*hi (3xTF32, error ~2^-21
+// per product).  `products` = 1 runs the hi*hi product only (tf32, the reduced-precision modes).
+// Shared memory 96 KB, TMEM 128 columns -> two CTAs per SM, so one CTA's exponentials overlap the other's MMAs.
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace vsg {
+
+constexpr int AT_BM = 128;   // queries per CTA (MMA M)
+constexpr int AT_KC = 64;    // keys per block (MMA N of the first product, K of the second)
+constexpr int AT_DH = 16;    // head dimension
+// shared-memory map (bytes, every tile 1024-byte aligned)
+constexpr int AT_OFF_QH = 0;                     // Q   [128 rows x 64 B]  SWIZZLE_64B
+constexpr int AT_OFF_QL = 8192;
+constexpr int AT_OFF_KH = 16384;                 // K   [ 64 rows x 64 B]  SWIZZLE_64B
+constexpr int AT_OFF_KL = 20480;
+constexpr int AT_OFF_VH = 24576;                 // V^T 2 panels x [16 rows x 128 B]  SWIZZLE_128B
+constexpr int AT_OFF_VL = 28672;
+constexpr int AT_OFF_PH = 32768;                 // P   2 panels x [128 rows x 128 B] SWIZZLE_128B
+constexpr int AT_OFF_PL = 65536;
+constexpr int AT_SMEM = 98304;
+constexpr int AT_TMEM_COLS = 128;                // S: columns [0, 64), O: [64, 80)
+
+__device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+__device__ __forceinline__ float4 tf32_lo(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(128, 2)
+mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
+                const int64_t* __restrict__ seg_off, const int32_t* __restrict__ blk_seg, const int32_t* __restrict__ blk_q0,
+                float scale_log2e, int products, float* __restrict__ O, int ldo) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  const int seg = blk_seg[blockIdx.x], q0 = blk_q0[blockIdx.x], h = blockIdx.y;
+  const int64_t r0 = seg_off[seg];
+  const int T = (int)(seg_off[seg + 1] - r0);
+  const int col0 = h * AT_DH;
+
+  if (tid == 0) { mbar_init(&mma_bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, AT_TMEM_COLS); tmem_relinquish(); }
+  // ---- Q tile: row r = query q0 + r, 4 chunks of 16 bytes; SWIZZLE_64B: chunk c of row r sits at chunk c ^ ((r >> 1) & 3) ----
+  for (int idx = tid; idx < AT_BM * 4; idx += 128) {
+    const int r = idx >> 2, c = idx & 3;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) x = *reinterpret_cast<const float4*>(Q + (r0 + q0 + r) * (int64_t)ldq + col0 + 4 * c);
+    const int o = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+    *reinterpret_cast<float4*>(smem + AT_OFF_QH + o) = x;
+    *reinterpret_cast<float4*>(smem + AT_OFF_QL + o) = tf32_lo(x);
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_s = tmem, t_o = tmem + AT_KC;
+  const uint32_t lane_base = (uint32_t)(warp * 32) << 16;          // this warp's TMEM lane quadrant
+  const uint32_t sbase = smem_u32(smem);
+  const int row = tid;                                             // the query row (TMEM lane) this thread owns
+  uint32_t phase = 0;
+  const int n_blocks = (T + AT_KC - 1) / AT_KC;
+
+  auto stage_k = [&](int k0) {
+    for (int idx = tid; idx < AT_KC * 4; idx += 128) {
+      const int r = idx >> 2, c = idx & 3;
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) x = *reinterpret_cast<const float4*>(K + (r0 + k0 + r) * (int64_t)ldk + col0 + 4 * c);
+      const int o = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
+      *reinterpret_cast<float4*>(smem + AT_OFF_KH + o) = x;
+      *reinterpret_cast<float4*>(smem + AT_OFF_KL + o) = tf32_lo(x);
+    }
+  };
+  // V^T: row d (0..15) of panel p holds keys 32p .. 32p+31 (128 bytes); SWIZZLE_128B: chunk q of row d sits at chunk q ^ (d & 7)
+  auto stage_v = [&](int k0) {
+    for (int idx = tid; idx < AT_KC * 4; idx += 128) {
+      const int r = idx >> 2, c = idx & 3;                         // key r of the block, dims 4c .. 4c+3
+      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) x = *reinterpret_cast<const float4*>(V + (r0 + k0 + r) * (int64_t)ldv + col0 + 4 * c);
+      const float xs[4] = {x.x, x.y, x.z, x.w};
+      const int p = r >> 5, kk = r & 31;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int d = 4 * c + j;
+        const int o = p * 2048 + d * 128 + (((kk >> 2) ^ (d & 7)) << 4) + (kk & 3) * 4;
+        *reinterpret_cast<float*>(smem + AT_OFF_VH + o) = xs[j];
+        *reinterpret_cast<float*>(smem + AT_OFF_VL + o) = tf32_lo(xs[j]);
+      }
+    }
+  };
+  // S[128 x n_s] = Q K^T for the staged key block (n_s = valid keys rounded up to 16); issued by one thread
+  auto issue_s = [&](int n_s) {
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(n_s >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+    const uint64_t qh = make_smem_desc<16>(sbase + AT_OFF_QH), ql = make_smem_desc<16>(sbase + AT_OFF_QL);
+    const uint64_t kh = make_smem_desc<16>(sbase + AT_OFF_KH), kl = make_smem_desc<16>(sbase + AT_OFF_KL);
+    uint32_t acc = 0;
+    if (products == 3) {
+#pragma unroll
+      for (int k = 0; k < 2; ++k) { umma_tf32(t_s, ql + 2 * k, kh + 2 * k, idesc, acc); acc = 1; }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) umma_tf32(t_s, qh + 2 * k, kl + 2 * k, idesc, 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < 2; ++k) { umma_tf32(t_s, qh + 2 * k, kh + 2 * k, idesc, acc); acc = 1; }
+    umma_commit(&mma_bar);
+  };
+
+  // ---------------- pass 1: row maxima ----------------
+  float m = -INFINITY;
+  for (int b = 0; b < n_blocks; ++b) {
+    const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
+    stage_k(k0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) { tc_fence_after(); issue_s(n_s); }
+    mbar_wait(&mma_bar, phase); phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      if (half * 32 < n_s) {                                       // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_base + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (half * 32 + j < valid) m = fmaxf(m, __uint_as_float(r[j]));
+      }
+    }
+    tc_fence_before();
+    __syncthreads();                                               // every row of S is read before the next block overwrites it / K
+  }
+
+  // ---------------- pass 2: P = exp(s - max), O += P V ----------------
+  float l = 0.f;
+  const float mscaled = m * scale_log2e;
+  for (int b = 0; b < n_blocks; ++b) {
+    const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
+    stage_k(k0);
+    stage_v(k0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) { tc_fence_after(); issue_s(n_s); }
+    mbar_wait(&mma_bar, phase); phase ^= 1;
+    tc_fence_after();
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+      uint8_t* ph = smem + AT_OFF_PH + half * 16384 + row * 128;
+      uint8_t* pl = smem + AT_OFF_PL + half * 16384 + row * 128;
+      if (half * 32 < n_s) {                                       // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_base + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 p;
+          p.x = (half * 32 + j + 0 < valid) ? exp2f(fmaf(__uint_as_float(r[j + 0]), scale_log2e, -mscaled)) : 0.f;
+          p.y = (half * 32 + j + 1 < valid) ? exp2f(fmaf(__uint_as_float(r[j + 1]), scale_log2e, -mscaled)) : 0.f;
+          p.z = (half * 32 + j + 2 < valid) ? exp2f(fmaf(__uint_as_float(r[j + 2]), scale_log2e, -mscaled)) : 0.f;
+          p.w = (half * 32 + j + 3 < valid) ? exp2f(fmaf(__uint_as_float(r[j + 3]), scale_log2e, -mscaled)) : 0.f;
+          l += (p.x + p.y) + (p.z + p.w);
+          const int o = ((j >> 2) ^ (row & 7)) << 4;                // SWIZZLE_128B
+          *reinterpret_cast<float4*>(ph + o) = p;
+          *reinterpret_cast<float4*>(pl + o) = tf32_lo(p);
+        }
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // O[128 x 16] += P[128 x ksteps*8] V[ksteps*8 x 16]; only the k steps that hold valid keys (the rest of P is stale / zero)
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(AT_DH >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+      const int ksteps = (valid + 7) >> 3;
+      uint32_t acc = b ? 1u : 0u;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int p = ks >> 2, k = ks & 3;
+        const uint64_t ph = make_smem_desc<32>(sbase + AT_OFF_PH + p * 16384) + 2 * k, pl = make_smem_desc<32>(sbase + AT_OFF_PL + p * 16384) + 2 * k;
+        const uint64_t vh = make_smem_desc<32>(sbase + AT_OFF_VH + p * 2048) + 2 * k, vl = make_smem_desc<32>(sbase + AT_OFF_VL + p * 2048) + 2 * k;
+        if (products == 3) {
+          umma_tf32(t_o, pl, vh, idesc, acc); acc = 1;
+          umma_tf32(t_o, ph, vl, idesc, 1u);
+        }
+        umma_tf32(t_o, ph, vh, idesc, acc); acc = 1;
+      }
+      umma_commit(&mma_bar);
+    }
+    mbar_wait(&mma_bar, phase); phase ^= 1;                        // P / V / K may be overwritten, S may be recomputed
+    tc_fence_after();
+  }
+
+  // ---------------- O / l -> global ----------------
+  {
+    uint32_t r[16];
+    tmem_ld16(t_o + lane_base, r);
+    tmem_ld_wait();
+    if (q0 + row < T) {
+      const float inv = 1.f / l;
+      float* o = O + (r0 + q0 + row) * (int64_t)ldo + col0;
+#pragma unroll
+      for (int j = 0; j < 16; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv,
+                                                        __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, AT_TMEM_COLS); }
+}
+
+}  // namespace vsg
+
+using namespace vsg;
+
+extern "C" int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off,
+                            int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
+                            void* stream) {
+  VSG_REQUIRE(n_blk >= 0 && n_head > 0 && n_head <= 65535, "vsg_mha_tc16: bad size");
+  if (n_blk == 0) return VSG_OK;
+  VSG_REQUIRE(Q && K && V && O && seg_off && blk_seg && blk_q0, "vsg_mha_tc16: null pointer");
+  VSG_REQUIRE(products == 1 || products == 3, "vsg_mha_tc16: products must be 1 (tf32) or 3 (3xTF32)");
+  VSG_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0,
+              "vsg_mha_tc16: Q / K / V / O must be 16-byte aligned with leading dimensions that are multiples of 4");
+  static PerDeviceFlag attr_done;
+  const int dev_ = current_device();
+  constexpr int SMEM = AT_SMEM + 1024;
+  if (!attr_done.is_set(dev_)) {
+    if (cudaFuncSetAttribute(mha16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+      set_error("vsg_mha_tc16: cannot raise dynamic shared memory to %d", SMEM);
+      return VSG_E_LAUNCH;
+    }
+    attr_done.set(dev_);
+  }
+  const float scale_log2e = 1.4426950408889634f / 4.0f;            // 1 / sqrt(16) * log2(e)
+  mha16_tc_kernel<<<dim3(n_blk, n_head), 128, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, blk_seg, blk_q0, scale_log2e,
+                                                                            products, O, ldo);
+  return check_launch("vsg_mha_tc16");
+}

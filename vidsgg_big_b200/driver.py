@@ -68,22 +68,31 @@ class StagedBatch(object):
         self.stream = stream if stream is not None else torch.cuda.Stream(device=device)
         live = [p for p in proposals if p.num_proposals > 0]
         self.nbytes = 0
+        self._keep = []
         dev_buf = {}
         with torch.cuda.stream(self.stream):
             for name, dt in self.FIELDS:
                 parts = [getattr(p, name) for p in live]
                 if not parts or any(t is None for t in parts):
                     continue
-                if all(t.is_cuda for t in parts):
-                    dev_buf[name] = torch.cat(parts, 0)
-                    continue
-                rows = sum(int(t.shape[0]) for t in parts)
-                host = torch.empty((rows,) + tuple(parts[0].shape[1:]), dtype=dt, pin_memory=True)
-                torch.cat([t.to(dt) for t in parts], 0, out=host)
-                dev_buf[name] = torch.empty(host.shape, dtype=dt, device=device)
-                dev_buf[name].copy_(host, non_blocking=True)
-                self.nbytes += host.numel() * host.element_size()
-                self._keep = getattr(self, "_keep", []) + [host]
+                host_ids = [k for k, t in enumerate(parts) if not t.is_cuda]
+                if host_ids:                                   # the host-resident pieces of this field: one pinned buffer, one async copy
+                    hp = [parts[k].to(dt) for k in host_ids]
+                    rows = sum(int(t.shape[0]) for t in hp)
+                    host = torch.empty((rows,) + tuple(hp[0].shape[1:]), dtype=dt, pin_memory=True)
+                    torch.cat(hp, 0, out=host)
+                    dev = torch.empty(host.shape, dtype=dt, device=device)
+                    dev.copy_(host, non_blocking=True)
+                    self.nbytes += host.numel() * host.element_size()
+                    self._keep.append(host)
+                    r = 0
+                    for k, t in zip(host_ids, hp):
+                        parts[k] = dev[r:r + t.shape[0]]
+                        r += t.shape[0]
+                if len(host_ids) == len(parts):
+                    dev_buf[name] = dev                        # every piece came from the host: the staged buffer IS the batch buffer
+                else:
+                    dev_buf[name] = torch.cat([t.to(dt) for t in parts], 0) if len(parts) > 1 else parts[0].to(dt)
             self.extra = None
             if extra is not None:
                 self.extra = []
@@ -91,7 +100,7 @@ class StagedBatch(object):
                     h = t if (t.is_cuda or t.is_pinned()) else t.pin_memory()
                     self.extra.append(h.to(device, non_blocking=True))
                     self.nbytes += 0 if t.is_cuda else t.numel() * t.element_size()
-                    self._keep = getattr(self, "_keep", []) + [h]
+                    self._keep.append(h)
             self.ready = torch.cuda.Event()
             self.ready.record(self.stream)
         self.proposals: List[TrajProposal] = []

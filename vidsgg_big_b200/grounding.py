@@ -160,6 +160,7 @@ class DEBUG(object):
                                _raw(out), stream_ptr(x.device)), "vsg_dwconv")
         return out
 
+    attention = "tc"         # mh_attn of the video / combined encoders: "tc" = tcgen05 kernel (csrc/attn_tc.cu), "simt" = fp32 SIMT kernel
     fuse_dwconv = True       # depthwise conv inside the point-wise GEMM's operand pipeline (False: separate vsg_dwconv launch)
 
     def _dw_pw(self, x, cw, sq, relu=False, residual=None):
@@ -178,6 +179,8 @@ class DEBUG(object):
         lens = np.diff(seq_off_host)
         return dict(off=seq_off, n=len(seq_off_host) - 1, rows=rows, pos=pos, rem=rem, max_len=int(lens.max()) if lens.size else 0,
                     blocks=linalg.mha_block_list(lens, dev),
+                    # sequences long enough to fill tensor-core tiles (the 3-word query sequences stay on the SIMT kernel)
+                    tc_blocks=linalg.mha_block_list(lens, dev, qb=128) if (lens.size and float(lens.mean()) >= 24) else None,
                     att_flops=4.0 * self.dim_hidden * float((lens.astype(np.float64) ** 2).sum()))     # QK^T + PV over all heads
 
     def _qanet(self, ew, x, sq):
@@ -194,9 +197,16 @@ class DEBUG(object):
         att = torch.empty(x.shape[0], H, dtype=torch.float32, device=x.device)
         ld = qkv.stride(0)
         with linalg._Profile.span("mha", sq["att_flops"]):
-            check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld, _raw(sq["off"]),
-                                sq["n"], 0, sq["max_len"], 8, H // 8, _raw(att), H, _raw(sq["blocks"][0]), _raw(sq["blocks"][1]), sq["blocks"][2],
-                                stream_ptr(x.device)), "vsg_mha")
+            if self.attention == "tc" and m != linalg.SIMT and sq["tc_blocks"] is not None:
+                # tcgen05 attention (csrc/attn_tc.cu): fp32-class modes split every operand 3xTF32-style, the reduced modes run one tf32 pass
+                products = 3 if m in (linalg.X3TF32, linalg.TF32_BF16X2) else 1
+                bs, bq, nb = sq["tc_blocks"]
+                check(lib().vsg_mha_tc16(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld,
+                                         _raw(sq["off"]), 8, _raw(att), H, _raw(bs), _raw(bq), nb, products, stream_ptr(x.device)), "vsg_mha_tc16")
+            else:
+                check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld, _raw(sq["off"]),
+                                    sq["n"], 0, sq["max_len"], 8, H // 8, _raw(att), H, _raw(sq["blocks"][0]), _raw(sq["blocks"][1]), sq["blocks"][2],
+                                    stream_ptr(x.device)), "vsg_mha")
         res = gemm(m, att, ew["out"], residual=res)                                 # attn + res (:129-130)
         out = self._ln(res, ew["norme"])
         return gemm(m, out, ew["fc"], relu=True, residual=res)                      # relu(fc(LN)) + res (:133-136)

@@ -70,14 +70,14 @@ class _Profile(object):
     with ``span``.  ``stage`` is a free-form label set by the caller (e.g. "bigc" / "grounding") and stored with each record."""
     enabled = False
     stage = ""
-    records = []          # (start_event, end_event, useful_flops, kind, stage)
+    records = []          # (start_event, end_event, useful_flops, kind, stage, meta)
 
     @classmethod
     def begin(cls):
         cls.enabled, cls.records, cls.stage = True, [], ""
 
     @classmethod
-    def span(cls, kind, flops=0.0):
+    def span(cls, kind, flops=0.0, meta=None):
         """Context manager: brackets the enclosed launches with events on the current stream (no-op unless enabled)."""
         import contextlib
 
@@ -90,7 +90,7 @@ class _Profile(object):
             ev0.record()
             yield
             ev1.record()
-            cls.records.append((ev0, ev1, float(flops), kind, cls.stage))
+            cls.records.append((ev0, ev1, float(flops), kind, cls.stage, meta))
         return cm()
 
     @classmethod
@@ -99,6 +99,16 @@ class _Profile(object):
         cls.enabled = False
         torch.cuda.synchronize()
         out = cls.summary(kind, stage)
+        return out
+
+    @classmethod
+    def table(cls, kind=None):
+        """[(kind, stage, meta, ms, useful TFLOP/s)] of every record (after ``end``)."""
+        out = []
+        for r in cls.records:
+            if kind is None or r[3] == kind:
+                ms = r[0].elapsed_time(r[1])
+                out.append((r[3], r[4], r[5], ms, r[2] / (ms * 1e-3) / 1e12 if ms > 0 else 0.0))
         return out
 
     @classmethod
@@ -121,7 +131,7 @@ def cast_bf16(x: torch.Tensor, K: Optional[int] = None, out: Optional[torch.Tens
         out = torch.empty(x.shape[0], ld, dtype=torch.bfloat16, device=x.device)
     assert out.dtype == torch.bfloat16 and out.stride(1) == 1 and out.stride(0) % 8 == 0 and out.shape[1] >= K
     LAUNCHES[0] += 1
-    with _Profile.span("cast"):
+    with _Profile.span("cast", 0.0, (x.shape[0], K)):
         check(lib().vsg_cast_bf16(_raw(x), x.stride(0) if x.shape[0] > 1 else max(x.stride(0), K), x.shape[0], K, _raw(out),
                                   out.stride(0) if x.shape[0] > 1 else max(out.stride(0), ld), stream_ptr(x.device)), "vsg_cast_bf16")
     return out
@@ -191,7 +201,7 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
                              _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
     if _Profile.enabled:
         ev1.record()
-        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage))
+        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage, (M, W.N, K)))
     return out
 
 
@@ -227,7 +237,7 @@ def _gemm_bf16(A, W, out, relu, rowbias, rb_index, rb_period, accumulate, bias, 
         a.C16 = out16.data_ptr(); a.ldc16 = out16.stride(0) if M > 1 else max(out16.stride(0), W.N)
     a.batch = 1; a.batch_inner = 1
     LAUNCHES[0] += 1
-    with _Profile.span("gemm", 2.0 * M * W.N * K):
+    with _Profile.span("gemm", 2.0 * M * W.N * K, (M, W.N, K)):
         check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
     return out if f32_out else out16
 
@@ -258,7 +268,7 @@ def gemm_batched(mode: int, A: torch.Tensor, W_hi: torch.Tensor, W_lo: Optional[
     check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(out.device)), "vsg_gemm_ex")
     if _Profile.enabled:
         ev1.record()
-        _Profile.records.append((ev0, ev1, 2.0 * M * N * K * batch, "gemm", _Profile.stage))
+        _Profile.records.append((ev0, ev1, 2.0 * M * N * K * batch, "gemm", _Profile.stage, (M, N, K, batch)))
     return out
 
 
