@@ -56,6 +56,8 @@ def parse():
     ap.add_argument("--vidor-videos", type=int, default=835, help="size of the VidOR-val-shaped set of the 'vidor' leg (0: skip the leg)")
     ap.add_argument("--vidor-passes", type=int, default=2, help="timed passes over the VidOR set")
     ap.add_argument("--chunk-rows", type=int, default=2_500_000, help="feature rows per resident chunk of the VidOR set")
+    ap.add_argument("--no-graph", action="store_true", help="issue the BIG-C forward's ~150 launches from Python every step instead of "
+                    "replaying the CUDA graph captured for the resident batch")
     ap.add_argument("--modes", default="", help="comma list of extra precisions to time on the top-level workload (e.g. bf16)")
     return ap.parse_args()
 
@@ -202,9 +204,9 @@ def peaks():
 # the step (our arm)
 # ------------------------------------------------------------------------------------------------------
 class Pipeline(object):
-    def __init__(self, kind, precision, device, rank=0):
+    def __init__(self, kind, precision, device, rank=0, graph=False):
         from vidsgg_big_b200 import bigc, grounding
-        self.rank, self.kind = rank, kind
+        self.rank, self.kind, self.graph = rank, kind, graph
         if kind == "vidor":
             gcfg = synth.grounding_config()
             self.grd = grounding.DEBUG(gcfg, is_train=False, precision=precision)
@@ -244,7 +246,7 @@ class Pipeline(object):
         viou, spans, mask, seg, _ = geometry.traj_viou_batched(tt, tt)                 # pair geometry, all videos, one launch
         if timers is not None:
             timers["geo1"].record()
-        packed = self.model.forward_packed(props, topk=self.wl["topk"], packed_videos=pk, sync=False)
+        packed = self.model.forward_packed(props, topk=self.wl["topk"], packed_videos=pk, sync=False, graph=self.graph)
         done = torch.cuda.Event()
         done.record()
         return dict(tt=tt, packed=packed, viou=viou, done=done, props=props)
@@ -534,9 +536,20 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     hbm_peak, tc_peak, peak_src = peaks()
     ev = lambda: torch.cuda.Event(enable_timing=True)
     timers = {"geo0": ev(), "geo1": ev(), "grd0": ev(), "grd1": ev()}
+    # The launches are issued from Python here (no graph replay) so that each can be bracketed by events.  Many of them run for less
+    # time than Python needs to issue the next one; an event pair would then also measure the GPU waiting for the host.  A spin kernel in
+    # front of each stage gives the host a head start, so the brackets hold kernel time only.
+    graph, pipe.graph = pipe.graph, False
+    spin = lambda ms: torch.cuda._sleep(int(ms * 1e-3 * 1.9e9))
     linalg._Profile.begin()
-    pipe.step(props, graphs, timers, gather=False)
+    spin(60)
+    h = pipe.launch(props, timers)
+    if pipe.kind == "vidor":
+        h["packed"].counts          # the grounding stage needs the query counts on the host (as in the timed path)
+        spin(30)
+    pipe.finish(h, graphs, gather=False, timers=timers)
     linalg._Profile.end()
+    pipe.graph = graph
     P = linalg._Profile
     slots = {"tf32+bf16x2": 4.0, "3xtf32": 6.0, "tf32": 2.0, "bf16": 1.0}.get(precision)      # bf16-equivalent tensor slots per useful MAC
     out = {}
@@ -847,7 +860,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    pipe = Pipeline(args.workload, args.precision, device, rank)
+    pipe = Pipeline(args.workload, args.precision, device, rank, graph=not args.no_graph)
     seeds = [1000 + 100000 * rank + i for i in range(args.videos)]
     cfg, wl, props, graphs, feats = make_videos(args.workload, seeds, device, seeds[0])
 
@@ -939,7 +952,7 @@ def main():
     # ---- other precisions on the same batch (same GT): time, triplet identity against the default mode's output ----
     modes = {}
     for prec in [m for m in args.modes.split(",") if m and m != args.precision]:
-        alt = Pipeline(args.workload, prec, device, rank)
+        alt = Pipeline(args.workload, prec, device, rank, graph=not args.no_graph)
         alt._gts = pipe._gts
         with torch.no_grad():
             a = alt.model(props, topk=alt.wl["topk"])
@@ -996,6 +1009,7 @@ def main():
             "run": {"videos_per_gpu": args.videos, "precision": args.precision,
                     "grounding": "in the 'vidor' object (VidVRD has no grounding stage, tools/eval_vidvrd.py)" if args.workload == "vidvrd" else "grd_model_v5 dims, 10 bins",
                     "l2": "inputs (%.1f GB per GPU) exceed L2" % (in_bytes / 1e9), "pipelined": bool(pipelined),
+                    "cuda_graph": "BIG-C forward of the resident batch replayed from a CUDA graph" if not args.no_graph else "off",
                     "result": {"mAP": metrics[0], "R@50": metrics[1], "R@100": metrics[2], "triplets": n_trip}},
             "roofline": roofline, "cpu_baseline": cpu, "parity_vs_cpu_oracle": parity, "e2e": e2e, "gpu_launches": n_launches,
             "clocks": clk, "modes": modes or None, "vidor": vidor,

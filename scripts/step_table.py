@@ -25,7 +25,12 @@ for prec in precs:
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); pipe.step(props, g2, gather=False); e1.record(); torch.cuda.synchronize()
     linalg._Profile.begin()
-    pipe.step(props, g2, gather=False)
+    torch.cuda._sleep(int(60e-3 * 1.9e9))          # head start for the host: the event brackets then hold kernel time only
+    h = pipe.launch(props)
+    if kind == "vidor":
+        h["packed"].counts
+        torch.cuda._sleep(int(30e-3 * 1.9e9))
+    pipe.finish(h, g2, gather=False)
     linalg._Profile.end()
     print("==== %s %s %d videos: step %.2f ms" % (kind, prec, n, e0.elapsed_time(e1)))
     agg = {}

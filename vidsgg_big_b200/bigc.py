@@ -561,16 +561,44 @@ class BIG_C(object):
         """Index arrays / packed views of a batch (reusable across calls while the batch is resident in HBM)."""
         return PackedVideos(proposal_list, self.device)
 
-    def forward_packed(self, proposal_list, topk=None, packed_videos=None, sync=True):
+    def forward_packed(self, proposal_list, topk=None, packed_videos=None, sync=True, graph=False):
         """Same computation as ``forward`` for a batch of non-empty videos, but the result stays packed on the device
-        (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``."""
+        (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``.
+        ``graph=True`` (needs ``packed_videos``): the ~150 launches of the forward are captured ONCE per packed batch into a CUDA graph
+        and replayed on later calls -- same kernels, same buffers, one launch call instead of ~150 Python-issued ones (the decoder's
+        launches are shorter than the time Python needs to issue them).  The batch's input buffers must stay at their addresses."""
         if self._w is None:
             raise VsgError("BIG_C has no weights on a CUDA device: call load_state_dict(...) and .cuda() first")
         self.topk = self.default_topk if topk is None else topk
         assert all(p.num_proposals > 0 for p in proposal_list)
         pk = packed_videos if packed_videos is not None else PackedVideos(proposal_list, self.device)
+        if graph and packed_videos is not None:
+            return self._forward_graph(pk, self.topk, sync)
         logits, so, _ = self._encode2decode(pk)
         return self._construct_triplets(pk, logits, so, self.topk, packed=True, sync=sync)
+
+    def _forward_graph(self, pk: PackedVideos, topk: int, sync: bool):
+        key = (id(self), topk, self.mode, self.attention)
+        graphs = pk.__dict__.setdefault("_graphs", {})
+        if key not in graphs:
+            # one eager pass first: lazy per-device initialisation (function attributes, tensor-map cache) must not happen under capture
+            logits, so, _ = self._encode2decode(pk)
+            self._construct_triplets(pk, logits, so, topk, packed=True, sync=False)
+            del logits, so
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                logits, so, _ = self._encode2decode(pk)
+                out = self._construct_triplets(pk, logits, so, topk, packed=True, sync=False)
+            graphs[key] = (g, out)
+        g, out = graphs[key]
+        g.replay()
+        # the graph's output buffers are overwritten by the next replay: hand out copies (a few MB, stream-ordered)
+        res = PackedTriplets(out.quint.clone(), out.scores.clone(), out.spans.clone(), out.qids.clone(), None, out.cap,
+                             counts_dev=out._counts_dev.clone())
+        if sync:
+            res.counts
+        return res
 
     def forward_debug(self, proposal):
         """(pred_queries, pred_logits [Q,P], att_matrx [2,Q,n]) of one video, like ``encode2decode`` (:434-475)."""

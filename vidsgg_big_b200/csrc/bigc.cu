@@ -996,6 +996,67 @@ extern "C" int vsg_broadcast_rows(const float* x, int period, int D, int64_t row
   return check_launch("vsg_broadcast_rows");
 }
 
+// Very short sequences (the grounding query encoder attends over the 3 words of a query, grd_model_v5.py:342): one THREAD per
+// (sequence, query position, head) -- scores, softmax and the weighted sum of <= 8 keys in registers.  The tiled kernel would stage
+// 90 KB of shared memory per 3-token sequence (measured: 0.53 ms for 19k sequences at 25 % occupancy).
+__global__ void __launch_bounds__(256)
+mha_tiny16_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
+                  const int64_t* __restrict__ seg_off, int n_seg, int max_len, int n_head, float scale, float* __restrict__ O, int ldo) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int h = (int)(i % n_head);
+  const int64_t t = i / n_head;
+  const int qi = (int)(t % max_len);
+  const int64_t seg = t / max_len;
+  if (seg >= n_seg) return;
+  const int64_t r0 = seg_off[seg];
+  const int L = (int)(seg_off[seg + 1] - r0);
+  if (qi >= L) return;
+  float q[16];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    const float4 x = *reinterpret_cast<const float4*>(Q + (r0 + qi) * (int64_t)ldq + h * 16 + 4 * c);
+    q[4 * c] = x.x; q[4 * c + 1] = x.y; q[4 * c + 2] = x.z; q[4 * c + 3] = x.w;
+  }
+  float sc[8];
+  float m = -INFINITY;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = -INFINITY;
+    if (j < L) {
+      float d = 0.f;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(K + (r0 + j) * (int64_t)ldk + h * 16 + 4 * c);
+        d = fmaf(q[4 * c], x.x, d); d = fmaf(q[4 * c + 1], x.y, d); d = fmaf(q[4 * c + 2], x.z, d); d = fmaf(q[4 * c + 3], x.w, d);
+      }
+      sc[j] = d * scale;
+      m = fmaxf(m, sc[j]);
+    }
+  }
+  float sum = 0.f;
+  float o[16];
+#pragma unroll
+  for (int c = 0; c < 16; ++c) o[c] = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    if (j < L) {
+      const float p = expf(sc[j] - m);
+      sum += p;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float4 x = *reinterpret_cast<const float4*>(V + (r0 + j) * (int64_t)ldv + h * 16 + 4 * c);
+        o[4 * c] = fmaf(p, x.x, o[4 * c]); o[4 * c + 1] = fmaf(p, x.y, o[4 * c + 1]);
+        o[4 * c + 2] = fmaf(p, x.z, o[4 * c + 2]); o[4 * c + 3] = fmaf(p, x.w, o[4 * c + 3]);
+      }
+    }
+  }
+  const float inv = 1.f / sum;
+#pragma unroll
+  for (int c = 0; c < 4; ++c)
+    *reinterpret_cast<float4*>(O + (r0 + qi) * (int64_t)ldo + h * 16 + 4 * c) =
+        make_float4(o[4 * c] * inv, o[4 * c + 1] * inv, o[4 * c + 2] * inv, o[4 * c + 3] * inv);
+}
+
 extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
                        int fixed_len, int max_len, int n_head, int head_dim, float* O, int ldo, const int32_t* blk_seg,
                        const int32_t* blk_q0, int n_blocks, void* stream) {
@@ -1008,6 +1069,12 @@ extern "C" int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const f
               "vsg_mha: Q/K/V must be 16-byte aligned with leading dimensions that are multiples of 4");
   VSG_REQUIRE((blk_seg == nullptr) == (blk_q0 == nullptr), "vsg_mha: blk_seg and blk_q0 go together");
   if (blk_seg && n_blocks == 0) return VSG_OK;
+  if (head_dim == 16 && seg_off != nullptr && max_len <= 8 && (ldo % 4) == 0 && aligned16(O)) {
+    const int64_t threads = (int64_t)n_seg * max_len * n_head;
+    mha_tiny16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, n_seg, max_len,
+                                                                                          n_head, scale, O, ldo);
+    return check_launch("vsg_mha(tiny)");
+  }
   dim3 grid(blk_seg ? n_blocks : n_seg, n_head, blk_seg ? 1 : (max_len + MHA_QB - 1) / MHA_QB);
   const int sk = head_dim >= 64 ? 128 : 256;
   const size_t smem = (size_t)(MHA_QB * head_dim + sk * head_dim + sk * MHA_PITCH) * sizeof(float);

@@ -402,6 +402,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                         ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     const bool bias_vec = (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0;
     const bool c16_vec = ((ep.ldc16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C16) & 7) == 0);
+    const bool c16_tile = ep.C16 && ((ep.ldc16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.C16) & 15) == 0);
     const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
       const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank);
@@ -496,6 +497,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               bulk_commit();
             }
             sbuf ^= 1;
+          }
+        } else if (!ep.C && c16_tile && slab_rows_ok && col0 + 32 <= ep.N && bias_vec) {       // warp-uniform
+          // bf16-only output (the A operand of the next bf16 GEMM): the lane's 32 values are packed to 64 bytes, transposed through the
+          // warp's staging buffer and written as 16-byte pieces, four lanes per row -- every store instruction covers 8 full rows
+          // (per-lane row stores would touch 32 different rows with 8 bytes each)
+          uint8_t* sb = stg;
+          __syncwarp();
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[j + i]);
+            if (ep.bias) {
+              const float4 b0 = *reinterpret_cast<const float4*>(ep.bias + col0 + j), b1 = *reinterpret_cast<const float4*>(ep.bias + col0 + j + 4);
+              v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w; v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+            }
+            if (rb) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += rb[col0 + j + i];
+            }
+            if (ep.relu) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] = fmaxf(v[i], 0.f);
+            }
+            if (res) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[i] += res[col0 + j + i];
+            }
+            __nv_bfloat162 p[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) p[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+            // 64-byte rows; 16-byte chunk q of row l sits at chunk q ^ ((l >> 1) & 3) (conflict-free for both access patterns)
+            *reinterpret_cast<uint4*>(sb + lane * 64 + ((((j >> 3)) ^ ((lane >> 1) & 3)) << 4)) = *reinterpret_cast<const uint4*>(p);
+          }
+          __syncwarp();
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int rr = i * 8 + (lane >> 2), q = lane & 3;
+            const uint4 x = *reinterpret_cast<const uint4*>(sb + rr * 64 + ((q ^ ((rr >> 1) & 3)) << 4));
+            *reinterpret_cast<uint4*>(ep.C16 + (size_t)(m0 + quad * 32 + rr) * ep.ldc16 + col0 + q * 8) = x;
           }
         } else if (row_ok) {
           if (col0 + 32 <= ep.N && (vec_ok || (!ep.C && bias_vec))) {
