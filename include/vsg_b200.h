@@ -340,6 +340,71 @@ int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int 
                           int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
                           void* stream);
 
+/* ---- Whole-forward entry points (last row): the BIG-C classification forward as ONE call -----------------------------
+ * vsg_bigc_forward runs models/model_0v10.py:434-507 (+ :707-785) / models/model_0v7.py:483-513 for a packed batch of videos: the same
+ * launch sequence the Python host layer (vidsgg_big_b200/bigc.py) issues, from C, so that a non-Python host can run the path and a
+ * step is one call (capturable into one CUDA graph).  Nothing is allocated: every intermediate lives in the caller's workspace
+ * (vsg_bigc_workspace_bytes), the outputs in the caller's VsgTripletOut buffers.  Results are bit-identical to the op-by-op path. */
+
+/* One nn.Linear / 1x1 conv / conv-tap weight [N][K] in the layouts the GEMM modes read (see vsg_gemm_ex): fp32 `w` always; `hi`/`lo`
+ * for VSG_GEMM_3XTF32; `w16`/`lo16` (+ optional `img`) for VSG_GEMM_TF32_BF16X2; `w16` for VSG_GEMM_BF16.  bias may be NULL. */
+typedef struct VsgLinear {
+  const float* w; const float* bias; int N, K, ldw;
+  const float* hi; const float* lo;
+  const void* w16; const void* lo16; int ld16;
+  const void* img; int img_bn;
+} VsgLinear;
+
+typedef struct VsgNorm { const float* gamma; const float* beta; } VsgNorm;
+
+typedef struct VsgBigCEncLayer { VsgLinear qkv, out, l1, l2; VsgNorm n1, n2; } VsgBigCEncLayer;                 /* model_0v10.py:103-117 */
+typedef struct VsgBigCDecLayer {                                                                                /* model_0v10.py:178-225 */
+  VsgLinear qk, v, out, p2a, e2a, r1_0, r1_1, r2, f1, f2;    /* qk / v: rows [0,2P) / [2P,3P) of in_proj; r2: fc_rolewise.{0,1}.2 concatenated along K */
+  VsgNorm n1, n2, n3;
+} VsgBigCDecLayer;
+
+#define VSG_MAX_LAYERS 12
+typedef struct VsgBigCWeights {
+  int variant;              /* 0 = model_0v10 (VidVRD), 1 = model_0v7 (VidOR) */
+  int dim_enti, dim_pred, dim_feat, dim_clsme, dim_i3d /* 0 = none */, num_querys, num_pred_cats, num_enti_cats;
+  int pool_len, n_enc, n_dec, n_head, use_clsme, has_entiemb, extra_width, dim_z;
+  int tc_attention;         /* 1: decoder self-attention as batched tcgen05 GEMMs (needs head_dim % 32 == 0, Q % 32 == 0) */
+  const float* bbox1_w; const float* bbox1_b;          /* fc_bbox2enti.0 [E][8], [E] */
+  VsgLinear bbox2, feat1, feat2, conv /* tap-major [3E][2E], no bias */, enco1, enco2, i3d, log, log1, log2;
+  const float* conv_b;
+  VsgBigCEncLayer enc[VSG_MAX_LAYERS];
+  VsgBigCDecLayer dec[VSG_MAX_LAYERS];
+  const float* pos; const float* query_init; const float* qk_init /* query_init + pos */;
+  const float* bias_matrix /* [C*C][P] */; const float* entiemb /* [C][dim_clsme] or NULL */;
+} VsgBigCWeights;
+
+/* A packed batch of videos (vidsgg_big_b200.bigc.PackedVideos): rows = box-frames of all tracks of all videos. */
+typedef struct VsgVideoBatch {
+  int n_videos, n_tracks, max_tracks; int64_t n_rows;
+  const float* boxes;          /* [R][4] */
+  const float* feats; int ld_feats;   /* [R][>= dim_feat + extra] */
+  const int64_t* off;          /* [N+1] row range of every track */
+  const int32_t* seg;          /* [V+1] track range of every video */
+  const int64_t* seg64;        /* the same as int64 (segment offsets of the encoder attention) */
+  const int32_t* tmax;         /* [N] longest track of the track's video */
+  const int32_t* track_vid;    /* [N] */
+  const float* wh;             /* [V][2] */
+  const int64_t* dura;         /* [N][2] closed spans */
+  const int64_t* cat_ids;      /* [N] */
+  const float* scores;         /* [N] */
+  const int32_t* mha_blk_seg; const int32_t* mha_blk_q0; int n_mha_blk;   /* ragged (video, 64-track block) work list of vsg_mha */
+} VsgVideoBatch;
+
+typedef struct VsgTripletOut {   /* video v owns rows [v*cap, v*cap + counts[v][0]); cap = num_querys * topk */
+  int64_t* quint; float* scores; int64_t* spans; int64_t* qids; int32_t* counts; int cap;
+} VsgTripletOut;
+
+/* Bytes of workspace vsg_bigc_forward needs for this batch / mode (256-byte aligned carve-up, peak over the forward). */
+int64_t vsg_bigc_workspace_bytes(const VsgBigCWeights* w, const VsgVideoBatch* b, int topk, int precision_mode);
+/* precision_mode = a VSG_GEMM_* mode.  workspace: device memory, 256-byte aligned.  Enqueues ~150 launches on `stream`; no sync. */
+int vsg_bigc_forward(const VsgBigCWeights* w, const VsgVideoBatch* b, VsgTripletOut* out, int topk, int precision_mode,
+                     void* workspace, int64_t workspace_bytes, void* stream);
+
 /* ---- Base-C pairwise baseline (models/model_pairwise_baseline.py) -----------------------------
  * The per-track encoding and the pair MLP are the BIG-C kernels + vsg_gemm; these two entry points are what is specific to it. */
 

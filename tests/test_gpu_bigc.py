@@ -294,3 +294,49 @@ def test_vidvrd_test_size_batch_identical_triplets_and_recall():
     ref = oe.evaluate(gts, prs)
     assert r50 == float(ref[1][50]) and r100 == float(ref[1][100])
     assert abs(m_ap - ref[0]) < 5e-5      # AP integrates over score ORDER: scores equal to 1e-6 can swap two near-tied predictions
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "tf32", "3xtf32", "tf32+bf16x2", "bf16"])
+@pytest.mark.parametrize("which", ["tiny_vidvrd", "tiny_vidor", "vidvrd", "vidor"])
+def test_c_forward_entry_equals_python_issued_launches(which, precision):
+    """vsg_bigc_forward (ONE C call: csrc/forward.cu, include/vsg_b200.h) against the same launches issued op by op from Python:
+    bit-identical triplets / scores / spans / query ids / counts for a ragged batch, in every precision mode and both model variants;
+    also through the CUDA-graph replay."""
+    from vidsgg_big_b200 import bigc
+    cfg = {"tiny_vidvrd": synth.tiny_vidvrd_config, "tiny_vidor": synth.tiny_vidor_config, "vidvrd": synth.vidvrd_config,
+           "vidor": synth.vidor_config}[which]()
+    if which == "tiny_vidor":
+        cfg["_force_entiemb"] = False
+    feat = cfg["dim_feat"] + (cfg.get("dim_i3d") or 0 if cfg["variant"] == "vidvrd" else cfg["dim_clsme"])
+    st = synth.make_bigc_state(3, cfg)
+    model = _model(cfg, st, precision)
+    props = [synth.make_proposal(4000 + i, n, vl, feat, cfg["num_enti_cats"], min_len=5, max_len=60).to(DEV)
+             for i, (n, vl) in enumerate([(7, 90), (1, 40), (19, 150), (12, 64)])]
+    topk = 3 if cfg["variant"] == "vidor" else 10
+    pk = model.pack(props)
+    outs = {}
+    with torch.no_grad():
+        for backend in ("py", "c"):
+            model.backend = backend
+            outs[backend] = model.forward_packed(props, topk=topk, packed_videos=pk)
+        model.backend = "c"
+        outs["graph"] = model.forward_packed(props, topk=topk, packed_videos=pk, graph=True)
+        outs["graph2"] = model.forward_packed(props, topk=topk, packed_videos=pk, graph=True)      # replay
+    a = outs["py"]
+    assert a.counts[:, 0].sum() > 0
+    for k in ("c", "graph", "graph2"):
+        b = outs[k]
+        assert np.array_equal(a.counts, b.counts), k
+        for v in range(len(props)):
+            n = int(a.counts[v, 0])
+            s = slice(v * a.cap, v * a.cap + n)
+            assert torch.equal(a.quint[s], b.quint[s]) and torch.equal(a.scores[s], b.scores[s]), (k, v)
+            assert torch.equal(a.spans[s], b.spans[s]) and torch.equal(a.qids[s], b.qids[s]), (k, v)
+    # the reference-style per-video API goes through the same entry point
+    model.backend = "c"
+    res = model(props, topk=topk)
+    for v, r in enumerate(res):
+        n = int(a.counts[v, 0])
+        assert (r is None) == (int(a.counts[v, 1]) == 0)
+        if r is not None:
+            assert torch.equal(r[0], a.quint[v * a.cap: v * a.cap + n])

@@ -42,6 +42,47 @@ class VsgGemmArgs(C.Structure):
                 ("A16", p), ("lda16", i32), ("C16", p), ("ldc16", i32)]
 
 
+class VsgLinear(C.Structure):
+    _fields_ = [("w", p), ("bias", p), ("N", i32), ("K", i32), ("ldw", i32), ("hi", p), ("lo", p), ("w16", p), ("lo16", p), ("ld16", i32),
+                ("img", p), ("img_bn", i32)]
+
+
+class VsgNorm(C.Structure):
+    _fields_ = [("gamma", p), ("beta", p)]
+
+
+class VsgBigCEncLayer(C.Structure):
+    _fields_ = [("qkv", VsgLinear), ("out", VsgLinear), ("l1", VsgLinear), ("l2", VsgLinear), ("n1", VsgNorm), ("n2", VsgNorm)]
+
+
+class VsgBigCDecLayer(C.Structure):
+    _fields_ = [(k, VsgLinear) for k in ("qk", "v", "out", "p2a", "e2a", "r1_0", "r1_1", "r2", "f1", "f2")] + \
+               [(k, VsgNorm) for k in ("n1", "n2", "n3")]
+
+
+VSG_MAX_LAYERS = 12
+
+
+class VsgBigCWeights(C.Structure):
+    _fields_ = [(k, i32) for k in ("variant", "dim_enti", "dim_pred", "dim_feat", "dim_clsme", "dim_i3d", "num_querys", "num_pred_cats",
+                                   "num_enti_cats", "pool_len", "n_enc", "n_dec", "n_head", "use_clsme", "has_entiemb", "extra_width", "dim_z",
+                                   "tc_attention")] + \
+               [("bbox1_w", p), ("bbox1_b", p)] + \
+               [(k, VsgLinear) for k in ("bbox2", "feat1", "feat2", "conv", "enco1", "enco2", "i3d", "log", "log1", "log2")] + \
+               [("conv_b", p), ("enc", VsgBigCEncLayer * VSG_MAX_LAYERS), ("dec", VsgBigCDecLayer * VSG_MAX_LAYERS),
+                ("pos", p), ("query_init", p), ("qk_init", p), ("bias_matrix", p), ("entiemb", p)]
+
+
+class VsgVideoBatch(C.Structure):
+    _fields_ = [("n_videos", i32), ("n_tracks", i32), ("max_tracks", i32), ("n_rows", i64), ("boxes", p), ("feats", p), ("ld_feats", i32),
+                ("off", p), ("seg", p), ("seg64", p), ("tmax", p), ("track_vid", p), ("wh", p), ("dura", p), ("cat_ids", p), ("scores", p),
+                ("mha_blk_seg", p), ("mha_blk_q0", p), ("n_mha_blk", i32)]
+
+
+class VsgTripletOut(C.Structure):
+    _fields_ = [("quint", p), ("scores", p), ("spans", p), ("qids", p), ("counts", p), ("cap", i32)]
+
+
 class VsgError(RuntimeError):
     pass
 
@@ -65,6 +106,8 @@ SIGNATURES = {
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
+    "vsg_bigc_workspace_bytes": (i64, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), i32, i32]),
+    "vsg_bigc_forward": (i32, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), C.POINTER(VsgTripletOut), i32, i32, p, i64, p]),
     "vsg_pair_ids_batched": (i32, [p, i32, p, i64, p, p, p]),
     "vsg_pair_construct_triplet": (i32, [p, i32, i32, i32, p, p, i64, p, i32, p, p, p, p, p, i32, i32, p, p, p, p, p, p, p]),
     "vsg_tiou": (i32, [p, i32, p, i32, i32, i32, i32, p, p]),

@@ -132,6 +132,7 @@ class BIG_C(object):
         self.precision = precision
         self.mode = linalg.MODES[precision]
         self.attention = "tc"      # decoder self-attention: "tc" = batched tcgen05 GEMMs (+ glue), "simt" = fp32 SIMT kernel
+        self.backend = "c"         # forward_packed: "c" = ONE call of vsg_bigc_forward (csrc/forward.cu), "py" = the same launches from Python
         self.topk = 10
         self.device = None
         self._w = None
@@ -261,6 +262,85 @@ class BIG_C(object):
         else:
             w["log"] = W("fc_pred2logits")
         self._w = w
+        self._cw = None            # VsgBigCWeights of the C entry point, built on first use
+
+    # ---- the whole forward as one C call (include/vsg_b200.h: vsg_bigc_forward) ---------------------------
+    def _c_weights(self):
+        from ._cabi import VsgBigCWeights, VsgLinear, VsgNorm, VSG_MAX_LAYERS
+        if self._cw is not None:
+            return self._cw
+        w = self._w
+        if self.n_enco_layers > VSG_MAX_LAYERS or self.n_deco_layers > VSG_MAX_LAYERS:
+            raise VsgError("vsg_bigc_forward holds at most %d layers" % VSG_MAX_LAYERS)
+        addr = lambda t: None if t is None else t.data_ptr()
+
+        def lin(W):
+            l = VsgLinear()
+            l.w, l.bias, l.N, l.K, l.ldw = addr(W.w), addr(W.bias), W.N, W.K, W.w.stride(0)
+            l.hi, l.lo, l.w16, l.lo16, l.ld16 = addr(W.hi), addr(W.lo), addr(W.w16), addr(W.lo16), getattr(W, "ld16", 0)
+            l.img, l.img_bn = addr(W.img), W.img_bn
+            return l
+
+        def norm(n):
+            v = VsgNorm()
+            v.gamma, v.beta = addr(n[0]), addr(n[1])
+            return v
+        c = VsgBigCWeights()
+        c.variant = 1 if self.variant == "vidor" else 0
+        c.dim_enti, c.dim_pred, c.dim_feat, c.dim_clsme, c.dim_i3d = self.dim_enti, self.dim_pred, self.dim_feat, self.dim_clsme, self.dim_i3d or 0
+        c.num_querys, c.num_pred_cats, c.num_enti_cats = self.num_querys, self.num_pred_cats, self.num_enti_cats
+        c.pool_len, c.n_enc, c.n_dec, c.n_head = self.enco_pool_len, self.n_enco_layers, self.n_deco_layers, self.n_att_head
+        c.use_clsme, c.has_entiemb = int(bool(getattr(self, "use_clsme", True))), int(bool(self.has_entiemb))
+        c.extra_width, c.dim_z, c.tc_attention = self.extra_width, self.dim_z, int(self.attention == "tc")
+        c.bbox1_w, c.bbox1_b, c.conv_b = addr(w["bbox1_w"]), addr(w["bbox1_b"]), addr(w["conv_b"])
+        for k in ("bbox2", "feat1", "feat2", "conv", "enco1", "enco2"):
+            setattr(c, k, lin(w[k]))
+        for k in ("i3d", "log", "log1", "log2"):
+            if k in w:
+                setattr(c, k, lin(w[k]))
+        for i, lw in enumerate(w["enc"]):
+            e = c.enc[i]
+            e.qkv, e.out, e.l1, e.l2, e.n1, e.n2 = lin(lw["qkv"]), lin(lw["out"]), lin(lw["l1"]), lin(lw["l2"]), norm(lw["n1"]), norm(lw["n2"])
+        for i, lw in enumerate(w["dec"]):
+            d = c.dec[i]
+            d.qk, d.v, d.out, d.p2a, d.e2a = lin(lw["qk"]), lin(lw["v"]), lin(lw["out"]), lin(lw["p2a"]), lin(lw["e2a"])
+            d.r1_0, d.r1_1, d.r2, d.f1, d.f2 = lin(lw["r1"][0]), lin(lw["r1"][1]), lin(lw["r2"]), lin(lw["f1"]), lin(lw["f2"])
+            d.n1, d.n2, d.n3 = norm(lw["n1"]), norm(lw["n2"]), norm(lw["n3"])
+        c.pos, c.query_init, c.qk_init, c.bias_matrix = addr(w["pos"]), addr(w["query_init"]), addr(w["qk_init"]), addr(w["bias_matrix"])
+        c.entiemb = addr(w.get("entiemb"))
+        self._cw = c
+        return c
+
+    def _forward_c(self, pk: "PackedVideos", topk: int, sync: bool):
+        """``_encode2decode`` + ``_construct_triplets`` through vsg_bigc_forward: one ctypes call, workspace and outputs owned here."""
+        from ._cabi import VsgTripletOut, VsgVideoBatch
+        dev = self.device
+        if pk.feats.shape[1] < self.dim_feat + self.extra_width:
+            raise VsgError("features have %d columns, model needs %d" % (pk.feats.shape[1], self.dim_feat + self.extra_width))
+        cw = self._c_weights()
+        cw.tc_attention = int(self.attention == "tc")
+        b = VsgVideoBatch()
+        b.n_videos, b.n_tracks, b.max_tracks, b.n_rows = pk.V, pk.N, pk.max_tracks, pk.R
+        b.boxes, b.feats, b.ld_feats = pk.boxes.data_ptr(), pk.feats.data_ptr(), pk.feats.stride(0)
+        b.off, b.seg, b.seg64, b.tmax, b.track_vid, b.wh = (t.data_ptr() for t in (pk.off, pk.seg, pk.seg64, pk.tmax, pk.track_vid, pk.wh))
+        b.dura, b.cat_ids, b.scores = pk.dura.data_ptr(), pk.cat_ids.data_ptr(), pk.scores.data_ptr()
+        b.mha_blk_seg, b.mha_blk_q0, b.n_mha_blk = pk.mha_blocks[0].data_ptr(), pk.mha_blocks[1].data_ptr(), pk.mha_blocks[2]
+        V, cap = pk.V, self.num_querys * topk
+        quint = torch.empty(V * cap, 5, dtype=torch.long, device=dev)
+        scores = torch.empty(V * cap, 3, dtype=torch.float32, device=dev)
+        spans = torch.empty(V * cap, 2, dtype=torch.long, device=dev)
+        qids = torch.empty(V * cap, dtype=torch.long, device=dev)
+        counts = torch.empty(V, 2, dtype=torch.int32, device=dev)
+        o = VsgTripletOut()
+        o.quint, o.scores, o.spans, o.qids, o.counts, o.cap = quint.data_ptr(), scores.data_ptr(), spans.data_ptr(), qids.data_ptr(), counts.data_ptr(), cap
+        need = int(lib().vsg_bigc_workspace_bytes(C.byref(cw), C.byref(b), topk, self.mode))
+        if need < 0:
+            check(-1, "vsg_bigc_workspace_bytes")
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        check(lib().vsg_bigc_forward(C.byref(cw), C.byref(b), C.byref(o), topk, self.mode, C.c_void_p(base), need - (base - ws.data_ptr()),
+                                     stream_ptr(dev)), "vsg_bigc_forward")
+        return PackedTriplets(quint, scores, spans, qids, counts.cpu().numpy() if sync else None, cap, counts_dev=counts)
 
     # ---- kernels ------------------------------------------------------------------------------------
     def _add_ln(self, x, a, norm, post=None, period=0, dual=False):
@@ -541,8 +621,7 @@ class BIG_C(object):
             if not batch:
                 return
             pk = PackedVideos([props[i] for i in batch], self.device)
-            logits, so, _ = self._encode2decode(pk)
-            for i, r in zip(batch, self._construct_triplets(pk, logits, so, self.topk)):
+            for i, r in zip(batch, self._forward_eager(pk, self.topk, True).per_video()):
                 results[i] = r
             batch, rows = [], 0
         for i in live:
@@ -574,22 +653,24 @@ class BIG_C(object):
         pk = packed_videos if packed_videos is not None else PackedVideos(proposal_list, self.device)
         if graph and packed_videos is not None:
             return self._forward_graph(pk, self.topk, sync)
+        return self._forward_eager(pk, self.topk, sync)
+
+    def _forward_eager(self, pk, topk, sync):
+        if self.backend == "c" and getattr(self, "_dbg", None) is None:
+            return self._forward_c(pk, topk, sync)
         logits, so, _ = self._encode2decode(pk)
-        return self._construct_triplets(pk, logits, so, self.topk, packed=True, sync=sync)
+        return self._construct_triplets(pk, logits, so, topk, packed=True, sync=sync)
 
     def _forward_graph(self, pk: PackedVideos, topk: int, sync: bool):
-        key = (id(self), topk, self.mode, self.attention)
+        key = (id(self), topk, self.mode, self.attention, self.backend)
         graphs = pk.__dict__.setdefault("_graphs", {})
         if key not in graphs:
             # one eager pass first: lazy per-device initialisation (function attributes, tensor-map cache) must not happen under capture
-            logits, so, _ = self._encode2decode(pk)
-            self._construct_triplets(pk, logits, so, topk, packed=True, sync=False)
-            del logits, so
+            self._forward_eager(pk, topk, False)
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                logits, so, _ = self._encode2decode(pk)
-                out = self._construct_triplets(pk, logits, so, topk, packed=True, sync=False)
+                out = self._forward_eager(pk, topk, False)
             graphs[key] = (g, out)
         g, out = graphs[key]
         g.replay()

@@ -85,23 +85,32 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   uint32_t phase = 0;
   const int n_blocks = (T + AT_KC - 1) / AT_KC;
 
-  auto stage_k = [&](int k0) {
-    for (int idx = tid; idx < AT_KC * 4; idx += 128) {
-      const int r = idx >> 2, c = idx & 3;
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < T) x = *reinterpret_cast<const float4*>(K + (r0 + k0 + r) * (int64_t)ldk + col0 + 4 * c);
+  // K / V blocks go global -> registers -> shared memory in two steps, so that the loads of block b+1 are in flight while block b is
+  // multiplied and exponentiated (the round-2 ncu capture had a third of all warp samples waiting on these loads).
+  // Item idx = it * 128 + tid: key r = idx >> 2 of the block, 16-byte chunk c = idx & 3 (dims 4c .. 4c+3).
+  auto load_kv = [&](const float* base, int ld, int k0, float4 (&x)[2]) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
+      x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) x[it] = *reinterpret_cast<const float4*>(base + (r0 + k0 + r) * (int64_t)ld + col0 + 4 * c);
+    }
+  };
+  auto store_k = [&](const float4 (&x)[2]) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
       const int o = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
-      *reinterpret_cast<float4*>(smem + AT_OFF_KH + o) = x;
-      *reinterpret_cast<float4*>(smem + AT_OFF_KL + o) = tf32_lo(x);
+      *reinterpret_cast<float4*>(smem + AT_OFF_KH + o) = x[it];
+      *reinterpret_cast<float4*>(smem + AT_OFF_KL + o) = tf32_lo(x[it]);
     }
   };
   // V^T: row d (0..15) of panel p holds keys 32p .. 32p+31 (128 bytes); SWIZZLE_128B: chunk q of row d sits at chunk q ^ (d & 7)
-  auto stage_v = [&](int k0) {
-    for (int idx = tid; idx < AT_KC * 4; idx += 128) {
-      const int r = idx >> 2, c = idx & 3;                         // key r of the block, dims 4c .. 4c+3
-      float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < T) x = *reinterpret_cast<const float4*>(V + (r0 + k0 + r) * (int64_t)ldv + col0 + 4 * c);
-      const float xs[4] = {x.x, x.y, x.z, x.w};
+  auto store_v = [&](const float4 (&x)[2]) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
+      const float xs[4] = {x[it].x, x[it].y, x[it].z, x[it].w};
       const int p = r >> 5, kk = r & 31;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
@@ -131,13 +140,17 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
 
   // ---------------- pass 1: row maxima ----------------
   float m = -INFINITY;
+  float4 kreg[2], vreg[2];
+  load_kv(K, ldk, 0, kreg);
   for (int b = 0; b < n_blocks; ++b) {
     const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
-    stage_k(k0);
+    store_k(kreg);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) { tc_fence_after(); issue_s(n_s); }
+    if (b + 1 < n_blocks) load_kv(K, ldk, k0 + AT_KC, kreg);        // next block of pass 1 ...
+    else { load_kv(K, ldk, 0, kreg); load_kv(V, ldv, 0, vreg); }   // ... or the first block of pass 2
     mbar_wait(&mma_bar, phase); phase ^= 1;
     tc_fence_after();
 #pragma unroll
@@ -160,12 +173,13 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   const float mscaled = m * scale_log2e;
   for (int b = 0; b < n_blocks; ++b) {
     const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
-    stage_k(k0);
-    stage_v(k0);
+    store_k(kreg);
+    store_v(vreg);
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) { tc_fence_after(); issue_s(n_s); }
+    if (b + 1 < n_blocks) { load_kv(K, ldk, k0 + AT_KC, kreg); load_kv(V, ldv, k0 + AT_KC, vreg); }
     mbar_wait(&mma_bar, phase); phase ^= 1;
     tc_fence_after();
 #pragma unroll

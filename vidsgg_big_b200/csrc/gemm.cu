@@ -401,6 +401,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const bool vec_ok = ((ep.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C) & 15) == 0) &&
                         ((reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0);
     const bool bias_vec = (reinterpret_cast<uintptr_t>(ep.bias) & 15) == 0;
+    const bool res_vec = ((ep.ld_res & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.residual) & 15) == 0);
     const bool c16_vec = ((ep.ldc16 & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.C16) & 7) == 0);
     const bool c16_tile = ep.C16 && ((ep.ldc16 & 7) == 0) && ((reinterpret_cast<uintptr_t>(ep.C16) & 15) == 0);
     const bool rb_vec = ((ep.ld_rb & 3) == 0) && ((reinterpret_cast<uintptr_t>(ep.rowbias) & 15) == 0);
@@ -455,7 +456,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
             }
             if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-            if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+            if (res) {
+              if (res_vec) { const float4 t4 = *reinterpret_cast<const float4*>(res + col0 + j); v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w; }
+              else { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+            }
             // SWIZZLE_128B: 16-byte chunk q of row r sits at chunk q ^ (r & 7) (buffer is 1024-byte aligned)
             *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
             if (crow16) {
@@ -556,7 +560,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 v.x += o.x; v.y += o.y; v.z += o.z; v.w += o.w;
               }
               if (ep.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              if (res) { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+              if (res) {
+              if (res_vec) { const float4 t4 = *reinterpret_cast<const float4*>(res + col0 + j); v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w; }
+              else { v.x += res[col0 + j]; v.y += res[col0 + j + 1]; v.z += res[col0 + j + 2]; v.w += res[col0 + j + 3]; }
+            }
               if (crow) *dst = v;
               if (crow16 && c16_vec) {
                 const __nv_bfloat162 p0 = __floats2bfloat162_rn(v.x, v.y), p1 = __floats2bfloat162_rn(v.z, v.w);
@@ -614,6 +621,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     int stage = 0;
     uint32_t phase = 0;
     for (int tile = tile0; tile < n_tiles; tile += tile_step) {
+      // CONV: a thread converts the same rows in every k block -- its rows' sequence positions are loaded once per tile (they were
+      // two global loads per 16-byte item and k block: the top stall of the fused kernel in the round-2 ncu capture)
+      constexpr int NI = TILE_A / 16 / 128;
+      int m0c = 0, seq_p[NI], seq_q[NI];
+      if (CONV) {
+        m0c = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank).m0;
+#pragma unroll
+        for (int i = 0; i < NI; ++i) {
+          const int grow = m0c + ((i * 128 + t) >> 2);
+          seq_p[i] = grow < ep.M ? ep.seq_pos[grow] : 0;
+          seq_q[i] = grow < ep.M ? ep.seq_rem[grow] : 0;
+        }
+      }
       for (int kb = 0; kb < kblocks; ++kb) {
         if ((stage % CF::SPLIT_GROUPS) != grp) { if (++stage == STAGES) { stage = 0; phase ^= 1; } continue; }
         mbar_wait(&full[stage], phase);
@@ -621,9 +641,8 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float4* src = reinterpret_cast<const float4*>(st);
         uint8_t* lo16 = st + CF::OFF_AL;
         uint8_t* a16 = st + CF::OFF_A16;
-        const int m0c = CONV ? tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank).m0 : 0;
 #pragma unroll
-        for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : TILE_A / 16 / 128); ++i) {
+        for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : NI); ++i) {
           const int idx = i * 128 + t;
           const int r = idx >> 2, l = (idx & 3) ^ ((r >> 1) & 3);   // logical chunk l = columns 4l .. 4l+3 of row r
           float4 x;
@@ -633,7 +652,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             const int grow = m0c + r, k = ep.dw_k, c = kb * BK + 4 * l;
             x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow < ep.M) {
-              const int p = ep.seq_pos[grow], q = ep.seq_rem[grow];
+              const int p = seq_p[i], q = seq_q[i];
               const float* wv = sdw + c * k;
               x = *reinterpret_cast<const float4*>(sdw + ep.K * k + c);
               const uint8_t* raw = st + CF::OFF_RAW;
