@@ -356,6 +356,7 @@ def run_e2e(pipe, hb, graphs, n_steps, barrier, device):
     """Same step through the public API with HOST buffers: pinned -> device every step, double-buffered on a copy stream so that the
     H2D transfer of step i+1 overlaps the kernels of step i; D2H of the hit arrays inside.  -> (seconds per step, n relations)."""
     copy_stream = torch.cuda.Stream(device=device)
+    graph, pipe.graph = pipe.graph, False      # every step brings a new batch: nothing resident to replay a captured graph on
     copied = [torch.cuda.Event(), torch.cuda.Event()]
     consumed = [torch.cuda.Event(), torch.cuda.Event()]
 
@@ -379,6 +380,7 @@ def run_e2e(pipe, hb, graphs, n_steps, barrier, device):
     w0 = time.perf_counter()
     _, n_rel, _ = run(n_steps)
     barrier()
+    pipe.graph = graph
     return (time.perf_counter() - w0) / n_steps, n_rel
 
 
@@ -488,6 +490,37 @@ def compare_triplets(gpu_trips, cpu_trips):
     return same, total
 
 
+def decision_flips(ref_pipe, alt_pipe, props):
+    """Discrete decisions of a reduced-precision mode against the parity mode on the same batch (SURVEY 8d parity gates): how many
+    queries change their (subject, object) arg-max, how many of the others change their top-k predicate set, and how close to a tie the
+    flipped decisions were in the parity mode (relative margin between the best and the second-best candidate)."""
+    edges = [1e-4, 1e-3, 1e-2, 1e-1]
+
+    def hist(m):
+        m = m.float().cpu().numpy()
+        return {"<1e-4": int((m < edges[0]).sum()), "<1e-3": int(((m >= edges[0]) & (m < edges[1])).sum()),
+                "<1e-2": int(((m >= edges[1]) & (m < edges[2])).sum()), "<1e-1": int(((m >= edges[2]) & (m < edges[3])).sum()),
+                ">=1e-1": int((m >= edges[3]).sum())}
+    with torch.no_grad():
+        pk = ref_pipe.model.pack(props)
+        la, soa, exa = ref_pipe.model._encode2decode(pk, want_att=True)
+        lb, sob, _ = alt_pipe.model._encode2decode(pk)
+    k = ref_pipe.wl["topk"]
+    P = ref_pipe.cfg["num_pred_cats"]
+    so_flip = (soa != sob).any(1)
+    top2 = torch.topk(exa["att"], 2, dim=-1)[0] if exa["att"].shape[-1] > 1 else None           # [VQ, 2 roles, 2]
+    att_margin = ((top2[..., 0] - top2[..., 1]) / top2[..., 0].clamp_min(1e-30)).min(1)[0] if top2 is not None else torch.ones(soa.shape[0], device=soa.device)
+    pa, pb = torch.softmax(la[:, :P], -1), torch.softmax(lb[:, :P], -1)
+    ta, tb = torch.topk(pa, k + 1, dim=-1), torch.topk(pb, k, dim=-1)
+    same_set = (torch.sort(ta[1][:, :k], -1)[0] == torch.sort(tb[1], -1)[0]).all(1)
+    topk_flip = (~same_set) & (~so_flip)
+    topk_margin = (ta[0][:, k - 1] - ta[0][:, k]) / ta[0][:, k - 1].clamp_min(1e-30)
+    return {"queries": int(soa.shape[0]), "so_argmax_flips": int(so_flip.sum()), "topk_set_flips_among_the_rest": int(topk_flip.sum()),
+            "parity_mode_margin_of_so_flips": hist(att_margin[so_flip]), "parity_mode_margin_of_topk_flips": hist(topk_margin[topk_flip]),
+            "parity_mode_margin_all_queries_so": hist(att_margin), "max_rel_logit_diff_unflipped": float(
+                ((la[:, :P] - lb[:, :P]).abs().max(1)[0][~so_flip].max() / la[:, :P].abs().max()).item()) if bool((~so_flip).any()) else None}
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -540,6 +573,7 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     # time than Python needs to issue the next one; an event pair would then also measure the GPU waiting for the host.  A spin kernel in
     # front of each stage gives the host a head start, so the brackets hold kernel time only.
     graph, pipe.graph = pipe.graph, False
+    backend, pipe.model.backend = pipe.model.backend, "py"          # op-by-op launches (bit-identical to the one-call C entry)
     spin = lambda ms: torch.cuda._sleep(int(ms * 1e-3 * 1.9e9))
     linalg._Profile.begin()
     spin(60)
@@ -549,7 +583,7 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
         spin(30)
     pipe.finish(h, graphs, gather=False, timers=timers)
     linalg._Profile.end()
-    pipe.graph = graph
+    pipe.graph, pipe.model.backend = graph, backend
     P = linalg._Profile
     slots = {"tf32+bf16x2": 4.0, "3xtf32": 6.0, "tf32": 2.0, "bf16": 1.0}.get(precision)      # bf16-equivalent tensor slots per useful MAC
     out = {}
@@ -967,6 +1001,7 @@ def main():
         if cpu_trips is not None:
             s2, t2 = compare_triplets(a[:len(cpu_trips)], cpu_trips)
             modes[prec]["videos_with_triplets_identical_to_cpu_oracle"] = s2
+        modes[prec]["decision_flips_vs_%s" % args.precision] = decision_flips(pipe, alt, props)
         del alt
 
     # ---- e2e: same metric through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
@@ -983,9 +1018,25 @@ def main():
         if world > 1:
             dist.all_reduce(tdt, op=dist.ReduceOp.MAX)
         d2h = n_trip_e * (8 + 4 + 24) + args.videos * 8 * 2         # hit scores, ranks, triplet ids; per-video counts
+        # what the platform gives for the same pinned buffer with nothing else running (all ranks copy at once): the e2e ceiling
+        barrier()
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        for _ in range(3):
+            hb.slots[0][0]["feats"].copy_(hb.h["feats"], non_blocking=True)
+        c1.record()
+        barrier()
+        bare = torch.tensor([3 * hb.h["feats"].numel() * 4 / (c0.elapsed_time(c1) * 1e-3) / 1e9], device=device)
+        bare_all = [bare.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(bare_all, bare)
+        bare_all = [float(t.item()) for t in bare_all]
         e2e = {"value": args.videos * world / float(tdt.item()), "unit": "videos/s", "h2d_bytes_per_step": int(hb.nbytes),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "note": "pinned host buffers, H2D double-buffered on a copy stream; GT relations resident"}
+               "bare_h2d_gbs_per_gpu": bare_all, "bare_h2d_gbs_total": sum(bare_all),
+               "h2d_bound_videos_per_s": args.videos * world / (hb.nbytes / (min(bare_all) * 1e9)),
+               "note": "pinned host buffers, H2D double-buffered on a copy stream; GT relations resident; bare_h2d = the same pinned feature "
+                       "buffer copied with every rank copying at once and no kernels running: the platform ceiling of this number"}
         del hb, hprops, hfeats
         torch.cuda.empty_cache()
     del pipe

@@ -460,6 +460,54 @@ int vsg_grounding_post(const float* regr, const float* conf, const float* cls, c
                        float tiou_th, float bins_th, float nms_th, float* pooled, float* probs, uint8_t* mask, int32_t* err_count,
                        void* stream);
 
+/* ---- grounding forward as ONE call (models/grd_model_v5.py:331-373 network + :530-576 post-processing) --------------------------------
+ * The launch sequence of vidsgg_big_b200/grounding.py:_forward_videos for a batch of videos with their classified queries; the
+ * data-dependent index tables (sequence offsets / positions, attention work lists, the per-video linspace clip table) are built by the
+ * caller (host arithmetic on the per-video T and query counts) and passed in VsgGrdBatch.  Bit-identical to the op-by-op path. */
+typedef struct VsgGrdConv { const float* dw_w /* [C][k] */; const float* dw_b; int k; VsgLinear pw; } VsgGrdConv;   /* DepthWiseSeparableConv1d :36-56 */
+typedef struct VsgGrdEncoder {                                                                                    /* QANetEncoderLayer :81-137 */
+  VsgGrdConv convs[4]; VsgLinear qkv, out, fc; VsgNorm normb, norm_seq[4], norme;
+} VsgGrdEncoder;
+typedef struct VsgGrdWeights {
+  int dim_hidden, num_bins, dim_feat;
+  int tc_attention;           /* 1: sequences of mean length >= 24 attend on vsg_mha_tc16 */
+  int fuse_dwconv;            /* 1: depthwise conv inside the point-wise GEMM (mode VSG_GEMM_TF32_BF16X2) */
+  VsgLinear video_fc, vq_fc, proj2sim;
+  const float* proj_enti; const float* proj_pred;      /* word embeddings pre-projected through query_fc: [81][H], [51][H] */
+  const float* temp_w; const float* temp_b; const float* freq; const float* phase;
+  VsgGrdEncoder video_encoder, query_encoder, combined_encoder;
+  VsgGrdConv cls_head[5], conf_head[5], regr_head[5];
+} VsgGrdWeights;
+
+typedef struct VsgGrdSeq {      /* one family of ragged sequences over packed rows */
+  const int64_t* off; int n; int64_t rows; const int32_t* pos; const int32_t* rem; int max_len;
+  const int32_t* blk_seg; const int32_t* blk_q0; int n_blk;          /* vsg_mha work list (64-query blocks) */
+  const int32_t* tc_blk_seg; const int32_t* tc_blk_q0; int n_tc_blk; /* vsg_mha_tc16 work list (128-query blocks); n_tc_blk < 0: not used */
+} VsgGrdSeq;
+
+typedef struct VsgGrdBatch {
+  int n_videos, n_queries, max_T;
+  const float* video_feats;     /* [sum T][dim_feat] */
+  const int64_t* quint;         /* [NQ][5] */
+  const int64_t* spans;         /* [NQ][2] */
+  const float* vlen;            /* [n_videos] video_len as float */
+  const int32_t* q_vid;         /* [NQ] video of every query */
+  const float* clip_tab;        /* [sum T] torch.linspace(0, 1, T_v) per video (:705) */
+  VsgGrdSeq video, query, combined;   /* sequences of clips per video / 3 words per query / clips per query */
+} VsgGrdBatch;
+
+typedef struct VsgGrdOut {
+  float* pooled;    /* [NQ][B+1][2] */
+  float* probs;     /* [NQ][B+1] */
+  uint8_t* mask;    /* [NQ][B+1] */
+  int32_t* err_count;   /* [1], zero-initialised by the caller: #(query, bin) with an empty pooling set (the reference raises there) */
+  float* regr; float* conf; float* cls;   /* optional: raw head outputs [rows_c][2B], [rows_c][B], [rows_c][B] (NULL: kept in the workspace) */
+} VsgGrdOut;
+
+int64_t vsg_grd_workspace_bytes(const VsgGrdWeights* w, const VsgGrdBatch* b, int precision_mode);
+int vsg_grd_forward(const VsgGrdWeights* w, const VsgGrdBatch* b, VsgGrdOut* out, float score_th, float tiou_th, float bins_th, float nms_th,
+                    int precision_mode, void* workspace, int64_t workspace_bytes, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -254,3 +254,28 @@ def test_grounding_vidor_size_vs_oracle(precision, tol):
     both = mask.cpu() & r["mask"]
     a, b = torch.round(pooled.cpu() * r["vl"])[both], torch.round(r["pooled"] * r["vl"])[both]
     assert (a == b).all(-1).float().mean().item() >= 0.97
+
+
+@pytest.mark.parametrize("precision", ["fp32_simt", "tf32", "3xtf32", "tf32+bf16x2", "bf16"])
+def test_c_grounding_forward_equals_python_issued_launches(golden, precision):
+    """vsg_grd_forward (ONE C call, csrc/forward.cu) against the same launches issued op by op from Python: bit-identical network
+    outputs and post-processing results for a ragged batch of videos, every precision mode, with and without the fused depthwise conv
+    and the tcgen05 attention."""
+    g = golden("grounding")
+    model = _model(precision)
+    feats, datas = [], []
+    for sd, n, vl, m in CASES:
+        k = "g%d" % sd
+        feats.append(synth.make_video_feature(sd, vl).to(DEV))
+        datas.append((torch.from_numpy(g[k + "_quint"]).to(DEV), torch.from_numpy(g[k + "_spans"]).to(DEV), vl))
+    for attention, fuse in (("tc", True), ("simt", False)):
+        model.attention, model.fuse_dwconv = attention, fuse
+        outs = {}
+        for backend in ("py", "c"):
+            model.backend = backend
+            outs[backend] = model(feats, datas, with_gt_data=False, **INF)
+            outs[backend + "_net"] = model.forward_propagation_debug(feats[1], datas[1][0], datas[1][1], datas[1][2], TH)
+        for a, b in zip(outs["py"], outs["c"]):
+            assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]), (attention, fuse)
+        for a, b in zip(outs["py_net"][:4], outs["c_net"][:4]):
+            assert torch.equal(a, b), (attention, fuse)

@@ -83,6 +83,37 @@ class VsgTripletOut(C.Structure):
     _fields_ = [("quint", p), ("scores", p), ("spans", p), ("qids", p), ("counts", p), ("cap", i32)]
 
 
+class VsgGrdConv(C.Structure):
+    _fields_ = [("dw_w", p), ("dw_b", p), ("k", i32), ("pw", VsgLinear)]
+
+
+class VsgGrdEncoder(C.Structure):
+    _fields_ = [("convs", VsgGrdConv * 4), ("qkv", VsgLinear), ("out", VsgLinear), ("fc", VsgLinear), ("normb", VsgNorm),
+                ("norm_seq", VsgNorm * 4), ("norme", VsgNorm)]
+
+
+class VsgGrdWeights(C.Structure):
+    _fields_ = [("dim_hidden", i32), ("num_bins", i32), ("dim_feat", i32), ("tc_attention", i32), ("fuse_dwconv", i32),
+                ("video_fc", VsgLinear), ("vq_fc", VsgLinear), ("proj2sim", VsgLinear), ("proj_enti", p), ("proj_pred", p),
+                ("temp_w", p), ("temp_b", p), ("freq", p), ("phase", p),
+                ("video_encoder", VsgGrdEncoder), ("query_encoder", VsgGrdEncoder), ("combined_encoder", VsgGrdEncoder),
+                ("cls_head", VsgGrdConv * 5), ("conf_head", VsgGrdConv * 5), ("regr_head", VsgGrdConv * 5)]
+
+
+class VsgGrdSeq(C.Structure):
+    _fields_ = [("off", p), ("n", i32), ("rows", i64), ("pos", p), ("rem", p), ("max_len", i32), ("blk_seg", p), ("blk_q0", p), ("n_blk", i32),
+                ("tc_blk_seg", p), ("tc_blk_q0", p), ("n_tc_blk", i32)]
+
+
+class VsgGrdBatch(C.Structure):
+    _fields_ = [("n_videos", i32), ("n_queries", i32), ("max_T", i32), ("video_feats", p), ("quint", p), ("spans", p), ("vlen", p),
+                ("q_vid", p), ("clip_tab", p), ("video", VsgGrdSeq), ("query", VsgGrdSeq), ("combined", VsgGrdSeq)]
+
+
+class VsgGrdOut(C.Structure):
+    _fields_ = [("pooled", p), ("probs", p), ("mask", p), ("err_count", p), ("regr", p), ("conf", p), ("cls", p)]
+
+
 class VsgError(RuntimeError):
     pass
 
@@ -108,6 +139,8 @@ SIGNATURES = {
     "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
     "vsg_bigc_workspace_bytes": (i64, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), i32, i32]),
     "vsg_bigc_forward": (i32, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), C.POINTER(VsgTripletOut), i32, i32, p, i64, p]),
+    "vsg_grd_workspace_bytes": (i64, [C.POINTER(VsgGrdWeights), C.POINTER(VsgGrdBatch), i32]),
+    "vsg_grd_forward": (i32, [C.POINTER(VsgGrdWeights), C.POINTER(VsgGrdBatch), C.POINTER(VsgGrdOut), f32, f32, f32, f32, i32, p, i64, p]),
     "vsg_pair_ids_batched": (i32, [p, i32, p, i64, p, p, p]),
     "vsg_pair_construct_triplet": (i32, [p, i32, i32, i32, p, p, i64, p, i32, p, p, p, p, p, i32, i32, p, p, p, p, p, p, p]),
     "vsg_tiou": (i32, [p, i32, p, i32, i32, i32, i32, p, p]),

@@ -26,9 +26,7 @@ struct Arena {
   void release(int64_t m) { off = m; }
 };
 
-struct Fwd {
-  const VsgBigCWeights* w;
-  const VsgVideoBatch* b;
+struct FwdBase {
   int mode;
   Arena ar;
   void* stream;
@@ -37,10 +35,11 @@ struct Fwd {
   bool live() const { return !ar.dry && rc == VSG_OK && !ar.overflow; }
 #define FWD_CALL(expr) do { if (live()) { int rc_ = (expr); if (rc_ != VSG_OK) rc = rc_; } } while (0)
 
-  // C[:, :N] = act(A[:, :K] W^T + bias (+ rowbias[idx]) (+ residual)) -- the argument conventions of linalg.gemm
+  // C[:, :N] = act(A[:, :K] W^T + bias (+ rowbias[idx])) (+ residual) -- the argument conventions of linalg.gemm
   void gemm(const float* A, int lda, const VsgLinear& W, float* C, int ldc, int64_t M, bool relu = false, bool use_bias = true, int K = -1,
             const float* rowbias = nullptr, const int32_t* rb_index = nullptr, int ld_rb = 0, float* C_lo = nullptr, int lo0 = 0, int lo1 = 0,
-            const void* A16 = nullptr, int lda16 = 0, void* C16 = nullptr, int ldc16 = 0) {
+            const void* A16 = nullptr, int lda16 = 0, void* C16 = nullptr, int ldc16 = 0, const float* residual = nullptr, int ld_res = 0,
+            const VsgGrdConv* dw = nullptr, const int32_t* seq_pos = nullptr, const int32_t* seq_rem = nullptr) {
     VsgGemmArgs a;
     memset(&a, 0, sizeof(a));
     if (K < 0) K = W.K;
@@ -50,6 +49,8 @@ struct Fwd {
     a.bias = use_bias ? W.bias : nullptr;
     a.rowbias = rowbias; a.rb_index = rb_index; a.ld_rb = ld_rb;
     a.relu = relu ? 1 : 0;
+    a.residual = residual; a.ld_res = ld_res;
+    if (dw) { a.dw_w = dw->dw_w; a.dw_b = dw->dw_b; a.dw_k = dw->k; a.seq_pos = seq_pos; a.seq_rem = seq_rem; }
     a.C = C; a.ldc = ldc; a.C_lo = C_lo; a.lo_col_begin = lo0; a.lo_col_end = lo1;
     a.batch = 1; a.batch_inner = 1;
     if (mode == VSG_GEMM_TF32_BF16X2) {
@@ -79,6 +80,11 @@ struct Fwd {
     if (out2) FWD_CALL(vsg_add_layernorm_dual(x, D, a, a ? D : 0, n.gamma, n.beta, post, period, rows, D, out, D, out2, D, stream));
     else FWD_CALL(vsg_add_layernorm(x, D, a, a ? D : 0, n.gamma, n.beta, post, period, rows, D, out, D, stream));
   }
+};
+
+struct Fwd : FwdBase {
+  const VsgBigCWeights* w;
+  const VsgVideoBatch* b;
 
   // bigc.BIG_C._mha_tc: S = Q K^T and O = P V as batched tcgen05 GEMMs (one problem per (segment, head)) + softmax / V^T glue
   void mha_tc(const float* qkv, const float* qkv_lo, int n_seg, int Q, int d, float* att) {
@@ -299,6 +305,119 @@ int Fwd::run(VsgTripletOut* out, int topk) {
   return rc;
 }
 
+// ------------------------------------------------------------------------------------------------------------------------------
+// grounding (vidsgg_big_b200/grounding.py: _forward_videos, _qanet, _dw_pw, _head, _post)
+// ------------------------------------------------------------------------------------------------------------------------------
+struct GrdFwd : FwdBase {
+  const VsgGrdWeights* w;
+  const VsgGrdBatch* b;
+
+  bool can_fuse(const VsgGrdConv& c) const {      // linalg.can_fuse_dwconv
+    return w->fuse_dwconv && mode == VSG_GEMM_TF32_BF16X2 && c.pw.w16 && c.pw.N <= 128 && c.pw.K % 16 == 0 && c.pw.K * (c.k + 1) <= 2048 &&
+           (c.k & 1) && c.k <= 7;
+  }
+  // DepthWiseSeparableConv1d (:36-56): depthwise conv over the sequence axis, then the 1x1 conv (+ ReLU, + residual)
+  void dw_pw(const float* x, const VsgGrdConv& c, const VsgGrdSeq& sq, float* out, bool relu, const float* residual) {
+    const int H = w->dim_hidden;
+    if (can_fuse(c)) {
+      gemm(x, H, c.pw, out, c.pw.N, sq.rows, relu, true, -1, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, residual, residual ? c.pw.N : 0,
+           &c, sq.pos, sq.rem);
+      return;
+    }
+    const int64_t m0 = ar.mark();
+    float* t = ar.get<float>(sq.rows * H);
+    FWD_CALL(vsg_dwconv(x, sq.pos, sq.rem, c.dw_w, c.dw_b, c.k, sq.rows, H, t, stream));
+    gemm(t, H, c.pw, out, c.pw.N, sq.rows, relu, true, -1, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, residual, residual ? c.pw.N : 0);
+    ar.release(m0);
+  }
+  // QANetEncoderLayer.forward (:110-137) on rows [rows][H] of ragged sequences; returns a buffer that outlives the call
+  float* qanet(const VsgGrdEncoder& e, const float* x, const VsgGrdSeq& sq) {
+    const int H = w->dim_hidden;
+    const int64_t rows = sq.rows;
+    float* result = ar.get<float>(rows * H);
+    const int64_t m0 = ar.mark();
+    float* res = ar.get<float>(rows * H);
+    float* res2 = ar.get<float>(rows * H);
+    float* o = ar.get<float>(rows * H);
+    FWD_CALL(vsg_pos_add_ln(x, sq.pos, w->freq, w->phase, e.normb.gamma, e.normb.beta, rows, H, res, o, stream));
+    for (int i = 0; i < 4; ++i) {
+      dw_pw(o, e.convs[i], sq, res2, true, res);                               // relu(conv) + res (:120-122)
+      float* sw = res; res = res2; res2 = sw;
+      FWD_CALL(vsg_add_layernorm(res, H, nullptr, 0, e.norm_seq[i].gamma, e.norm_seq[i].beta, nullptr, 0, rows, H, o, H, stream));
+    }
+    float* qkv = ar.get<float>(rows * 3 * H);
+    float* att = ar.get<float>(rows * H);
+    gemm(o, H, e.qkv, qkv, 3 * H, rows);
+    if (w->tc_attention && mode != VSG_GEMM_SIMT && sq.n_tc_blk >= 0) {
+      const int products = (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2) ? 3 : 1;
+      FWD_CALL(vsg_mha_tc16(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, sq.off, 8, att, H, sq.tc_blk_seg, sq.tc_blk_q0, sq.n_tc_blk, products, stream));
+    } else {
+      FWD_CALL(vsg_mha(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, sq.off, sq.n, 0, sq.max_len, 8, H / 8, att, H, sq.blk_seg, sq.blk_q0,
+                       sq.n_blk, stream));
+    }
+    gemm(att, H, e.out, res2, H, rows, false, true, -1, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, res, H);   // attn + res (:129-130)
+    FWD_CALL(vsg_add_layernorm(res2, H, nullptr, 0, e.norme.gamma, e.norme.beta, nullptr, 0, rows, H, o, H, stream));
+    gemm(o, H, e.fc, result, H, rows, true, true, -1, nullptr, nullptr, 0, nullptr, 0, 0, nullptr, 0, nullptr, 0, res2, H);    // relu(fc(LN)) + res (:133-136)
+    ar.release(m0);
+    return result;
+  }
+  void head(const VsgGrdConv* hw, const float* x, const VsgGrdSeq& sq, float* out) {
+    const int H = w->dim_hidden;
+    const int64_t m0 = ar.mark();
+    float* a = ar.get<float>(sq.rows * H);
+    float* c = ar.get<float>(sq.rows * H);
+    const float* y = x;
+    for (int i = 0; i < 4; ++i) {
+      float* dst = (i & 1) ? c : a;
+      dw_pw(y, hw[i], sq, dst, true, nullptr);
+      y = dst;
+    }
+    dw_pw(y, hw[4], sq, out, false, nullptr);
+    ar.release(m0);
+  }
+
+  int run(VsgGrdOut* out, float score_th, float tiou_th, float bins_th, float nms_th) {
+    const int H = w->dim_hidden, B = w->num_bins, NQ = b->n_queries;
+    const int64_t rows_v = b->video.rows, rows_c = b->combined.rows;
+    float* v0 = ar.get<float>(rows_v * H);
+    gemm(b->video_feats, w->dim_feat, w->video_fc, v0, H, rows_v);
+    float* q0 = ar.get<float>((int64_t)3 * NQ * H);
+    float* so_norm = ar.get<float>((int64_t)NQ * 2);
+    FWD_CALL(vsg_grd_query_init(b->quint, b->spans, b->vlen, b->q_vid, NQ, w->proj_enti, w->proj_pred, w->temp_w, w->temp_b, H, q0, so_norm, stream));
+    float* v = qanet(w->video_encoder, v0, b->video);
+    float* q = qanet(w->query_encoder, q0, b->query);
+    float* pv = ar.get<float>(rows_v * H);
+    gemm(v, H, w->proj2sim, pv, H, rows_v, false, false);
+    float* comb0 = ar.get<float>(rows_c * H);
+    {
+      const int64_t m0 = ar.mark();
+      float* comb_in = ar.get<float>(rows_c * 4 * H);
+      FWD_CALL(vsg_cq_attention(v, pv, q, b->video.off, b->q_vid, b->combined.off, NQ, H, b->max_T, comb_in, stream));
+      gemm(comb_in, 4 * H, w->vq_fc, comb0, H, rows_c);
+      ar.release(m0);
+    }
+    float* comb = qanet(w->combined_encoder, comb0, b->combined);
+    float* regr = out->regr ? out->regr : ar.get<float>(rows_c * 2 * B);
+    float* conf = out->conf ? out->conf : ar.get<float>(rows_c * B);
+    float* cls = out->cls ? out->cls : ar.get<float>(rows_c * B);
+    head(w->regr_head, comb, b->combined, regr);
+    head(w->conf_head, comb, b->combined, conf);
+    head(w->cls_head, comb, b->combined, cls);
+    if (live())
+      FWD_CALL(vsg_grounding_post(regr, conf, cls, b->combined.off, so_norm, b->clip_tab, b->video.off, b->q_vid, NQ, B, 0, score_th, tiou_th, bins_th,
+                                  nms_th, out->pooled, out->probs, out->mask, out->err_count, stream));
+    return rc;
+  }
+};
+
+static int check_grd(const VsgGrdWeights* w, const VsgGrdBatch* b, int mode) {
+  VSG_REQUIRE(w && b, "vsg_grd_forward: null weights / batch");
+  VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_BF16, "vsg_grd_forward: unknown precision mode %d", mode);
+  VSG_REQUIRE(w->dim_hidden == 128, "vsg_grd_forward: dim_hidden must be 128 (the context-query kernel's instantiation)");
+  VSG_REQUIRE(b->n_videos > 0 && b->n_queries > 0 && b->video.rows > 0 && b->combined.rows > 0, "vsg_grd_forward: empty batch");
+  return VSG_OK;
+}
+
 static int check_args(const VsgBigCWeights* w, const VsgVideoBatch* b, int topk, int mode) {
   VSG_REQUIRE(w && b, "vsg_bigc_forward: null weights / batch");
   VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_BF16, "vsg_bigc_forward: unknown precision mode %d", mode);
@@ -340,5 +459,39 @@ extern "C" int vsg_bigc_forward(const VsgBigCWeights* w, const VsgVideoBatch* b,
               (long long)need, (long long)workspace_bytes);
   rc = f.run(out, topk);
   if (rc == VSG_OK && f.ar.overflow) { set_error("vsg_bigc_forward: workspace overflow"); return VSG_E_INVALID; }
+  return rc;
+}
+
+extern "C" int64_t vsg_grd_workspace_bytes(const VsgGrdWeights* w, const VsgGrdBatch* b, int precision_mode) {
+  if (check_grd(w, b, precision_mode) != VSG_OK) return -1;
+  GrdFwd f;
+  f.w = w; f.b = b; f.mode = precision_mode; f.stream = nullptr; f.rc = VSG_OK;
+  f.ar.base = nullptr; f.ar.cap = 0; f.ar.off = 0; f.ar.peak = 0; f.ar.dry = true; f.ar.overflow = false;
+  VsgGrdOut dummy;
+  memset(&dummy, 0, sizeof(dummy));
+  f.run(&dummy, 0.f, 0.f, 0.f, 0.f);
+  return f.ar.peak + 256;
+}
+
+extern "C" int vsg_grd_forward(const VsgGrdWeights* w, const VsgGrdBatch* b, VsgGrdOut* out, float score_th, float tiou_th, float bins_th,
+                               float nms_th, int precision_mode, void* workspace, int64_t workspace_bytes, void* stream) {
+  int rc = check_grd(w, b, precision_mode);
+  if (rc != VSG_OK) return rc;
+  VSG_REQUIRE(out && out->pooled && out->probs && out->mask && out->err_count, "vsg_grd_forward: output buffers missing");
+  VSG_REQUIRE(workspace && (reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "vsg_grd_forward: workspace must be 256-byte aligned");
+  VsgGrdOut sized = *out;
+  const int64_t need = [&] {
+    GrdFwd d;
+    d.w = w; d.b = b; d.mode = precision_mode; d.stream = nullptr; d.rc = VSG_OK;
+    d.ar.base = nullptr; d.ar.cap = 0; d.ar.off = 0; d.ar.peak = 0; d.ar.dry = true; d.ar.overflow = false;
+    d.run(&sized, 0.f, 0.f, 0.f, 0.f);
+    return d.ar.peak;
+  }();
+  VSG_REQUIRE(workspace_bytes >= need, "vsg_grd_forward: workspace too small (%lld bytes needed, %lld given)", (long long)need, (long long)workspace_bytes);
+  GrdFwd f;
+  f.w = w; f.b = b; f.mode = precision_mode; f.stream = stream; f.rc = VSG_OK;
+  f.ar.base = reinterpret_cast<uint8_t*>(workspace); f.ar.cap = workspace_bytes; f.ar.off = 0; f.ar.peak = 0; f.ar.dry = false; f.ar.overflow = false;
+  rc = f.run(out, score_th, tiou_th, bins_th, nms_th);
+  if (rc == VSG_OK && f.ar.overflow) { set_error("vsg_grd_forward: workspace overflow"); return VSG_E_INVALID; }
   return rc;
 }

@@ -146,6 +146,57 @@ class DEBUG(object):
         phases = [0 if i % 2 == 0 else np.pi / 2 for i in range(H)]
         w["freq"], w["phase"] = torch.Tensor(freqs).to(dev), torch.Tensor(phases).to(dev)
         self._w = w
+        self._cw = None
+
+    # ---- the whole forward as one C call (include/vsg_b200.h: vsg_grd_forward) ----------------------------------
+    def _c_weights(self):
+        from ._cabi import VsgGrdConv, VsgGrdWeights, VsgLinear, VsgNorm
+        if self._cw is not None:
+            return self._cw
+        w = self._w
+        addr = lambda t: None if t is None else t.data_ptr()
+
+        def lin(W):
+            l = VsgLinear()
+            l.w, l.bias, l.N, l.K, l.ldw = addr(W.w), addr(W.bias), W.N, W.K, W.w.stride(0)
+            l.hi, l.lo, l.w16, l.lo16, l.ld16 = addr(W.hi), addr(W.lo), addr(W.w16), addr(W.lo16), getattr(W, "ld16", 0)
+            l.img, l.img_bn = addr(W.img), W.img_bn
+            return l
+
+        def conv(dst, cw):
+            dst.dw_w, dst.dw_b, dst.k, dst.pw = addr(cw["dw_w"]), addr(cw["dw_b"]), cw["k"], lin(cw["pw"])
+
+        def norm(dst, n):
+            dst.gamma, dst.beta = addr(n[0]), addr(n[1])
+        c = VsgGrdWeights()
+        c.dim_hidden, c.num_bins, c.dim_feat = self.dim_hidden, self.num_bins, self.dim_feat
+        c.video_fc, c.vq_fc, c.proj2sim = lin(w["video_fc"]), lin(w["vq_fc"]), lin(w["proj2sim"])
+        c.proj_enti, c.proj_pred = addr(w["proj_enti"]), addr(w["proj_pred"])
+        c.temp_w, c.temp_b, c.freq, c.phase = addr(w["temp_w"]), addr(w["temp_b"]), addr(w["freq"]), addr(w["phase"])
+        for name in ("video_encoder", "query_encoder", "combined_encoder"):
+            e, ew = getattr(c, name), w[name]
+            for i in range(4):
+                conv(e.convs[i], ew["convs"][i])
+                norm(e.norm_seq[i], ew["norm_seq"][i])
+            e.qkv, e.out, e.fc = lin(ew["qkv"]), lin(ew["out"]), lin(ew["fc"])
+            norm(e.normb, ew["normb"]); norm(e.norme, ew["norme"])
+        for name in ("cls_head", "conf_head", "regr_head"):
+            for i in range(5):
+                conv(getattr(c, name)[i], w[name][i])
+        self._cw = c
+        return c
+
+    @staticmethod
+    def _c_seq(sq):
+        from ._cabi import VsgGrdSeq
+        q = VsgGrdSeq()
+        q.off, q.n, q.rows, q.pos, q.rem, q.max_len = sq["off"].data_ptr(), sq["n"], sq["rows"], sq["pos"].data_ptr(), sq["rem"].data_ptr(), sq["max_len"]
+        q.blk_seg, q.blk_q0, q.n_blk = sq["blocks"][0].data_ptr(), sq["blocks"][1].data_ptr(), sq["blocks"][2]
+        if sq["tc_blocks"] is not None:
+            q.tc_blk_seg, q.tc_blk_q0, q.n_tc_blk = sq["tc_blocks"][0].data_ptr(), sq["tc_blocks"][1].data_ptr(), sq["tc_blocks"][2]
+        else:
+            q.n_tc_blk = -1
+        return q
 
     # ---- building blocks --------------------------------------------------------------------------------
     def _ln(self, x, norm):
@@ -160,6 +211,7 @@ class DEBUG(object):
                                _raw(out), stream_ptr(x.device)), "vsg_dwconv")
         return out
 
+    backend = "c"            # _forward_videos: "c" = ONE call of vsg_grd_forward (csrc/forward.cu), "py" = the same launches from Python
     attention = "tc"         # mh_attn of the video / combined encoders: "tc" = tcgen05 kernel (csrc/attn_tc.cu), "simt" = fp32 SIMT kernel
     fuse_dwconv = True       # depthwise conv inside the point-wise GEMM's operand pipeline (False: separate vsg_dwconv launch)
 
@@ -235,6 +287,8 @@ class DEBUG(object):
         q_vid = torch.from_numpy(q_vid_h).to(dev)
         clip = torch.cat([torch.linspace(0, 1, t) for t in T]).to(dev)          # (:705) host-evaluated table, see grounding.cu
         sv, sq3, sc = self._seq(vid_off_h), self._seq(np.arange(NQ + 1, dtype=np.int64) * 3), self._seq(comb_off_h)
+        if self.backend == "c":
+            return self._forward_c(vf, quint, spans, vlen, q_vid, clip, sv, sq3, sc, T, nq, NQ, th, want_net)
         # --- embeddings
         v0 = gemm(m, vf, w["video_fc"])
         q0 = torch.empty(3 * NQ, H, dtype=torch.float32, device=dev)
@@ -254,6 +308,47 @@ class DEBUG(object):
         out = self._post(regr, conf, cls, sc["off"], so_norm, clip, sv["off"], q_vid, NQ, nq, th, regr_activated=False)
         if want_net:
             return out, (regr, conf, cls, so_norm)
+        return out
+
+    def _forward_c(self, vf, quint, spans, vlen, q_vid, clip, sv, sq3, sc, T, nq, NQ, th, want_net):
+        """The network + post-processing of ``_forward_videos`` through vsg_grd_forward (one ctypes call)."""
+        from ._cabi import VsgGrdBatch, VsgGrdOut
+        dev, B = self.device, self.num_bins
+        cw = self._c_weights()
+        cw.tc_attention, cw.fuse_dwconv = int(self.attention == "tc"), int(bool(self.fuse_dwconv))
+        b = VsgGrdBatch()
+        b.n_videos, b.n_queries, b.max_T = len(T), NQ, max(T)
+        b.video_feats, b.quint, b.spans, b.vlen = vf.data_ptr(), quint.data_ptr(), spans.data_ptr(), vlen.data_ptr()
+        b.q_vid, b.clip_tab = q_vid.data_ptr(), clip.data_ptr()
+        b.video, b.query, b.combined = self._c_seq(sv), self._c_seq(sq3), self._c_seq(sc)
+        pooled = torch.empty(NQ, B + 1, 2, dtype=torch.float32, device=dev)
+        probs = torch.empty(NQ, B + 1, dtype=torch.float32, device=dev)
+        mask = torch.empty(NQ, B + 1, dtype=torch.uint8, device=dev)
+        err = torch.zeros(1, dtype=torch.int32, device=dev)
+        o = VsgGrdOut()
+        o.pooled, o.probs, o.mask, o.err_count = pooled.data_ptr(), probs.data_ptr(), mask.data_ptr(), err.data_ptr()
+        net = None
+        if want_net:
+            rows_c = sc["rows"]
+            net = (torch.empty(rows_c, 2 * B, dtype=torch.float32, device=dev), torch.empty(rows_c, B, dtype=torch.float32, device=dev),
+                   torch.empty(rows_c, B, dtype=torch.float32, device=dev))
+            o.regr, o.conf, o.cls = (t.data_ptr() for t in net)
+        need = int(lib().vsg_grd_workspace_bytes(C.byref(cw), C.byref(b), self.mode))
+        if need < 0:
+            check(-1, "vsg_grd_workspace_bytes")
+        ws = torch.empty(need, dtype=torch.uint8, device=dev)
+        base = (ws.data_ptr() + 255) // 256 * 256
+        check(lib().vsg_grd_forward(C.byref(cw), C.byref(b), C.byref(o), float(th[0]), float(th[1]), float(th[2]), float(th[3]), self.mode,
+                                    C.c_void_p(base), need - (base - ws.data_ptr()), stream_ptr(dev)), "vsg_grd_forward")
+        if int(err.item()) > 0:
+            raise RuntimeError("temporal_pooling: %d (query, bin) pairs have an empty pooling set" % int(err.item()))
+        out, r = [], 0
+        for n in nq:
+            out.append((pooled[r:r + n], probs[r:r + n], mask[r:r + n].bool()))
+            r += n
+        if want_net:
+            so_norm = spans.float() / vlen[q_vid.long()][:, None]         # == the kernel's so_norm (span / video_len, fp32)
+            return out, (net[0], net[1], net[2], so_norm)
         return out
 
     def _post(self, regr, conf, cls, comb_off, so_norm, clip, vid_off, q_vid, NQ, nq, th, regr_activated):
