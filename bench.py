@@ -573,7 +573,9 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     # time than Python needs to issue the next one; an event pair would then also measure the GPU waiting for the host.  A spin kernel in
     # front of each stage gives the host a head start, so the brackets hold kernel time only.
     graph, pipe.graph = pipe.graph, False
-    backend, pipe.model.backend = pipe.model.backend, "py"          # op-by-op launches (bit-identical to the one-call C entry)
+    backend, pipe.model.backend = pipe.model.backend, "py"          # op-by-op launches (bit-identical to the one-call C entries)
+    if pipe.kind == "vidor":
+        gbackend, pipe.grd.backend = pipe.grd.backend, "py"
     spin = lambda ms: torch.cuda._sleep(int(ms * 1e-3 * 1.9e9))
     linalg._Profile.begin()
     spin(60)
@@ -584,6 +586,8 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     pipe.finish(h, graphs, gather=False, timers=timers)
     linalg._Profile.end()
     pipe.graph, pipe.model.backend = graph, backend
+    if pipe.kind == "vidor":
+        pipe.grd.backend = gbackend
     P = linalg._Profile
     slots = {"tf32+bf16x2": 4.0, "3xtf32": 6.0, "tf32": 2.0, "bf16": 1.0}.get(precision)      # bf16-equivalent tensor slots per useful MAC
     out = {}

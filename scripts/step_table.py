@@ -19,6 +19,8 @@ for p in props:
 for prec in precs:
     pipe = bench.Pipeline(kind, prec, dev)
     pipe.model.backend = "py"                      # op-by-op launches so that every GEMM can be bracketed
+    if kind == "vidor":
+        pipe.grd.backend = "py"
     g2, _ = bench.gt_from_predictions(pipe, props, cfg, seeds, dev)
     for _ in range(3):
         pipe.step(props, g2, gather=False)
