@@ -118,6 +118,17 @@ def fill_features(buf, gen, block=1 << 22):
         flat[a:b].normal_(0.0, 0.5, generator=gen)
 
 
+def fill_features_per_video(buf, rows_per_video, seeds, device):
+    """Each video's feature rows from its OWN seed, so that a video's inputs do not depend on how the set is chunked / sharded
+    (the metrics of the VidOR set are then the same at every GPU count)."""
+    g = torch.Generator(device=device)
+    r = 0
+    for L, seed in zip(rows_per_video, seeds):
+        g.manual_seed(int(seed) * 2 + 1)
+        buf[r:r + L].normal_(0.0, 0.5, generator=g)
+        r += L
+
+
 def attach_features(props, feats):
     r = 0
     for p in props:
@@ -690,20 +701,25 @@ def vidor_leg(args, rank, world, device, dist, barrier):
     for ci, ids in enumerate(my_chunks):
         seeds = [info[i]["seed"] for i in ids]
         rows = sum(info[i]["rows"] for i in ids)
-        feat_seed = VIDOR_SEED0 + 7919 * (ids[0] + 1)
+        vrows = [info[i]["rows"] for i in ids]
         buf = shared_buf[:rows] if shared_buf is not None else torch.empty(rows, wl["feat_total"], dtype=torch.float32, device=device)
-        fill_features(buf, torch.Generator(device=device).manual_seed(feat_seed))
-        _, _, props, _, _ = make_videos("vidor", seeds, device, feat_seed + 1, feats=buf, with_gt=False)
+        fill_features_per_video(buf, vrows, seeds, device)
+        g = torch.Generator(device=device)
+        i3d = []
+        for i in ids:                                           # clip features from the video's own seed, too
+            g.manual_seed(int(info[i]["seed"]) * 2)
+            i3d.append(torch.randn((info[i]["video_len"] + 7) // 8, 1024, generator=g, device=device, dtype=torch.float32) * 0.05)
+        _, _, props, _, _ = make_videos("vidor", seeds, device, 0, feats=buf, i3d=i3d, with_gt=False)
         for p in props:
             f = p.features
             p.to(device)
             p.features = f
-        ch = dict(ids=ids, seeds=seeds, props=props, feat_seed=feat_seed, buf=buf, rows=rows)
+        ch = dict(ids=ids, seeds=seeds, props=props, vrows=vrows, buf=buf, rows=rows)
         chunks.append(ch)
 
     def refill(ch):
         if shared_buf is not None:
-            fill_features(ch["buf"], torch.Generator(device=device).manual_seed(ch["feat_seed"]))
+            fill_features_per_video(ch["buf"], ch["vrows"], ch["seeds"], device)
 
     cpu, parity = None, None
     if do_cpu:
