@@ -58,7 +58,8 @@ def parse():
     ap.add_argument("--chunk-rows", type=int, default=2_500_000, help="feature rows per resident chunk of the VidOR set")
     ap.add_argument("--no-graph", action="store_true", help="issue the BIG-C forward's ~150 launches from Python every step instead of "
                     "replaying the CUDA graph captured for the resident batch")
-    ap.add_argument("--modes", default="", help="comma list of extra precisions to time on the top-level workload (e.g. bf16)")
+    ap.add_argument("--modes", default="bf16", help="comma list of extra precisions timed on the top-level workload next to --precision, with their decision-flip report "
+                    "('' = none)")
     return ap.parse_args()
 
 
