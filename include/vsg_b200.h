@@ -340,6 +340,13 @@ int vsg_construct_triplet(const float* logits, int ld_logits, int P, int Q, int 
                           int64_t* quint, float* scores, int64_t* spans, int64_t* qids, int32_t* counts, int cap,
                           void* stream);
 
+/* Cost matrix of the Hungarian matching of the training forward (models/model_0v10.py:606-636, f3 "then" clause of SURVEY 8f):
+ * cost f32[Q][G] = c_cls * CE(logit[q], gt_pred[g]) + c_adj * mean over (2 roles, n tracklets) of BCE(att[role][q][:], adj[role][g][:])
+ * (torch's BCE log clamp at -100).  logit f32[Q][P], gt_pred int64[G], att f32[2][Q][n], adj f32[2][G][n].  The assignment itself
+ * (scipy linear_sum_assignment) stays on the host. */
+int vsg_bipartite_cost(const float* logit, int Q, int P, const int64_t* gt_pred, int G, const float* att, const float* adj, int n,
+                       float c_cls, float c_adj, float* cost, void* stream);
+
 /* ---- Whole-forward entry points (last row): the BIG-C classification forward as ONE call -----------------------------
  * vsg_bigc_forward runs models/model_0v10.py:434-507 (+ :707-785) / models/model_0v7.py:483-513 for a packed batch of videos: the same
  * launch sequence the Python host layer (vidsgg_big_b200/bigc.py) issues, from C, so that a non-Python host can run the path and a

@@ -197,3 +197,16 @@ def forward(st, cfg, proposal_list, topk: int):
         _, logits, att = encode2decode(st, cfg, p)
         out.append(construct_triplet(p, logits, att, topk))
     return out
+
+
+def bipartite_cost(pred_logit, gt_pred, att_matrx, gt_adj_enti_align, c_cls: float, c_adj: float):
+    """Cost matrix of the Hungarian matching, models/model_0v10.py:606-636: cross-entropy of every query against every GT predicate plus
+    the binary cross-entropy between the query's attention rows and the GT's aligned adjacency rows, averaged over roles and tracklets
+    (torch's BCE clamps its logs at -100).  -> f32[Q, G]."""
+    logp = torch.log_softmax(pred_logit, dim=-1)                       # [Q, P]
+    cost_cls = -logp[:, gt_pred]                                        # [Q, G]
+    a = att_matrx[:, :, None, :]                                        # [2, Q, 1, n]
+    t = gt_adj_enti_align[:, None, :, :]                                # [2, 1, G, n]
+    bce = -(t * torch.clamp(torch.log(a), min=-100.0) + (1.0 - t) * torch.clamp(torch.log(1.0 - a), min=-100.0))
+    cost_adj = bce.mean(dim=(0, 3))
+    return cost_cls * c_cls + cost_adj * c_adj

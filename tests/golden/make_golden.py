@@ -315,6 +315,35 @@ def gen_align():
     save("align", **out)
 
 
+# ------------------------------------------------------------------ bipartite_match cost matrices ----
+def gen_bipartite():
+    """Cost matrix of the Hungarian matching (model_0v10.py:606-639): the reference's own ``bipartite_match`` with scipy's
+    ``linear_sum_assignment`` wrapped so that the matrix it receives is captured."""
+    import models.model_0v10 as M
+    out = {}
+    cfg = synth.tiny_vidvrd_config()
+    model = build_ref_bigc(cfg, synth.make_bigc_state(7, cfg), BIG_C_vidvrd)
+    captured = []
+    real = M.linear_sum_assignment
+
+    def spy(cost):
+        captured.append(cost.clone())
+        return real(cost)
+    M.linear_sum_assignment = spy
+    try:
+        for sd, n_gt, n_enti in ((451, 5, 9), (452, 17, 23), (453, 1, 4)):
+            logit, gt_pred, att, adj = synth.make_bipartite_case(sd, cfg["num_querys"], cfg["num_pred_cats"], n_gt, n_enti)
+            with torch.no_grad():
+                idx = model.bipartite_match(logit, gt_pred, att, adj)
+            cost = captured[-1]
+            oc_ = ob.bipartite_cost(logit, gt_pred, att, adj, cfg["cost_coeff_dict"]["classification"], cfg["cost_coeff_dict"]["adj_matrix"])
+            assert torch.allclose(cost, oc_, rtol=1e-6, atol=1e-6)
+            out["cost_%d" % sd] = cost.numpy(); out["row_%d" % sd] = np.asarray(idx[0]); out["col_%d" % sd] = np.asarray(idx[1])
+    finally:
+        M.linear_sum_assignment = real
+    save("bipartite", **out)
+
+
 # ------------------------------------------------------------------ grounding ----------
 def gen_grounding():
     out = {}
@@ -393,4 +422,4 @@ if __name__ == "__main__":
     which = sys.argv[1:] or ["geometry", "eval", "bigc", "align", "grounding", "grounding_gt", "basec"]
     for w in which:
         {"geometry": gen_geometry, "eval": gen_eval, "bigc": gen_bigc, "align": gen_align, "grounding": gen_grounding,
-         "grounding_gt": gen_grounding_gt, "basec": gen_basec}[w]()
+         "grounding_gt": gen_grounding_gt, "basec": gen_basec, "bipartite": gen_bipartite}[w]()

@@ -340,3 +340,17 @@ def test_c_forward_entry_equals_python_issued_launches(which, precision):
         assert (r is None) == (int(a.counts[v, 1]) == 0)
         if r is not None:
             assert torch.equal(r[0], a.quint[v * a.cap: v * a.cap + n])
+
+
+def test_bipartite_cost_matrix_vs_reference(golden):
+    """f3 'then' clause: the Hungarian cost matrix (model_0v10.py:606-636) on the device against the matrix the reference computed, and
+    the same assignment from scipy."""
+    g = golden("bipartite")
+    cfg = synth.tiny_vidvrd_config()
+    model = _model(cfg, synth.make_bigc_state(7, cfg), "fp32_simt")
+    for sd, n_gt, n_enti in ((451, 5, 9), (452, 17, 23), (453, 1, 4)):
+        logit, gt_pred, att, adj = [t.to(DEV) for t in synth.make_bipartite_case(sd, cfg["num_querys"], cfg["num_pred_cats"], n_gt, n_enti)]
+        cost = model.bipartite_cost(logit, gt_pred, att, adj)
+        np.testing.assert_allclose(cost.cpu().numpy(), g["cost_%d" % sd], rtol=2e-5, atol=2e-5)
+        row, col = model.bipartite_match(logit, gt_pred, att, adj)
+        assert np.array_equal(row, g["row_%d" % sd]) and np.array_equal(col, g["col_%d" % sd])

@@ -137,6 +137,7 @@ SIGNATURES = {
     "vsg_viou_pairs_f64": (i32, [p, p, p, p, p, p, i32, p, p]),
     "vsg_gemm": (i32, [i32, p, i32, p, p, i32, i32, i32, i32, p, p, p, i32, i32, i32, i32, p, i32, p, i32, p]),
     "vsg_gemm_ex": (i32, [C.POINTER(VsgGemmArgs), p]),
+    "vsg_bipartite_cost": (i32, [p, i32, i32, p, i32, p, p, i32, f32, f32, p, p]),
     "vsg_bigc_workspace_bytes": (i64, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), i32, i32]),
     "vsg_bigc_forward": (i32, [C.POINTER(VsgBigCWeights), C.POINTER(VsgVideoBatch), C.POINTER(VsgTripletOut), i32, i32, p, i64, p]),
     "vsg_grd_workspace_bytes": (i64, [C.POINTER(VsgGrdWeights), C.POINTER(VsgGrdBatch), i32]),

@@ -681,6 +681,25 @@ class BIG_C(object):
             res.counts
         return res
 
+    def bipartite_cost(self, pred_logit, gt_pred, att_matrx, gt_adj_enti_align):
+        """Cost matrix of ``bipartite_match`` (model_0v10.py:606-636) on the device: f32[n_querys, n_gt_pred]."""
+        require_cuda(pred_logit, gt_pred, att_matrx, gt_adj_enti_align)
+        Q, P = pred_logit.shape
+        G, n = gt_adj_enti_align.shape[1], gt_adj_enti_align.shape[2]
+        assert att_matrx.shape == (2, Q, n) and gt_pred.shape[0] == G
+        cf = self.config.get("cost_coeff_dict", dict(classification=1.0, adj_matrix=30.0))
+        cost = torch.empty(Q, G, dtype=torch.float32, device=pred_logit.device)
+        check(lib().vsg_bipartite_cost(_raw(pred_logit.float().contiguous()), Q, P, _raw(gt_pred.long().contiguous()), G,
+                                       _raw(att_matrx.float().contiguous()), _raw(gt_adj_enti_align.float().contiguous()), n,
+                                       float(cf["classification"]), float(cf["adj_matrix"]), _raw(cost), stream_ptr(pred_logit.device)),
+              "vsg_bipartite_cost")
+        return cost
+
+    def bipartite_match(self, pred_logit, gt_pred, att_matrx, gt_adj_enti_align):
+        """model_0v10.py:606-639: the cost matrix comes from the device, the assignment from scipy on the host (as in the reference)."""
+        from scipy.optimize import linear_sum_assignment
+        return linear_sum_assignment(self.bipartite_cost(pred_logit, gt_pred, att_matrx, gt_adj_enti_align).cpu())
+
     def forward_debug(self, proposal):
         """(pred_queries, pred_logits [Q,P], att_matrx [2,Q,n]) of one video, like ``encode2decode`` (:434-475)."""
         pk = PackedVideos([proposal], self.device)

@@ -896,6 +896,44 @@ construct_triplet_kernel(const float* __restrict__ logits, int ld_logits, int P,
   (void)m;
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Cost matrix of the Hungarian matching of the training forward (model_0v10.py:606-636): for query q and GT predicate g
+//   cost[q][g] = c_cls * (logsumexp(logit[q]) - logit[q][gt_pred[g]]) + c_adj * mean_{role, tracklet} BCE(att[role][q][e], adj[role][g][e])
+// with torch's BCE log clamp at -100.  One CTA per query: block-wide logsumexp of its logit row, then threads over the GT predicates.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+bipartite_cost_kernel(const float* __restrict__ logit, int P, const int64_t* __restrict__ gt_pred, int G, const float* __restrict__ att,
+                      const float* __restrict__ adj, int Q, int n, float c_cls, float c_adj, float* __restrict__ cost) {
+  __shared__ float red[4];
+  const int q = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const float* row = logit + (int64_t)q * P;
+  float m = -INFINITY;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) m = fmaxf(m, row[c]);
+  m = warp_max(m);
+  if (lane == 0) red[warp] = m;
+  __syncthreads();
+  m = fmaxf(fmaxf(red[0], red[1]), fmaxf(red[2], red[3]));
+  __syncthreads();
+  float s = 0.f;
+  for (int c = threadIdx.x; c < P; c += blockDim.x) s += expf(row[c] - m);
+  s = warp_sum(s);
+  if (lane == 0) red[warp] = s;
+  __syncthreads();
+  const float lse = m + logf((red[0] + red[1]) + (red[2] + red[3]));
+  for (int g = threadIdx.x; g < G; g += blockDim.x) {
+    float acc = 0.f;
+    for (int r = 0; r < 2; ++r) {
+      const float* a = att + ((int64_t)r * Q + q) * n;
+      const float* t = adj + ((int64_t)r * G + g) * n;
+      for (int e = 0; e < n; ++e) {
+        const float p = a[e], y = t[e];
+        acc -= y * fmaxf(logf(p), -100.f) + (1.f - y) * fmaxf(logf(1.f - p), -100.f);
+      }
+    }
+    cost[(int64_t)q * G + g] = c_cls * (lse - row[gt_pred[g]]) + c_adj * (acc / (float)(2 * n));
+  }
+}
+
 static inline int grid_cap(int64_t blocks, int per_sm) {
   const int64_t cap = (int64_t)sm_count() * per_sm;
   return (int)(blocks < 1 ? 1 : (blocks < cap ? blocks : cap));
@@ -1185,4 +1223,13 @@ extern "C" int vsg_construct_triplet(const float* logits, int ld_logits, int P, 
   construct_triplet_kernel<<<n_vid, 512, 0, (cudaStream_t)stream>>>(logits, ld_logits, P, Q, topk, so, seg, dura, cat_ids,
                                                                    enti_scores, o);
   return check_launch("vsg_construct_triplet");
+}
+
+extern "C" int vsg_bipartite_cost(const float* logit, int Q, int P, const int64_t* gt_pred, int G, const float* att, const float* adj, int n,
+                                  float c_cls, float c_adj, float* cost, void* stream) {
+  VSG_REQUIRE(Q >= 0 && P > 0 && G >= 0 && n > 0, "vsg_bipartite_cost: bad size");
+  if (Q == 0 || G == 0) return VSG_OK;
+  VSG_REQUIRE(logit && gt_pred && att && adj && cost, "vsg_bipartite_cost: null pointer");
+  bipartite_cost_kernel<<<Q, 128, 0, (cudaStream_t)stream>>>(logit, P, gt_pred, G, att, adj, Q, n, c_cls, c_adj, cost);
+  return check_launch("vsg_bipartite_cost");
 }

@@ -304,6 +304,23 @@ def make_gt_from_predictions(seed: int, proposal: TrajProposal, triplets, n_rel=
     return g
 
 
+def make_bipartite_case(seed: int, n_querys: int, num_pred_cats: int, n_gt: int, n_enti: int):
+    """Inputs of ``BIG_C.bipartite_match`` (model_0v10.py:606-639): logits f32[Q,P], GT predicate ids i64[G], attention f32[2,Q,n] in (0,1)
+    (softmax over tracklets x softmax over roles, like the decoder emits), aligned GT adjacency f32[2,G,n] (0/1)."""
+    rng = np.random.default_rng(seed + 11_000_000)
+    logit = torch.from_numpy(rng.standard_normal((n_querys, num_pred_cats), dtype=np.float32) * np.float32(2.0))
+    gt_pred = torch.from_numpy(rng.integers(1, num_pred_cats, size=n_gt).astype(np.int64))
+    raw = torch.from_numpy(rng.standard_normal((2, n_querys, n_enti), dtype=np.float32) * np.float32(3.0))
+    att = torch.softmax(raw, -1) * torch.softmax(raw, 0)
+    att[0, 0, 0] = 0.0                                   # exact zeros / ones hit the BCE log clamp (-100)
+    att[1, 1, min(1, n_enti - 1)] = 1.0
+    adj = torch.zeros(2, n_gt, n_enti)
+    for g in range(n_gt):
+        adj[0, g, int(rng.integers(0, n_enti))] = 1.0
+        adj[1, g, int(rng.integers(0, n_enti))] = 1.0
+    return logit, gt_pred, att, adj
+
+
 def vidvrd_video_shape(rng) -> Tuple[int, int]:
     """(video_len, n) of SURVEY §8d config 2."""
     return int(rng.integers(90, 1201)), int(rng.integers(5, 51))
