@@ -1000,12 +1000,19 @@ def main():
     # ---- per-kernel roofline legs (a separate, instrumented step; CUDA events on the launch stream) ----
     legs = instrumented_step(pipe, props, graphs, args.precision, ms_step)
     roofline = legs.pop("bigc_gemm")
-    roofline["traffic_note"] = "dram bytes per launch are in profiles/ (ncu pass of the same command); not measured inside this run"
+    # DRAM bytes per launch: a CONSTANT read from the committed ncu pass of the same command (profiles/), not measured inside this run
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.summary.json")))
+        if args.workload == "vidvrd" and args.videos == 200 and args.precision == "tf32+bf16x2":
+            roofline["traffic"] = tj["dram_bytes_per_launch"]
+            roofline["traffic_source"] = "constant from profiles/r02_gemm_traffic.summary.json: " + tj["source"]
+    except Exception:
+        pass
     roofline["also"] = legs.pop("k1_geometry")
     roofline.update({k: v for k, v in legs.items()})
 
     # ---- other precisions on the same batch (same GT): time, triplet identity against the default mode's output ----
-    modes = {}
+    modes, alts = {}, {}
     for prec in [m for m in args.modes.split(",") if m and m != args.precision]:
         alt = Pipeline(args.workload, prec, device, rank, graph=not args.no_graph)
         alt._gts = pipe._gts
@@ -1023,7 +1030,7 @@ def main():
             s2, t2 = compare_triplets(a[:len(cpu_trips)], cpu_trips)
             modes[prec]["videos_with_triplets_identical_to_cpu_oracle"] = s2
         modes[prec]["decision_flips_vs_%s" % args.precision] = decision_flips(pipe, alt, props)
-        del alt
+        alts[prec] = alt
 
     # ---- e2e: same metric through the public API with HOST buffers (pinned), H2D + D2H inside the timed region ----
     e2e = None
@@ -1058,8 +1065,29 @@ def main():
                "h2d_bound_videos_per_s": args.videos * world / (hb.nbytes / (min(bare_all) * 1e9)),
                "note": "pinned host buffers, H2D double-buffered on a copy stream; GT relations resident; bare_h2d = the same pinned feature "
                        "buffer copied with every rank copying at once and no kernels running: the platform ceiling of this number"}
-        del hb, hprops, hfeats
+        del hb
         torch.cuda.empty_cache()
+        if "bf16" in alts:
+            # Opt-in of the bf16 mode: the loader hands the features over as bf16 (half the H2D bytes, no cast pass).  This CHANGES THE INPUT
+            # CONTRACT of the reference (fp32 .npy features), so it is reported next to the fp32 number, never instead of it.
+            import copy
+            h16 = torch.empty(hfeats.shape, dtype=torch.bfloat16, pin_memory=True)
+            h16.copy_(hfeats)
+            p16 = [copy.copy(p) for p in hprops]
+            attach_features(p16, h16)
+            hb16 = HostBatch(p16, device)
+            dt16, _ = run_e2e(alts["bf16"], hb16, graphs, n_e2e, barrier, device)
+            t16 = torch.tensor([dt16], device=device)
+            if world > 1:
+                dist.all_reduce(t16, op=dist.ReduceOp.MAX)
+            modes["bf16"]["e2e_bf16_transport"] = {"value": args.videos * world / float(t16.item()), "unit": "videos/s",
+                                                   "h2d_bytes_per_step": int(hb16.nbytes), "steps": n_e2e,
+                                                   "note": "opt-in: features handed over as bf16 in pinned host memory (input contract differs "
+                                                           "from the reference's fp32 features); same H2D double buffering"}
+            del hb16, h16, p16
+        del hprops, hfeats
+        torch.cuda.empty_cache()
+    alts.clear()
     del pipe
     torch.cuda.empty_cache()
 

@@ -273,6 +273,9 @@ int vsg_bbox_feat_mlp1_bf16(const float* boxes, const int64_t* off, int n_tracks
  * model_0v7.py:473; stretch = stack_with_repeat_2d :18-46): out f32[N][ldo]. */
 int vsg_stretched_mean(const float* feat, int ldf, int col0, int width, const int64_t* off, const int32_t* tmax,
                        int n_tracks, float* out, int ldo, void* stream);
+/* Same over features stored as bf16 [R][ldf] (the opt-in bf16 feature transport of the bf16 mode). */
+int vsg_stretched_mean_bf16(const void* feat16, int ldf, int col0, int width, const int64_t* off, const int32_t* tmax,
+                            int n_tracks, float* out, int ldo, void* stream);
 
 /* conv_feat2enti (k3,s2,p1 over stretched time) + adaptive_max_pool1d (model_0v10.py:450-457) from the three tap
  * products Y f32[R][3E] (tap-major); out f32[N][E*pool] flattened channel-major (c*pool+p). */
@@ -400,6 +403,8 @@ typedef struct VsgVideoBatch {
   const int64_t* cat_ids;      /* [N] */
   const float* scores;         /* [N] */
   const int32_t* mha_blk_seg; const int32_t* mha_blk_q0; int n_mha_blk;   /* ragged (video, 64-track block) work list of vsg_mha */
+  int feats_bf16;              /* 1 (mode VSG_GEMM_BF16 only): `feats` points to bf16 [R][ld_feats] (ld_feats a multiple of 8) -- the opt-in
+                                  bf16 feature transport: half the H2D bytes, no cast pass */
 } VsgVideoBatch;
 
 typedef struct VsgTripletOut {   /* video v owns rows [v*cap, v*cap + counts[v][0]); cap = num_querys * topk */

@@ -354,3 +354,33 @@ def test_bipartite_cost_matrix_vs_reference(golden):
         np.testing.assert_allclose(cost.cpu().numpy(), g["cost_%d" % sd], rtol=2e-5, atol=2e-5)
         row, col = model.bipartite_match(logit, gt_pred, att, adj)
         assert np.array_equal(row, g["row_%d" % sd]) and np.array_equal(col, g["col_%d" % sd])
+
+
+def test_bf16_feature_transport_equals_cast_path():
+    """Opt-in bf16 feature transport of the bf16 mode: features handed over as bf16 give exactly the result of fp32 features that hold
+    the same (bf16-representable) values -- through the Python-issued launches and through vsg_bigc_forward; the fp32-class modes reject
+    bf16 features."""
+    from vidsgg_big_b200 import bigc
+    from vidsgg_big_b200._cabi import VsgError
+    import copy
+    cfg = synth.tiny_vidvrd_config(dim_feat=96, dim_i3d=40)          # 136 feature columns: row stride a multiple of 8
+    st = synth.make_bigc_state(3, cfg)
+    model = _model(cfg, st, "bf16")
+    props32, props16 = [], []
+    for i, (n, vl) in enumerate([(7, 90), (12, 64)]):
+        p = synth.make_proposal(4100 + i, n, vl, 136, cfg["num_enti_cats"], min_len=5, max_len=60)
+        p.features = p.features.to(torch.bfloat16).float()            # values a bf16 loader would deliver
+        q = copy.copy(p)
+        q.features = p.features.to(torch.bfloat16)
+        props32.append(p.to(DEV)); props16.append(q.to(DEV))
+    for backend in ("py", "c"):
+        model.backend = backend
+        a = model.forward_packed(props32, topk=5)
+        b = model.forward_packed(props16, topk=5)
+        assert np.array_equal(a.counts, b.counts) and a.counts[:, 0].sum() > 0
+        for v in range(len(props32)):
+            sl = slice(v * a.cap, v * a.cap + int(a.counts[v, 0]))
+            assert torch.equal(a.quint[sl], b.quint[sl]) and torch.equal(a.scores[sl], b.scores[sl]) and torch.equal(a.spans[sl], b.spans[sl])
+    strict = _model(cfg, st, "tf32+bf16x2")
+    with pytest.raises(VsgError):
+        strict.forward_packed(props16, topk=5)

@@ -76,7 +76,7 @@ class VsgBigCWeights(C.Structure):
 class VsgVideoBatch(C.Structure):
     _fields_ = [("n_videos", i32), ("n_tracks", i32), ("max_tracks", i32), ("n_rows", i64), ("boxes", p), ("feats", p), ("ld_feats", i32),
                 ("off", p), ("seg", p), ("seg64", p), ("tmax", p), ("track_vid", p), ("wh", p), ("dura", p), ("cat_ids", p), ("scores", p),
-                ("mha_blk_seg", p), ("mha_blk_q0", p), ("n_mha_blk", i32)]
+                ("mha_blk_seg", p), ("mha_blk_q0", p), ("n_mha_blk", i32), ("feats_bf16", i32)]
 
 
 class VsgTripletOut(C.Structure):
@@ -165,6 +165,7 @@ SIGNATURES = {
     "vsg_bbox_feat_mlp1_bf16": (i32, [p, p, i32, i64, p, p, p, p, i32, p, i32, p]),
     "vsg_conv_pool_bf16": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
     "vsg_stretched_mean": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
+    "vsg_stretched_mean_bf16": (i32, [p, i32, i32, i32, p, p, i32, p, i32, p]),
     "vsg_conv_pool": (i32, [p, i32, i32, p, p, p, i32, i32, p, p]),
     "vsg_add_layernorm": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p]),
     "vsg_add_layernorm_dual": (i32, [p, i32, p, i32, p, p, p, i32, i64, i32, p, i32, p, i32, p]),

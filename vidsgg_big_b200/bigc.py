@@ -53,7 +53,9 @@ class PackedVideos(object):
         wh = torch.tensor([[float(p.video_wh[0]), float(p.video_wh[1])] for p in self.proposals], dtype=torch.float32)
         from .geometry import cat_rows as cat
         self.boxes = cat([p.bboxes.to(device, torch.float32) for p in self.proposals])
-        self.feats = cat([p.features.to(device, torch.float32) for p in self.proposals])
+        # features: fp32 (the reference's contract) or -- opt-in, bf16 mode only -- bf16 as handed over by a loader that stores them so
+        fdt = torch.bfloat16 if all(p.features is not None and p.features.dtype == torch.bfloat16 for p in self.proposals) else torch.float32
+        self.feats = cat([p.features.to(device, fdt) for p in self.proposals])
         self.dura = cat([p.traj_durations.to(device, torch.long) for p in self.proposals])
         self.cat_ids = cat([p.cat_ids.to(device, torch.long) for p in self.proposals])
         self.scores = cat([p.scores.to(device, torch.float32) for p in self.proposals])
@@ -322,6 +324,9 @@ class BIG_C(object):
         b = VsgVideoBatch()
         b.n_videos, b.n_tracks, b.max_tracks, b.n_rows = pk.V, pk.N, pk.max_tracks, pk.R
         b.boxes, b.feats, b.ld_feats = pk.boxes.data_ptr(), pk.feats.data_ptr(), pk.feats.stride(0)
+        b.feats_bf16 = int(pk.feats.dtype == torch.bfloat16)
+        if b.feats_bf16 and self.mode != linalg.BF16:
+            raise VsgError("bf16 features are the opt-in transport of precision='bf16'; the fp32-class modes take fp32 features")
         b.off, b.seg, b.seg64, b.tmax, b.track_vid, b.wh = (t.data_ptr() for t in (pk.off, pk.seg, pk.seg64, pk.tmax, pk.track_vid, pk.wh))
         b.dura, b.cat_ids, b.scores = pk.dura.data_ptr(), pk.cat_ids.data_ptr(), pk.scores.data_ptr()
         b.mha_blk_seg, b.mha_blk_q0, b.n_mha_blk = pk.mha_blocks[0].data_ptr(), pk.mha_blocks[1].data_ptr(), pk.mha_blocks[2]
@@ -402,6 +407,8 @@ class BIG_C(object):
             raise VsgError("features have %d columns, model needs %d" % (pk.feats.shape[1], F_in + self.extra_width))
         if m == linalg.BF16:
             return self._track_encoding_bf16(pk)
+        if pk.feats.dtype != torch.float32:
+            raise VsgError("bf16 features are the opt-in transport of precision='bf16'; the fp32-class modes take fp32 features")
         # --- per-frame MLPs on the unique frames, written into the two halves of X [R, 2E]
         X = torch.empty(R, 2 * E, dtype=torch.float32, device=dev)
         h = torch.empty(R, E, dtype=torch.float32, device=dev)
@@ -447,7 +454,7 @@ class BIG_C(object):
         check(L.vsg_bbox_feat_mlp1_bf16(_raw(pk.boxes), _raw(pk.off), N, R, _raw(pk.track_vid), _raw(pk.wh), _raw(w["bbox1_w"]),
                                         _raw(w["bbox1_b"]), E, _raw(h16), E, sp), "vsg_bbox_feat_mlp1_bf16")
         gemm(m, h16, w["bbox2"], out16=X16[:, :E], relu=True, f32_out=False)
-        F16 = linalg.cast_bf16(pk.feats, K=F_in)
+        F16 = pk.feats if pk.feats.dtype == bf else linalg.cast_bf16(pk.feats, K=F_in)      # bf16 transport: no cast pass
         gemm(m, F16, w["feat1"], out16=h16, relu=True, f32_out=False, K=F_in)
         del F16
         gemm(m, h16, w["feat2"], out16=X16[:, E:], relu=True, f32_out=False)
@@ -461,8 +468,9 @@ class BIG_C(object):
         extra = None
         if self.extra_width:
             extra = torch.empty(N, self.extra_width, dtype=torch.float32, device=dev)
-            check(L.vsg_stretched_mean(_raw(pk.feats), pk.feats.stride(0), F_in, self.extra_width, _raw(pk.off), _raw(pk.tmax), N,
-                                       _raw(extra), self.extra_width, sp), "vsg_stretched_mean")
+            fn = L.vsg_stretched_mean_bf16 if pk.feats.dtype == bf else L.vsg_stretched_mean
+            check(fn(_raw(pk.feats), pk.feats.stride(0), F_in, self.extra_width, _raw(pk.off), _raw(pk.tmax), N,
+                     _raw(extra), self.extra_width, sp), "vsg_stretched_mean")
         return enti2enco, extra
 
     def _encode2decode(self, pk: PackedVideos, want_att: bool = False):

@@ -49,7 +49,9 @@ class TrajProposal(object):
         self.scores = torch.as_tensor(scores, dtype=torch.float32)
         self.traj_durations = _as_long(traj_durations).reshape(-1, 2)
         self.bboxes = torch.as_tensor(bboxes, dtype=torch.float32).reshape(-1, 4)
-        self.features = None if features is None else torch.as_tensor(features, dtype=torch.float32)
+        # fp32 like the reference; a bf16 tensor is kept as is (the opt-in bf16 feature transport of precision="bf16")
+        self.features = None if features is None else (features if (torch.is_tensor(features) and features.dtype == torch.bfloat16)
+                                                      else torch.as_tensor(features, dtype=torch.float32))
         if lengths is None:
             lengths = (self.traj_durations[:, 1] - self.traj_durations[:, 0] + 1).cpu()
         self.lengths = _as_long(lengths).cpu()

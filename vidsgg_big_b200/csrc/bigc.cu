@@ -93,8 +93,12 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
 // Time-mean of the extra feature columns over the STRETCHED sequence (model_0v10.py:470, model_0v7.py:473):
 // mean_j x[src(j)] = sum_i reps(i) * x[i] / Tmax.   One CTA per track, threads over channels.
 // ---------------------------------------------------------------------------------------------------
+__device__ __forceinline__ float to_f32(float x) { return x; }
+__device__ __forceinline__ float to_f32(__nv_bfloat16 x) { return __bfloat162float(x); }
+
+template <typename TF>
 __global__ void __launch_bounds__(256)
-stretched_mean_kernel(const float* __restrict__ feat, int ldf, int col0, int width, const int64_t* __restrict__ off,
+stretched_mean_kernel(const TF* __restrict__ feat, int ldf, int col0, int width, const int64_t* __restrict__ off,
                       const int32_t* __restrict__ tmax, float* __restrict__ out, int ldo) {
   const int t = blockIdx.x;
   const int64_t r0 = off[t];
@@ -102,8 +106,8 @@ stretched_mean_kernel(const float* __restrict__ feat, int ldf, int col0, int wid
   const Stretch st(L, tmax[t]);
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float acc = 0.f;
-    const float* p = feat + r0 * (int64_t)ldf + col0 + c;
-    for (int i = 0; i < L; ++i) acc = fmaf((float)st.reps(i), p[(int64_t)i * ldf], acc);
+    const TF* p = feat + r0 * (int64_t)ldf + col0 + c;
+    for (int i = 0; i < L; ++i) acc = fmaf((float)st.reps(i), to_f32(p[(int64_t)i * ldf]), acc);
     out[(int64_t)t * ldo + c] = acc / (float)tmax[t];
   }
 }
@@ -961,8 +965,17 @@ extern "C" int vsg_stretched_mean(const float* feat, int ldf, int col0, int widt
   VSG_REQUIRE(n_tracks >= 0 && width >= 0, "vsg_stretched_mean: bad size");
   if (n_tracks == 0 || width == 0) return VSG_OK;
   VSG_REQUIRE(feat && off && tmax && out, "vsg_stretched_mean: null pointer");
-  stretched_mean_kernel<<<n_tracks, 256, 0, (cudaStream_t)stream>>>(feat, ldf, col0, width, off, tmax, out, ldo);
+  stretched_mean_kernel<float><<<n_tracks, 256, 0, (cudaStream_t)stream>>>(feat, ldf, col0, width, off, tmax, out, ldo);
   return check_launch("vsg_stretched_mean");
+}
+
+extern "C" int vsg_stretched_mean_bf16(const void* feat16, int ldf, int col0, int width, const int64_t* off, const int32_t* tmax,
+                                       int n_tracks, float* out, int ldo, void* stream) {
+  VSG_REQUIRE(n_tracks >= 0 && width >= 0, "vsg_stretched_mean_bf16: bad size");
+  if (n_tracks == 0 || width == 0) return VSG_OK;
+  VSG_REQUIRE(feat16 && off && tmax && out, "vsg_stretched_mean_bf16: null pointer");
+  stretched_mean_kernel<__nv_bfloat16><<<n_tracks, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)feat16, ldf, col0, width, off, tmax, out, ldo);
+  return check_launch("vsg_stretched_mean_bf16");
 }
 
 extern "C" int vsg_conv_pool(const float* Y, int ldy, int E, const float* bias, const int64_t* off, const int32_t* tmax,

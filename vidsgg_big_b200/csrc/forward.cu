@@ -145,7 +145,9 @@ int Fwd::run(VsgTripletOut* out, int topk) {
       uint16_t* h16 = ar.get<uint16_t>(R * E);
       FWD_CALL(vsg_bbox_feat_mlp1_bf16(b->boxes, b->off, N, R, b->track_vid, b->wh, w->bbox1_w, w->bbox1_b, E, h16, E, stream));
       gemm(nullptr, 0, w->bbox2, nullptr, 0, R, true, true, -1, nullptr, nullptr, 0, nullptr, 0, 0, h16, E, X16, 2 * E);
-      {
+      if (b->feats_bf16) {                       // bf16 feature transport: the features ARE the A operand
+        gemm(nullptr, 0, w->feat1, nullptr, 0, R, true, true, F_in, nullptr, nullptr, 0, nullptr, 0, 0, b->feats, b->ld_feats, h16, E);
+      } else {
         const int ldf = (F_in + 7) / 8 * 8;
         const int64_t m1 = ar.mark();
         uint16_t* F16 = ar.get<uint16_t>(R * ldf);
@@ -166,8 +168,10 @@ int Fwd::run(VsgTripletOut* out, int topk) {
     gemm(pooled, E * w->pool_len, w->enco1, t, E, N, true);
     gemm(t, E, w->enco2, enti2enco, E, N, true);
   }
-  if (w->extra_width)
-    FWD_CALL(vsg_stretched_mean(b->feats, b->ld_feats, F_in, w->extra_width, b->off, b->tmax, N, extra, w->extra_width, stream));
+  if (w->extra_width) {
+    if (b->feats_bf16) FWD_CALL(vsg_stretched_mean_bf16(b->feats, b->ld_feats, F_in, w->extra_width, b->off, b->tmax, N, extra, w->extra_width, stream));
+    else FWD_CALL(vsg_stretched_mean(b->feats, b->ld_feats, F_in, w->extra_width, b->off, b->tmax, N, extra, w->extra_width, stream));
+  }
 
   // ---------------- encoder (post-norm, tokens = tracks of a video) ----------------
   const float* x = enti2enco;
@@ -425,6 +429,7 @@ static int check_args(const VsgBigCWeights* w, const VsgVideoBatch* b, int topk,
   VSG_REQUIRE(w->dim_enti == w->dim_pred, "vsg_bigc_forward: dim_enti must equal dim_pred");
   VSG_REQUIRE(b->n_videos > 0 && b->n_tracks > 0 && b->n_rows > 0, "vsg_bigc_forward: empty batch");
   VSG_REQUIRE(topk > 0 && topk <= w->num_pred_cats, "vsg_bigc_forward: bad topk");
+  VSG_REQUIRE(!b->feats_bf16 || (mode == VSG_GEMM_BF16 && b->ld_feats % 8 == 0), "vsg_bigc_forward: bf16 features need mode VSG_GEMM_BF16 and ld_feats %% 8 == 0");
   return VSG_OK;
 }
 
