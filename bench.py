@@ -53,6 +53,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-pipeline", action="store_true", help="run the K timed steps strictly one after another (no overlap of step i-1's "
                     "evaluation host work with step i's classification kernels)")
+    ap.add_argument("--force-pipeline", action="store_true", help="experiment: pipeline the steps of the VidOR-shaped top-level workload too")
     ap.add_argument("--vidor-videos", type=int, default=835, help="size of the VidOR-val-shaped set of the 'vidor' leg (0: skip the leg)")
     ap.add_argument("--vidor-passes", type=int, default=2, help="timed passes over the VidOR set")
     ap.add_argument("--chunk-rows", type=int, default=2_500_000, help="feature rows per resident chunk of the VidOR set")
@@ -950,7 +951,7 @@ def main():
                   "cpu_oracle_metrics": {"mAP": float(cpu_metrics[0]), "R@50": float(cpu_metrics[1][50]), "R@100": float(cpu_metrics[1][100])}
                   if args.cpu_sample == args.videos and args.workload == "vidvrd" else None}
     del gpu_trips
-    pipelined = (not args.no_pipeline) and args.workload == "vidvrd"     # VidOR: the grounding kernels of step i-1 on a side stream compete
+    pipelined = (not args.no_pipeline) and (args.workload == "vidvrd" or args.force_pipeline)     # VidOR: the grounding kernels of step i-1 on a side stream compete
     side = torch.cuda.Stream(device=device, priority=-1) if pipelined else None   # with step i's GEMMs for the SMs (measured 7 % slower)
 
     def run_steps(n, pl=pipe):

@@ -313,6 +313,8 @@ int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, in
 int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off,
                  int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
                  void* stream);
+/* Tuning / validation knob: keys per block of vsg_mha_tc16 (32: 4 CTAs per SM, default; 64: 2 CTAs per SM).  Returns the old value. */
+int vsg_mha_tc16_set_kc(int kc);
 
 /* Glue of the tensor-core attention path (QK^T and PV are batched vsg_gemm_ex problems, one per (video, head)):
  * in-place row softmax of scale*S over the first n (<= 256) columns, and the transpose of an activation block

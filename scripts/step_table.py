@@ -12,6 +12,9 @@ kind = sys.argv[1] if len(sys.argv) > 1 else "vidvrd"
 n = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 precs = sys.argv[3:] or ["tf32+bf16x2", "bf16"]
 dev = torch.device("cuda", 0)
+if os.environ.get("VSG_KC"):                          # key-block size of the tcgen05 attention kernel (32 / 64)
+    from vidsgg_big_b200._cabi import lib
+    lib().vsg_mha_tc16_set_kc(int(os.environ["VSG_KC"]))
 seeds = [1000 + i for i in range(n)]
 cfg, wl, props, graphs, feats = bench.make_videos(kind, seeds, dev, seeds[0])
 for p in props:

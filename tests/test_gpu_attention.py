@@ -40,9 +40,18 @@ def _ref(qkv, lens):
     return torch.cat(outs, 0)
 
 
-@pytest.mark.parametrize("lens", [[1], [17, 64, 65], [130, 3, 128, 129, 300], [675, 16, 613], [63] * 40 + [200] * 9],
-                         ids=["one", "small", "mixed", "vidor-max", "many"])
-def test_mha_tc16_vs_fp64(lens):
+@pytest.fixture(params=[32, 64], ids=["kc32", "kc64"])
+def kc(request):
+    """Both key-block sizes of the kernel (vsg_mha_tc16_set_kc)."""
+    from vidsgg_big_b200._cabi import lib
+    old = lib().vsg_mha_tc16_set_kc(request.param)
+    yield request.param
+    lib().vsg_mha_tc16_set_kc(old)
+
+
+@pytest.mark.parametrize("lens", [[1], [17, 64, 65], [130, 3, 128, 129, 300], [675, 16, 613], [63] * 40 + [200] * 9, [31, 32, 33, 95, 96, 97]],
+                         ids=["one", "small", "mixed", "vidor-max", "many", "block-edges"])
+def test_mha_tc16_vs_fp64(lens, kc):
     g = torch.Generator(device="cpu").manual_seed(sum(lens))
     rows = sum(lens)
     # scores with a spread of a few units (post-LayerNorm activations through in_proj), so that the softmax is far from uniform
@@ -62,7 +71,7 @@ def test_mha_tc16_vs_fp64(lens):
     assert e1 < 2e-2
 
 
-def test_mha_tc16_in_column_slices_of_a_wider_buffer():
+def test_mha_tc16_in_column_slices_of_a_wider_buffer(kc):
     """Q / K / V / O strides: the kernel is called on column slices (row stride 384) exactly like grounding._qanet does."""
     lens = [90, 200]
     g = torch.Generator(device="cpu").manual_seed(5)

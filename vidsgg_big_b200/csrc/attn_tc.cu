@@ -23,19 +23,21 @@
 namespace vsg {
 
 constexpr int AT_BM = 128;   // queries per CTA (MMA M)
-constexpr int AT_KC = 64;    // keys per block (MMA N of the first product, K of the second)
 constexpr int AT_DH = 16;    // head dimension
-// shared-memory map (bytes, every tile 1024-byte aligned)
-constexpr int AT_OFF_QH = 0;                     // Q   [128 rows x 64 B]  SWIZZLE_64B
-constexpr int AT_OFF_QL = 8192;
-constexpr int AT_OFF_KH = 16384;                 // K   [ 64 rows x 64 B]  SWIZZLE_64B
-constexpr int AT_OFF_KL = 20480;
-constexpr int AT_OFF_VH = 24576;                 // V^T 2 panels x [16 rows x 128 B]  SWIZZLE_128B
-constexpr int AT_OFF_VL = 28672;
-constexpr int AT_OFF_PH = 32768;                 // P   2 panels x [128 rows x 128 B] SWIZZLE_128B
-constexpr int AT_OFF_PL = 65536;
-constexpr int AT_SMEM = 98304;
-constexpr int AT_TMEM_COLS = 128;                // S: columns [0, 64), O: [64, 80)
+// KC = keys per block (MMA N of the first product, K of the second): 64 -> 96 KB of shared memory, 2 CTAs / SM; 32 -> 56 KB, 4 CTAs / SM
+// (twice the MMA round trips per key, but twice the CTAs to overlap them with -- the kernel is latency-bound).
+// shared-memory map (bytes, every tile 1024-byte aligned): Q hi/lo [128 rows x 64 B] SWIZZLE_64B | K hi/lo [KC rows x 64 B] SWIZZLE_64B |
+// V^T hi/lo KC/32 panels x [16 rows x 128 B] SWIZZLE_128B | P hi/lo KC/32 panels x [128 rows x 128 B] SWIZZLE_128B
+template <int KC> struct AtCfg {
+  static constexpr int PANELS = KC / 32;
+  static constexpr int OFF_QH = 0, OFF_QL = 8192;
+  static constexpr int OFF_KH = 16384, OFF_KL = OFF_KH + KC * 64;
+  static constexpr int OFF_VH = OFF_KL + KC * 64, OFF_VL = OFF_VH + PANELS * 2048;
+  static constexpr int OFF_PH = ((OFF_VL + PANELS * 2048 + 1023) / 1024) * 1024, OFF_PL = OFF_PH + PANELS * 16384;
+  static constexpr int SMEM = OFF_PL + PANELS * 16384;
+  static constexpr int TMEM_COLS = KC == 64 ? 128 : 64;        // S: columns [0, KC), O: [KC, KC + 16)
+  static constexpr int CTAS = KC == 64 ? 2 : 4;
+};
 
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 tf32_lo(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
@@ -49,7 +51,8 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-__global__ void __launch_bounds__(128, 2)
+template <int KC>
+__global__ void __launch_bounds__(128, AtCfg<KC>::CTAS)
 mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
                 const int64_t* __restrict__ seg_off, const int32_t* __restrict__ blk_seg, const int32_t* __restrict__ blk_q0,
                 float scale_log2e, int products, float* __restrict__ O, int ldo) {
@@ -57,6 +60,10 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_slot;
+  using CF = AtCfg<KC>;
+  constexpr int AT_KC = KC, AT_OFF_QH = CF::OFF_QH, AT_OFF_QL = CF::OFF_QL, AT_OFF_KH = CF::OFF_KH, AT_OFF_KL = CF::OFF_KL;
+  constexpr int AT_OFF_VH = CF::OFF_VH, AT_OFF_VL = CF::OFF_VL, AT_OFF_PH = CF::OFF_PH, AT_OFF_PL = CF::OFF_PL, AT_TMEM_COLS = CF::TMEM_COLS;
+  constexpr int NX = KC / 32;                       // 16-byte K / V items per thread and block
   const int tid = threadIdx.x, warp = tid >> 5;
   const int seg = blk_seg[blockIdx.x], q0 = blk_q0[blockIdx.x], h = blockIdx.y;
   const int64_t r0 = seg_off[seg];
@@ -88,17 +95,17 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   // K / V blocks go global -> registers -> shared memory in two steps, so that the loads of block b+1 are in flight while block b is
   // multiplied and exponentiated (the round-2 ncu capture had a third of all warp samples waiting on these loads).
   // Item idx = it * 128 + tid: key r = idx >> 2 of the block, 16-byte chunk c = idx & 3 (dims 4c .. 4c+3).
-  auto load_kv = [&](const float* base, int ld, int k0, float4 (&x)[2]) {
+  auto load_kv = [&](const float* base, int ld, int k0, float4 (&x)[NX]) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < NX; ++it) {
       const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
       x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (k0 + r < T) x[it] = *reinterpret_cast<const float4*>(base + (r0 + k0 + r) * (int64_t)ld + col0 + 4 * c);
     }
   };
-  auto store_k = [&](const float4 (&x)[2]) {
+  auto store_k = [&](const float4 (&x)[NX]) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < NX; ++it) {
       const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
       const int o = r * 64 + ((c ^ ((r >> 1) & 3)) << 4);
       *reinterpret_cast<float4*>(smem + AT_OFF_KH + o) = x[it];
@@ -106,9 +113,9 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     }
   };
   // V^T: row d (0..15) of panel p holds keys 32p .. 32p+31 (128 bytes); SWIZZLE_128B: chunk q of row d sits at chunk q ^ (d & 7)
-  auto store_v = [&](const float4 (&x)[2]) {
+  auto store_v = [&](const float4 (&x)[NX]) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
+    for (int it = 0; it < NX; ++it) {
       const int idx = it * 128 + tid, r = idx >> 2, c = idx & 3;
       const float xs[4] = {x[it].x, x[it].y, x[it].z, x[it].w};
       const int p = r >> 5, kk = r & 31;
@@ -140,7 +147,7 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
 
   // ---------------- pass 1: row maxima ----------------
   float m = -INFINITY;
-  float4 kreg[2], vreg[2];
+  float4 kreg[NX], vreg[NX];
   load_kv(K, ldk, 0, kreg);
   for (int b = 0; b < n_blocks; ++b) {
     const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
@@ -154,7 +161,7 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     mbar_wait(&mma_bar, phase); phase ^= 1;
     tc_fence_after();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < NX; ++half) {
       if (half * 32 < n_s) {                                       // warp-uniform
         uint32_t r[32];
         tmem_ld32(t_s + lane_base + half * 32, r);
@@ -183,7 +190,7 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     mbar_wait(&mma_bar, phase); phase ^= 1;
     tc_fence_after();
 #pragma unroll
-    for (int half = 0; half < 2; ++half) {
+    for (int half = 0; half < NX; ++half) {
       uint8_t* ph = smem + AT_OFF_PH + half * 16384 + row * 128;
       uint8_t* pl = smem + AT_OFF_PL + half * 16384 + row * 128;
       if (half * 32 < n_s) {                                       // warp-uniform
@@ -252,6 +259,29 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
 
 using namespace vsg;
 
+static int g_at_kc = 32;
+/* validation / tuning knob: keys per block of the tcgen05 attention kernel (32 or 64); returns the old value */
+extern "C" int vsg_mha_tc16_set_kc(int kc) { int old = g_at_kc; if (kc == 32 || kc == 64) g_at_kc = kc; return old; }
+
+template <int KC>
+static int launch_mha16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_head, float* O,
+                        int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products, void* stream) {
+  static PerDeviceFlag attr_done;
+  const int dev_ = current_device();
+  constexpr int SMEM = AtCfg<KC>::SMEM + 1024;
+  if (!attr_done.is_set(dev_)) {
+    if (cudaFuncSetAttribute(mha16_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+      set_error("vsg_mha_tc16: cannot raise dynamic shared memory to %d", SMEM);
+      return VSG_E_LAUNCH;
+    }
+    attr_done.set(dev_);
+  }
+  const float scale_log2e = 1.4426950408889634f / 4.0f;            // 1 / sqrt(16) * log2(e)
+  mha16_tc_kernel<KC><<<dim3(n_blk, n_head), 128, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, blk_seg, blk_q0, scale_log2e,
+                                                                                products, O, ldo);
+  return check_launch("vsg_mha_tc16");
+}
+
 extern "C" int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off,
                             int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
                             void* stream) {
@@ -261,18 +291,6 @@ extern "C" int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, co
   VSG_REQUIRE(products == 1 || products == 3, "vsg_mha_tc16: products must be 1 (tf32) or 3 (3xTF32)");
   VSG_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0,
               "vsg_mha_tc16: Q / K / V / O must be 16-byte aligned with leading dimensions that are multiples of 4");
-  static PerDeviceFlag attr_done;
-  const int dev_ = current_device();
-  constexpr int SMEM = AT_SMEM + 1024;
-  if (!attr_done.is_set(dev_)) {
-    if (cudaFuncSetAttribute(mha16_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
-      set_error("vsg_mha_tc16: cannot raise dynamic shared memory to %d", SMEM);
-      return VSG_E_LAUNCH;
-    }
-    attr_done.set(dev_);
-  }
-  const float scale_log2e = 1.4426950408889634f / 4.0f;            // 1 / sqrt(16) * log2(e)
-  mha16_tc_kernel<<<dim3(n_blk, n_head), 128, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, blk_seg, blk_q0, scale_log2e,
-                                                                            products, O, ldo);
-  return check_launch("vsg_mha_tc16");
+  return g_at_kc == 64 ? launch_mha16<64>(Q, ldq, K, ldk, V, ldv, seg_off, n_head, O, ldo, blk_seg, blk_q0, n_blk, products, stream)
+                       : launch_mha16<32>(Q, ldq, K, ldk, V, ldv, seg_off, n_head, O, ldo, blk_seg, blk_q0, n_blk, products, stream);
 }
