@@ -4,19 +4,20 @@
 // over ragged sequences: the video encoder (one sequence of T clips), the query encoder (nq sequences of 3 words) and the combined
 // encoder (nq sequences of T clips) -- the last one is 4 T^2 128 flops per query, the largest non-GEMM kernel of the VidOR step.
 //
-// One CTA = (sequence, block of 128 queries, head).  Per block of 64 keys:
-//   S  = Q K^T      tcgen05.mma kind::tf32, M = 128, N = 64, K = 16: Q / K tiles staged by the CTA's threads as K-major SWIZZLE_64B
+// One CTA = (sequence, block of 128 queries, head).  Per block of KC (32 or 64) keys:
+//   S  = Q K^T      tcgen05.mma kind::tf32, M = 128, N = KC, K = 16: Q / K tiles staged by the CTA's threads as K-major SWIZZLE_64B
 //                   tiles (64-byte rows = the 16 floats of one head), accumulator in TMEM columns [0, 64)
 //   P  = exp(...)   the 128 threads read their own row of S with tcgen05.ld (one TMEM lane each), exponentiate and write P as the
 //                   A operand of the second product: two K-major SWIZZLE_128B panels of 32 keys
-//   O += P V        tcgen05.mma M = 128, N = 16, K = 64 against V^T (staged transposed: 16 rows x 32 keys per panel), accumulator in
-//                   TMEM columns [64, 80)
-// Softmax is two-pass (pass 1: row maxima over all key blocks, pass 2: exp / sum / PV), i.e. exactly softmax(s - max) of the reference;
-// recomputing S costs six MMAs per key block, nothing next to the exponentials.
+//   O += P V        tcgen05.mma M = 128, N = 16, K = KC against V^T (staged transposed: 16 rows x 32 keys per panel), accumulator in
+//                   TMEM columns [KC, KC + 16)
+// Softmax is online (running row maximum and sum; when a block raises the maximum the TMEM accumulator is rescaled through
+// tcgen05.ld / tcgen05.st), i.e. softmax(s - max) of the reference up to rounding (measured <= 4e-6 against fp64).
 // fp32-class precision (`products` = 3, the default of the fp32-class GEMM modes): every operand is split into hi = trunc_tf32(x) (the raw
 // fp32 value -- the MMA ignores the low 13 mantissa bits) and lo = x - hi, and each product is lo*hi + hi*lo + hi*hi (3xTF32, error ~2^-21
 // per product).  `products` = 1 runs the hi*hi product only (tf32, the reduced-precision modes).
-// Shared memory 96 KB, TMEM 128 columns -> two CTAs per SM, so one CTA's exponentials overlap the other's MMAs.
+// Shared memory 56 KB (KC = 32) / 96 KB (KC = 64), TMEM 64 / 128 columns -> three / two CTAs per SM, so one CTA's exponentials overlap
+// the others' MMA round trips (the kernel is latency-bound: K = 16 and N = 16 MMAs are tiny).
 #include "common.cuh"
 #include "tc_ptx.cuh"
 
@@ -41,6 +42,15 @@ template <int KC> struct AtCfg {
 
 __device__ __forceinline__ float tf32_lo(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
 __device__ __forceinline__ float4 tf32_lo(float4 x) { return make_float4(tf32_lo(x.x), tf32_lo(x.y), tf32_lo(x.z), tf32_lo(x.w)); }
+
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -145,39 +155,14 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     umma_commit(&mma_bar);
   };
 
-  // ---------------- pass 1: row maxima ----------------
-  float m = -INFINITY;
+  // ---------------- one pass over the key blocks: online softmax ----------------
+  // m = running row maximum, l = running sum of exp(s - m); when a block raises the maximum, the output accumulated so far (TMEM) and l
+  // are rescaled by exp(m_old - m_new) -- softmax(s) V exactly, without a separate pass over S for the maxima (which cost one more
+  // K staging + MMA round trip per block).  The rescale is skipped warp-wide when no row of the warp changed its maximum.
+  float m = -INFINITY, l = 0.f;
   float4 kreg[NX], vreg[NX];
   load_kv(K, ldk, 0, kreg);
-  for (int b = 0; b < n_blocks; ++b) {
-    const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
-    store_k(kreg);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    if (tid == 0) { tc_fence_after(); issue_s(n_s); }
-    if (b + 1 < n_blocks) load_kv(K, ldk, k0 + AT_KC, kreg);        // next block of pass 1 ...
-    else { load_kv(K, ldk, 0, kreg); load_kv(V, ldv, 0, vreg); }   // ... or the first block of pass 2
-    mbar_wait(&mma_bar, phase); phase ^= 1;
-    tc_fence_after();
-#pragma unroll
-    for (int half = 0; half < NX; ++half) {
-      if (half * 32 < n_s) {                                       // warp-uniform
-        uint32_t r[32];
-        tmem_ld32(t_s + lane_base + half * 32, r);
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (half * 32 + j < valid) m = fmaxf(m, __uint_as_float(r[j]));
-      }
-    }
-    tc_fence_before();
-    __syncthreads();                                               // every row of S is read before the next block overwrites it / K
-  }
-
-  // ---------------- pass 2: P = exp(s - max), O += P V ----------------
-  float l = 0.f;
-  const float mscaled = m * scale_log2e;
+  load_kv(V, ldv, 0, vreg);
   for (int b = 0; b < n_blocks; ++b) {
     const int k0 = b * AT_KC, valid = min(AT_KC, T - k0), n_s = (valid + 15) & ~15;
     store_k(kreg);
@@ -186,9 +171,35 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     tc_fence_before();
     __syncthreads();
     if (tid == 0) { tc_fence_after(); issue_s(n_s); }
-    if (b + 1 < n_blocks) { load_kv(K, ldk, k0 + AT_KC, kreg); load_kv(V, ldv, k0 + AT_KC, vreg); }
+    if (b + 1 < n_blocks) { load_kv(K, ldk, k0 + AT_KC, kreg); load_kv(V, ldv, k0 + AT_KC, vreg); }   // in flight during this block
     mbar_wait(&mma_bar, phase); phase ^= 1;
     tc_fence_after();
+    float bm = -INFINITY;
+#pragma unroll
+    for (int half = 0; half < NX; ++half) {
+      if (half * 32 < n_s) {                                       // warp-uniform
+        uint32_t r[32];
+        tmem_ld32(t_s + lane_base + half * 32, r);
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (half * 32 + j < valid) bm = fmaxf(bm, __uint_as_float(r[j]));
+      }
+    }
+    const float m_new = fmaxf(m, bm);
+    if (b > 0 && __any_sync(0xffffffffu, m_new > m)) {             // warp-uniform: tcgen05.ld / .st are warp-collective
+      const float alpha = exp2f((m - m_new) * scale_log2e);        // 1 for rows whose maximum did not move
+      uint32_t o[16];
+      tmem_ld16(t_o + lane_base, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 16; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+      tmem_st16(t_o + lane_base, o);
+      tmem_st_wait();
+      l *= alpha;
+    }
+    m = m_new;
+    const float mscaled = m * scale_log2e;
 #pragma unroll
     for (int half = 0; half < NX; ++half) {
       uint8_t* ph = smem + AT_OFF_PH + half * 16384 + row * 128;
@@ -232,7 +243,7 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
       }
       umma_commit(&mma_bar);
     }
-    mbar_wait(&mma_bar, phase); phase ^= 1;                        // P / V / K may be overwritten, S may be recomputed
+    mbar_wait(&mma_bar, phase); phase ^= 1;                        // P / V / K may be overwritten, S recomputed, O rescaled
     tc_fence_after();
   }
 
