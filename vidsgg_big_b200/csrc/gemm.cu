@@ -409,10 +409,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const TileCoord tc = tile_coord(ep, tile, tiles_m, tiles_n, BN, CL >= 2 ? 2 : 1, rank);
       const int m0 = tc.m0, n0 = tc.n0;
       const int row = m0 + row_in_tile;
+      const bool row_ok = row < ep.M;
+      // While this tile's mainloop is still running: pull the lane's residual / accumulate row (one 128-byte line per 32-column chunk)
+      // towards L2.  The operands come straight from HBM (written by the previous launch); unprefetched, every chunk of the epilogue
+      // waited a full DRAM round trip for them (the residual adds were the top stall of the conv-fused grounding GEMM).
+      if (row_ok && (ep.residual || ep.accumulate)) {
+        const float* pre = ep.residual ? ep.residual + (size_t)row * ep.ld_res : ep.C + tc.c_off + (size_t)row * ep.ldc;
+#pragma unroll 1
+        for (int c = 0; c < BN / 32; ++c)
+          if (n0 + c * 32 < ep.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(pre + n0 + c * 32));
+      }
       mbar_wait(&acc_full[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr = tmem_base + acc * ACC_COLS + ((uint32_t)(quad * 32) << 16);
-      const bool row_ok = row < ep.M;
       const bool slab_rows_ok = m0 + quad * 32 + 32 <= ep.M;                 // warp-uniform
       const float* rb = nullptr;
       if (row_ok && ep.rowbias) {
