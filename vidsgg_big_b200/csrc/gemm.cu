@@ -438,8 +438,46 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (col0 >= ep.N) break;                                              // warp-uniform
         uint32_t r[32];
         tmem_ld32(taddr + c * 32, r);
-        tmem_ld_wait();
         const bool fast = ep.C && ep.tma_store && vec_ok && slab_rows_ok && col0 + 32 <= ep.N;   // warp-uniform
+        // LEAN path (nearly every launch: bias / ReLU / residual only): the generic loop below re-derives four optional operand
+        // pointers per 16 bytes and waits for each bias load right before its add -- ~700 SASS instructions and eight exposed load
+        // latencies per 32-column chunk, which made the epilogue (not the MMAs, not HBM) the limit of the N = K = 128 grounding GEMMs
+        // and of the K = 512 decoder GEMMs (round-2 ncu source view).  Here the chunk's bias comes from ONE coalesced load (lane l holds
+        // column col0 + l, broadcast by shuffles) and the residual row from eight independent loads, all issued before the TMEM wait.
+        const bool lean = fast && !rb && !ep.accumulate && !crow_lo && !crow16 && (!res || res_vec) && bias_vec;   // warp-uniform
+        if (lean) {
+          const float bl = ep.bias ? ep.bias[col0 + lane] : 0.f;
+          float4 rv[8];
+          if (res) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) rv[j] = *reinterpret_cast<const float4*>(res + col0 + 4 * j);
+          }
+          tmem_ld_wait();
+          uint8_t* sb = stg + sbuf * 4096;
+          if (lane == 0) bulk_wait_read<1>();                                 // the store that last read this buffer is done
+          __syncwarp();
+          const float floor_v = ep.relu ? 0.f : -INFINITY;
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            if (ep.bias) {
+              v.x += __shfl_sync(0xffffffffu, bl, j); v.y += __shfl_sync(0xffffffffu, bl, j + 1);
+              v.z += __shfl_sync(0xffffffffu, bl, j + 2); v.w += __shfl_sync(0xffffffffu, bl, j + 3);
+            }
+            v.x = fmaxf(v.x, floor_v); v.y = fmaxf(v.y, floor_v); v.z = fmaxf(v.z, floor_v); v.w = fmaxf(v.w, floor_v);
+            if (res) { const float4 t4 = rv[j >> 2]; v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w; }
+            *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
+          }
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&mapC, smem_u32(sb), tc.c_col + col0, tc.c_row + m0 + quad * 32);
+            bulk_commit();
+          }
+          sbuf ^= 1;
+          continue;
+        }
+        tmem_ld_wait();
         if (fast) {
           uint8_t* sb = stg + sbuf * 4096;
           const bool lo_slab = ep.lo_tma && col0 >= ep.lo_c0 && col0 + 32 <= ep.lo_c1;   // warp-uniform: the low parts leave by TMA too
