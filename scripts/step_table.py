@@ -24,6 +24,8 @@ for prec in precs:
     pipe.model.backend = "py"                      # op-by-op launches so that every GEMM can be bracketed
     if kind == "vidor":
         pipe.grd.backend = "py"
+        if os.environ.get("VSG_NOFUSE"):               # depthwise conv as a separate launch instead of inside the point-wise GEMM
+            pipe.grd.fuse_dwconv = False
     g2, _ = bench.gt_from_predictions(pipe, props, cfg, seeds, dev)
     for _ in range(3):
         pipe.step(props, g2, gather=False)

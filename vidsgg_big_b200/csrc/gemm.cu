@@ -688,6 +688,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const float4* src = reinterpret_cast<const float4*>(st);
         uint8_t* lo16 = st + CF::OFF_AL;
         uint8_t* a16 = st + CF::OFF_A16;
+        // CONV: a thread's items (rows i * 32 + t / 4) all fall on the SAME logical 16-byte chunk, (t & 3) ^ ((t >> 3) & 3): the depthwise
+        // weights and bias of its 4 channels are loaded once per k block into registers (they were 4 shared-memory loads per tap and item:
+        // the fused kernel ran at the shared-memory pipe's limit)
+        float wq[CONV ? 4 : 1][CONV ? 7 : 1];
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (CONV) {
+          const int cq = kb * BK + 4 * ((t & 3) ^ ((t >> 3) & 3)), k = ep.dw_k;
+#pragma unroll
+          for (int ch = 0; ch < 4; ++ch)
+#pragma unroll
+            for (int j = 0; j < 7; ++j) wq[ch][j] = j < k ? sdw[(cq + ch) * k + j] : 0.f;
+          bq = *reinterpret_cast<const float4*>(sdw + ep.K * k + cq);
+        }
 #pragma unroll
         for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : NI); ++i) {
           const int idx = i * 128 + t;
@@ -696,22 +709,22 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (CONV) {
             // x = dwconv(X)[m0 + r][kb*16 + 4l .. +3] = b + sum_j w[c][j] * X[row + j - k/2][c] inside the row's sequence (same operation
             // order as dwconv_kernel, so the fused product is bit-identical to dwconv followed by the plain GEMM); written to the A tile
-            const int grow = m0c + r, k = ep.dw_k, c = kb * BK + 4 * l;
+            const int grow = m0c + r, k = ep.dw_k;
             x = make_float4(0.f, 0.f, 0.f, 0.f);
             if (grow < ep.M) {
               const int p = seq_p[i], q = seq_q[i];
-              const float* wv = sdw + c * k;
-              x = *reinterpret_cast<const float4*>(sdw + ep.K * k + c);
+              x = bq;
               const uint8_t* raw = st + CF::OFF_RAW;
-              for (int j = 0; j < k; ++j) {
+#pragma unroll
+              for (int j = 0; j < 7; ++j) {
                 const int d = j - k / 2;
-                if (d < -p || d > q) continue;
+                if (j >= k || d < -p || d > q) continue;
                 const int rr = r + 3 + d;
                 const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
-                x.x = fmaf(wv[j], xin.x, x.x);
-                x.y = fmaf(wv[k + j], xin.y, x.y);
-                x.z = fmaf(wv[2 * k + j], xin.z, x.z);
-                x.w = fmaf(wv[3 * k + j], xin.w, x.w);
+                x.x = fmaf(wq[0][j], xin.x, x.x);
+                x.y = fmaf(wq[1][j], xin.y, x.y);
+                x.z = fmaf(wq[2][j], xin.z, x.z);
+                x.w = fmaf(wq[3][j], xin.w, x.w);
               }
             }
             reinterpret_cast<float4*>(st)[idx] = x;
