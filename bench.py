@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 from vidsgg_big_b200 import synth  # noqa: E402
 
-PRECISIONS = ["3xtf32", "tf32+bf16x2", "tf32", "bf16", "fp32_simt"]
+PRECISIONS = ["3xtf32", "tf32+bf16x2", "fp16x3", "tf32", "bf16", "fp32_simt"]
 VIDOR_SEED0 = 700000          # seeds of the VidOR-val-shaped set
 METRIC = "videos/sec (classify+ground+vIoU)"
 
@@ -59,7 +59,7 @@ def parse():
     ap.add_argument("--chunk-rows", type=int, default=2_500_000, help="feature rows per resident chunk of the VidOR set")
     ap.add_argument("--no-graph", action="store_true", help="issue the BIG-C forward's ~150 launches from Python every step instead of "
                     "replaying the CUDA graph captured for the resident batch")
-    ap.add_argument("--modes", default="bf16", help="comma list of extra precisions timed on the top-level workload next to --precision, with their decision-flip report "
+    ap.add_argument("--modes", default="fp16x3,bf16", help="comma list of extra precisions timed on the top-level workload next to --precision, with their decision-flip report "
                     "('' = none)")
     return ap.parse_args()
 
@@ -602,7 +602,7 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     if pipe.kind == "vidor":
         pipe.grd.backend = gbackend
     P = linalg._Profile
-    slots = {"tf32+bf16x2": 4.0, "3xtf32": 6.0, "tf32": 2.0, "bf16": 1.0}.get(precision)      # bf16-equivalent tensor slots per useful MAC
+    slots = {"tf32+bf16x2": 4.0, "fp16x3": 3.0, "3xtf32": 6.0, "tf32": 2.0, "bf16": 1.0}.get(precision)      # bf16-equivalent tensor slots per useful MAC
     out = {}
 
     def tensor_leg(kernel, n, flops, ms, extra=None):
@@ -624,7 +624,7 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
     n, fl, ms = P.summary("gemm", "bigc")
     out["bigc_gemm"] = tensor_leg("gemm_tc_kernel (tcgen05 %s), BIG-C launches" % precision, n, fl, ms,
                                   {"note": "achieved = useful 2MNK flops; the fp32-class modes issue several tensor passes per useful product "
-                                           "(3xtf32: 3 tf32 = 6 bf16-equivalent slots, tf32+bf16x2: 1 tf32 + 2 bf16 = 4 slots, bf16: 1)"})
+                                           "(3xtf32: 3 tf32 = 6 bf16-equivalent slots, tf32+bf16x2: 1 tf32 + 2 bf16 = 4 slots, fp16x3: 3 fp16 = 3 slots, bf16: 1)"})
     geo_ms = timers["geo0"].elapsed_time(timers["geo1"])
     out["k1_geometry"] = hbm_leg("traj_viou_warp_kernel (+ track volumes, spans)", algorithmic_bytes_geometry(props), geo_ms,
                                  {"note": "SURVEY 8d K1 bytes; a video's tracks fit in L2, so DRAM only sees the compulsory bytes"})

@@ -172,6 +172,9 @@ int vsg_unique_rows(const int64_t* rows, int n, int d, int32_t* order, int32_t* 
 #define VSG_GEMM_TF32_BF16X2 3 /* fp32-class: tf32 main product + the two correction products as bf16 MMAs (kind::f16);
                                   needs W_b16 / W_lo16 from vsg_split_bf16; vsg_gemm_ex only, plain (non-batched) problems */
 #define VSG_GEMM_BF16 4   /* reduced precision: bf16 operands (A16, W_b16), ONE kind::f16 pass, fp32 accumulate; outputs fp32 C and / or bf16 C16 */
+#define VSG_GEMM_FP16X3 5 /* fp32-class at 3 tensor slots per MAC (mode 3: 4): A and W split into fp16 hi / lo pairs, three kind::f16 products,
+                             power-of-two range scaling (W image pre-scaled, A_lo carried x 2^11); needs W_img16 / w_alpha from
+                             vsg_build_weight_image_fp16; |A| < 65504; vsg_gemm_ex only, plain problems */
 
 /* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ) (+ residual[M][N]),
  * fp32 row-major; the residual is added after the activation (QANet blocks, models/grd_model_v5.py:118-135).
@@ -217,6 +220,9 @@ typedef struct VsgGemmArgs {
    * bf16 copy [M][ldc16] of the stored values; in mode 4, C may then be NULL (bf16 output only). */
   const void* A16; int lda16;
   void* C16; int ldc16;
+  /* mode VSG_GEMM_FP16X3 (5): fp16 weight-tile image of vsg_build_weight_image_fp16 (built for tile width img16_bn == vsg_gemm_tile_n(N)
+   * over exactly this N and K) and w_alpha = 1 / scale of that image; A is the fp32 operand, W_hi the fp32 weight (only its extents are used). */
+  const void* W_img16; int img16_bn; float w_alpha;
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 
@@ -254,6 +260,12 @@ int64_t vsg_weight_image_bytes(int N, int K, int bn);
 int vsg_build_weight_image(const float* w, int ldw, int N, int K, int bn, void* img, void* stream);
 /* Validation knob: 0 = ignore W_img (tensor-map loads); 1 (default).  Bit-identical C.  Returns the old value. */
 int vsg_gemm_set_weight_image(int on);
+/* Weight-tile images of mode VSG_GEMM_FP16X3: per (N tile of `bn` rows, 16-column k block) three fp16 sub-images (bn rows x 32 B, SWIZZLE_32B,
+ * edges zero-padded): hi = fp16_rn(w * scale), fp16_rn(hi * 2^-11), fp16_rn(w * scale - hi).  `scale` must be a power of two; pick it so that
+ * max |w| * scale lies in [2^13, 2^14) (fp16 overflows at 65504; low parts stay normal for |w| >= 2^-16 max |w|) and pass w_alpha = 1 / scale.
+ * Reference counterpart: none (models/model_0v10.py multiplies in fp32); this is how the fp32 product is rebuilt on fp16 tensor cores. */
+int64_t vsg_weight_image_fp16_bytes(int N, int K, int bn);
+int vsg_build_weight_image_fp16(const float* w, int ldw, int N, int K, int bn, float scale, void* img, void* stream);
 
 /* ---- BIG-C classification stage, non-GEMM kernels -------------------------
  * Batch layout: rows = all box-frames of all tracks of all videos; off int64[N+1]; seg int32[V+1] track range
@@ -359,12 +371,13 @@ int vsg_bipartite_cost(const float* logit, int Q, int P, const int64_t* gt_pred,
  * (vsg_bigc_workspace_bytes), the outputs in the caller's VsgTripletOut buffers.  Results are bit-identical to the op-by-op path. */
 
 /* One nn.Linear / 1x1 conv / conv-tap weight [N][K] in the layouts the GEMM modes read (see vsg_gemm_ex): fp32 `w` always; `hi`/`lo`
- * for VSG_GEMM_3XTF32; `w16`/`lo16` (+ optional `img`) for VSG_GEMM_TF32_BF16X2; `w16` for VSG_GEMM_BF16.  bias may be NULL. */
+ * for VSG_GEMM_3XTF32; `w16`/`lo16` (+ optional `img`) for VSG_GEMM_TF32_BF16X2; `w16` for VSG_GEMM_BF16; `img16`/`alpha` for VSG_GEMM_FP16X3.  bias may be NULL. */
 typedef struct VsgLinear {
   const float* w; const float* bias; int N, K, ldw;
   const float* hi; const float* lo;
   const void* w16; const void* lo16; int ld16;
   const void* img; int img_bn;
+  const void* img16; int img16_bn; float alpha;   /* VSG_GEMM_FP16X3: fp16 tile image, its tile width, 1 / its scale */
 } VsgLinear;
 
 typedef struct VsgNorm { const float* gamma; const float* beta; } VsgNorm;

@@ -12,19 +12,20 @@ SHAPES = [  # M, N, K
 ]
 # 3xTF32: the tensor core accumulates with truncation, so the error grows ~K/8 * 2^-24 (1e-5 at K=2048)
 # tf32 + 2 x bf16 corrections (mode 3): per-product error <= 2^-18 on top of the same accumulation error
-TOL = {0: 2e-6, 1: 2e-3, 2: 2e-5, 3: 3e-5}
+# fp16x3 (mode 5): per-product error ~2^-22, same accumulation error
+TOL = {0: 2e-6, 1: 2e-3, 2: 2e-5, 3: 3e-5, 5: 3e-5}
 
 
 def _weight(mode, W, bias=None):
     from vidsgg_big_b200 import linalg
-    return linalg.Weight(W, bias, split="bf16" if mode == 3 else True)
+    return linalg.Weight(W, bias, split="bf16" if mode == 3 else "fp16" if mode == 5 else True)
 
 
 def _ref(A, W, bias):
     return A.double() @ W.double().t() + (bias.double() if bias is not None else 0)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5])
 @pytest.mark.parametrize("shape", SHAPES, ids=["%dx%dx%d" % s for s in SHAPES])
 def test_gemm_modes(mode, shape):
     from vidsgg_big_b200 import linalg
@@ -42,7 +43,7 @@ def test_gemm_modes(mode, shape):
     assert err <= TOL[mode] * scale, "mode %d shape %s: max err %.3e (scale %.3e)" % (mode, shape, err, scale)
 
 
-@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3, 5])
 def test_gemm_epilogue_options(mode):
     from vidsgg_big_b200 import linalg
     g = torch.Generator(device="cpu").manual_seed(5)
@@ -103,6 +104,38 @@ def test_gemm_tf32_bf16x2_is_fp32_class():
         assert emix <= 4 * e3x + 1e-7 * ref.abs().max().item() and e1x > 20 * emix
 
 
+def test_gemm_fp16x3_is_fp32_class_over_operand_ranges():
+    """Mode 5 (three kind::f16 products on fp16 hi / lo pairs): same error class as 3xTF32 (within 4x) and >20x better than plain tf32
+    whatever the magnitude of the operands -- the weight image is scaled by a power of two and the A correction travels as lo * 2^11, so
+    tiny weights / activations keep their low parts (an unscaled fp16 split degrades to ~1e-5 there) -- and for operands that span orders
+    of magnitude.  |A| must stay below the fp16 range (65504); the result is compared with an emulation of the scheme as well."""
+    from vidsgg_big_b200 import linalg
+    g = torch.Generator(device="cpu").manual_seed(12)
+    for a_scale, w_scale, spread in ((1.0, 1 / 45.0, 0.0), (1e-3, 1e-3, 0.0), (300.0, 1e-5, 0.0), (1e-2, 40.0, 0.0), (1.0, 1 / 45.0, 1.5)):
+        A = torch.randn(1024, 2048, generator=g) * a_scale * torch.exp(spread * torch.randn(1024, 2048, generator=g))
+        W = torch.randn(512, 2048, generator=g) * w_scale * torch.exp(spread * torch.randn(512, 2048, generator=g))
+        A, W = A.to(DEV), W.to(DEV)
+        assert A.abs().max().item() < 65504
+        ref = A.double() @ W.double().t()
+        scale = ref.abs().max().item()
+        wt5 = _weight(5, W)
+        e3x = (linalg.gemm(2, A, linalg.Weight(W)).double() - ref).abs().max().item()
+        out5 = linalg.gemm(5, A, wt5)
+        e5 = (out5.double() - ref).abs().max().item()
+        e1x = (linalg.gemm(1, A, linalg.Weight(W)).double() - ref).abs().max().item()
+        print("A %.0e W %.0e spread %.1f: 3xtf32 err %.3e  fp16x3 err %.3e  tf32 err %.3e  (scale %.3e, alpha %g)" % (a_scale, w_scale, spread, e3x, e5, e1x, scale, wt5.alpha))
+        assert e5 <= 4 * e3x + 1e-7 * scale and e1x > 20 * e5
+        # emulation: the three products of the split operands in fp64 (the kernel only adds fp32 accumulation error)
+        Ws = W.double() / wt5.alpha
+        w_hi = Ws.to(torch.float16).double()
+        w_his = (w_hi / 2048).to(torch.float16).double()
+        w_lo = (Ws - w_hi).to(torch.float16).double()
+        a_hi = A.to(torch.float16).double()
+        a_lo = ((A.double() - a_hi).float() * 2048).to(torch.float16).double()
+        emu = (a_lo @ w_his.t() + a_hi @ w_lo.t() + a_hi @ w_hi.t()) * wt5.alpha
+        assert (out5.double() - emu).abs().max().item() <= 2e-5 * scale
+
+
 def test_tf32_mma_ignores_low_mantissa_bits():
     """The 3xTF32 kernel leaves the raw fp32 A tile in shared memory as the 'high' operand.  That is only valid if
     tcgen05 kind::tf32 ignores the low 13 mantissa bits: the result must be BIT-IDENTICAL to the variant that masks them."""
@@ -122,7 +155,7 @@ def test_tf32_mma_ignores_low_mantissa_bits():
     assert torch.equal(masked, raw)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 def test_wide_tiles_equal_narrow_tiles(mode):
     """The 128x256-tile kernel against the 128x128-tile kernel: bit-identical in tf32 mode (same accumulation order over K);
     in 3xTF32 mode the wide kernel walks K in blocks of 16 instead of 32, which reorders the three partial products."""
@@ -137,16 +170,18 @@ def test_wide_tiles_equal_narrow_tiles(mode):
         wide = linalg.gemm(mode, A, wt, relu=True).clone()
         old = lib().vsg_gemm_force_bn(128)
         try:
+            if mode == 5:       # the fp16 image is the only source of W: built for the tile width in force
+                wt = _weight(mode, W, b)
             narrow = linalg.gemm(mode, A, wt, relu=True).clone()
         finally:
             lib().vsg_gemm_force_bn(old)
-        if mode in (1, 3):       # same K walk (mode 3 uses 16-column blocks for both tile widths)
+        if mode in (1, 3, 5):    # same K walk (modes 3 / 5 use 16-column blocks for both tile widths)
             assert torch.equal(wide, narrow), (M, N, K)
         else:
             assert (wide - narrow).abs().max().item() <= 1e-5 * narrow.abs().max().item(), (M, N, K)
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 def test_tma_store_epilogue_equals_direct_stores(mode):
     """The TMA-store epilogue (32x32 slabs staged in shared memory) against the per-row store epilogue: bit-identical C, also
     for ragged M / N (edge slabs fall back to direct stores), column-slice outputs and every epilogue option."""
@@ -183,7 +218,7 @@ def test_tma_store_epilogue_equals_direct_stores(mode):
         assert bool((lo[:, :c0] == 0).all()) and bool((lo[:, c1:] == 0).all())
 
 
-@pytest.mark.parametrize("mode", [1, 2, 3])
+@pytest.mark.parametrize("mode", [1, 2, 3, 5])
 def test_cta_pair_multicast_equals_single_cta(mode):
     """CTA-pair MMAs (cta_group::2) and CTA pairs with W multicast against one CTA per tile: bit-identical C, including an odd
     number of M tiles (the pair's second CTA runs a dummy tile), a single pair, ragged edges and wide / narrow N tiles."""
@@ -257,7 +292,8 @@ def test_weight_images_equal_tensor_map_loads():
         assert (outs[0].double() - ref).abs().max().item() <= TOL[3] * ref.abs().max().item()
 
 
-def test_fused_dwconv_gemm_equals_dwconv_then_gemm():
+@pytest.mark.parametrize("mode", [3, 5])
+def test_fused_dwconv_gemm_equals_dwconv_then_gemm(mode):
     """The CONV variant (depthwise conv computed by the split warps from a raw X tile with halo rows) against vsg_dwconv followed by the
     plain mode-3 GEMM: bit-identical, for k = 7 / 3, ragged sequences (incl. length-1 / length-2 ones and sequences that straddle
     tile boundaries), M not a multiple of 128, ReLU + residual epilogues, N = 128 and narrower."""
@@ -277,14 +313,14 @@ def test_fused_dwconv_gemm_equals_dwconv_then_gemm():
         W = torch.randn(N, H, generator=g).to(DEV) / H ** 0.5
         b = torch.randn(N, generator=g).to(DEV)
         res = torch.randn(M, N, generator=g).to(DEV)
-        wt = _weight(3, W, b)
-        assert linalg.can_fuse_dwconv(3, wt, k=k)
+        wt = _weight(mode, W, b)
+        assert linalg.can_fuse_dwconv(mode, wt, k=k)
         t = torch.empty_like(x)
         check(lib().vsg_dwconv(C.c_void_p(x.data_ptr()), C.c_void_p(pos.data_ptr()), C.c_void_p(rem.data_ptr()), C.c_void_p(dw_w.data_ptr()),
                                C.c_void_p(dw_b.data_ptr()), k, M, H, C.c_void_p(t.data_ptr()), stream_ptr(x.device)), "vsg_dwconv")
         for relu, rs in ((False, None), (True, res)):
-            want = linalg.gemm(3, t, wt, relu=relu, residual=rs)
-            got = linalg.gemm(3, x, wt, relu=relu, residual=rs, dwconv=(dw_w, dw_b, k, pos, rem))
+            want = linalg.gemm(mode, t, wt, relu=relu, residual=rs)
+            got = linalg.gemm(mode, x, wt, relu=relu, residual=rs, dwconv=(dw_w, dw_b, k, pos, rem))
             assert torch.equal(got, want), (lens, N, k, relu)
         # and the conv itself against a plain torch restatement (zero padding inside each sequence)
         ref = torch.zeros_like(x)

@@ -22,7 +22,7 @@ def _model(precision):
 
 
 # measured on B200 (profiles/r02_parity_errors.txt): fp32_simt <= 5.1e-7, 3xtf32 <= 2.0e-6, tf32+bf16x2 <= 2.2e-6, tf32 <= 9.2e-4
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5), ("tf32", 5e-3)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5), ("fp16x3", 2e-5), ("tf32", 5e-3)])
 def test_grounding_network_vs_reference(golden, precision, tol):
     g = golden("grounding")
     model = _model(precision)
@@ -53,7 +53,7 @@ def test_grounding_post_exact_on_reference_outputs(golden):
         np.testing.assert_allclose(probs.cpu().numpy(), g[k + "_probs"], rtol=0, atol=2e-6)
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32", "tf32+bf16x2"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "3xtf32", "tf32+bf16x2", "fp16x3"])
 def test_grounding_forward_end_to_end(golden, precision):
     g = golden("grounding")
     model = _model(precision)
@@ -224,7 +224,7 @@ def _large_reference():
     return _LARGE_REF
 
 
-@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5)])
+@pytest.mark.parametrize("precision,tol", [("fp32_simt", 5e-6), ("3xtf32", 2e-5), ("tf32+bf16x2", 2e-5), ("fp16x3", 2e-5)])
 def test_grounding_vidor_size_vs_oracle(precision, tol):
     """Grounding parity at VidOR size (T = 613 clips >= 600, nq >= 500 queries, 10 bins): network outputs against the oracle's, the
     post-processing pinned EXACTLY on the oracle's network outputs, and the end-to-end outputs up to near-tie flips."""
@@ -256,7 +256,7 @@ def test_grounding_vidor_size_vs_oracle(precision, tol):
     assert (a == b).all(-1).float().mean().item() >= 0.97
 
 
-@pytest.mark.parametrize("precision", ["fp32_simt", "tf32", "3xtf32", "tf32+bf16x2", "bf16"])
+@pytest.mark.parametrize("precision", ["fp32_simt", "tf32", "3xtf32", "tf32+bf16x2", "fp16x3", "bf16"])
 def test_c_grounding_forward_equals_python_issued_launches(golden, precision):
     """vsg_grd_forward (ONE C call, csrc/forward.cu) against the same launches issued op by op from Python: bit-identical network
     outputs and post-processing results for a ragged batch of videos, every precision mode, with and without the fused depthwise conv

@@ -39,12 +39,13 @@ class VsgGemmArgs(C.Structure):
                 ("lo_col_begin", i32), ("lo_col_end", i32), ("W_b16", p), ("W_lo16", p), ("ldw16", i32),
                 ("W_img", p), ("img_bn", i32),
                 ("dw_w", p), ("dw_b", p), ("seq_pos", p), ("seq_rem", p), ("dw_k", i32),
-                ("A16", p), ("lda16", i32), ("C16", p), ("ldc16", i32)]
+                ("A16", p), ("lda16", i32), ("C16", p), ("ldc16", i32),
+                ("W_img16", p), ("img16_bn", i32), ("w_alpha", C.c_float)]
 
 
 class VsgLinear(C.Structure):
     _fields_ = [("w", p), ("bias", p), ("N", i32), ("K", i32), ("ldw", i32), ("hi", p), ("lo", p), ("w16", p), ("lo16", p), ("ld16", i32),
-                ("img", p), ("img_bn", i32)]
+                ("img", p), ("img_bn", i32), ("img16", p), ("img16_bn", i32), ("alpha", C.c_float)]
 
 
 class VsgNorm(C.Structure):
@@ -155,6 +156,8 @@ SIGNATURES = {
     "vsg_gemm_tile_n": (i32, [i32]),
     "vsg_weight_image_bytes": (i64, [i32, i32, i32]),
     "vsg_build_weight_image": (i32, [p, i32, i32, i32, i32, p, p]),
+    "vsg_weight_image_fp16_bytes": (i64, [i32, i32, i32]),
+    "vsg_build_weight_image_fp16": (i32, [p, i32, i32, i32, i32, C.c_float, p, p]),
     "vsg_gemm_set_weight_image": (i32, [i32]),
     "vsg_split_bf16": (i32, [p, i32, i32, i32, p, p, i32, p]),
     "vsg_softmax_rows": (i32, [p, i32, i32, i64, f32, p]),

@@ -281,6 +281,7 @@ class BIG_C(object):
             l.w, l.bias, l.N, l.K, l.ldw = addr(W.w), addr(W.bias), W.N, W.K, W.w.stride(0)
             l.hi, l.lo, l.w16, l.lo16, l.ld16 = addr(W.hi), addr(W.lo), addr(W.w16), addr(W.lo16), getattr(W, "ld16", 0)
             l.img, l.img_bn = addr(W.img), W.img_bn
+            l.img16, l.img16_bn, l.alpha = addr(W.img16), W.img16_bn, W.alpha
             return l
 
         def norm(n):

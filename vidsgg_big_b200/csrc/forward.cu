@@ -57,6 +57,7 @@ struct FwdBase {
       a.W_b16 = W.w16; a.W_lo16 = W.lo16; a.ldw16 = W.ld16;
       if (W.img && K == W.K) { a.W_img = W.img; a.img_bn = W.img_bn; }
     }
+    if (mode == VSG_GEMM_FP16X3) { a.W_img16 = W.img16; a.img16_bn = W.img16_bn; a.w_alpha = W.alpha; }
     if (mode == VSG_GEMM_BF16) {
       a.W_b16 = W.w16; a.ldw16 = W.ld16;
       if (A16) { a.A16 = A16; a.lda16 = lda16; }
@@ -90,7 +91,7 @@ struct Fwd : FwdBase {
   void mha_tc(const float* qkv, const float* qkv_lo, int n_seg, int Q, int d, float* att) {
     const int H = w->n_head, dh = d / H;
     const int64_t rows = (int64_t)n_seg * Q;
-    const int m = mode == VSG_GEMM_BF16 ? VSG_GEMM_TF32 : (mode == VSG_GEMM_TF32_BF16X2 ? VSG_GEMM_3XTF32 : mode);   // linalg.attention_mode
+    const int m = mode == VSG_GEMM_BF16 ? VSG_GEMM_TF32 : ((mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3) ? VSG_GEMM_3XTF32 : mode);   // linalg.attention_mode
     float* S = ar.get<float>(rows * H * Q);
     VsgGemmArgs a;
     memset(&a, 0, sizeof(a));
@@ -203,7 +204,7 @@ int Fwd::run(VsgTripletOut* out, int topk) {
   float* hid = ar.get<float>(VQ * 2 * Pd);
   float* qkv = ar.get<float>(VQ * 3 * Pd);
   const bool use_tc = w->tc_attention && mode != VSG_GEMM_SIMT && (Pd / H) % 32 == 0 && Q % 32 == 0;
-  const bool need_lo = use_tc && (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2);
+  const bool need_lo = use_tc && (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3);
   float* qkv_lo = need_lo ? ar.get<float>(VQ * 3 * Pd) : nullptr;
   float* att = ar.get<float>(VQ * Pd);
   float* t1 = ar.get<float>(VQ * Pd);
@@ -317,7 +318,7 @@ struct GrdFwd : FwdBase {
   const VsgGrdBatch* b;
 
   bool can_fuse(const VsgGrdConv& c) const {      // linalg.can_fuse_dwconv
-    return w->fuse_dwconv && mode == VSG_GEMM_TF32_BF16X2 && c.pw.w16 && c.pw.N <= 128 && c.pw.K % 16 == 0 && c.pw.K * (c.k + 1) <= 2048 &&
+    return w->fuse_dwconv && ((mode == VSG_GEMM_TF32_BF16X2 && c.pw.w16) || (mode == VSG_GEMM_FP16X3 && c.pw.img16)) && c.pw.N <= 128 && c.pw.K % 16 == 0 && c.pw.K * (c.k + 1) <= 2048 &&
            (c.k & 1) && c.k <= 7;
   }
   // DepthWiseSeparableConv1d (:36-56): depthwise conv over the sequence axis, then the 1x1 conv (+ ReLU, + residual)
@@ -353,7 +354,7 @@ struct GrdFwd : FwdBase {
     float* att = ar.get<float>(rows * H);
     gemm(o, H, e.qkv, qkv, 3 * H, rows);
     if (w->tc_attention && mode != VSG_GEMM_SIMT && sq.n_tc_blk >= 0) {
-      const int products = (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2) ? 3 : 1;
+      const int products = (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3) ? 3 : 1;
       FWD_CALL(vsg_mha_tc16(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, sq.off, 8, att, H, sq.tc_blk_seg, sq.tc_blk_q0, sq.n_tc_blk, products, stream));
     } else {
       FWD_CALL(vsg_mha(qkv, 3 * H, qkv + H, 3 * H, qkv + 2 * H, 3 * H, sq.off, sq.n, 0, sq.max_len, 8, H / 8, att, H, sq.blk_seg, sq.blk_q0,
@@ -416,7 +417,7 @@ struct GrdFwd : FwdBase {
 
 static int check_grd(const VsgGrdWeights* w, const VsgGrdBatch* b, int mode) {
   VSG_REQUIRE(w && b, "vsg_grd_forward: null weights / batch");
-  VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_BF16, "vsg_grd_forward: unknown precision mode %d", mode);
+  VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_FP16X3, "vsg_grd_forward: unknown precision mode %d", mode);
   VSG_REQUIRE(w->dim_hidden == 128, "vsg_grd_forward: dim_hidden must be 128 (the context-query kernel's instantiation)");
   VSG_REQUIRE(b->n_videos > 0 && b->n_queries > 0 && b->video.rows > 0 && b->combined.rows > 0, "vsg_grd_forward: empty batch");
   return VSG_OK;
@@ -424,7 +425,7 @@ static int check_grd(const VsgGrdWeights* w, const VsgGrdBatch* b, int mode) {
 
 static int check_args(const VsgBigCWeights* w, const VsgVideoBatch* b, int topk, int mode) {
   VSG_REQUIRE(w && b, "vsg_bigc_forward: null weights / batch");
-  VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_BF16, "vsg_bigc_forward: unknown precision mode %d", mode);
+  VSG_REQUIRE(mode >= VSG_GEMM_SIMT && mode <= VSG_GEMM_FP16X3, "vsg_bigc_forward: unknown precision mode %d", mode);
   VSG_REQUIRE(w->n_enc >= 0 && w->n_enc <= VSG_MAX_LAYERS && w->n_dec >= 1 && w->n_dec <= VSG_MAX_LAYERS, "vsg_bigc_forward: layer counts out of range");
   VSG_REQUIRE(w->dim_enti == w->dim_pred, "vsg_bigc_forward: dim_enti must equal dim_pred");
   VSG_REQUIRE(b->n_videos > 0 && b->n_tracks > 0 && b->n_rows > 0, "vsg_bigc_forward: empty batch");

@@ -20,6 +20,14 @@
 //                        epilogue or by vsg_cast_bf16), fp32 accumulate, C as fp32 and / or bf16.  Runs as the single-pass kernel
 //                        (MODE 1 geometry: 128-byte stage rows = 64 bf16) with B16 = true; CTA pairs use cta_group::2 MMAs.
 //
+//   VSG_GEMM_FP16X3 (5)  fp32-class at 3/4 of the tensor time of (3): BOTH operands are split into fp16 pairs, x = hi + lo with
+//                        hi = fp16_rn(x) (11 significant bits) and lo = fp16_rn(x - hi) (11 more), and all three products run as kind::f16
+//                        MMAs (1 issue slot per MAC each): D += (A_lo 2^11) * (W_hi 2^-11) + A_hi * W_lo + A_hi * W_hi.  fp16 has 5 exponent
+//                        bits, so range is handled explicitly: W is pre-scaled by an exact power of two (max |W 2^s| in [2^13, 2^14), undone
+//                        by `alpha` = 2^-s in the epilogue), the A correction is carried as lo * 2^11 against a 2^-11-scaled copy of W_hi,
+//                        which keeps both low parts normal for |a| >= 2^-13 and |w| >= 2^-16 max|W|.  |a| must stay below 65504 (else inf).
+//                        Per-product error ~2^-22; W operands come as pre-swizzled tile images only (vsg_build_weight_image_fp16).
+//
 // tcgen05 kernel anatomy (persistent, one CTA per SM; 128 x BN output tiles per CTA, BN = 256 where N allows, else 128):
 //   warp 0       TMA producer: A tiles by cp.async.bulk.tensor.2d (mbarrier complete_tx), W tiles by tensor loads or -- mode 3 -- by
 //                contiguous cp.async.bulk copies of pre-swizzled weight-tile images (vsg_build_weight_image)
@@ -36,6 +44,8 @@
 #include "tc_ptx.cuh"
 #include <cuda.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <math.h>
 #include <mutex>
 #include <unordered_map>
 #include <string>
@@ -70,7 +80,8 @@ struct GemmEpilogue {
   int lo_c0, lo_c1;         // C_lo is written for columns in [lo_c0, lo_c1) only
   int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
   int lo_tma;               // 1: C_lo slabs that lie fully inside the column window leave the same way (mapClo is valid)
-  const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null
+  const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null; MODE 5: required
+  float alpha;              // MODE 5: the accumulator is multiplied by alpha (= 2^-s of the weight image's power-of-two scale) first
   const float* dw_w;        // CONV: depthwise weights [K][dw_k], bias dw_b [K], per-row position in / rows remaining of its sequence
   const float* dw_b;
   const int32_t* seq_pos;
@@ -109,22 +120,27 @@ __device__ __forceinline__ TileCoord tile_coord(const GemmEpilogue& ep, int tile
 // CONV: the A operand is dwconv(X) (depthwise conv over the row axis, DepthWiseSeparableConv1d of grd_model_v5.py:36-56) computed by the
 // split warps from a raw X tile with a 3-row halo on each side, so the separate dwconv pass (one HBM round trip) disappears.
 template <int MODE, int BN_, bool PAIR = false, bool CONV = false> struct Cfg {
-  static constexpr int BK = ((MODE == 2 && BN_ == 256) || MODE == 3) ? 16 : 32;
+  static constexpr int BK = ((MODE == 2 && BN_ == 256) || MODE == 3 || MODE == 5) ? 16 : 32;
   static constexpr int TILE_A = BM * BK * 4;
   static constexpr int TILE_B = (PAIR ? BN_ / 2 : BN_) * BK * 4;
   static constexpr int RAW_ROWS = BM + 8;                                        // 3-row halo each side, rounded to the 8-row swizzle atom
   static constexpr int RAW_TX = RAW_ROWS * BK * 4;                               // bytes the raw-tile TMA delivers
   static constexpr int RAW_BYTES = CONV ? ((RAW_TX + 1023) / 1024) * 1024 : 0;
-  static constexpr int OFF_RAW = (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);
-  static constexpr int STAGE_BYTES = OFF_RAW + RAW_BYTES;                        // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles) (+ raw X)
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16)
+  // MODE 5: [A f32 (CONV: raw X with halo) | f16(A_lo 2^11) | f16(A_hi) | f16(W_hi) | f16(W_hi 2^-11) | f16(W_lo)]: nothing but the split warps
+  // reads the fp32 A region, so the CONV variant keeps its raw tile there
+  static constexpr int AREG5 = CONV ? RAW_BYTES : TILE_A;
+  static constexpr int OFF_RAW = MODE == 5 ? 0 : (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);
+  static constexpr int STAGE_BYTES = MODE == 5 ? AREG5 + TILE_A + 3 * (TILE_B / 2) : OFF_RAW + RAW_BYTES;   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles) (+ raw X)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16), 6/4 (fp16x3)
   static constexpr int DW_BYTES = CONV ? 8 * 1024 : 0;                           // depthwise weights [K][k] + bias [K] (K <= 224 channels, k <= 7)
   static constexpr int SPLIT_GROUPS = 2;                                         // groups of 4 split warps that alternate stages
   static constexpr int THREADS = MODE >= 2 ? 256 + 128 * SPLIT_GROUPS : 256;
   // MODE 2: [A | B_hi | A_lo | B_lo] fp32.   MODE 3: [A f32 | W f32 | bf16(A_lo) | bf16(A) | bf16(W) | bf16(W_lo)]
-  static constexpr int OFF_BH = TILE_A, OFF_AL = TILE_A + TILE_B;
-  static constexpr int OFF_A16 = OFF_AL + TILE_A / 2, OFF_B16 = OFF_AL + TILE_A;
-  static constexpr int OFF_BL = MODE == 3 ? OFF_B16 + TILE_B / 2 : 2 * TILE_A + TILE_B;
+  static constexpr int OFF_BH = MODE == 5 ? AREG5 + TILE_A : TILE_A;
+  static constexpr int OFF_AL = MODE == 5 ? AREG5 : TILE_A + TILE_B;
+  static constexpr int OFF_A16 = OFF_AL + TILE_A / 2, OFF_B16 = MODE == 5 ? OFF_BH + TILE_B / 2 : OFF_AL + TILE_A;
+  static constexpr int OFF_BL = MODE == 5 ? OFF_BH + TILE_B : (MODE == 3 ? OFF_B16 + TILE_B / 2 : 2 * TILE_A + TILE_B);
+  static constexpr int W_TX = MODE == 5 ? 3 * (TILE_B / 2) : (MODE >= 2 ? 2 : 1) * TILE_B;   // W bytes a stage receives
   static constexpr int TMEM_COLS = 2 * BN_;                                      // double-buffered fp32 accumulator
   static constexpr int STAGING_BYTES = 4 * 2 * 32 * 128;                         // TMA-store staging of the epilogue warps
 };
@@ -218,7 +234,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         for (int kb = 0; kb < kblocks; ++kb) {
           if (PROBE && (ep.dbg & 32)) mbar_spin(&empty[stage], phase ^ 1); else mbar_wait(&empty[stage], phase ^ 1);
           uint8_t* st = smem + stage * STAGE_BYTES;
-          if (PROBE && (ep.dbg & 9)) {   // timing probes only (results are garbage)
+          if (PROBE && MODE != 5 && (ep.dbg & 9)) {   // timing probes only (results are garbage)
             const bool la = !(ep.dbg & 8), lw = !(ep.dbg & 1);
             if (!la && !lw) { mbar_arrive(&full[stage]); }
             else {
@@ -233,10 +249,25 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (++stage == STAGES) { stage = 0; phase ^= 1; }
             continue;
           }
-          mbar_expect_tx(&full[stage], (CONV ? CF::RAW_TX : TILE_A) + (MODE >= 2 ? 2 : 1) * CF::TILE_B);
+          mbar_expect_tx(&full[stage], (CONV ? CF::RAW_TX : TILE_A) + CF::W_TX);
           if (CONV) tma_load_2d(smem_u32(st + CF::OFF_RAW), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row - 3);   // rows m0-3 .. m0+132 (OOB = 0)
           else tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row);
-          if (PAIR) {
+          if (MODE == 5) {
+            // three fp16 sub-images [W_hi | W_hi 2^-11 | W_lo] of BN rows x 32 B per (N tile, k block), adjacent in the image and in the stage
+            constexpr int SUB = BN * 32;                   // one sub-image of the whole N tile
+            const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(3 * SUB);
+            if (PAIR) {                                    // this CTA's 128 rows of each sub-image
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                bulk_load(smem_u32(st + CF::OFF_BH + j * (SUB / 2)), img + j * SUB + rank * (SUB / 2), SUB / 2, &full[stage]);
+            } else if (CL == 2) {                          // half of each sub-image, written into both CTAs of the pair
+#pragma unroll
+              for (int j = 0; j < 3; ++j)
+                bulk_load_mc(smem_u32(st + CF::OFF_BH + j * SUB + rank * (SUB / 2)), img + j * SUB + rank * (SUB / 2), SUB / 2, &full[stage], 3);
+            } else {
+              bulk_load(smem_u32(st + CF::OFF_BH), img, 3 * SUB, &full[stage]);
+            }
+          } else if (PAIR) {
             // this CTA's half of the W rows only; the pair's MMA reads the other half from the peer's shared memory
             constexpr int TB = CF::TILE_B;                 // per-CTA W f32 bytes
             if (MODE == 3 && ep.w_img != nullptr) {
@@ -318,6 +349,12 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (B16) umma2_bf16(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_BF16, (kb | k) ? 1u : 0u);
                 else umma2_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_TF32, (kb | k) ? 1u : 0u);
               }
+            } else if (MODE == 5) {
+              // corrections first: (A_lo 2^11)(W_hi 2^-11), A_hi W_lo; then A_hi W_hi -- three K = 16 kind::f16 instructions on fp16 tiles
+              constexpr uint32_t ID_F16 = IDesc<BN_, 256>::f16;
+              umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), ID_F16, kb ? 1u : 0u);
+              umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), ID_F16, 1u);
+              umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), ID_F16, 1u);
             } else if (MODE == 3) {
               umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), ID_BF16, kb ? 1u : 0u);
               umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), ID_BF16, 1u);
@@ -342,6 +379,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           };
           const uint64_t a_hi = desc(0, DESC_HI), b_hi = desc(CF::OFF_BH, DESC_HI);
           if (PROBE && (ep.dbg & 4)) {
+          } else if (MODE == 5) {
+            umma_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), IDesc<BN_>::f16, kb ? 1u : 0u);
+            umma_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), IDesc<BN_>::f16, 1u);
+            umma_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), IDesc<BN_>::f16, 1u);
           } else if (MODE == 3) {
             // corrections first (bf16, one K=16 instruction each), then the tf32 main product
             umma_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), IDesc<BN_>::bf16, kb ? 1u : 0u);
@@ -453,6 +494,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 8; ++j) rv[j] = *reinterpret_cast<const float4*>(res + col0 + 4 * j);
           }
           tmem_ld_wait();
+          if (MODE == 5) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * ep.alpha);
+          }
           uint8_t* sb = stg + sbuf * 4096;
           if (lane == 0) bulk_wait_read<1>();                                 // the store that last read this buffer is done
           __syncwarp();
@@ -478,6 +523,10 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           continue;
         }
         tmem_ld_wait();
+        if (MODE == 5) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * ep.alpha);
+        }
         if (fast) {
           uint8_t* sb = stg + sbuf * 4096;
           const bool lo_slab = ep.lo_tma && col0 >= ep.lo_c0 && col0 + 32 <= ep.lo_c1;   // warp-uniform: the low parts leave by TMA too
@@ -655,7 +704,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (lane == 0) bulk_wait_all();                                           // staging reads AND global writes complete before exit
-  } else if (MODE == 3 && warp >= 8) {
+  } else if ((MODE == 3 || MODE == 5) && warp >= 8) {
     // ================= bf16 correction operands of the A tile =================
     // fp32 tile: 128 rows x 16 floats, 64-byte rows, SWIZZLE_64B: 16-byte chunk c of row r sits at chunk c ^ ((r >> 1) & 3).
     // bf16 tiles: 128 rows x 16 bf16, 32-byte rows, SWIZZLE_32B: 16-byte chunk m of row r sits at chunk m ^ ((r >> 2) & 1).
@@ -727,9 +776,20 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 x.w = fmaf(wq[3][j], xin.w, x.w);
               }
             }
-            reinterpret_cast<float4*>(st)[idx] = x;
+            if (MODE == 3) reinterpret_cast<float4*>(st)[idx] = x;       // MODE 5: no MMA reads the fp32 tile
           } else {
             x = src[idx];
+          }
+          const int dst = r * 32 + ((((l >> 1) ^ ((r >> 2) & 1))) << 4) + (l & 1) * 8;
+          if (MODE == 5) {
+            // fp16 pair: hi = fp16_rn(x), lo = fp16_rn((x - hi) * 2^11) (the 2^-11 sits in the W_hi copy this tile is multiplied with)
+            const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+            const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+            const __half2 l0 = __floats2half2_rn((x.x - f0.x) * 2048.f, (x.y - f0.y) * 2048.f);
+            const __half2 l1 = __floats2half2_rn((x.z - f1.x) * 2048.f, (x.w - f1.y) * 2048.f);
+            *reinterpret_cast<uint2*>(lo16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+            *reinterpret_cast<uint2*>(a16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            continue;
           }
           float4 lo;
           lo.x = x.x - __uint_as_float(__float_as_uint(x.x) & 0xFFFFE000u);
@@ -738,7 +798,6 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           lo.w = x.w - __uint_as_float(__float_as_uint(x.w) & 0xFFFFE000u);
           const __nv_bfloat162 l0 = __floats2bfloat162_rn(lo.x, lo.y), l1 = __floats2bfloat162_rn(lo.z, lo.w);
           const __nv_bfloat162 h0 = __floats2bfloat162_rn(x.x, x.y), h1 = __floats2bfloat162_rn(x.z, x.w);
-          const int dst = r * 32 + ((((l >> 1) ^ ((r >> 2) & 1))) << 4) + (l & 1) * 8;
           *reinterpret_cast<uint2*>(lo16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
           *reinterpret_cast<uint2*>(a16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
         }
@@ -923,6 +982,35 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int ldw, int N,
     const int dst = r * 32 + ((((c >> 1) ^ ((r >> 2) & 1))) << 4) + (c & 1) * 8;
     *reinterpret_cast<uint2*>(base + tile_b + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
     *reinterpret_cast<uint2*>(base + tile_b + tile_b / 2 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+  }
+}
+
+// Weight-tile images of mode 5 (fp16x3, BK = 16): for every (N tile, k block) one contiguous block of three fp16 sub-images, bn rows x 32 B
+// each, SWIZZLE_32B:  [ hi = fp16_rn(w 2^s) | fp16_rn(hi 2^-11) | fp16_rn(w 2^s - hi) ].  One thread per 4 elements.
+__global__ void weight_image_fp16_kernel(const float* __restrict__ w, int ldw, int N, int K, int bn, float scale, uint8_t* __restrict__ img) {
+  const int kblocks = (K + 15) / 16, tiles_n = (N + bn - 1) / bn;
+  const int64_t total = (int64_t)tiles_n * kblocks * bn * 4;
+  const int sub = bn * 32;
+  for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 3);
+    const int r = (int)((i >> 2) % bn);
+    const int64_t blk = (i >> 2) / bn;                 // nt * kblocks + kb
+    const int kb = (int)(blk % kblocks), nt = (int)(blk / kblocks);
+    const int row = nt * bn + r, col = kb * 16 + c * 4;
+    __half hi[4], his[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float x = ((row < N && col + j < K) ? w[(size_t)row * ldw + col + j] : 0.f) * scale;
+      hi[j] = __float2half_rn(x);
+      const float h = __half2float(hi[j]);
+      his[j] = __float2half_rn(h * (1.f / 2048.f));
+      lo[j] = __float2half_rn(x - h);
+    }
+    uint8_t* base = img + blk * (int64_t)(3 * sub);
+    const int dst = r * 32 + ((((c >> 1) ^ ((r >> 2) & 1))) << 4) + (c & 1) * 8;
+    *reinterpret_cast<uint2*>(base + dst) = *reinterpret_cast<const uint2*>(hi);
+    *reinterpret_cast<uint2*>(base + sub + dst) = *reinterpret_cast<const uint2*>(his);
+    *reinterpret_cast<uint2*>(base + 2 * sub + dst) = *reinterpret_cast<const uint2*>(lo);
   }
 }
 
@@ -1143,6 +1231,23 @@ extern "C" int64_t vsg_weight_image_bytes(int N, int K, int bn) {
   return (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * (int64_t)(2 * bn * 64);
 }
 
+extern "C" int64_t vsg_weight_image_fp16_bytes(int N, int K, int bn) {
+  if (N <= 0 || K <= 0 || (bn != 128 && bn != 256)) return 0;
+  return (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * (int64_t)(3 * bn * 32);
+}
+
+extern "C" int vsg_build_weight_image_fp16(const float* w, int ldw, int N, int K, int bn, float scale, void* img, void* stream) {
+  VSG_REQUIRE(N > 0 && K > 0 && ldw >= K && (bn == 128 || bn == 256), "vsg_build_weight_image_fp16: bad extents");
+  VSG_REQUIRE(w && img && aligned16(img), "vsg_build_weight_image_fp16: null or unaligned pointer");
+  int ex = 0;
+  VSG_REQUIRE(scale > 0.f && frexpf(scale, &ex) == 0.5f, "vsg_build_weight_image_fp16: scale must be a power of two");
+  const int64_t total = (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * bn * 4;
+  int64_t blocks = (total + 255) / 256;
+  if (blocks > (int64_t)sm_count() * 16) blocks = (int64_t)sm_count() * 16;
+  weight_image_fp16_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(w, ldw, N, K, bn, scale, (uint8_t*)img);
+  return check_launch("vsg_build_weight_image_fp16");
+}
+
 extern "C" int vsg_build_weight_image(const float* w, int ldw, int N, int K, int bn, void* img, void* stream) {
   VSG_REQUIRE(N > 0 && K > 0 && ldw >= K && (bn == 128 || bn == 256), "vsg_build_weight_image: bad extents");
   VSG_REQUIRE(w && img && aligned16(img), "vsg_build_weight_image: null or unaligned pointer");
@@ -1192,7 +1297,8 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.C16 = (__nv_bfloat16*)a->C16; ep.ldc16 = a->ldc16;
   ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.lo_tma = 0; ep.w_img = nullptr;
   ep.dw_w = nullptr; ep.dw_b = nullptr; ep.seq_pos = nullptr; ep.seq_rem = nullptr; ep.dw_k = 0;
-  VSG_REQUIRE(a->dw_w == nullptr || (a->mode == 3 && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for mode 3, plain problems");
+  VSG_REQUIRE(a->dw_w == nullptr || ((a->mode == 3 || a->mode == 5) && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for modes 3 and 5, plain problems");
+  ep.alpha = 1.f;
   if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
   ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
   ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
@@ -1245,6 +1351,23 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
     }
     return wide ? launch_tc_auto<3, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16)
                 : launch_tc_auto<3, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, a->W_lo16, a->ldw, w_rows, w_cols, ep, st, a->W_b16, a->ldw16);
+  }
+  if (mode == 5) {
+    VSG_REQUIRE(batch == 1, "vsg_gemm_ex: mode 5 (fp16x3) takes plain problems only; batched attention problems use mode 2");
+    VSG_REQUIRE(a->W_img16 && aligned16(a->W_img16) && a->img16_bn == (wide ? 256 : 128),
+                "vsg_gemm_ex: mode 5 needs the fp16 weight-tile image of vsg_build_weight_image_fp16 for tile width %d", wide ? 256 : 128);
+    VSG_REQUIRE(a->w_alpha > 0.f, "vsg_gemm_ex: mode 5 needs w_alpha = 1 / (the image's scale)");
+    ep.w_img = (const uint8_t*)a->W_img16; ep.alpha = a->w_alpha;
+    if (a->dw_w) {
+      VSG_REQUIRE(!wide && N <= 128, "vsg_gemm_ex: the fused depthwise conv needs N <= 128 (128-wide tiles)");
+      VSG_REQUIRE(a->dw_b && a->seq_pos && a->seq_rem && aligned16(a->dw_b), "vsg_gemm_ex: fused depthwise conv needs dw_b, seq_pos, seq_rem");
+      VSG_REQUIRE(a->dw_k >= 1 && a->dw_k <= 7 && (a->dw_k & 1) && K % 16 == 0 && K * (a->dw_k + 1) <= 2048,
+                  "vsg_gemm_ex: fused depthwise conv supports odd k <= 7, K %% 16 == 0 and K * (k + 1) <= 2048 (got k %d, K %d)", a->dw_k, K);
+      ep.dw_w = a->dw_w; ep.dw_b = a->dw_b; ep.seq_pos = a->seq_pos; ep.seq_rem = a->seq_rem; ep.dw_k = a->dw_k;
+      return launch_tc<5, 128, 1, true>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st);
+    }
+    return wide ? launch_tc_auto<5, 256>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st)
+                : launch_tc_auto<5, 128>(a->A, a->lda, a_rows, a_cols, a->W_hi, nullptr, a->ldw, w_rows, w_cols, ep, st);
   }
   set_error("vsg_gemm: unknown mode %d", mode);
   return VSG_E_UNSUPPORTED;

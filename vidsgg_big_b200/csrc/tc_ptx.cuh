@@ -241,6 +241,7 @@ __device__ __forceinline__ uint64_t make_smem_desc_b16(uint32_t smem_addr) {
 template <int BN_, int M_ = 128> struct IDesc {
   static constexpr uint32_t tf32 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
   static constexpr uint32_t bf16 = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);
+  static constexpr uint32_t f16 = (1u << 4) | (0u << 7) | (0u << 10) | ((uint32_t)(BN_ >> 3) << 17) | ((uint32_t)(M_ >> 4) << 24);   // kind::f16, fp16 A / B
 };
 
 

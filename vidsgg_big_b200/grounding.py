@@ -161,6 +161,7 @@ class DEBUG(object):
             l.w, l.bias, l.N, l.K, l.ldw = addr(W.w), addr(W.bias), W.N, W.K, W.w.stride(0)
             l.hi, l.lo, l.w16, l.lo16, l.ld16 = addr(W.hi), addr(W.lo), addr(W.w16), addr(W.lo16), getattr(W, "ld16", 0)
             l.img, l.img_bn = addr(W.img), W.img_bn
+            l.img16, l.img16_bn, l.alpha = addr(W.img16), W.img16_bn, W.alpha
             return l
 
         def conv(dst, cw):
@@ -251,7 +252,7 @@ class DEBUG(object):
         with linalg._Profile.span("mha", sq["att_flops"]):
             if self.attention == "tc" and m != linalg.SIMT and sq["tc_blocks"] is not None:
                 # tcgen05 attention (csrc/attn_tc.cu): fp32-class modes split every operand 3xTF32-style, the reduced modes run one tf32 pass
-                products = 3 if m in (linalg.X3TF32, linalg.TF32_BF16X2) else 1
+                products = 3 if m in linalg.FP32_CLASS else 1
                 bs, bq, nb = sq["tc_blocks"]
                 check(lib().vsg_mha_tc16(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * H), ld, C.c_void_p(qkv.data_ptr() + 8 * H), ld,
                                          _raw(sq["off"]), 8, _raw(att), H, _raw(bs), _raw(bq), nb, products, stream_ptr(x.device)), "vsg_mha_tc16")

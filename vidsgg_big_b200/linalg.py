@@ -8,15 +8,17 @@ import torch
 
 from ._cabi import check, lib, ptr, require_cuda, stream_ptr
 
-SIMT, TF32, X3TF32, TF32_BF16X2, BF16 = 0, 1, 2, 3, 4
-MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2, "bf16": BF16}
-SPLITS = {X3TF32: "tf32", TF32_BF16X2: "bf16", BF16: "bf16w"}      # mode -> what ``Weight`` must precompute (default: nothing)
+SIMT, TF32, X3TF32, TF32_BF16X2, BF16, FP16X3 = 0, 1, 2, 3, 4, 5
+MODES = {"fp32_simt": SIMT, "tf32": TF32, "3xtf32": X3TF32, "tf32+bf16x2": TF32_BF16X2, "bf16": BF16, "fp16x3": FP16X3}
+SPLITS = {X3TF32: "tf32", TF32_BF16X2: "bf16", BF16: "bf16w", FP16X3: "fp16"}      # mode -> what ``Weight`` must precompute (default: nothing)
+FP32_CLASS = (X3TF32, TF32_BF16X2, FP16X3)      # modes whose products carry >= 19 significant bits (parity modes)
 
 
 def can_fuse_dwconv(mode: int, W: "Weight", K: Optional[int] = None, k: int = 7) -> bool:
     """The depthwise conv can run inside the GEMM's operand pipeline (csrc/gemm.cu, CONV variant)."""
     K = W.K if K is None else K
-    return mode == TF32_BF16X2 and W.w16 is not None and W.N <= 128 and K % 16 == 0 and K * (k + 1) <= 2048 and k % 2 == 1 and k <= 7
+    ready = (mode == TF32_BF16X2 and W.w16 is not None) or (mode == FP16X3 and W.img16 is not None)
+    return ready and W.N <= 128 and K % 16 == 0 and K * (k + 1) <= 2048 and k % 2 == 1 and k <= 7
 
 
 def attention_mode(mode: int) -> int:
@@ -24,7 +26,7 @@ def attention_mode(mode: int) -> int:
     operand, which only exist for real weights -- those few problems stay on the 3xTF32 kernel."""
     if mode == BF16:
         return TF32             # reduced-precision mode: single-pass tf32 attention products
-    return X3TF32 if mode == TF32_BF16X2 else mode
+    return X3TF32 if mode in (TF32_BF16X2, FP16X3) else mode
 
 
 class Weight(object):
@@ -37,8 +39,22 @@ class Weight(object):
         self.w = w.detach().float().contiguous()
         self.bias = None if bias is None else bias.detach().float().contiguous()
         self.N, self.K = self.w.shape
-        self.hi = self.lo = self.w16 = self.lo16 = self.img = None
-        self.img_bn = 0
+        self.hi = self.lo = self.w16 = self.lo16 = self.img = self.img16 = None
+        self.img_bn = self.img16_bn = 0
+        self.alpha = 1.0
+        if split == "fp16":
+            # fp16x3 mode: power-of-two scale that puts max |w| into [2^13, 2^14) (exact; undone by alpha in the GEMM epilogue)
+            import math
+            wmax = float(self.w.abs().max()) if self.w.numel() else 0.0
+            s = 13 - math.frexp(wmax)[1] + 1 if wmax > 0 and math.isfinite(wmax) else 0
+            s = max(-100, min(100, s))
+            self.alpha = 2.0 ** (-s)
+            self.img16_bn = int(lib().vsg_gemm_tile_n(self.N))
+            nbytes = int(lib().vsg_weight_image_fp16_bytes(self.N, self.K, self.img16_bn))
+            self.img16 = torch.empty(nbytes, dtype=torch.uint8, device=self.w.device)
+            check(lib().vsg_build_weight_image_fp16(ptr(self.w), self.w.stride(0), self.N, self.K, self.img16_bn, 2.0 ** s, ptr(self.img16),
+                                                    stream_ptr(self.w.device)), "vsg_build_weight_image_fp16")
+            return
         if split in ("bf16", "bf16w"):
             self.ld16 = (self.K + 7) // 8 * 8
             self.w16 = torch.empty(self.N, self.ld16, dtype=torch.bfloat16, device=self.w.device)
@@ -172,7 +188,9 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
     if mode == TF32_BF16X2 and (W.w16 is None or W.lo16 is None):
         raise ValueError("gemm: mode tf32+bf16x2 needs a Weight built with split='bf16'")
     assert dwconv is None or can_fuse_dwconv(mode, W, K)
-    if out_lo is not None or mode == TF32_BF16X2:
+    if mode == FP16X3 and (W.img16 is None or K != W.K):
+        raise ValueError("gemm: mode fp16x3 needs a Weight built with split='fp16' and K == W.K")
+    if out_lo is not None or mode in (TF32_BF16X2, FP16X3):
         from ._cabi import VsgGemmArgs
         import ctypes as C
         assert out_lo is None or (out_lo.shape == out.shape and out_lo.stride() == out.stride())
@@ -186,11 +204,13 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
         a.C = out.data_ptr(); a.C_lo = None if out_lo is None else out_lo.data_ptr(); a.ldc = ldc; a.batch = 1; a.batch_inner = 1
         if lo_cols is not None:
             a.lo_col_begin, a.lo_col_end = int(lo_cols[0]), int(lo_cols[1])
+        if dwconv is not None:
+            dw_w, dw_b, dw_k, seq_pos, seq_rem = dwconv
+            a.dw_w, a.dw_b, a.dw_k, a.seq_pos, a.seq_rem = dw_w.data_ptr(), dw_b.data_ptr(), int(dw_k), seq_pos.data_ptr(), seq_rem.data_ptr()
+        if mode == FP16X3:
+            a.W_img16, a.img16_bn, a.w_alpha = W.img16.data_ptr(), W.img16_bn, W.alpha
         if mode == TF32_BF16X2:
             a.W_b16, a.W_lo16, a.ldw16 = W.w16.data_ptr(), W.lo16.data_ptr(), W.ld16
-            if dwconv is not None:
-                dw_w, dw_b, dw_k, seq_pos, seq_rem = dwconv
-                a.dw_w, a.dw_b, a.dw_k, a.seq_pos, a.seq_rem = dw_w.data_ptr(), dw_b.data_ptr(), int(dw_k), seq_pos.data_ptr(), seq_rem.data_ptr()
             if W.img is not None and K == W.K:           # the image's k blocks cover the whole of W.K
                 a.W_img, a.img_bn = W.img.data_ptr(), W.img_bn
         check(lib().vsg_gemm_ex(C.byref(a), stream_ptr(A.device)), "vsg_gemm_ex")
