@@ -325,6 +325,14 @@ int vsg_mha(const float* Q, int ldq, const float* K, int ldk, const float* V, in
 int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off,
                  int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
                  void* stream);
+/* Same for 64-wide heads, with fp16 hi / lo operand pairs on kind::f16 MMAs (products = 3: fp32-class, error <= 3e-6 vs fp64; 1: hi parts
+ * only): the BIG-C decoder's self-attention over the num_querys queries of every video (nn.MultiheadAttention(512, 8) of
+ * models/model_0v10.py:181-186) as ONE launch instead of two batched GEMMs + softmax + V^T transpose.  seg_off != NULL: ragged sequences
+ * with the (sequence, first query) work list of 128-query blocks as for vsg_mha_tc16; seg_off == NULL: n_seg sequences of fixed_len rows
+ * back to back (the work list is implicit).  |Q|, |K|, |V| < 65504. */
+int vsg_mha_tc64(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
+                 int fixed_len, int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
+                 void* stream);
 /* Tuning / validation knob: keys per block of vsg_mha_tc16 (32: 4 CTAs per SM, default; 64: 2 CTAs per SM).  Returns the old value. */
 int vsg_mha_tc16_set_kc(int kc);
 
@@ -393,7 +401,8 @@ typedef struct VsgBigCWeights {
   int variant;              /* 0 = model_0v10 (VidVRD), 1 = model_0v7 (VidOR) */
   int dim_enti, dim_pred, dim_feat, dim_clsme, dim_i3d /* 0 = none */, num_querys, num_pred_cats, num_enti_cats;
   int pool_len, n_enc, n_dec, n_head, use_clsme, has_entiemb, extra_width, dim_z;
-  int tc_attention;         /* 1: decoder self-attention as batched tcgen05 GEMMs (needs head_dim % 32 == 0, Q % 32 == 0) */
+  int tc_attention;         /* 1: decoder self-attention on vsg_mha_tc64 (64-wide heads; otherwise as 2); 2: as batched tcgen05 GEMMs + softmax /
+                               transpose glue (needs head_dim % 32 == 0, Q % 32 == 0); 0: fp32 SIMT kernel */
   const float* bbox1_w; const float* bbox1_b;          /* fc_bbox2enti.0 [E][8], [E] */
   VsgLinear bbox2, feat1, feat2, conv /* tap-major [3E][2E], no bias */, enco1, enco2, i3d, log, log1, log2;
   const float* conv_b;

@@ -258,7 +258,10 @@ def test_tensor_core_attention_equals_simt_attention(precision):
     exact = (torch.softmax(q @ k.transpose(-1, -2) / (d // 8) ** 0.5, -1) @ v).transpose(1, 2).reshape(V * Q, d)
     e_ref = (ref.double() - exact).abs().max().item()
     e_got = (got.double() - exact).abs().max().item()
-    print("attention max err vs fp64: simt %.2e  tensor-core %s %.2e" % (e_ref, precision, e_got))
+    fused = model._mha_tc64(qkv, d, V, Q)                              # the default path: one fused launch (fp16 pairs / fp16 hi parts)
+    e_fused = (fused.double() - exact).abs().max().item()
+    print("attention max err vs fp64: simt %.2e  tensor-core %s %.2e  fused %.2e" % (e_ref, precision, e_got, e_fused))
+    assert e_fused < (2e-5 if precision == "3xtf32" else 5e-3)
     assert e_ref < 1e-5
     assert e_got < (2e-5 if precision == "3xtf32" else 5e-3)
 

@@ -176,6 +176,7 @@ SIGNATURES = {
     "vsg_mha": (i32, [p, i32, p, i32, p, i32, p, i32, i32, i32, i32, i32, p, i32, p, p, i32, p]),
     "vsg_mha_tc16": (i32, [p, i32, p, i32, p, i32, p, i32, p, i32, p, p, i32, i32, p]),
     "vsg_mha_tc16_set_kc": (i32, [i32]),
+    "vsg_mha_tc64": (i32, [p, i32, p, i32, p, i32, p, i32, i32, i32, p, i32, p, p, i32, i32, p]),
     "vsg_role_attention": (i32, [p, p, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),
     "vsg_gather_concat": (i32, [C.POINTER(p), C.POINTER(p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i64, p, i32, p]),
     "vsg_so_category": (i32, [p, p, i32, i64, p, p, p]),

@@ -133,7 +133,9 @@ class BIG_C(object):
             raise VsgError("attention kernel is instantiated for head_dim 16 / 32 / 64")
         self.precision = precision
         self.mode = linalg.MODES[precision]
-        self.attention = "tc"      # decoder self-attention: "tc" = batched tcgen05 GEMMs (+ glue), "simt" = fp32 SIMT kernel
+        # decoder self-attention: "tc" = ONE fused tcgen05 kernel (64-wide heads; csrc/attn_tc.cu mha64_tc_kernel), else as "tc_gemm";
+        # "tc_gemm" = batched tcgen05 GEMMs + softmax / transpose glue through HBM; "simt" = fp32 SIMT kernel
+        self.attention = "tc"
         self.backend = "c"         # forward_packed: "c" = ONE call of vsg_bigc_forward (csrc/forward.cu), "py" = the same launches from Python
         self.topk = 10
         self.device = None
@@ -294,7 +296,7 @@ class BIG_C(object):
         c.num_querys, c.num_pred_cats, c.num_enti_cats = self.num_querys, self.num_pred_cats, self.num_enti_cats
         c.pool_len, c.n_enc, c.n_dec, c.n_head = self.enco_pool_len, self.n_enco_layers, self.n_deco_layers, self.n_att_head
         c.use_clsme, c.has_entiemb = int(bool(getattr(self, "use_clsme", True))), int(bool(self.has_entiemb))
-        c.extra_width, c.dim_z, c.tc_attention = self.extra_width, self.dim_z, int(self.attention == "tc")
+        c.extra_width, c.dim_z, c.tc_attention = self.extra_width, self.dim_z, {"tc": 1, "tc_gemm": 2}.get(self.attention, 0)
         c.bbox1_w, c.bbox1_b, c.conv_b = addr(w["bbox1_w"]), addr(w["bbox1_b"]), addr(w["conv_b"])
         for k in ("bbox2", "feat1", "feat2", "conv", "enco1", "enco2"):
             setattr(c, k, lin(w[k]))
@@ -321,7 +323,7 @@ class BIG_C(object):
         if pk.feats.shape[1] < self.dim_feat + self.extra_width:
             raise VsgError("features have %d columns, model needs %d" % (pk.feats.shape[1], self.dim_feat + self.extra_width))
         cw = self._c_weights()
-        cw.tc_attention = int(self.attention == "tc")
+        cw.tc_attention = {"tc": 1, "tc_gemm": 2}.get(self.attention, 0)
         b = VsgVideoBatch()
         b.n_videos, b.n_tracks, b.max_tracks, b.n_rows = pk.V, pk.N, pk.max_tracks, pk.R
         b.boxes, b.feats, b.ld_feats = pk.boxes.data_ptr(), pk.feats.data_ptr(), pk.feats.stride(0)
@@ -369,6 +371,16 @@ class BIG_C(object):
         check(lib().vsg_mha(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * d), ld, C.c_void_p(qkv.data_ptr() + 8 * d), ld,
                             _raw(seg_off), n_seg, fixed_len, max_len, self.n_att_head, d // self.n_att_head, _raw(out), d,
                             _raw(bs), _raw(bq), nb, stream_ptr(qkv.device)), "vsg_mha")
+        return out
+
+    def _mha_tc64(self, qkv, d, n_seg, Q):
+        """Self-attention of ``n_seg`` fixed-length segments of ``Q`` rows with 64-wide heads as one fused tcgen05 launch."""
+        out = torch.empty(qkv.shape[0], d, dtype=torch.float32, device=qkv.device)
+        ld = qkv.stride(0)
+        with linalg._Profile.span("mha", 4.0 * n_seg * Q * Q * d, (n_seg, Q, d)):
+            check(lib().vsg_mha_tc64(_raw(qkv), ld, C.c_void_p(qkv.data_ptr() + 4 * d), ld, C.c_void_p(qkv.data_ptr() + 8 * d), ld, None, n_seg, Q,
+                                     self.n_att_head, _raw(out), d, None, None, 0, 3 if self.mode in linalg.FP32_CLASS else 1,
+                                     stream_ptr(qkv.device)), "vsg_mha_tc64")
         return out
 
     def _mha_tc(self, qkv, qkv_lo, n_seg, Q, d):
@@ -514,9 +526,14 @@ class BIG_C(object):
             x = w["query_init"] if li == 0 else query
             x_qk = w["qk_init"] if li == 0 else query_pos
             nv = 1 if li == 0 else V
-            use_tc = self.attention == "tc" and m != linalg.SIMT and (Pd // self.n_att_head) % 32 == 0 and Q % 32 == 0
+            use_tc = self.attention in ("tc", "tc_gemm") and m != linalg.SIMT and (Pd // self.n_att_head) % 32 == 0 and Q % 32 == 0
+            use_fused = self.attention == "tc" and m != linalg.SIMT and Pd // self.n_att_head == 64
             qkv = torch.empty(x.shape[0], 3 * Pd, dtype=torch.float32, device=dev)
-            if use_tc:
+            if use_fused:
+                gemm(m, x_qk, lw["qk"], out=qkv[:, :2 * Pd])
+                gemm(m, x, lw["v"], out=qkv[:, 2 * Pd:])
+                att = self._mha_tc64(qkv, Pd, nv, Q)
+            elif use_tc:
                 qkv_lo = torch.empty_like(qkv) if linalg.attention_mode(m) == linalg.X3TF32 else None
                 gemm(m, x_qk, lw["qk"], out=qkv[:, :2 * Pd], out_lo=None if qkv_lo is None else qkv_lo[:, :2 * Pd],
                      lo_cols=(Pd, 2 * Pd))                                              # only K's low part is read

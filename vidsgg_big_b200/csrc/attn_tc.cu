@@ -20,6 +20,7 @@
 // the others' MMA round trips (the kernel is latency-bound: K = 16 and N = 16 MMAs are tiny).
 #include "common.cuh"
 #include "tc_ptx.cuh"
+#include <cuda_fp16.h>
 
 namespace vsg {
 
@@ -266,6 +267,271 @@ mha16_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, AT_TMEM_COLS); }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------------------------
+// head_dim 64: the BIG-C decoder's self-attention over the Q queries of a video (models/model_0v10.py:181-186, nn.MultiheadAttention(512, 8))
+// -- and any other ragged / fixed-length family of sequences with 64-wide heads -- as ONE kernel: S never leaves the SM (it used to be two
+// batched GEMMs + a softmax pass + a V^T transpose through HBM: 2.5 of the 22 ms VidVRD step).
+//
+// Same anatomy as mha16_tc_kernel (CTA = (sequence, 128 queries, head), blocks of 64 keys, online softmax, accumulators in TMEM), but the
+// operands are fp16 hi / lo PAIRS and every product is kind::f16 (K = 16 per instruction): x = hi + lo with hi = fp16_rn(x),
+// lo = fp16_rn(x - hi), S = Ql Kh + Qh Kl + Qh Kh, O += Pl Vh + Ph Vl + Ph Vh -- 22 significant bits per operand wherever |x| >= 2^-2 and an
+// absolute 2^-25 below (scores and probabilities are O(1) quantities, so that is fp32-class; measured <= 3e-6 against fp64).  `products` = 1
+// keeps the hi parts only (11 bits, like tf32: the reduced-precision modes).  |q|, |k|, |v| must stay below the fp16 range (65504).
+// Shared memory 96 KB, TMEM 128 columns -> 2 CTAs per SM.
+constexpr int A6_DH = 64, A6_KC = 64;
+constexpr int A6_QH = 0, A6_QL = 16384, A6_KH = 32768, A6_KL = 40960, A6_VH = 49152, A6_VL = 57344, A6_PH = 65536, A6_PL = 81920;
+constexpr int A6_SMEM = 98304;
+
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]), "r"(r[10]),
+        "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]),
+        "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+
+// float4 -> 4 fp16 (hi) and the fp16 of the remainders (lo), each packed into 8 bytes
+__device__ __forceinline__ void split_f16(const float4 x, uint2& hi, uint2& lo) {
+  const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
+  const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
+  const __half2 l0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y), l1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
+  hi = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+  lo = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
+}
+
+// 256 threads: warp w owns TMEM lane quadrant w & 3 (query rows 32 (w & 3) ..) and column half w >> 2 of S / P / O -- two threads per
+// query row, which halves the exponential / conversion chain of a block (the kernel is bound by that chain and by the MMA round trips,
+// not by the tensor pipe); the halves exchange their block maxima through shared memory.
+__global__ void __launch_bounds__(256, 2)
+mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
+                const int64_t* __restrict__ seg_off, int fixed_len, const int32_t* __restrict__ blk_seg, const int32_t* __restrict__ blk_q0,
+                float scale_log2e, int products, float* __restrict__ O, int ldo) {
+  extern __shared__ __align__(1024) uint8_t at_smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(at_smem_raw) + 1023) & ~(uintptr_t)1023);
+  __shared__ uint64_t mma_bar;
+  __shared__ uint32_t tmem_slot;
+  __shared__ float xch[2][AT_BM];                                  // block maxima / final sums of the two column halves
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int quad = warp & 3, half = warp >> 2;
+  int seg, q0, T;
+  int64_t r0;
+  if (seg_off) {                                                   // ragged sequences: work list of (sequence, first query) blocks
+    seg = blk_seg[blockIdx.x]; q0 = blk_q0[blockIdx.x];
+    r0 = seg_off[seg]; T = (int)(seg_off[seg + 1] - r0);
+  } else {                                                         // sequences of `fixed_len` rows, back to back
+    const int per = (fixed_len + AT_BM - 1) / AT_BM;
+    seg = blockIdx.x / per; q0 = (blockIdx.x - seg * per) * AT_BM;
+    r0 = (int64_t)seg * fixed_len; T = fixed_len;
+  }
+  const int col0 = blockIdx.y * A6_DH;
+  const bool split = products == 3;
+
+  if (tid == 0) { mbar_init(&mma_bar, 1); fence_barrier_init(); }
+  if (warp == 0) { tmem_alloc(&tmem_slot, 128); tmem_relinquish(); }
+  // ---- Q tile: row r = query q0 + r, 128-byte rows of 64 fp16; SWIZZLE_128B: 16-byte chunk c of row r sits at chunk c ^ (r & 7).
+  //      Item = 4 floats -> 8 bytes: chunk c4 >> 1, half (c4 & 1) ----
+#pragma unroll 4
+  for (int idx = tid; idx < AT_BM * 16; idx += 256) {
+    const int r = idx >> 4, c4 = idx & 15;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q0 + r < T) x = *reinterpret_cast<const float4*>(Q + (r0 + q0 + r) * (int64_t)ldq + col0 + 4 * c4);
+    uint2 hi, lo;
+    split_f16(x, hi, lo);
+    const int o = r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+    *reinterpret_cast<uint2*>(smem + A6_QH + o) = hi;
+    if (split) *reinterpret_cast<uint2*>(smem + A6_QL + o) = lo;
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_slot;
+  const uint32_t t_s = tmem + half * 32, t_o = tmem + A6_KC + half * 32;         // this thread's 32 columns of S and of O
+  const uint32_t lane_base = (uint32_t)(quad * 32) << 16;
+  const uint32_t sbase = smem_u32(smem);
+  const int row = quad * 32 + lane;
+  const bool live = q0 + quad * 32 < T;                            // warp-uniform: some row of this warp is a real query
+  uint32_t phase = 0;
+  const int n_blocks = (T + A6_KC - 1) / A6_KC;
+
+  // K block: 64 keys x 16 float4 items = 4 per thread (item idx = it * 256 + tid: key idx >> 4, chunk idx & 15), coalesced.
+  // V block: TRANSPOSED into [dim][key] rows; a thread takes the same 4 dims of a PAIR of keys (2j, 2j + 1), so that every store is one
+  // 32-bit word and a warp's 32 key pairs fill one whole 128-byte row: 32 pairs x 16 chunks = 2 pair items per thread.
+  auto load_k = [&](int k0, float4 (&x)[4]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = it * 256 + tid, r = idx >> 4, c4 = idx & 15;
+      x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (k0 + r < T) x[it] = *reinterpret_cast<const float4*>(K + (r0 + k0 + r) * (int64_t)ldk + col0 + 4 * c4);
+    }
+  };
+  auto load_v = [&](int k0, float4 (&x)[4]) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int c4 = warp + 8 * it;
+#pragma unroll
+      for (int e = 0; e < 2; ++e) {
+        x[2 * it + e] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (k0 + 2 * lane + e < T) x[2 * it + e] = *reinterpret_cast<const float4*>(V + (r0 + k0 + 2 * lane + e) * (int64_t)ldv + col0 + 4 * c4);
+      }
+    }
+  };
+  auto store_k = [&](const float4 (&x)[4]) {
+#pragma unroll
+    for (int it = 0; it < 4; ++it) {
+      const int idx = it * 256 + tid, r = idx >> 4, c4 = idx & 15;
+      uint2 hi, lo;
+      split_f16(x[it], hi, lo);
+      const int o = r * 128 + (((c4 >> 1) ^ (r & 7)) << 4) + (c4 & 1) * 8;
+      *reinterpret_cast<uint2*>(smem + A6_KH + o) = hi;
+      if (split) *reinterpret_cast<uint2*>(smem + A6_KL + o) = lo;
+    }
+  };
+  auto store_v = [&](const float4 (&x)[4]) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int c4 = warp + 8 * it;
+      const float a[4] = {x[2 * it].x, x[2 * it].y, x[2 * it].z, x[2 * it].w};
+      const float b[4] = {x[2 * it + 1].x, x[2 * it + 1].y, x[2 * it + 1].z, x[2 * it + 1].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int d = 4 * c4 + e;
+        const __half2 h = __floats2half2_rn(a[e], b[e]);
+        const float2 f = __half22float2(h);
+        const int o = d * 128 + ((((2 * lane) >> 3) ^ (d & 7)) << 4) + ((2 * lane) & 7) * 2;
+        *reinterpret_cast<uint32_t*>(smem + A6_VH + o) = *reinterpret_cast<const uint32_t*>(&h);
+        if (split) {
+          const __half2 l = __floats2half2_rn(a[e] - f.x, b[e] - f.y);
+          *reinterpret_cast<uint32_t*>(smem + A6_VL + o) = *reinterpret_cast<const uint32_t*>(&l);
+        }
+      }
+    }
+  };
+  // S[128 x n_s] = Q K^T over the 64 dims (4 K = 16 steps per product)
+  auto issue_s = [&](int n_s) {
+    const uint32_t idesc = (1u << 4) | ((uint32_t)(n_s >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);      // kind::f16, fp16 A / B, fp32 D
+    const uint64_t qh = make_smem_desc<32>(sbase + A6_QH), ql = make_smem_desc<32>(sbase + A6_QL);
+    const uint64_t kh = make_smem_desc<32>(sbase + A6_KH), kl = make_smem_desc<32>(sbase + A6_KL);
+    uint32_t acc = 0;
+    if (split) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) { umma_bf16(tmem, ql + 2 * k, kh + 2 * k, idesc, acc); acc = 1; }
+#pragma unroll
+      for (int k = 0; k < 4; ++k) umma_bf16(tmem, qh + 2 * k, kl + 2 * k, idesc, 1u);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { umma_bf16(tmem, qh + 2 * k, kh + 2 * k, idesc, acc); acc = 1; }
+    umma_commit(&mma_bar);
+  };
+
+  float m = -INFINITY, l = 0.f;                                    // l: this thread's column half only
+  float4 kreg[4], vreg[4];
+  load_k(0, kreg);
+  load_v(0, vreg);
+  for (int b = 0; b < n_blocks; ++b) {
+    const int k0 = b * A6_KC, valid = min(A6_KC, T - k0), n_s = (valid + 15) & ~15;
+    store_k(kreg);
+    store_v(vreg);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) { tc_fence_after(); issue_s(n_s); }
+    if (b + 1 < n_blocks) { load_k(k0 + A6_KC, kreg); load_v(k0 + A6_KC, vreg); }      // in flight during this block
+    mbar_wait(&mma_bar, phase); phase ^= 1;
+    tc_fence_after();
+    // this thread's 32 scores of the block, read once
+    const bool cols = live && half * 32 < n_s;                     // warp-uniform
+    uint32_t sr[32];
+    float bm = -INFINITY;
+    if (cols) {
+      tmem_ld32(t_s + lane_base, sr);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        if (half * 32 + j < valid) bm = fmaxf(bm, __uint_as_float(sr[j]));
+    }
+    xch[half][row] = bm;
+    __syncthreads();
+    const float m_new = fmaxf(m, fmaxf(xch[0][row], xch[1][row]));
+    if (live && b > 0 && __any_sync(0xffffffffu, m_new > m)) {     // warp-uniform: tcgen05.ld / .st are warp-collective
+      const float alpha = exp2f((m - m_new) * scale_log2e);
+      uint32_t o[32];
+      tmem_ld32(t_o + lane_base, o);
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) o[j] = __float_as_uint(__uint_as_float(o[j]) * alpha);
+      tmem_st32(t_o + lane_base, o);
+      tmem_st_wait();
+      l *= alpha;
+    }
+    m = m_new;
+    if (cols) {
+      const float mscaled = m * scale_log2e;
+      uint8_t* ph = smem + A6_PH + row * 128;
+      uint8_t* pl = smem + A6_PL + row * 128;
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {                             // 8 probabilities = one 16-byte chunk of fp16
+        float pv[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          pv[e] = (half * 32 + cc * 8 + e < valid) ? exp2f(fmaf(__uint_as_float(sr[cc * 8 + e]), scale_log2e, -mscaled)) : 0.f;
+          l += pv[e];
+        }
+        uint2 h0, l0, h1, l1;
+        split_f16(make_float4(pv[0], pv[1], pv[2], pv[3]), h0, l0);
+        split_f16(make_float4(pv[4], pv[5], pv[6], pv[7]), h1, l1);
+        const int o = (((half * 4 + cc) ^ (row & 7)) << 4);
+        *reinterpret_cast<uint4*>(ph + o) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+        if (split) *reinterpret_cast<uint4*>(pl + o) = make_uint4(l0.x, l0.y, l1.x, l1.y);
+      }
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+      tc_fence_after();
+      // O[128 x 64] += P[128 x n_s] V[n_s x 64]: K = 16 keys per instruction; P is zero for the invalid keys inside the last step
+      const uint32_t idesc = (1u << 4) | ((uint32_t)(A6_DH >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
+      const uint64_t pH = make_smem_desc<32>(sbase + A6_PH), pL = make_smem_desc<32>(sbase + A6_PL);
+      const uint64_t vH = make_smem_desc<32>(sbase + A6_VH), vL = make_smem_desc<32>(sbase + A6_VL);
+      const int ksteps = n_s >> 4;
+      uint32_t acc = b ? 1u : 0u;
+      for (int ks = 0; ks < ksteps; ++ks) {
+        if (split) {
+          umma_bf16(tmem + A6_KC, pL + 2 * ks, vH + 2 * ks, idesc, acc); acc = 1;
+          umma_bf16(tmem + A6_KC, pH + 2 * ks, vL + 2 * ks, idesc, 1u);
+        }
+        umma_bf16(tmem + A6_KC, pH + 2 * ks, vH + 2 * ks, idesc, acc); acc = 1;
+      }
+      umma_commit(&mma_bar);
+    }
+    mbar_wait(&mma_bar, phase); phase ^= 1;                        // P / V / K may be overwritten, S recomputed, O rescaled
+    tc_fence_after();
+  }
+
+  // ---------------- O / l -> global ----------------
+  xch[half][row] = l;
+  __syncthreads();
+  if (live) {
+    const float inv = 1.f / (xch[0][row] + xch[1][row]);
+    uint32_t r[32];
+    tmem_ld32(t_o + lane_base, r);
+    tmem_ld_wait();
+    if (q0 + row < T) {
+      float* o = O + (r0 + q0 + row) * (int64_t)ldo + col0 + half * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<float4*>(o + j) = make_float4(__uint_as_float(r[j]) * inv, __uint_as_float(r[j + 1]) * inv,
+                                                        __uint_as_float(r[j + 2]) * inv, __uint_as_float(r[j + 3]) * inv);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
 }  // namespace vsg
 
 using namespace vsg;
@@ -304,4 +570,38 @@ extern "C" int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, co
               "vsg_mha_tc16: Q / K / V / O must be 16-byte aligned with leading dimensions that are multiples of 4");
   return g_at_kc == 64 ? launch_mha16<64>(Q, ldq, K, ldk, V, ldv, seg_off, n_head, O, ldo, blk_seg, blk_q0, n_blk, products, stream)
                        : launch_mha16<32>(Q, ldq, K, ldk, V, ldv, seg_off, n_head, O, ldo, blk_seg, blk_q0, n_blk, products, stream);
+}
+
+extern "C" int vsg_mha_tc64(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
+                            int fixed_len, int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
+                            void* stream) {
+  VSG_REQUIRE(n_head > 0 && n_head <= 65535 && n_seg >= 0, "vsg_mha_tc64: bad size");
+  VSG_REQUIRE(products == 1 || products == 3, "vsg_mha_tc64: products must be 1 (hi parts only) or 3 (fp16 hi / lo pairs)");
+  long long blocks;
+  if (seg_off) {
+    VSG_REQUIRE(n_blk >= 0 && (n_blk == 0 || (blk_seg && blk_q0)), "vsg_mha_tc64: ragged sequences need the (sequence, first query) work list");
+    blocks = n_blk;
+  } else {
+    VSG_REQUIRE(fixed_len > 0, "vsg_mha_tc64: seg_off == NULL needs fixed_len > 0");
+    blocks = (long long)n_seg * ((fixed_len + AT_BM - 1) / AT_BM);
+  }
+  if (blocks == 0) return VSG_OK;
+  VSG_REQUIRE(blocks <= 0x7fffffffLL, "vsg_mha_tc64: too many blocks");
+  VSG_REQUIRE(Q && K && V && O, "vsg_mha_tc64: null pointer");
+  VSG_REQUIRE(aligned16(Q) && aligned16(K) && aligned16(V) && aligned16(O) && ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 4 == 0,
+              "vsg_mha_tc64: Q / K / V / O must be 16-byte aligned with leading dimensions that are multiples of 4");
+  static PerDeviceFlag attr_done;
+  const int dev_ = current_device();
+  constexpr int SMEM = A6_SMEM + 1024;
+  if (!attr_done.is_set(dev_)) {
+    if (cudaFuncSetAttribute(mha64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+      set_error("vsg_mha_tc64: cannot raise dynamic shared memory to %d", SMEM);
+      return VSG_E_LAUNCH;
+    }
+    attr_done.set(dev_);
+  }
+  const float scale_log2e = 1.4426950408889634f / 8.0f;            // 1 / sqrt(64) * log2(e)
+  mha64_tc_kernel<<<dim3((unsigned)blocks, n_head), 256, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, blk_seg, blk_q0,
+                                                                                       scale_log2e, products, O, ldo);
+  return check_launch("vsg_mha_tc64");
 }

@@ -203,7 +203,8 @@ int Fwd::run(VsgTripletOut* out, int topk) {
   float* values = ar.get<float>(VQ * 2 * E);
   float* hid = ar.get<float>(VQ * 2 * Pd);
   float* qkv = ar.get<float>(VQ * 3 * Pd);
-  const bool use_tc = w->tc_attention && mode != VSG_GEMM_SIMT && (Pd / H) % 32 == 0 && Q % 32 == 0;
+  const bool use_fused = w->tc_attention == 1 && mode != VSG_GEMM_SIMT && Pd / H == 64;      // vsg_mha_tc64: S never leaves the SM
+  const bool use_tc = !use_fused && w->tc_attention && mode != VSG_GEMM_SIMT && (Pd / H) % 32 == 0 && Q % 32 == 0;
   const bool need_lo = use_tc && (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3);
   float* qkv_lo = need_lo ? ar.get<float>(VQ * 3 * Pd) : nullptr;
   float* att = ar.get<float>(VQ * Pd);
@@ -227,7 +228,12 @@ int Fwd::run(VsgTripletOut* out, int topk) {
     const int nv = li == 0 ? 1 : V;
     const int64_t rows = (int64_t)nv * Q;
     const int64_t mk = ar.mark();
-    if (use_tc) {
+    if (use_fused) {
+      gemm(x_qk, Pd, lw.qk, qkv, 3 * Pd, rows);
+      gemm(xin, Pd, lw.v, qkv + 2 * Pd, 3 * Pd, rows);
+      const int products = (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3) ? 3 : 1;
+      FWD_CALL(vsg_mha_tc64(qkv, 3 * Pd, qkv + Pd, 3 * Pd, qkv + 2 * Pd, 3 * Pd, nullptr, nv, Q, H, att, Pd, nullptr, nullptr, 0, products, stream));
+    } else if (use_tc) {
       gemm(x_qk, Pd, lw.qk, qkv, 3 * Pd, rows, false, true, -1, nullptr, nullptr, 0, qkv_lo, qkv_lo ? Pd : 0, qkv_lo ? 2 * Pd : 0);
       gemm(xin, Pd, lw.v, qkv + 2 * Pd, 3 * Pd, rows);
       mha_tc(qkv, qkv_lo, nv, Q, Pd, att);
