@@ -348,6 +348,13 @@ int vsg_transpose_split(const float* X, int ld, int64_t rows, int cols, float* T
 int vsg_role_attention(const float* p2a, const float* e2a, const float* enco, const int32_t* seg, int n_vid, int Q, int E,
                        int max_tracks, float inv_sqrt_d, float* values, float* att_out, int att_ld, int32_t* so_out,
                        void* stream);
+/* Role attention with the first fc_rolewise layer folded in (model_0v10.py:190-214): hid f32[V*Q][2E] = ReLU(att[r] @ G[r] + bias[r]) with
+ * G f32[N][ld_g >= 2E] = enco @ [fc_rolewise.0.0.weight ; fc_rolewise.1.0.weight]^T computed once per TRACK (one GEMM), i.e.
+ * fc_rolewise[r].0(att[r] @ enco) re-associated: the V*Q x 2E `values` rows and the two V*Q-row GEMMs on them disappear.  e2a f32[N][ld_e2a].
+ * bias f32[2E] = the two first-layer biases.  att_out / so_out as for vsg_role_attention.  E in {128, 512}. */
+int vsg_role_attention_hid(const float* p2a, const float* e2a, int ld_e2a, const float* G, int ld_g, const float* bias, const int32_t* seg,
+                           int n_vid, int Q, int E, int max_tracks, float inv_sqrt_d, float* hid, float* att_out, int att_ld, int32_t* so_out,
+                           void* stream);
 
 /* Row-wise concat of up to 8 (optionally gathered) pieces: the prediction_head input (model_0v10.py:501/503). */
 int vsg_gather_concat(const float* const* src_host, const int32_t* const* idx_host, const int* idx_stride_host,
@@ -394,6 +401,7 @@ typedef struct VsgBigCEncLayer { VsgLinear qkv, out, l1, l2; VsgNorm n1, n2; } V
 typedef struct VsgBigCDecLayer {                                                                                /* model_0v10.py:178-225 */
   VsgLinear qk, v, out, p2a, e2a, r1_0, r1_1, r2, f1, f2;    /* qk / v: rows [0,2P) / [2P,3P) of in_proj; r2: fc_rolewise.{0,1}.2 concatenated along K */
   VsgNorm n1, n2, n3;
+  const float* r1_bias;     /* role_fold: [2P] = fc_rolewise.0.0.bias | fc_rolewise.1.0.bias */
 } VsgBigCDecLayer;
 
 #define VSG_MAX_LAYERS 12
@@ -410,6 +418,11 @@ typedef struct VsgBigCWeights {
   VsgBigCDecLayer dec[VSG_MAX_LAYERS];
   const float* pos; const float* query_init; const float* qk_init /* query_init + pos */;
   const float* bias_matrix /* [C*C][P] */; const float* entiemb /* [C][dim_clsme] or NULL */;
+  /* role_fold = 1 (dim_enti in {128, 512}): the track-side projections of EVERY decoder layer as one GEMM over the encoder output,
+   * eg_all = [fc_enti2att ; fc_rolewise.0.0 ; fc_rolewise.1.0] of layer 0, 1, ... stacked along N (N = n_dec * 3E; bias = fc_enti2att's, zeros
+   * for the fc_rolewise rows), consumed by vsg_role_attention_hid (fc_rolewise[r].0(att @ enco) re-associated as att @ (enco W^T)). */
+  int role_fold;
+  VsgLinear eg_all;
 } VsgBigCWeights;
 
 /* A packed batch of videos (vidsgg_big_b200.bigc.PackedVideos): rows = box-frames of all tracks of all videos. */

@@ -394,3 +394,37 @@ def test_bf16_feature_transport_equals_cast_path():
     strict = _model(cfg, st, "tf32+bf16x2")
     with pytest.raises(VsgError):
         strict.forward_packed(props16, topk=5)
+
+
+@pytest.mark.parametrize("which", ["tiny_vidvrd", "mid128", "vidvrd", "vidor"])
+def test_role_fold_equals_unfolded_role_attention(which):
+    """fc_rolewise[r].0(att[r] @ enco) re-associated as att[r] @ (enco W_r^T) inside vsg_role_attention_hid (one GEMM over the tracks for all
+    decoder layers, no V*Q-row `values`) against the reference's order of operations (vsg_role_attention + two V*Q-row GEMMs): same (s,o)
+    arg-max for every query, attention matrix and logits equal to fp32 rounding, identical triplets; ragged videos incl. a 1-track one and
+    more tracks than one staged chunk."""
+    mid = lambda: synth.tiny_vidvrd_config(dim_enti=128, dim_pred=128, dim_att=128, dim_ffn=192, num_querys=40)     # Q % 16 != 0
+    cfg = {"tiny_vidvrd": synth.tiny_vidvrd_config, "mid128": mid, "vidvrd": synth.vidvrd_config, "vidor": synth.vidor_config}[which]()
+    feat = cfg["dim_feat"] + (cfg.get("dim_i3d") or 0 if cfg["variant"] == "vidvrd" else cfg["dim_clsme"])
+    st = synth.make_bigc_state(5, cfg)
+    props = [synth.make_proposal(4100 + i, n, vl, feat, cfg["num_enti_cats"], min_len=5, max_len=60).to(DEV)
+             for i, (n, vl) in enumerate([(7, 90), (1, 40), (37, 150), (16, 64), (17, 70)])]
+    outs = {}
+    for fold in (True, False):
+        model = _model(cfg, st, "fp32_simt")
+        model.role_fold = fold
+        model._prepare()
+        assert ("eg_all" in model._w) == (fold and cfg["dim_enti"] in (128, 512))
+        pk = model.pack(props)
+        with torch.no_grad():
+            logits, so, ex = model._encode2decode(pk, want_att=True)
+            outs[fold] = (logits.clone(), so.clone(), ex["att"].clone(), model.forward_packed(props, topk=5, packed_videos=pk))
+    if cfg["dim_enti"] not in (128, 512):
+        pytest.skip("dim_enti %d: the folded kernel is instantiated for 128 / 512" % cfg["dim_enti"])
+    (la, soa, atta, pa), (lb, sob, attb, pb) = outs[True], outs[False]
+    assert torch.equal(soa, sob)
+    assert (atta - attb).abs().max().item() <= 1e-5      # pass 1 sums the 256-d dots in another order (measured 2e-6)
+    assert (la - lb).abs().max().item() <= 2e-5 * lb.abs().max().item()
+    assert np.array_equal(pa.counts, pb.counts)
+    for v in range(len(props)):
+        s = slice(v * pa.cap, v * pa.cap + int(pa.counts[v, 0]))
+        assert torch.equal(pa.quint[s], pb.quint[s]) and torch.equal(pa.spans[s], pb.spans[s])

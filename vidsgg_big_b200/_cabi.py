@@ -58,7 +58,7 @@ class VsgBigCEncLayer(C.Structure):
 
 class VsgBigCDecLayer(C.Structure):
     _fields_ = [(k, VsgLinear) for k in ("qk", "v", "out", "p2a", "e2a", "r1_0", "r1_1", "r2", "f1", "f2")] + \
-               [(k, VsgNorm) for k in ("n1", "n2", "n3")]
+               [(k, VsgNorm) for k in ("n1", "n2", "n3")] + [("r1_bias", p)]
 
 
 VSG_MAX_LAYERS = 12
@@ -71,7 +71,7 @@ class VsgBigCWeights(C.Structure):
                [("bbox1_w", p), ("bbox1_b", p)] + \
                [(k, VsgLinear) for k in ("bbox2", "feat1", "feat2", "conv", "enco1", "enco2", "i3d", "log", "log1", "log2")] + \
                [("conv_b", p), ("enc", VsgBigCEncLayer * VSG_MAX_LAYERS), ("dec", VsgBigCDecLayer * VSG_MAX_LAYERS),
-                ("pos", p), ("query_init", p), ("qk_init", p), ("bias_matrix", p), ("entiemb", p)]
+                ("pos", p), ("query_init", p), ("qk_init", p), ("bias_matrix", p), ("entiemb", p), ("role_fold", i32), ("eg_all", VsgLinear)]
 
 
 class VsgVideoBatch(C.Structure):
@@ -178,6 +178,7 @@ SIGNATURES = {
     "vsg_mha_tc16_set_kc": (i32, [i32]),
     "vsg_mha_tc64": (i32, [p, i32, p, i32, p, i32, p, i32, i32, i32, p, i32, p, p, i32, i32, p]),
     "vsg_role_attention": (i32, [p, p, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),
+    "vsg_role_attention_hid": (i32, [p, p, i32, p, i32, p, p, i32, i32, i32, i32, f32, p, p, i32, p, p]),
     "vsg_gather_concat": (i32, [C.POINTER(p), C.POINTER(p), C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), i32, i64, p, i32, p]),
     "vsg_so_category": (i32, [p, p, i32, i64, p, p, p]),
     "vsg_seq_positions": (i32, [p, i32, i64, p, p, p]),

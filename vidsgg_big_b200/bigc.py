@@ -136,6 +136,7 @@ class BIG_C(object):
         # decoder self-attention: "tc" = ONE fused tcgen05 kernel (64-wide heads; csrc/attn_tc.cu mha64_tc_kernel), else as "tc_gemm";
         # "tc_gemm" = batched tcgen05 GEMMs + softmax / transpose glue through HBM; "simt" = fp32 SIMT kernel
         self.attention = "tc"
+        self.role_fold = True      # first fc_rolewise layer folded into the role attention (csrc/bigc.cu role_attention_hid_kernel)
         self.backend = "c"         # forward_packed: "c" = ONE call of vsg_bigc_forward (csrc/forward.cu), "py" = the same launches from Python
         self.topk = 10
         self.device = None
@@ -258,6 +259,16 @@ class BIG_C(object):
                 n1=(st[p + "norm1.weight"].contiguous(), st[p + "norm1.bias"].contiguous()),
                 n2=(st[p + "norm2.weight"].contiguous(), st[p + "norm2.bias"].contiguous()),
                 n3=(st[p + "norm3.weight"].contiguous(), st[p + "norm3.bias"].contiguous())))
+        # role_fold: fc_rolewise[r].0 (att[r] @ enco) == att[r] @ (enco W_r^T): the track-side projections of every decoder layer
+        # ([fc_enti2att ; fc_rolewise.0.0 ; fc_rolewise.1.0] x n_dec layers) become ONE GEMM over the encoder output
+        if self.role_fold and self.dim_enti in (128, 512) and w["dec"]:
+            ws, bs = [], []
+            for i in range(self.n_deco_layers):
+                p = "decoder_layers.%d." % i
+                ws += [st[p + "fc_enti2att.weight"], st[p + "fc_rolewise.0.0.weight"], st[p + "fc_rolewise.1.0.weight"]]
+                bs += [st[p + "fc_enti2att.bias"], torch.zeros(2 * Pd, device=dev)]
+                w["dec"][i]["b1"] = torch.cat([st[p + "fc_rolewise.0.0.bias"], st[p + "fc_rolewise.1.0.bias"]]).contiguous()
+            w["eg_all"] = Weight(torch.cat(ws, 0).contiguous(), torch.cat(bs).contiguous(), split=split)
         w["bias_matrix"] = st["bias_matrix"].reshape(self.num_enti_cats * self.num_enti_cats, self.num_pred_cats).contiguous()
         if self.has_entiemb:
             w["entiemb"] = st["EntiNameEmb"].contiguous()
@@ -311,8 +322,12 @@ class BIG_C(object):
             d.qk, d.v, d.out, d.p2a, d.e2a = lin(lw["qk"]), lin(lw["v"]), lin(lw["out"]), lin(lw["p2a"]), lin(lw["e2a"])
             d.r1_0, d.r1_1, d.r2, d.f1, d.f2 = lin(lw["r1"][0]), lin(lw["r1"][1]), lin(lw["r2"]), lin(lw["f1"]), lin(lw["f2"])
             d.n1, d.n2, d.n3 = norm(lw["n1"]), norm(lw["n2"]), norm(lw["n3"])
+            d.r1_bias = addr(lw.get("b1"))
         c.pos, c.query_init, c.qk_init, c.bias_matrix = addr(w["pos"]), addr(w["query_init"]), addr(w["qk_init"]), addr(w["bias_matrix"])
         c.entiemb = addr(w.get("entiemb"))
+        c.role_fold = int("eg_all" in w)
+        if "eg_all" in w:
+            c.eg_all = lin(w["eg_all"])
         self._cw = c
         return c
 
@@ -509,8 +524,10 @@ class BIG_C(object):
         VQ = V * Q
         so = torch.empty(VQ, 2, dtype=torch.int32, device=dev)
         att_out = torch.zeros(VQ, 2, max(pk.max_tracks, 1), dtype=torch.float32, device=dev) if want_att else None
-        values = torch.empty(VQ, 2 * E, dtype=torch.float32, device=dev)
+        fold = "eg_all" in w
+        values = None if fold else torch.empty(VQ, 2 * E, dtype=torch.float32, device=dev)
         hid = torch.empty(VQ, 2 * Pd, dtype=torch.float32, device=dev)
+        EG = gemm(m, enco, w["eg_all"]) if fold else None              # [N, n_dec * 3E]: per layer [e2a | G_subject | G_object]
         n_dec = len(w["dec"])
 
         def bcast(x):
@@ -549,13 +566,20 @@ class BIG_C(object):
                 query, p2a = bcast(x), bcast(p2a)
             else:
                 query = x
-            e2a = gemm(m, enco, lw["e2a"])
-            check(L.vsg_role_attention(_raw(p2a), _raw(e2a), _raw(enco), _raw(pk.seg), V, Q, E, pk.max_tracks,
-                                       float(1.0 / np.sqrt(self.dim_enti)), _raw(values),
-                                       _raw(att_out) if last else None, 0 if att_out is None else att_out.shape[2],
-                                       _raw(so) if last else None, sp), "vsg_role_attention")
-            gemm(m, values[:, :E], lw["r1"][0], out=hid[:, :Pd], relu=True)
-            gemm(m, values[:, E:], lw["r1"][1], out=hid[:, Pd:], relu=True)
+            if fold:
+                e2a, G = EG[:, li * 3 * E:li * 3 * E + E], EG[:, li * 3 * E + E:(li + 1) * 3 * E]
+                check(L.vsg_role_attention_hid(_raw(p2a), _raw(e2a), EG.stride(0), _raw(G), EG.stride(0), _raw(lw["b1"]), _raw(pk.seg), V, Q, E,
+                                               pk.max_tracks, float(1.0 / np.sqrt(self.dim_enti)), _raw(hid),
+                                               _raw(att_out) if last else None, 0 if att_out is None else att_out.shape[2],
+                                               _raw(so) if last else None, sp), "vsg_role_attention_hid")
+            else:
+                e2a = gemm(m, enco, lw["e2a"])
+                check(L.vsg_role_attention(_raw(p2a), _raw(e2a), _raw(enco), _raw(pk.seg), V, Q, E, pk.max_tracks,
+                                           float(1.0 / np.sqrt(self.dim_enti)), _raw(values),
+                                           _raw(att_out) if last else None, 0 if att_out is None else att_out.shape[2],
+                                           _raw(so) if last else None, sp), "vsg_role_attention")
+                gemm(m, values[:, :E], lw["r1"][0], out=hid[:, :Pd], relu=True)
+                gemm(m, values[:, E:], lw["r1"][1], out=hid[:, Pd:], relu=True)
             query = self._add_ln(query, gemm(m, hid, lw["r2"]), lw["n2"])
             ffn = gemm(m, gemm(m, query, lw["f1"], relu=True), lw["f2"])
             if last:

@@ -712,6 +712,176 @@ role_attention_smem_kernel(const float* __restrict__ p2a, const float* __restric
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Role attention with the first fc_rolewise layer folded in (model_0v10.py:190-214):
+//   hid[r][q] = ReLU( fc_rolewise[r].0 (att[r][q] @ enco) ) = ReLU( sum_e att[r][q][e] * G[r][e] + b[r] ),   G[r] = enco W_r^T (one GEMM over
+// the TRACKS, shared by every query) -- the per-query [2E] `values` rows and the two V*Q-row GEMMs that consumed them disappear.
+// One CTA per (video, 16 queries), 8 warps:
+//   pass 1  logits: a warp owns 2 queries, a lane E/32 dims (lanes 0-15: subject half, 16-31: object half); the e2a rows of 16 tracks are
+//           staged in shared memory, each lane accumulates its partial dot for the 16 tracks, and a 4-step transposing butterfly leaves the
+//           complete dot of track i in lane i of each half-warp (15 shuffles per 16 tracks instead of 10 per track)
+//   softmax over tracks x softmax over roles, arg-max / attention output as in role_attention_kernel; att is stored transposed
+//           [role][track][16 queries] for pass 2
+//   pass 2  a warp owns E/4 output columns of one role for ALL 16 queries (lane: E/128 columns x 16 accumulators): every staged G value is
+//           read once per CTA, the 16 attention weights of a track come from four broadcast 16-byte loads
+// ---------------------------------------------------------------------------------------------------
+constexpr int RA2_QB = 16;      // queries per CTA
+constexpr int RA2_CH = 16;      // tracks per staged chunk
+
+template <int E>
+__global__ void __launch_bounds__(256)
+role_attention_hid_kernel(const float* __restrict__ p2a, const float* __restrict__ e2a, int ld_e2a, const float* __restrict__ G, int ld_g,
+                          const float* __restrict__ bias, const int32_t* __restrict__ seg, int Q, int ld_t, float inv_sqrt_d,
+                          float* __restrict__ hid, float* __restrict__ att_out, int att_ld, int32_t* __restrict__ so_out) {
+  constexpr int PER = E / 32;            // dims per lane in pass 1
+  constexpr int VW = E / 128;            // output columns per lane in pass 2 (a warp owns E / 4 columns of one role)
+  extern __shared__ __align__(16) float ra2_smem[];
+  float* sRows = ra2_smem;                                         // pass 1: [RA2_CH][E] e2a rows; pass 2: [RA2_CH][2E] G rows
+  float* sL = ra2_smem + RA2_CH * 2 * E;                           // [RA2_QB][2][ld_t] logits
+  float* sAT = sL + RA2_QB * 2 * ld_t;                             // [2][ld_t][RA2_QB] attention, transposed
+  const int v = blockIdx.x, q0 = blockIdx.y * RA2_QB;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int t0 = seg[v], n = seg[v + 1] - t0;
+  const int hl = lane & 15, role1 = lane >> 4;
+  // ---- pass 1: logits of this warp's two queries ----
+  // a lane's dims: float4 number j * 16 + hl (j < PER / 4) of its role half -- a quarter-warp then reads 128 contiguous bytes of a staged row
+  float pq[2][PER];
+#pragma unroll
+  for (int u = 0; u < 2; ++u) {
+    const int q = min(q0 + 2 * warp + u, Q - 1);
+    const float4* src = reinterpret_cast<const float4*>(p2a + ((int64_t)v * Q + q) * E) + role1 * (E / 8) + hl;
+#pragma unroll
+    for (int j = 0; j < PER / 4; ++j) {
+      const float4 t = src[j * 16];
+      pq[u][4 * j] = t.x; pq[u][4 * j + 1] = t.y; pq[u][4 * j + 2] = t.z; pq[u][4 * j + 3] = t.w;
+    }
+  }
+  for (int c0 = 0; c0 < n; c0 += RA2_CH) {
+    const int cn = min(RA2_CH, n - c0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < cn * (E / 4); i += 256) {
+      const int e = i / (E / 4), c = i - e * (E / 4);
+      reinterpret_cast<float4*>(sRows)[i] = reinterpret_cast<const float4*>(e2a + (int64_t)(t0 + c0 + e) * ld_e2a)[c];
+    }
+    __syncthreads();
+    float acc[2][RA2_CH];
+#pragma unroll
+    for (int e = 0; e < RA2_CH; ++e) {
+      float x[PER];
+      const float4* xr = reinterpret_cast<const float4*>(sRows + (e < cn ? e : 0) * E) + role1 * (E / 8) + hl;
+#pragma unroll
+      for (int j = 0; j < PER / 4; ++j) {
+        const float4 t = xr[j * 16];
+        x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+      }
+      float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+      for (int i = 0; i < PER; ++i) { a0 = fmaf(pq[0][i], x[i], a0); a1 = fmaf(pq[1][i], x[i], a1); }
+      acc[0][e] = a0; acc[1][e] = a1;
+    }
+    // transposing butterfly inside each half-warp: after the step with offset o a lane keeps the tracks whose bit o matches its own
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+#pragma unroll
+      for (int o = 8; o > 0; o >>= 1) {
+        const bool up = (hl & o) != 0;
+#pragma unroll
+        for (int j = 0; j < o; ++j) {
+          const float send = up ? acc[u][j] : acc[u][j + o];
+          const float keep = up ? acc[u][j + o] : acc[u][j];
+          acc[u][j] = keep + __shfl_xor_sync(0xffffffffu, send, o);
+        }
+      }
+      if (hl < cn) sL[((2 * warp + u) * 2 + role1) * ld_t + c0 + hl] = acc[u][0] * inv_sqrt_d;
+    }
+  }
+  __syncwarp();
+  // ---- softmax over tracks (per role) x softmax over roles (per track), arg-max; same operation order as role_attention_kernel ----
+#pragma unroll 1
+  for (int u = 0; u < 2; ++u) {
+    const int ql = 2 * warp + u, q = q0 + ql;
+    float* l0p = sL + (ql * 2 + 0) * ld_t;
+    float* l1p = sL + (ql * 2 + 1) * ld_t;
+    float mx[2] = {-INFINITY, -INFINITY};
+    for (int e = lane; e < n; e += 32) { mx[0] = fmaxf(mx[0], l0p[e]); mx[1] = fmaxf(mx[1], l1p[e]); }
+    mx[0] = warp_max(mx[0]); mx[1] = warp_max(mx[1]);
+    float sm[2] = {0.f, 0.f};
+    for (int e = lane; e < n; e += 32) { sm[0] += expf(l0p[e] - mx[0]); sm[1] += expf(l1p[e] - mx[1]); }
+    sm[0] = warp_sum(sm[0]); sm[1] = warp_sum(sm[1]);
+    float best[2] = {-INFINITY, -INFINITY};
+    int best_e[2] = {0x7fffffff, 0x7fffffff};
+    const bool active = q < Q;
+    const int64_t qrow = (int64_t)v * Q + (active ? q : 0);
+    for (int e = lane; e < n; e += 32) {
+      const float l0 = l0p[e], l1 = l1p[e];
+      const float m = fmaxf(l0, l1);
+      const float e0 = expf(l0 - m), e1 = expf(l1 - m);
+      const float a0 = (expf(l0 - mx[0]) / sm[0]) * (e0 / (e0 + e1));
+      const float a1 = (expf(l1 - mx[1]) / sm[1]) * (e1 / (e0 + e1));
+      sAT[(0 * ld_t + e) * RA2_QB + ql] = a0;
+      sAT[(1 * ld_t + e) * RA2_QB + ql] = a1;
+      if (a0 > best[0]) { best[0] = a0; best_e[0] = e; }
+      if (a1 > best[1]) { best[1] = a1; best_e[1] = e; }
+      if (att_out && active) { att_out[(qrow * 2 + 0) * att_ld + e] = a0; att_out[(qrow * 2 + 1) * att_ld + e] = a1; }
+    }
+    if (so_out) {
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+          const float ob = __shfl_xor_sync(0xffffffffu, best[r], o);
+          const int oe = __shfl_xor_sync(0xffffffffu, best_e[r], o);
+          if (ob > best[r] || (ob == best[r] && oe < best_e[r])) { best[r] = ob; best_e[r] = oe; }
+        }
+      }
+      if (lane == 0 && active) { so_out[qrow * 2] = t0 + best_e[0]; so_out[qrow * 2 + 1] = t0 + best_e[1]; }
+    }
+  }
+  // ---- pass 2: hid[q][r*E + c] = ReLU(sum_e att[r][q][e] G[e][r*E + c] + bias[r*E + c]) ----
+  const int role = warp >> 2;
+  const int colb = role * E + (warp & 3) * (E / 4) + lane * VW;    // this lane's first output column (of 2E)
+  float acc2[RA2_QB][VW];
+#pragma unroll
+  for (int qi = 0; qi < RA2_QB; ++qi)
+#pragma unroll
+    for (int j = 0; j < VW; ++j) acc2[qi][j] = 0.f;
+  for (int c0 = 0; c0 < n; c0 += RA2_CH) {
+    const int cn = min(RA2_CH, n - c0);
+    __syncthreads();                                               // also orders the sAT writes of every warp before the first read
+    for (int i = threadIdx.x; i < cn * (2 * E / 4); i += 256) {
+      const int e = i / (2 * E / 4), c = i - e * (2 * E / 4);
+      reinterpret_cast<float4*>(sRows)[i] = reinterpret_cast<const float4*>(G + (int64_t)(t0 + c0 + e) * ld_g)[c];
+    }
+    __syncthreads();
+    for (int e = 0; e < cn; ++e) {
+      float x[VW];
+      load_row<VW>(sRows + e * 2 * E + colb, x);
+      float a[RA2_QB];
+      load_row<RA2_QB>(sAT + (role * ld_t + c0 + e) * RA2_QB, a);
+#pragma unroll
+      for (int qi = 0; qi < RA2_QB; ++qi)
+#pragma unroll
+        for (int j = 0; j < VW; ++j) acc2[qi][j] = fmaf(a[qi], x[j], acc2[qi][j]);
+    }
+  }
+  float b[VW];
+  load_row<VW>(bias + colb, b);
+#pragma unroll
+  for (int qi = 0; qi < RA2_QB; ++qi) {
+    if (q0 + qi < Q) {
+      float o[VW];
+#pragma unroll
+      for (int j = 0; j < VW; ++j) o[j] = fmaxf(acc2[qi][j] + b[j], 0.f);
+      float* dst = hid + ((int64_t)v * Q + q0 + qi) * (2 * E) + colb;
+      if constexpr (VW == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+      else {
+#pragma unroll
+        for (int j = 0; j < VW; ++j) dst[j] = o[j];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Head input: Z[row] = concat of up to 8 pieces, each a (possibly gathered) row of a source matrix
 // (prediction_head concat, model_0v10.py:501/503, model_0v7.py:506/508).  idx < 0 => identity row.
 // ---------------------------------------------------------------------------------------------------
@@ -1165,6 +1335,43 @@ extern "C" int vsg_transpose_split(const float* X, int ld, int64_t rows, int col
   dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((cols + 31) / 32));
   transpose_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(X, ld, rows, cols, T_hi, T_lo, ld_t);
   return check_launch("vsg_transpose_split");
+}
+
+extern "C" int vsg_role_attention_hid(const float* p2a, const float* e2a, int ld_e2a, const float* G, int ld_g, const float* bias,
+                                      const int32_t* seg, int n_vid, int Q, int E, int max_tracks, float inv_sqrt_d, float* hid, float* att_out,
+                                      int att_ld, int32_t* so_out, void* stream) {
+  VSG_REQUIRE(n_vid >= 0 && Q > 0, "vsg_role_attention_hid: bad size");
+  if (n_vid == 0) return VSG_OK;
+  VSG_REQUIRE(p2a && e2a && G && bias && seg && hid, "vsg_role_attention_hid: null pointer");
+  VSG_REQUIRE(E == 128 || E == 512, "vsg_role_attention_hid: dim %d unsupported (128, 512)", E);
+  VSG_REQUIRE(max_tracks >= 0 && max_tracks <= RA_MAX_TRACKS, "vsg_role_attention_hid: more than %d tracks in a video", RA_MAX_TRACKS);
+  VSG_REQUIRE(aligned16(p2a) && aligned16(e2a) && aligned16(G) && aligned16(bias) && aligned16(hid) && ld_e2a % 4 == 0 && ld_g % 4 == 0 &&
+              ld_e2a >= E && ld_g >= 2 * E, "vsg_role_attention_hid: misaligned pointer or leading dimension");
+  const int ld_t = ((max_tracks > 0 ? max_tracks : 1) + 3) / 4 * 4;
+  const size_t smem = (size_t)(RA2_CH * 2 * E + 2 * RA2_QB * 2 * ld_t) * sizeof(float);
+  dim3 grid(n_vid, (Q + RA2_QB - 1) / RA2_QB);
+  static PerDeviceFlag attr_done[2];
+  const int dev_ = current_device();
+  auto raise = [&](const void* fn, PerDeviceFlag& flag) -> int {
+    if (!flag.is_set(dev_)) {
+      if (cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((RA2_CH * 2 * 512 + 2 * RA2_QB * 2 * RA_MAX_TRACKS) * sizeof(float))) != cudaSuccess) {
+        set_error("vsg_role_attention_hid: cannot raise dynamic shared memory");
+        return VSG_E_LAUNCH;
+      }
+      flag.set(dev_);
+    }
+    return VSG_OK;
+  };
+  if (E == 512) {
+    if (raise((const void*)role_attention_hid_kernel<512>, attr_done[0]) != VSG_OK) return VSG_E_LAUNCH;
+    role_attention_hid_kernel<512><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, ld_e2a, G, ld_g, bias, seg, Q, ld_t, inv_sqrt_d, hid, att_out,
+                                                                             att_ld, so_out);
+  } else {
+    if (raise((const void*)role_attention_hid_kernel<128>, attr_done[1]) != VSG_OK) return VSG_E_LAUNCH;
+    role_attention_hid_kernel<128><<<grid, 256, smem, (cudaStream_t)stream>>>(p2a, e2a, ld_e2a, G, ld_g, bias, seg, Q, ld_t, inv_sqrt_d, hid, att_out,
+                                                                             att_ld, so_out);
+  }
+  return check_launch("vsg_role_attention_hid");
 }
 
 extern "C" int vsg_role_attention(const float* p2a, const float* e2a, const float* enco, const int32_t* seg, int n_vid, int Q, int E,

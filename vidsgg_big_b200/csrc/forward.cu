@@ -200,8 +200,15 @@ int Fwd::run(VsgTripletOut* out, int topk) {
 
   // ---------------- decoder ----------------
   int32_t* so = ar.get<int32_t>(VQ * 2);
-  float* values = ar.get<float>(VQ * 2 * E);
+  const bool fold = w->role_fold && (E == 128 || E == 512) && w->n_dec > 0;
+  float* values = fold ? nullptr : ar.get<float>(VQ * 2 * E);
   float* hid = ar.get<float>(VQ * 2 * Pd);
+  float* EG = nullptr;                             // [N][n_dec * 3E]: per layer [e2a | G_subject | G_object] (bigc.py role_fold)
+  const int ld_eg = w->n_dec * 3 * E;
+  if (fold) {
+    EG = ar.get<float>((int64_t)N * ld_eg);
+    gemm(enco, E, w->eg_all, EG, ld_eg, N);
+  }
   float* qkv = ar.get<float>(VQ * 3 * Pd);
   const bool use_fused = w->tc_attention == 1 && mode != VSG_GEMM_SIMT && Pd / H == 64;      // vsg_mha_tc64: S never leaves the SM
   const bool use_tc = !use_fused && w->tc_attention && mode != VSG_GEMM_SIMT && (Pd / H) % 32 == 0 && Q % 32 == 0;
@@ -255,11 +262,16 @@ int Fwd::run(VsgTripletOut* out, int topk) {
     } else {
       qcur = xq;
     }
-    gemm(enco, E, lw.e2a, e2a, lw.e2a.N, N);
-    FWD_CALL(vsg_role_attention(p2a_use, e2a, enco, b->seg, V, Q, E, b->max_tracks, 1.0f / sqrtf((float)E), values, nullptr, 0,
-                                last ? so : nullptr, stream));
-    gemm(values, 2 * E, lw.r1_0, hid, 2 * Pd, VQ, true);
-    gemm(values + E, 2 * E, lw.r1_1, hid + Pd, 2 * Pd, VQ, true);
+    if (fold) {
+      FWD_CALL(vsg_role_attention_hid(p2a_use, EG + (int64_t)li * 3 * E, ld_eg, EG + (int64_t)li * 3 * E + E, ld_eg, lw.r1_bias, b->seg, V, Q, E,
+                                      b->max_tracks, 1.0f / sqrtf((float)E), hid, nullptr, 0, last ? so : nullptr, stream));
+    } else {
+      gemm(enco, E, lw.e2a, e2a, lw.e2a.N, N);
+      FWD_CALL(vsg_role_attention(p2a_use, e2a, enco, b->seg, V, Q, E, b->max_tracks, 1.0f / sqrtf((float)E), values, nullptr, 0,
+                                  last ? so : nullptr, stream));
+      gemm(values, 2 * E, lw.r1_0, hid, 2 * Pd, VQ, true);
+      gemm(values + E, 2 * E, lw.r1_1, hid + Pd, 2 * Pd, VQ, true);
+    }
     gemm(hid, 2 * Pd, lw.r2, t1, Pd, VQ);
     float* q2 = (qcur == query2) ? query : query2;         // norm2 output must not alias its input
     add_ln(qcur, t1, lw.n2, nullptr, 0, VQ, Pd, q2);
