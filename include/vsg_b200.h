@@ -173,8 +173,8 @@ int vsg_unique_rows(const int64_t* rows, int n, int d, int32_t* order, int32_t* 
                                   needs W_b16 / W_lo16 from vsg_split_bf16; vsg_gemm_ex only, plain (non-batched) problems */
 #define VSG_GEMM_BF16 4   /* reduced precision: bf16 operands (A16, W_b16), ONE kind::f16 pass, fp32 accumulate; outputs fp32 C and / or bf16 C16 */
 #define VSG_GEMM_FP16X3 5 /* fp32-class at 3 tensor slots per MAC (mode 3: 4): A and W split into fp16 hi / lo pairs, three kind::f16 products,
-                             power-of-two range scaling (W image pre-scaled, A_lo carried x 2^11); needs W_img16 / w_alpha from
-                             vsg_build_weight_image_fp16; |A| < 65504; vsg_gemm_ex only, plain problems */
+                             power-of-two range scaling (W image pre-scaled, optional a_scale); needs W_img16 / w_alpha from
+                             vsg_build_weight_image_fp16; 1e-2 <~ |A a_scale| < 65504; vsg_gemm_ex only, plain problems */
 
 /* C[M][N] (ldc) = act( A[M][K] (lda) * W[N][K]^T (ldw) + bias[N] + rowbias[idx(row)][N] (+ C) ) (+ residual[M][N]),
  * fp32 row-major; the residual is added after the activation (QANet blocks, models/grd_model_v5.py:118-135).
@@ -223,6 +223,8 @@ typedef struct VsgGemmArgs {
   /* mode VSG_GEMM_FP16X3 (5): fp16 weight-tile image of vsg_build_weight_image_fp16 (built for tile width img16_bn == vsg_gemm_tile_n(N)
    * over exactly this N and K) and w_alpha = 1 / scale of that image; A is the fp32 operand, W_hi the fp32 weight (only its extents are used). */
   const void* W_img16; int img16_bn; float w_alpha;
+  float a_scale;            /* mode 5: 0 (= 1) or a power of two applied to A before its fp16 split (undone in the epilogue): keeps |A a_scale| inside
+                               fp16's comfortable range [~1e-2, 65504) for layers whose activations are known to be tiny or huge */
 } VsgGemmArgs;
 int vsg_gemm_ex(const VsgGemmArgs* args, void* stream);
 
@@ -260,9 +262,9 @@ int64_t vsg_weight_image_bytes(int N, int K, int bn);
 int vsg_build_weight_image(const float* w, int ldw, int N, int K, int bn, void* img, void* stream);
 /* Validation knob: 0 = ignore W_img (tensor-map loads); 1 (default).  Bit-identical C.  Returns the old value. */
 int vsg_gemm_set_weight_image(int on);
-/* Weight-tile images of mode VSG_GEMM_FP16X3: per (N tile of `bn` rows, 16-column k block) three fp16 sub-images (bn rows x 32 B, SWIZZLE_32B,
- * edges zero-padded): hi = fp16_rn(w * scale), fp16_rn(hi * 2^-11), fp16_rn(w * scale - hi).  `scale` must be a power of two; pick it so that
- * max |w| * scale lies in [2^13, 2^14) (fp16 overflows at 65504; low parts stay normal for |w| >= 2^-16 max |w|) and pass w_alpha = 1 / scale.
+/* Weight-tile images of mode VSG_GEMM_FP16X3: per (N tile of `bn` rows, 16-column k block) two fp16 sub-images (bn rows x 32 B, SWIZZLE_32B,
+ * edges zero-padded): hi = fp16_rn(w * scale), lo = fp16_rn(w * scale - hi).  `scale` must be a power of two; pick it so that max |w| * scale
+ * lies in [2^13, 2^14) (fp16 overflows at 65504; the low part stays normal for |w| >= 2^-16 max |w|) and pass w_alpha = 1 / scale.
  * Reference counterpart: none (models/model_0v10.py multiplies in fp32); this is how the fp32 product is rebuilt on fp16 tensor cores. */
 int64_t vsg_weight_image_fp16_bytes(int N, int K, int bn);
 int vsg_build_weight_image_fp16(const float* w, int ldw, int N, int K, int bn, float scale, void* img, void* stream);

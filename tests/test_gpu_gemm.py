@@ -105,34 +105,39 @@ def test_gemm_tf32_bf16x2_is_fp32_class():
 
 
 def test_gemm_fp16x3_is_fp32_class_over_operand_ranges():
-    """Mode 5 (three kind::f16 products on fp16 hi / lo pairs): same error class as 3xTF32 (within 4x) and >20x better than plain tf32
-    whatever the magnitude of the operands -- the weight image is scaled by a power of two and the A correction travels as lo * 2^11, so
-    tiny weights / activations keep their low parts (an unscaled fp16 split degrades to ~1e-5 there) -- and for operands that span orders
-    of magnitude.  |A| must stay below the fp16 range (65504); the result is compared with an emulation of the scheme as well."""
+    """Mode 5 (three kind::f16 products on fp16 hi / lo pairs): same error class as 3xTF32 (within 4x) and >20x better than plain tf32 for
+    O(1) activations, for weights of ANY magnitude (the weight image is scaled by a power of two), for operands that span orders of
+    magnitude, and -- with the power-of-two ``a_scale`` of the weight set -- for tiny activations; without it the low part of a tiny A goes
+    subnormal (absolute 2^-25) and the error degrades gracefully (still 10x better than tf32).  Compared with an emulation of the scheme too."""
     from vidsgg_big_b200 import linalg
     g = torch.Generator(device="cpu").manual_seed(12)
-    for a_scale, w_scale, spread in ((1.0, 1 / 45.0, 0.0), (1e-3, 1e-3, 0.0), (300.0, 1e-5, 0.0), (1e-2, 40.0, 0.0), (1.0, 1 / 45.0, 1.5)):
-        A = torch.randn(1024, 2048, generator=g) * a_scale * torch.exp(spread * torch.randn(1024, 2048, generator=g))
-        W = torch.randn(512, 2048, generator=g) * w_scale * torch.exp(spread * torch.randn(512, 2048, generator=g))
+    for a_mag, w_mag, spread, a_scale in ((1.0, 1 / 45.0, 0.0, 1.0), (1e-3, 1e-3, 0.0, 1024.0), (300.0, 1e-5, 0.0, 1.0), (1e-2, 40.0, 0.0, 64.0),
+                                          (1.0, 1 / 45.0, 1.5, 1.0), (1e-3, 1e-3, 0.0, 1.0)):
+        A = torch.randn(1024, 2048, generator=g) * a_mag * torch.exp(spread * torch.randn(1024, 2048, generator=g))
+        W = torch.randn(512, 2048, generator=g) * w_mag * torch.exp(spread * torch.randn(512, 2048, generator=g))
         A, W = A.to(DEV), W.to(DEV)
-        assert A.abs().max().item() < 65504
+        assert A.abs().max().item() * a_scale < 65504
         ref = A.double() @ W.double().t()
         scale = ref.abs().max().item()
         wt5 = _weight(5, W)
+        wt5.a_scale = a_scale
         e3x = (linalg.gemm(2, A, linalg.Weight(W)).double() - ref).abs().max().item()
         out5 = linalg.gemm(5, A, wt5)
         e5 = (out5.double() - ref).abs().max().item()
         e1x = (linalg.gemm(1, A, linalg.Weight(W)).double() - ref).abs().max().item()
-        print("A %.0e W %.0e spread %.1f: 3xtf32 err %.3e  fp16x3 err %.3e  tf32 err %.3e  (scale %.3e, alpha %g)" % (a_scale, w_scale, spread, e3x, e5, e1x, scale, wt5.alpha))
-        assert e5 <= 4 * e3x + 1e-7 * scale and e1x > 20 * e5
+        print("A %.0e W %.0e spread %.1f a_scale %g: 3xtf32 err %.3e  fp16x3 err %.3e  tf32 err %.3e  (scale %.3e, alpha %g)" %
+              (a_mag, w_mag, spread, a_scale, e3x, e5, e1x, scale, wt5.alpha))
+        if a_mag * a_scale >= 0.5:
+            assert e5 <= 4 * e3x + 1e-7 * scale and e1x > 20 * e5
+        else:                                         # tiny activations without a_scale: documented graceful degradation
+            assert e1x > 10 * e5
         # emulation: the three products of the split operands in fp64 (the kernel only adds fp32 accumulation error)
-        Ws = W.double() / wt5.alpha
+        Ws, As = W.double() / wt5.alpha, A.double() * a_scale
         w_hi = Ws.to(torch.float16).double()
-        w_his = (w_hi / 2048).to(torch.float16).double()
         w_lo = (Ws - w_hi).to(torch.float16).double()
-        a_hi = A.to(torch.float16).double()
-        a_lo = ((A.double() - a_hi).float() * 2048).to(torch.float16).double()
-        emu = (a_lo @ w_his.t() + a_hi @ w_lo.t() + a_hi @ w_hi.t()) * wt5.alpha
+        a_hi = As.to(torch.float16).double()
+        a_lo = (As - a_hi).float().to(torch.float16).double()
+        emu = (a_lo @ w_hi.t() + a_hi @ w_lo.t() + a_hi @ w_hi.t()) * (wt5.alpha / a_scale)
         assert (out5.double() - emu).abs().max().item() <= 2e-5 * scale
 
 

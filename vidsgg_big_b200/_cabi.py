@@ -40,7 +40,7 @@ class VsgGemmArgs(C.Structure):
                 ("W_img", p), ("img_bn", i32),
                 ("dw_w", p), ("dw_b", p), ("seq_pos", p), ("seq_rem", p), ("dw_k", i32),
                 ("A16", p), ("lda16", i32), ("C16", p), ("ldc16", i32),
-                ("W_img16", p), ("img16_bn", i32), ("w_alpha", C.c_float)]
+                ("W_img16", p), ("img16_bn", i32), ("w_alpha", C.c_float), ("a_scale", C.c_float)]
 
 
 class VsgLinear(C.Structure):

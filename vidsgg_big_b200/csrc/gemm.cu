@@ -20,13 +20,18 @@
 //                        epilogue or by vsg_cast_bf16), fp32 accumulate, C as fp32 and / or bf16.  Runs as the single-pass kernel
 //                        (MODE 1 geometry: 128-byte stage rows = 64 bf16) with B16 = true; CTA pairs use cta_group::2 MMAs.
 //
-//   VSG_GEMM_FP16X3 (5)  fp32-class at 3/4 of the tensor time of (3): BOTH operands are split into fp16 pairs, x = hi + lo with
+//   VSG_GEMM_FP16X3 (5)  fp32-class at 3/4 of the tensor slots of (3): BOTH operands are split into fp16 pairs, x = hi + lo with
 //                        hi = fp16_rn(x) (11 significant bits) and lo = fp16_rn(x - hi) (11 more), and all three products run as kind::f16
-//                        MMAs (1 issue slot per MAC each): D += (A_lo 2^11) * (W_hi 2^-11) + A_hi * W_lo + A_hi * W_hi.  fp16 has 5 exponent
-//                        bits, so range is handled explicitly: W is pre-scaled by an exact power of two (max |W 2^s| in [2^13, 2^14), undone
-//                        by `alpha` = 2^-s in the epilogue), the A correction is carried as lo * 2^11 against a 2^-11-scaled copy of W_hi,
-//                        which keeps both low parts normal for |a| >= 2^-13 and |w| >= 2^-16 max|W|.  |a| must stay below 65504 (else inf).
-//                        Per-product error ~2^-22; W operands come as pre-swizzled tile images only (vsg_build_weight_image_fp16).
+//                        MMAs (1 issue slot per MAC each): D += A_lo * W_hi + A_hi * W_lo + A_hi * W_hi.  fp16 has 5 exponent bits, so range
+//                        is handled explicitly: W is pre-scaled by an exact power of two (max |W 2^s| in [2^13, 2^14): its low part stays
+//                        normal for |w| >= 2^-16 max |W|), A optionally by `a_scale` (a power of two, default 1); both are undone by `alpha`
+//                        in the epilogue.  A's low part is exact to 2^-25 ABSOLUTE for |a a_scale| < 2^-2 (fp16 subnormals) and to 2^-23
+//                        relative above, i.e. the product is fp32-class as long as the bulk of |A a_scale| is >= ~1e-2; |A a_scale| must
+//                        stay below 65504 (else inf).  The split warps build the two fp16 A tiles IN PLACE over the fp32 tile the TMA
+//                        delivered (8 KB -> 4 + 4 KB; reads and writes of a group separated by a named barrier), so a stage holds loaded
+//                        bytes only: 16 KB per CTA of a pair -> 12 stages in flight (the fp32-class kernels are bound by the latency of
+//                        the load -> split -> MMA -> free loop divided by the stage count, not by the tensor pipe).  W operands come as
+//                        pre-swizzled tile images only (vsg_build_weight_image_fp16).
 //
 // tcgen05 kernel anatomy (persistent, one CTA per SM; 128 x BN output tiles per CTA, BN = 256 where N allows, else 128):
 //   warp 0       TMA producer: A tiles by cp.async.bulk.tensor.2d (mbarrier complete_tx), W tiles by tensor loads or -- mode 3 -- by
@@ -81,7 +86,8 @@ struct GemmEpilogue {
   int tma_store;            // 1: full 32x32 output slabs leave through shared memory + cp.async.bulk.tensor (mapC is valid)
   int lo_tma;               // 1: C_lo slabs that lie fully inside the column window leave the same way (mapClo is valid)
   const uint8_t* w_img;     // MODE 3: pre-swizzled shared-memory images of the W tiles (vsg_build_weight_image), or null; MODE 5: required
-  float alpha;              // MODE 5: the accumulator is multiplied by alpha (= 2^-s of the weight image's power-of-two scale) first
+  float alpha;              // MODE 5: the accumulator is multiplied by alpha (= 1 / (weight image scale * a_scale)) first
+  float a_scale;            // MODE 5: power of two applied to A before the fp16 split
   const float* dw_w;        // CONV: depthwise weights [K][dw_k], bias dw_b [K], per-row position in / rows remaining of its sequence
   const float* dw_b;
   const int32_t* seq_pos;
@@ -126,21 +132,22 @@ template <int MODE, int BN_, bool PAIR = false, bool CONV = false> struct Cfg {
   static constexpr int RAW_ROWS = BM + 8;                                        // 3-row halo each side, rounded to the 8-row swizzle atom
   static constexpr int RAW_TX = RAW_ROWS * BK * 4;                               // bytes the raw-tile TMA delivers
   static constexpr int RAW_BYTES = CONV ? ((RAW_TX + 1023) / 1024) * 1024 : 0;
-  // MODE 5: [A f32 (CONV: raw X with halo) | f16(A_lo 2^11) | f16(A_hi) | f16(W_hi) | f16(W_hi 2^-11) | f16(W_lo)]: nothing but the split warps
-  // reads the fp32 A region, so the CONV variant keeps its raw tile there
-  static constexpr int AREG5 = CONV ? RAW_BYTES : TILE_A;
+  // MODE 5: [f16(A_hi) | f16(A_lo)] built in place over the fp32 A tile (CONV: raw X with halo first, then the two fp16 tiles), then
+  // [f16(W_hi) | f16(W_lo)]: only loaded bytes (and for CONV the conv output) live in a stage
+  static constexpr int AREG5 = CONV ? RAW_BYTES + TILE_A : TILE_A;
   static constexpr int OFF_RAW = MODE == 5 ? 0 : (MODE >= 2 ? 2 : 1) * (TILE_A + TILE_B);
-  static constexpr int STAGE_BYTES = MODE == 5 ? AREG5 + TILE_A + 3 * (TILE_B / 2) : OFF_RAW + RAW_BYTES;   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles) (+ raw X)
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16), 6/4 (fp16x3)
+  static constexpr int STAGE_BYTES = MODE == 5 ? AREG5 + TILE_B : OFF_RAW + RAW_BYTES;   // [A | B_hi] (+ [A_lo | B_lo]; MODE 3: four bf16 tiles) (+ raw X)
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;                      // 6/4 (tf32), 3/4 (3xTF32), 6/4 (tf32+2xbf16), 12/8 (fp16x3)
   static constexpr int DW_BYTES = CONV ? 8 * 1024 : 0;                           // depthwise weights [K][k] + bias [K] (K <= 224 channels, k <= 7)
   static constexpr int SPLIT_GROUPS = 2;                                         // groups of 4 split warps that alternate stages
   static constexpr int THREADS = MODE >= 2 ? 256 + 128 * SPLIT_GROUPS : 256;
   // MODE 2: [A | B_hi | A_lo | B_lo] fp32.   MODE 3: [A f32 | W f32 | bf16(A_lo) | bf16(A) | bf16(W) | bf16(W_lo)]
-  static constexpr int OFF_BH = MODE == 5 ? AREG5 + TILE_A : TILE_A;
-  static constexpr int OFF_AL = MODE == 5 ? AREG5 : TILE_A + TILE_B;
-  static constexpr int OFF_A16 = OFF_AL + TILE_A / 2, OFF_B16 = MODE == 5 ? OFF_BH + TILE_B / 2 : OFF_AL + TILE_A;
-  static constexpr int OFF_BL = MODE == 5 ? OFF_BH + TILE_B : (MODE == 3 ? OFF_B16 + TILE_B / 2 : 2 * TILE_A + TILE_B);
-  static constexpr int W_TX = MODE == 5 ? 3 * (TILE_B / 2) : (MODE >= 2 ? 2 : 1) * TILE_B;   // W bytes a stage receives
+  static constexpr int OFF_BH = MODE == 5 ? AREG5 : TILE_A;
+  static constexpr int OFF_AL = MODE == 5 ? AREG5 - TILE_A / 2 : TILE_A + TILE_B;                    // MODE 5: f16(A_lo) after f16(A_hi)
+  static constexpr int OFF_A16 = MODE == 5 ? AREG5 - TILE_A : OFF_AL + TILE_A / 2, OFF_B16 = OFF_AL + TILE_A;
+  static constexpr int OFF_BL = MODE == 5 ? OFF_BH + TILE_B / 2 : (MODE == 3 ? OFF_B16 + TILE_B / 2 : 2 * TILE_A + TILE_B);
+  static constexpr int W_TX = MODE == 5 ? TILE_B : (MODE >= 2 ? 2 : 1) * TILE_B;   // W bytes a stage receives
+  static constexpr int BAR_BYTES = 512;                                          // mbarriers (3 per stage + 4) + the TMEM slot
   static constexpr int TMEM_COLS = 2 * BN_;                                      // double-buffered fp32 accumulator
   static constexpr int STAGING_BYTES = 4 * 2 * 32 * 128;                         // TMA-store staging of the epilogue warps
 };
@@ -177,7 +184,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   uint64_t* acc_full = bars + 3 * STAGES;  // [2]
   uint64_t* acc_empty = acc_full + 2;      // [2]
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
-  float* sdw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + 256);      // CONV: [K][dw_k] weights, then [K] bias
+  float* sdw = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + CF::BAR_BYTES);      // CONV: [K][dw_k] weights, then [K] bias
   if (CONV) {
     for (int i = threadIdx.x; i < ep.K * ep.dw_k; i += blockDim.x) sdw[i] = ep.dw_w[i];
     for (int i = threadIdx.x; i < ep.K; i += blockDim.x) sdw[ep.K * ep.dw_k + i] = ep.dw_b[i];
@@ -253,19 +260,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           if (CONV) tma_load_2d(smem_u32(st + CF::OFF_RAW), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row - 3);   // rows m0-3 .. m0+132 (OOB = 0)
           else tma_load_2d(smem_u32(st), &mapA, &full[stage], kb * BKE + tc.a_col, tc.a_row);
           if (MODE == 5) {
-            // three fp16 sub-images [W_hi | W_hi 2^-11 | W_lo] of BN rows x 32 B per (N tile, k block), adjacent in the image and in the stage
+            // two fp16 sub-images [W_hi | W_lo] of BN rows x 32 B per (N tile, k block), adjacent in the image and in the stage
             constexpr int SUB = BN * 32;                   // one sub-image of the whole N tile
-            const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(3 * SUB);
+            const uint8_t* img = ep.w_img + ((size_t)(tc.n0 / BN) * kblocks + kb) * (size_t)(2 * SUB);
             if (PAIR) {                                    // this CTA's 128 rows of each sub-image
 #pragma unroll
-              for (int j = 0; j < 3; ++j)
+              for (int j = 0; j < 2; ++j)
                 bulk_load(smem_u32(st + CF::OFF_BH + j * (SUB / 2)), img + j * SUB + rank * (SUB / 2), SUB / 2, &full[stage]);
             } else if (CL == 2) {                          // half of each sub-image, written into both CTAs of the pair
 #pragma unroll
-              for (int j = 0; j < 3; ++j)
+              for (int j = 0; j < 2; ++j)
                 bulk_load_mc(smem_u32(st + CF::OFF_BH + j * SUB + rank * (SUB / 2)), img + j * SUB + rank * (SUB / 2), SUB / 2, &full[stage], 3);
             } else {
-              bulk_load(smem_u32(st + CF::OFF_BH), img, 3 * SUB, &full[stage]);
+              bulk_load(smem_u32(st + CF::OFF_BH), img, 2 * SUB, &full[stage]);
             }
           } else if (PAIR) {
             // this CTA's half of the W rows only; the pair's MMA reads the other half from the peer's shared memory
@@ -350,9 +357,9 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 else umma2_tf32(d_tmem, a_hi + 2 * k, b_hi + 2 * k, ID_TF32, (kb | k) ? 1u : 0u);
               }
             } else if (MODE == 5) {
-              // corrections first: (A_lo 2^11)(W_hi 2^-11), A_hi W_lo; then A_hi W_hi -- three K = 16 kind::f16 instructions on fp16 tiles
+              // corrections first: A_lo W_hi, A_hi W_lo; then A_hi W_hi -- three K = 16 kind::f16 instructions on fp16 tiles
               constexpr uint32_t ID_F16 = IDesc<BN_, 256>::f16;
-              umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), ID_F16, kb ? 1u : 0u);
+              umma2_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), ID_F16, kb ? 1u : 0u);
               umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), ID_F16, 1u);
               umma2_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), ID_F16, 1u);
             } else if (MODE == 3) {
@@ -380,7 +387,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint64_t a_hi = desc(0, DESC_HI), b_hi = desc(CF::OFF_BH, DESC_HI);
           if (PROBE && (ep.dbg & 4)) {
           } else if (MODE == 5) {
-            umma_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_B16, DESC_HI_B16), IDesc<BN_>::f16, kb ? 1u : 0u);
+            umma_bf16(d_tmem, desc(CF::OFF_AL, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), IDesc<BN_>::f16, kb ? 1u : 0u);
             umma_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BL, DESC_HI_B16), IDesc<BN_>::f16, 1u);
             umma_bf16(d_tmem, desc(CF::OFF_A16, DESC_HI_B16), desc(CF::OFF_BH, DESC_HI_B16), IDesc<BN_>::f16, 1u);
           } else if (MODE == 3) {
@@ -750,6 +757,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 7; ++j) wq[ch][j] = j < k ? sdw[(cq + ch) * k + j] : 0.f;
           bq = *reinterpret_cast<const float4*>(sdw + ep.K * k + cq);
         }
+        // MODE 5 without CONV: the two fp16 tiles overwrite the fp32 tile they are made from -- every thread of the group holds its
+        // items in registers before anybody writes (named barrier 1 + grp over the group's 128 threads)
+        float4 xpre[(MODE == 5 && !CONV) ? NI : 1];
+        if (MODE == 5 && !CONV) {
+#pragma unroll
+          for (int i = 0; i < NI; ++i) xpre[i] = src[i * 128 + t];
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + grp) : "memory");
+        }
 #pragma unroll
         for (int i = 0; i < ((PROBE && (ep.dbg & 2)) ? 0 : NI); ++i) {
           const int idx = i * 128 + t;
@@ -777,16 +792,19 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               }
             }
             if (MODE == 3) reinterpret_cast<float4*>(st)[idx] = x;       // MODE 5: no MMA reads the fp32 tile
+          } else if (MODE == 5) {
+            x = xpre[i];
           } else {
             x = src[idx];
           }
           const int dst = r * 32 + ((((l >> 1) ^ ((r >> 2) & 1))) << 4) + (l & 1) * 8;
           if (MODE == 5) {
-            // fp16 pair: hi = fp16_rn(x), lo = fp16_rn((x - hi) * 2^11) (the 2^-11 sits in the W_hi copy this tile is multiplied with)
+            // fp16 pair of the (optionally power-of-two scaled) value: hi = fp16_rn(x), lo = fp16_rn(x - hi)
+            x.x *= ep.a_scale; x.y *= ep.a_scale; x.z *= ep.a_scale; x.w *= ep.a_scale;
             const __half2 h0 = __floats2half2_rn(x.x, x.y), h1 = __floats2half2_rn(x.z, x.w);
             const float2 f0 = __half22float2(h0), f1 = __half22float2(h1);
-            const __half2 l0 = __floats2half2_rn((x.x - f0.x) * 2048.f, (x.y - f0.y) * 2048.f);
-            const __half2 l1 = __floats2half2_rn((x.z - f1.x) * 2048.f, (x.w - f1.y) * 2048.f);
+            const __half2 l0 = __floats2half2_rn(x.x - f0.x, x.y - f0.y);
+            const __half2 l1 = __floats2half2_rn(x.z - f1.x, x.w - f1.y);
             *reinterpret_cast<uint2*>(lo16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&l0), *reinterpret_cast<const uint32_t*>(&l1));
             *reinterpret_cast<uint2*>(a16 + dst) = make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
             continue;
@@ -985,8 +1003,8 @@ __global__ void weight_image_kernel(const float* __restrict__ w, int ldw, int N,
   }
 }
 
-// Weight-tile images of mode 5 (fp16x3, BK = 16): for every (N tile, k block) one contiguous block of three fp16 sub-images, bn rows x 32 B
-// each, SWIZZLE_32B:  [ hi = fp16_rn(w 2^s) | fp16_rn(hi 2^-11) | fp16_rn(w 2^s - hi) ].  One thread per 4 elements.
+// Weight-tile images of mode 5 (fp16x3, BK = 16): for every (N tile, k block) one contiguous block of two fp16 sub-images, bn rows x 32 B
+// each, SWIZZLE_32B:  [ hi = fp16_rn(w 2^s) | fp16_rn(w 2^s - hi) ].  One thread per 4 elements.
 __global__ void weight_image_fp16_kernel(const float* __restrict__ w, int ldw, int N, int K, int bn, float scale, uint8_t* __restrict__ img) {
   const int kblocks = (K + 15) / 16, tiles_n = (N + bn - 1) / bn;
   const int64_t total = (int64_t)tiles_n * kblocks * bn * 4;
@@ -997,20 +1015,17 @@ __global__ void weight_image_fp16_kernel(const float* __restrict__ w, int ldw, i
     const int64_t blk = (i >> 2) / bn;                 // nt * kblocks + kb
     const int kb = (int)(blk % kblocks), nt = (int)(blk / kblocks);
     const int row = nt * bn + r, col = kb * 16 + c * 4;
-    __half hi[4], his[4], lo[4];
+    __half hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const float x = ((row < N && col + j < K) ? w[(size_t)row * ldw + col + j] : 0.f) * scale;
       hi[j] = __float2half_rn(x);
-      const float h = __half2float(hi[j]);
-      his[j] = __float2half_rn(h * (1.f / 2048.f));
-      lo[j] = __float2half_rn(x - h);
+      lo[j] = __float2half_rn(x - __half2float(hi[j]));
     }
-    uint8_t* base = img + blk * (int64_t)(3 * sub);
+    uint8_t* base = img + blk * (int64_t)(2 * sub);
     const int dst = r * 32 + ((((c >> 1) ^ ((r >> 2) & 1))) << 4) + (c & 1) * 8;
     *reinterpret_cast<uint2*>(base + dst) = *reinterpret_cast<const uint2*>(hi);
-    *reinterpret_cast<uint2*>(base + sub + dst) = *reinterpret_cast<const uint2*>(his);
-    *reinterpret_cast<uint2*>(base + 2 * sub + dst) = *reinterpret_cast<const uint2*>(lo);
+    *reinterpret_cast<uint2*>(base + sub + dst) = *reinterpret_cast<const uint2*>(lo);
   }
 }
 
@@ -1128,7 +1143,7 @@ static int launch_tc(const float* A, int lda, int a_rows, int a_cols, const floa
       }
     }
   }
-  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + 256 /*barriers*/ + CF::DW_BYTES;
+  constexpr int SMEM = CF::STAGES * CF::STAGE_BYTES + CF::STAGING_BYTES + 1024 /*align*/ + CF::BAR_BYTES + CF::DW_BYTES;
   constexpr bool HAS_PROBE = (CL == 1) && !CONV && !B16;   // the timing probes exist for the single-CTA kernel only (compile time)
   static PerDeviceFlag attr_set;
   const int dev_ = current_device();
@@ -1233,7 +1248,7 @@ extern "C" int64_t vsg_weight_image_bytes(int N, int K, int bn) {
 
 extern "C" int64_t vsg_weight_image_fp16_bytes(int N, int K, int bn) {
   if (N <= 0 || K <= 0 || (bn != 128 && bn != 256)) return 0;
-  return (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * (int64_t)(3 * bn * 32);
+  return (int64_t)((N + bn - 1) / bn) * ((K + 15) / 16) * (int64_t)(2 * bn * 32);
 }
 
 extern "C" int vsg_build_weight_image_fp16(const float* w, int ldw, int N, int K, int bn, float scale, void* img, void* stream) {
@@ -1298,7 +1313,7 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
   ep.lo_c0 = 0; ep.lo_c1 = N; ep.tma_store = 0; ep.lo_tma = 0; ep.w_img = nullptr;
   ep.dw_w = nullptr; ep.dw_b = nullptr; ep.seq_pos = nullptr; ep.seq_rem = nullptr; ep.dw_k = 0;
   VSG_REQUIRE(a->dw_w == nullptr || ((a->mode == 3 || a->mode == 5) && batch == 1), "vsg_gemm_ex: the fused depthwise conv exists for modes 3 and 5, plain problems");
-  ep.alpha = 1.f;
+  ep.alpha = 1.f; ep.a_scale = 1.f;
   if (a->lo_col_end > a->lo_col_begin) { ep.lo_c0 = a->lo_col_begin; ep.lo_c1 = a->lo_col_end; }
   ep.ldc = a->ldc; ep.M = M; ep.N = N; ep.K = K;
   ep.batch = batch; ep.batch_inner = a->batch_inner > 0 ? a->batch_inner : 1;
@@ -1357,7 +1372,12 @@ extern "C" int vsg_gemm_ex(const VsgGemmArgs* a, void* stream) {
     VSG_REQUIRE(a->W_img16 && aligned16(a->W_img16) && a->img16_bn == (wide ? 256 : 128),
                 "vsg_gemm_ex: mode 5 needs the fp16 weight-tile image of vsg_build_weight_image_fp16 for tile width %d", wide ? 256 : 128);
     VSG_REQUIRE(a->w_alpha > 0.f, "vsg_gemm_ex: mode 5 needs w_alpha = 1 / (the image's scale)");
-    ep.w_img = (const uint8_t*)a->W_img16; ep.alpha = a->w_alpha;
+    {
+      int ex = 0;
+      VSG_REQUIRE(a->a_scale == 0.f || (a->a_scale > 0.f && frexpf(a->a_scale, &ex) == 0.5f), "vsg_gemm_ex: a_scale must be 0 (= 1) or a power of two");
+    }
+    ep.a_scale = a->a_scale > 0.f ? a->a_scale : 1.f;
+    ep.w_img = (const uint8_t*)a->W_img16; ep.alpha = a->w_alpha / ep.a_scale;
     if (a->dw_w) {
       VSG_REQUIRE(!wide && N <= 128, "vsg_gemm_ex: the fused depthwise conv needs N <= 128 (128-wide tiles)");
       VSG_REQUIRE(a->dw_b && a->seq_pos && a->seq_rem && aligned16(a->dw_b), "vsg_gemm_ex: fused depthwise conv needs dw_b, seq_pos, seq_rem");

@@ -42,6 +42,7 @@ class Weight(object):
         self.hi = self.lo = self.w16 = self.lo16 = self.img = self.img16 = None
         self.img_bn = self.img16_bn = 0
         self.alpha = 1.0
+        self.a_scale = 1.0         # fp16x3: optional power of two applied to the A operand before its fp16 split (csrc/gemm.cu mode 5)
         if split == "fp16":
             # fp16x3 mode: power-of-two scale that puts max |w| into [2^13, 2^14) (exact; undone by alpha in the GEMM epilogue)
             import math
@@ -208,7 +209,7 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
             dw_w, dw_b, dw_k, seq_pos, seq_rem = dwconv
             a.dw_w, a.dw_b, a.dw_k, a.seq_pos, a.seq_rem = dw_w.data_ptr(), dw_b.data_ptr(), int(dw_k), seq_pos.data_ptr(), seq_rem.data_ptr()
         if mode == FP16X3:
-            a.W_img16, a.img16_bn, a.w_alpha = W.img16.data_ptr(), W.img16_bn, W.alpha
+            a.W_img16, a.img16_bn, a.w_alpha, a.a_scale = W.img16.data_ptr(), W.img16_bn, W.alpha, float(W.a_scale)
         if mode == TF32_BF16X2:
             a.W_b16, a.W_lo16, a.ldw16 = W.w16.data_ptr(), W.lo16.data_ptr(), W.ld16
             if W.img is not None and K == W.K:           # the image's k blocks cover the whole of W.K
