@@ -506,13 +506,14 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) * ep.alpha);
           }
           uint8_t* sb = stg + sbuf * 4096;
-          if (lane == 0) bulk_wait_read<1>();                                 // the store that last read this buffer is done
+          if (PROBE && (ep.dbg & 128)) { sbuf ^= 1; continue; }               // probe: TMEM read only
+          if (lane == 0 && !(PROBE && (ep.dbg & 256))) bulk_wait_read<1>();   // the store that last read this buffer is done
           __syncwarp();
           const float floor_v = ep.relu ? 0.f : -INFINITY;
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 v = make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
-            if (ep.bias) {
+            if (ep.bias && !(PROBE && (ep.dbg & 64))) {
               v.x += __shfl_sync(0xffffffffu, bl, j); v.y += __shfl_sync(0xffffffffu, bl, j + 1);
               v.z += __shfl_sync(0xffffffffu, bl, j + 2); v.w += __shfl_sync(0xffffffffu, bl, j + 3);
             }
@@ -520,6 +521,7 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             if (res) { const float4 t4 = rv[j >> 2]; v.x += t4.x; v.y += t4.y; v.z += t4.z; v.w += t4.w; }
             *reinterpret_cast<float4*>(sb + lane * 128 + (((j >> 2) ^ (lane & 7)) << 4)) = v;
           }
+          if (PROBE && (ep.dbg & 256)) { sbuf ^= 1; continue; }               // probe: no fence / TMA store
           fence_proxy_async();
           __syncwarp();
           if (lane == 0) {
@@ -1193,7 +1195,8 @@ using namespace vsg;
 
 static int g_store_hi = 0;
 static int g_dbg = 0;
-/* timing probes (results become garbage): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads, 16 free stages by a plain arrive, 32 producer / issuer poll with test_wait; 0 = normal */
+/* timing probes (results become garbage): 1 skip W loads, 2 skip the A split, 4 skip MMAs, 8 skip A loads, 16 free stages by a plain arrive, 32 producer / issuer poll with test_wait;
+   lean epilogue: 64 skip the bias shuffles, 128 stop after the TMEM read, 256 skip the fence + TMA store; 0 = normal */
 /* validation knob: 0 = the epilogue writes C with per-row 16-byte stores only, 1 (default) = full 32x32 slabs leave through TMA stores */
 extern "C" int vsg_gemm_set_tma_store(int on) { int old = vsg::g_tma_store; vsg::g_tma_store = on ? 1 : 0; return old; }
 /* validation knob: 1 = one CTA per tile; 2 = CTA pairs that multicast the W tile (per-CTA MMAs); 3 (default) = CTA-pair MMAs
