@@ -745,7 +745,7 @@ def vidor_leg(args, rank, world, device, dist, barrier):
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
 
-    def one_pass():
+    def one_pass(pipe=pipe):
         """All chunks of this rank; -> (device ms inside the chunk brackets, records, relations)."""
         brackets, recs, n_rel = [], [], 0
         for ch in chunks:
@@ -783,6 +783,26 @@ def vidor_leg(args, rank, world, device, dist, barrier):
         dist.all_gather(per_rank, mine)
     per_rank = [float(t.item()) for t in per_rank]
     ms_pass = max(per_rank)
+
+    # ---- the other fp32-class mode(s) of --modes on the same set and GT: one warm-up pass, one timed pass ----
+    alt_modes = {}
+    for prec in [m for m in args.modes.split(",") if m in ("fp16x3", "3xtf32", "tf32+bf16x2") and m != args.precision]:
+        alt = Pipeline("vidor", prec, device, rank)
+        one_pass(alt)
+        barrier()
+        ms_a, rec_a, _ = one_pass(alt)
+        allrec_a = shard.gather_records(torch.from_numpy(rec_a).to(device)).cpu().numpy()
+        mine_a = torch.tensor([ms_a], device=device)
+        per_a = [mine_a.clone() for _ in range(world)]
+        if world > 1:
+            dist.all_gather(per_a, mine_a)
+        per_a = [float(t.item()) for t in per_a]
+        m_a = evalapi.metrics_from_records(allrec_a)
+        alt_modes[prec] = {"value": n_set / (max(per_a) / 1e3), "unit": "videos/s", "ms_per_pass": max(per_a), "passes": 1, "per_rank_ms": per_a,
+                           "result": {"mAP": float(m_a[0]), "R@50": float(m_a[1][50]), "R@100": float(m_a[1][100])},
+                           "note": "same set, same sharding, GT from the parity mode's predictions; the record all_gather is outside this bracket"}
+        del alt
+        torch.cuda.empty_cache()
 
     # ---- roofline legs: one instrumented step on this rank's largest chunk ----
     big = max(chunks, key=lambda c: c["rows"])
@@ -838,6 +858,7 @@ def vidor_leg(args, rank, world, device, dist, barrier):
                               "OUTSIDE its timed bracket, timed region = sum of the chunk brackets + the record all_gather")},
         "result": {"mAP": float(metrics[0]), "R@50": float(metrics[1][50]), "R@100": float(metrics[1][100]), "relations_after_grounding_rank0": n_rel},
         "roofline": dict(roof, measured_on=roof_ctx), "cpu_baseline": cpu, "parity_vs_cpu_oracle": parity, "e2e": e2e,
+        "modes": alt_modes or None,
         "gpu_launches": n_launches, "leg_wall_s": time.perf_counter() - t_leg,
     }
 
@@ -1003,10 +1024,10 @@ def main():
     roofline = legs.pop("bigc_gemm")
     # DRAM bytes per launch: a CONSTANT read from the committed ncu pass of the same command (profiles/), not measured inside this run
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic.summary.json")))
+        tj = json.load(open(os.path.join(ROOT, "profiles", "r02_gemm_traffic_v2.summary.json")))
         if args.workload == "vidvrd" and args.videos == 200 and args.precision == "tf32+bf16x2":
             roofline["traffic"] = tj["dram_bytes_per_launch"]
-            roofline["traffic_source"] = "constant from profiles/r02_gemm_traffic.summary.json: " + tj["source"]
+            roofline["traffic_source"] = "constant from profiles/r02_gemm_traffic_v2.summary.json: " + tj["source"]
     except Exception:
         pass
     roofline["also"] = legs.pop("k1_geometry")
