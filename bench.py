@@ -765,9 +765,10 @@ def vidor_leg(args, rank, world, device, dist, barrier):
         one_pass()
     launches0 = int(_cabi.lib().vsg_launch_count())
     barrier()
-    pass_ms, metrics, n_rel = [], None, 0
+    pass_ms, compute_ms, metrics, n_rel = [], [], None, 0
     for _ in range(max(1, args.vidor_passes)):
         ms, rec, n_rel = one_pass()
+        compute_ms.append(ms)
         g0, g1 = ev(), ev()
         g0.record()
         allrec = shard.gather_records(torch.from_numpy(rec).to(device)).cpu().numpy()      # the one exchange: 64 B / video
@@ -783,6 +784,11 @@ def vidor_leg(args, rank, world, device, dist, barrier):
         dist.all_gather(per_rank, mine)
     per_rank = [float(t.item()) for t in per_rank]
     ms_pass = max(per_rank)
+    mine_c = torch.tensor([float(np.mean(compute_ms))], device=device)         # chunk brackets only: shows the load balance (the gather equalises)
+    per_rank_compute = [mine_c.clone() for _ in range(world)]
+    if world > 1:
+        dist.all_gather(per_rank_compute, mine_c)
+    per_rank_compute = [float(t.item()) for t in per_rank_compute]
 
     # ---- the other fp32-class mode(s) of --modes on the same set and GT: one warm-up pass, one timed pass ----
     alt_modes = {}
@@ -847,6 +853,7 @@ def vidor_leg(args, rank, world, device, dist, barrier):
     return {
         "metric": METRIC, "value": n_set / (ms_pass / 1e3), "unit": "videos/s", "n_gpus": world, "scaling": "strong",
         "ms_per_pass": ms_pass, "passes": len(pass_ms), "warmup_passes": n_warm, "per_rank_ms": per_rank,
+        "per_rank_compute_ms": per_rank_compute,
         "config": dict(bench_config("vidor", wl), videos=n_set, sharding="shard.assign_lpt on useful-flop costs (BIG-C over ragged rows + grounding)",
                        precision=args.precision),
         "set": {"videos": n_set, "feature_rows": int(sum(v["rows"] for v in info)), "feature_gb": sum(v["rows"] for v in info) * wl["feat_total"] * 4 / 1e9,
