@@ -922,6 +922,8 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (the product path has no CPU fallback)"
     torch.cuda.set_device(local)
     device = torch.device("cuda", local)
+    from vidsgg_big_b200 import shard as _shard
+    numa = _shard.bind_to_gpu_numa_node(local)      # pinned buffers are then first-touched next to the GPU (no-op where sysfs shows no topology)
     if world > 1:
         # NCCL prints its version banner (and any NCCL_DEBUG output) on stdout while the communicator is created: point fd 1 at stderr for
         # that moment so that stdout carries the ONE JSON line only
@@ -1090,7 +1092,7 @@ def main():
         bare_all = [float(t.item()) for t in bare_all]
         e2e = {"value": args.videos * world / float(tdt.item()), "unit": "videos/s", "h2d_bytes_per_step": int(hb.nbytes),
                "d2h_bytes_per_step": int(d2h), "steps": n_e2e,
-               "bare_h2d_gbs_per_gpu": bare_all, "bare_h2d_gbs_total": sum(bare_all),
+               "bare_h2d_gbs_per_gpu": bare_all, "bare_h2d_gbs_total": sum(bare_all), "numa_binding_rank0": numa,
                "h2d_bound_videos_per_s": args.videos * world / (hb.nbytes / (min(bare_all) * 1e9)),
                "note": "pinned host buffers, H2D double-buffered on a copy stream; GT relations resident; bare_h2d = the same pinned feature "
                        "buffer copied with every rank copying at once and no kernels running: the platform ceiling of this number"}

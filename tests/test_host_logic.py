@@ -299,3 +299,16 @@ def test_c_structs_match_the_header_layout():
     subprocess.run(["g++", os.path.join(d, "s.cpp"), "-o", os.path.join(d, "s")], check=True)
     sizes = [int(x) for x in subprocess.run([os.path.join(d, "s")], capture_output=True, text=True).stdout.split()]
     assert sizes == [C.sizeof(getattr(_cabi, n)) for n in names]
+
+
+def test_cpulist_parsing_and_numa_binding_is_best_effort():
+    """shard.bind_to_gpu_numa_node never raises (no GPU / no sysfs topology -> unbound) and the sysfs cpulist parser handles ranges."""
+    from vidsgg_big_b200 import shard
+    assert shard._parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert shard._parse_cpulist("") == []
+    import os
+    before = os.sched_getaffinity(0)
+    info = shard.bind_to_gpu_numa_node(0)
+    assert info["device"] == 0 and isinstance(info["bound"], bool)
+    if not info["bound"]:
+        assert os.sched_getaffinity(0) == before

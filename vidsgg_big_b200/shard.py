@@ -127,3 +127,40 @@ def traj_viou_row_sharded(boxes_list, dura: torch.Tensor, group=None):
     mask = mask.reshape(r1 - r0, n)
     return (gather_row_blocks(viou, n, group), gather_row_blocks(spans, n, group),
             gather_row_blocks(mask.to(torch.uint8), n, group).bool())
+
+
+def _parse_cpulist(text: str) -> List[int]:
+    cpus: List[int] = []
+    for part in text.strip().split(","):
+        if not part:
+            continue
+        a, _, b = part.partition("-")
+        cpus.extend(range(int(a), int(b or a) + 1))
+    return cpus
+
+
+def bind_to_gpu_numa_node(device_index: int) -> dict:
+    """One process per GPU: pin this process to the CPUs that are local to its GPU (``/sys/bus/pci/devices/<bus id>/local_cpulist``), so
+    that pinned host buffers allocated afterwards are first-touched on the GPU's own NUMA node and the H2D copies do not cross the socket
+    interconnect.  No reference counterpart (the reference copies pageable tensors with ``.to(device)``, tools/eval_vidor.py:96).  Best
+    effort: returns what it did; leaves the affinity alone when sysfs has no topology for the device (containers) or there is one node."""
+    import os
+    info = {"device": int(device_index), "bound": False}
+    try:
+        p = torch.cuda.get_device_properties(device_index)
+        bus = "%04x:%02x:%02x.0" % (getattr(p, "pci_domain_id", 0), p.pci_bus_id, p.pci_device_id)
+        info["pci"] = bus
+        base = "/sys/bus/pci/devices/" + bus
+        node = int(open(base + "/numa_node").read().strip())
+        cpus = _parse_cpulist(open(base + "/local_cpulist").read())
+        info["numa_node"], info["local_cpus"] = node, len(cpus)
+        allowed = sorted(os.sched_getaffinity(0))
+        info["allowed_cpus"] = len(allowed)
+        target = sorted(set(cpus) & set(allowed))
+        if node < 0 or not target or len(target) == len(allowed):
+            return info
+        os.sched_setaffinity(0, target)
+        info["bound"] = True
+    except Exception as e:          # no sysfs entry, no permission, ...: keep running unbound
+        info["error"] = "%s: %s" % (type(e).__name__, e)
+    return info
