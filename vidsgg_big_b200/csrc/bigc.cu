@@ -44,6 +44,60 @@ bbox_feat_mlp1_kernel(const float4* __restrict__ boxes, const int64_t* __restric
   const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int64_t n_warps = ((int64_t)gridDim.x * blockDim.x) >> 5;
   const bool vec4 = (E % 4 == 0) && (ldo % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out16) & 7) == 0);
+  const int G = (E + 127) / 128;                 // groups of 128 channels
+  if (vec4 && !feat8_out && (G == 1 || G == 2 || G == 4)) {
+    // Register-resident weights: a warp owns ONE group of 128 channels (4 per lane: 8 weights + bias = 36 registers) and walks the rows;
+    // the G warps that share a row recompute its 8 features (broadcast loads).  The shared-memory form below issues 9 LDS.128 per 4
+    // outputs -- 144 shared-memory wavefronts per 2 KB row, which made this write-only kernel LDS-bound at ~1/3 of the HBM write rate.
+    // Same fmaf order per channel (bias, then k = 0..7), so the outputs are bit-identical.
+    const int g = (int)(warp % G), c = g * 128 + lane * 4;
+    const bool on = c < E;
+    float4 wr[8], bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) wr[k] = on ? *reinterpret_cast<const float4*>(sw + k * E + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (on) bias4 = *reinterpret_cast<const float4*>(sw + 8 * E + c);
+    // rows in blocks of 32: lane l derives the 8 features of row r0 + l (one binary search per lane, all 32 in parallel), then the warp walks
+    // the block and broadcasts each row's features by shuffles
+    const int64_t n_blocks = (n_rows + 31) / 32;
+    for (int64_t blk = warp / G; blk < n_blocks; blk += n_warps / G) {
+      const int64_t r0 = blk * 32, rl = r0 + lane;
+      float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+      if (rl < n_rows) {
+        const int t = find_track(off, n_tracks, rl);
+        const bool last = (rl + 1 == off[t + 1]);
+        const int v = track_vid[t];
+        const float w = wh[2 * v], h = wh[2 * v + 1];
+        float4 a = boxes[rl];
+        float4 b = last ? a : boxes[rl + 1];
+        a.x = a.x / w; a.z = a.z / w; a.y = a.y / h; a.w = a.w / h;
+        b.x = b.x / w; b.z = b.z / w; b.y = b.y / h; b.w = b.w / h;
+        const float cx = (a.z + a.x) / 2, cy = (a.w + a.y) / 2, bw = a.z - a.x, bh = a.w - a.y;
+        const float cx2 = (b.z + b.x) / 2, cy2 = (b.w + b.y) / 2, bw2 = b.z - b.x, bh2 = b.w - b.y;
+        f[0] = cx; f[1] = last ? 0.f : cx2 - cx;
+        f[2] = cy; f[3] = last ? 0.f : cy2 - cy;
+        f[4] = bw; f[5] = last ? 0.f : bw2 - bw;
+        f[6] = bh; f[7] = last ? 0.f : bh2 - bh;
+      }
+      const int nr = (int)min((int64_t)32, n_rows - r0);
+      for (int j = 0; j < nr; ++j) {
+        float4 acc = bias4;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) {
+          const float fk = __shfl_sync(0xffffffffu, f[k], j);
+          acc.x = fmaf(fk, wr[k].x, acc.x); acc.y = fmaf(fk, wr[k].y, acc.y); acc.z = fmaf(fk, wr[k].z, acc.z); acc.w = fmaf(fk, wr[k].w, acc.w);
+        }
+        if (!on) continue;
+        const int64_t r = r0 + j;
+        if (out16) {
+          const __nv_bfloat162 p0 = __floats2bfloat162_rn(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f)), p1 = __floats2bfloat162_rn(fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+          *reinterpret_cast<uint2*>(out16 + r * (int64_t)ldo + c) = make_uint2(*reinterpret_cast<const uint32_t*>(&p0), *reinterpret_cast<const uint32_t*>(&p1));
+        } else {
+          *reinterpret_cast<float4*>(out + r * (int64_t)ldo + c) = make_float4(fmaxf(acc.x, 0.f), fmaxf(acc.y, 0.f), fmaxf(acc.z, 0.f), fmaxf(acc.w, 0.f));
+        }
+      }
+    }
+    return;
+  }
   for (int64_t r = warp; r < n_rows; r += n_warps) {
     const int t = find_track(off, n_tracks, r);
     const bool last = (r + 1 == off[t + 1]);
