@@ -158,6 +158,36 @@ stretched_mean_kernel(const TF* __restrict__ feat, int ldf, int col0, int width,
   const int64_t r0 = off[t];
   const int L = (int)(off[t + 1] - r0);
   const Stretch st(L, tmax[t]);
+  if constexpr (sizeof(TF) == 4) {
+    // fp32 rows: 4 channels per thread (16-byte loads), 4 rows in flight per thread -- the scalar loop below keeps one 4-byte load per
+    // thread in flight (measured 0.36 ms for 1.6 GB: ~2/3 of the HBM rate).  Same accumulation order per channel (rows in sequence).
+    const float* base = reinterpret_cast<const float*>(feat) + r0 * (int64_t)ldf + col0;
+    if ((width & 3) == 0 && (ldf & 3) == 0 && (ldo & 3) == 0 && ((reinterpret_cast<uintptr_t>(base) & 15) == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0)) {
+      const float inv_den = (float)tmax[t];
+      for (int c4 = threadIdx.x; c4 < width / 4; c4 += blockDim.x) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        const float* p = base + 4 * c4;
+        int i = 0;
+        for (; i + 4 <= L; i += 4) {
+          float4 x[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) x[u] = ldg_stream(reinterpret_cast<const float4*>(p + (int64_t)(i + u) * ldf));
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const float w = (float)st.reps(i + u);
+            acc.x = fmaf(w, x[u].x, acc.x); acc.y = fmaf(w, x[u].y, acc.y); acc.z = fmaf(w, x[u].z, acc.z); acc.w = fmaf(w, x[u].w, acc.w);
+          }
+        }
+        for (; i < L; ++i) {
+          const float4 x = ldg_stream(reinterpret_cast<const float4*>(p + (int64_t)i * ldf));
+          const float w = (float)st.reps(i);
+          acc.x = fmaf(w, x.x, acc.x); acc.y = fmaf(w, x.y, acc.y); acc.z = fmaf(w, x.z, acc.z); acc.w = fmaf(w, x.w, acc.w);
+        }
+        *reinterpret_cast<float4*>(out + (int64_t)t * ldo + 4 * c4) = make_float4(acc.x / inv_den, acc.y / inv_den, acc.z / inv_den, acc.w / inv_den);
+      }
+      return;
+    }
+  }
   for (int c = threadIdx.x; c < width; c += blockDim.x) {
     float acc = 0.f;
     const TF* p = feat + r0 * (int64_t)ldf + col0 + c;
