@@ -781,16 +781,39 @@ gemm_tc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const int p = seq_p[i], q = seq_q[i];
               x = bq;
               const uint8_t* raw = st + CF::OFF_RAW;
+              const int hk = k >> 1;
+              if ((k == 7 || k == 3) && p >= hk && q >= hk) {
+                // interior row (all taps inside its sequence: > 98 % of the rows): no per-tap range predicates -- the predicated loop below
+                // made the split warps' instruction stream the limit of this kernel (round-2 ncu: IPC 2.2, issue slots 55 % busy, no hot spot)
+                if (k == 7) {
 #pragma unroll
-              for (int j = 0; j < 7; ++j) {
-                const int d = j - k / 2;
-                if (j >= k || d < -p || d > q) continue;
-                const int rr = r + 3 + d;
-                const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
-                x.x = fmaf(wq[0][j], xin.x, x.x);
-                x.y = fmaf(wq[1][j], xin.y, x.y);
-                x.z = fmaf(wq[2][j], xin.z, x.z);
-                x.w = fmaf(wq[3][j], xin.w, x.w);
+                  for (int j = 0; j < 7; ++j) {
+                    const int rr = r + j;
+                    const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
+                    x.x = fmaf(wq[0][j], xin.x, x.x); x.y = fmaf(wq[1][j], xin.y, x.y);
+                    x.z = fmaf(wq[2][j], xin.z, x.z); x.w = fmaf(wq[3][j], xin.w, x.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int j = 0; j < 3; ++j) {
+                    const int rr = r + 2 + j;
+                    const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
+                    x.x = fmaf(wq[0][j], xin.x, x.x); x.y = fmaf(wq[1][j], xin.y, x.y);
+                    x.z = fmaf(wq[2][j], xin.z, x.z); x.w = fmaf(wq[3][j], xin.w, x.w);
+                  }
+                }
+              } else {
+#pragma unroll
+                for (int j = 0; j < 7; ++j) {
+                  const int d = j - hk;
+                  if (j >= k || d < -p || d > q) continue;
+                  const int rr = r + 3 + d;
+                  const float4 xin = *reinterpret_cast<const float4*>(raw + rr * 64 + ((l ^ ((rr >> 1) & 3)) << 4));
+                  x.x = fmaf(wq[0][j], xin.x, x.x);
+                  x.y = fmaf(wq[1][j], xin.y, x.y);
+                  x.z = fmaf(wq[2][j], xin.z, x.z);
+                  x.w = fmaf(wq[3][j], xin.w, x.w);
+                }
               }
             }
             if (MODE == 3) reinterpret_cast<float4*>(st)[idx] = x;       // MODE 5: no MMA reads the fp32 tile
