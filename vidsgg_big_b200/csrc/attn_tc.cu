@@ -305,6 +305,9 @@ __device__ __forceinline__ void split_f16(const float4 x, uint2& hi, uint2& lo) 
 // 256 threads: warp w owns TMEM lane quadrant w & 3 (query rows 32 (w & 3) ..) and column half w >> 2 of S / P / O -- two threads per
 // query row, which halves the exponential / conversion chain of a block (the kernel is bound by that chain and by the MMA round trips,
 // not by the tensor pipe); the halves exchange their block maxima through shared memory.
+// FULLK: every sequence length is a multiple of 64 keys (the decoder: Q = 192), so no key is ever masked -- the per-element `col < valid`
+// selects, the per-load `key < T` predicates and the variable MMA shapes drop out of the instruction stream (the kernel is instruction-bound).
+template <bool FULLK>
 __global__ void __launch_bounds__(256, 2)
 mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ K, int ldk, const float* __restrict__ V, int ldv,
                 const int64_t* __restrict__ seg_off, int fixed_len, const int32_t* __restrict__ blk_seg, const int32_t* __restrict__ blk_q0,
@@ -364,7 +367,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
     for (int it = 0; it < 4; ++it) {
       const int idx = it * 256 + tid, r = idx >> 4, c4 = idx & 15;
       x[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (k0 + r < T) x[it] = *reinterpret_cast<const float4*>(K + (r0 + k0 + r) * (int64_t)ldk + col0 + 4 * c4);
+      if (FULLK || k0 + r < T) x[it] = *reinterpret_cast<const float4*>(K + (r0 + k0 + r) * (int64_t)ldk + col0 + 4 * c4);
     }
   };
   auto load_v = [&](int k0, float4 (&x)[4]) {
@@ -374,7 +377,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
 #pragma unroll
       for (int e = 0; e < 2; ++e) {
         x[2 * it + e] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (k0 + 2 * lane + e < T) x[2 * it + e] = *reinterpret_cast<const float4*>(V + (r0 + k0 + 2 * lane + e) * (int64_t)ldv + col0 + 4 * c4);
+        if (FULLK || k0 + 2 * lane + e < T) x[2 * it + e] = *reinterpret_cast<const float4*>(V + (r0 + k0 + 2 * lane + e) * (int64_t)ldv + col0 + 4 * c4);
       }
     }
   };
@@ -431,7 +434,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   load_k(0, kreg);
   load_v(0, vreg);
   for (int b = 0; b < n_blocks; ++b) {
-    const int k0 = b * A6_KC, valid = min(A6_KC, T - k0), n_s = (valid + 15) & ~15;
+    const int k0 = b * A6_KC, valid = FULLK ? A6_KC : min(A6_KC, T - k0), n_s = FULLK ? A6_KC : ((valid + 15) & ~15);
     store_k(kreg);
     store_v(vreg);
     fence_proxy_async();
@@ -450,7 +453,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
       tmem_ld_wait();
 #pragma unroll
       for (int j = 0; j < 32; ++j)
-        if (half * 32 + j < valid) bm = fmaxf(bm, __uint_as_float(sr[j]));
+        if (FULLK || half * 32 + j < valid) bm = fmaxf(bm, __uint_as_float(sr[j]));
     }
     xch[half][row] = bm;
     __syncthreads();
@@ -476,7 +479,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
         float pv[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-          pv[e] = (half * 32 + cc * 8 + e < valid) ? exp2f(fmaf(__uint_as_float(sr[cc * 8 + e]), scale_log2e, -mscaled)) : 0.f;
+          pv[e] = (FULLK || half * 32 + cc * 8 + e < valid) ? exp2f(fmaf(__uint_as_float(sr[cc * 8 + e]), scale_log2e, -mscaled)) : 0.f;
           l += pv[e];
         }
         uint2 h0, l0, h1, l1;
@@ -496,9 +499,10 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
       const uint32_t idesc = (1u << 4) | ((uint32_t)(A6_DH >> 3) << 17) | ((uint32_t)(AT_BM >> 4) << 24);
       const uint64_t pH = make_smem_desc<32>(sbase + A6_PH), pL = make_smem_desc<32>(sbase + A6_PL);
       const uint64_t vH = make_smem_desc<32>(sbase + A6_VH), vL = make_smem_desc<32>(sbase + A6_VL);
-      const int ksteps = n_s >> 4;
+      const int ksteps = FULLK ? 4 : (n_s >> 4);
       uint32_t acc = b ? 1u : 0u;
-      for (int ks = 0; ks < ksteps; ++ks) {
+#pragma unroll
+      for (int ks = 0; ks < (FULLK ? 4 : ksteps); ++ks) {
         if (split) {
           umma_bf16(tmem + A6_KC, pL + 2 * ks, vH + 2 * ks, idesc, acc); acc = 1;
           umma_bf16(tmem + A6_KC, pH + 2 * ks, vL + 2 * ks, idesc, 1u);
@@ -594,14 +598,19 @@ extern "C" int vsg_mha_tc64(const float* Q, int ldq, const float* K, int ldk, co
   const int dev_ = current_device();
   constexpr int SMEM = A6_SMEM + 1024;
   if (!attr_done.is_set(dev_)) {
-    if (cudaFuncSetAttribute(mha64_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
+    if (cudaFuncSetAttribute(mha64_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess ||
+        cudaFuncSetAttribute(mha64_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM) != cudaSuccess) {
       set_error("vsg_mha_tc64: cannot raise dynamic shared memory to %d", SMEM);
       return VSG_E_LAUNCH;
     }
     attr_done.set(dev_);
   }
   const float scale_log2e = 1.4426950408889634f / 8.0f;            // 1 / sqrt(64) * log2(e)
-  mha64_tc_kernel<<<dim3((unsigned)blocks, n_head), 256, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, blk_seg, blk_q0,
-                                                                                       scale_log2e, products, O, ldo);
+  if (!seg_off && fixed_len % A6_KC == 0)
+    mha64_tc_kernel<true><<<dim3((unsigned)blocks, n_head), 256, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, blk_seg, blk_q0,
+                                                                                               scale_log2e, products, O, ldo);
+  else
+    mha64_tc_kernel<false><<<dim3((unsigned)blocks, n_head), 256, SMEM, (cudaStream_t)stream>>>(Q, ldq, K, ldk, V, ldv, seg_off, fixed_len, blk_seg, blk_q0,
+                                                                                                scale_log2e, products, O, ldo);
   return check_launch("vsg_mha_tc64");
 }
