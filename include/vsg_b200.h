@@ -330,8 +330,9 @@ int vsg_mha_tc16(const float* Q, int ldq, const float* K, int ldk, const float* 
 /* Same for 64-wide heads, with fp16 hi / lo operand pairs on kind::f16 MMAs (products = 3: fp32-class, error <= 3e-6 vs fp64; 1: hi parts
  * only): the BIG-C decoder's self-attention over the num_querys queries of every video (nn.MultiheadAttention(512, 8) of
  * models/model_0v10.py:181-186) as ONE launch instead of two batched GEMMs + softmax + V^T transpose.  seg_off != NULL: ragged sequences
- * with the (sequence, first query) work list of 128-query blocks as for vsg_mha_tc16; seg_off == NULL: n_seg sequences of fixed_len rows
- * back to back (the work list is implicit).  |Q|, |K|, |V| < 65504. */
+ * with the (sequence, first query) work list of 128-query blocks as for vsg_mha_tc16 (entries whose first query is not a multiple of 128 are
+ * skipped, so the 64-query list of vsg_mha can be passed as is); seg_off == NULL: n_seg sequences of fixed_len rows back to back (the work
+ * list is implicit).  |Q|, |K|, |V| < 65504. */
 int vsg_mha_tc64(const float* Q, int ldq, const float* K, int ldk, const float* V, int ldv, const int64_t* seg_off, int n_seg,
                  int fixed_len, int n_head, float* O, int ldo, const int32_t* blk_seg, const int32_t* blk_q0, int n_blk, int products,
                  void* stream);

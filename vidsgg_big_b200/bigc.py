@@ -514,7 +514,14 @@ class BIG_C(object):
         x = enti2enco
         for lw in w["enc"]:
             qkv = gemm(m, x, lw["qkv"])
-            att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks, pk.mha_blocks)
+            if self.attention == "tc" and m != linalg.SIMT and E // self.n_att_head == 64:
+                att = torch.empty(qkv.shape[0], E, dtype=torch.float32, device=dev)       # ragged tracks-per-video sequences on the fused tcgen05 kernel
+                bs, bq, nb = pk.mha_blocks
+                check(L.vsg_mha_tc64(_raw(qkv), 3 * E, C.c_void_p(qkv.data_ptr() + 4 * E), 3 * E, C.c_void_p(qkv.data_ptr() + 8 * E), 3 * E,
+                                     _raw(pk.seg64), V, 0, self.n_att_head, _raw(att), E, _raw(bs), _raw(bq), nb,
+                                     3 if m in linalg.FP32_CLASS else 1, sp), "vsg_mha_tc64")
+            else:
+                att = self._mha(qkv, E, pk.seg64, V, 0, pk.max_tracks, pk.mha_blocks)
             x = self._add_ln(x, gemm(m, att, lw["out"]), lw["n1"])
             x = self._add_ln(x, gemm(m, gemm(m, x, lw["l1"], relu=True), lw["l2"]), lw["n2"])
             if dbg is not None:

@@ -323,6 +323,7 @@ mha64_tc_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ 
   int64_t r0;
   if (seg_off) {                                                   // ragged sequences: work list of (sequence, first query) blocks
     seg = blk_seg[blockIdx.x]; q0 = blk_q0[blockIdx.x];
+    if (q0 & (AT_BM - 1)) return;                                  // entries of a finer (64-query) work list that do not start a 128-query block
     r0 = seg_off[seg]; T = (int)(seg_off[seg + 1] - r0);
   } else {                                                         // sequences of `fixed_len` rows, back to back
     const int per = (fixed_len + AT_BM - 1) / AT_BM;

@@ -186,8 +186,14 @@ int Fwd::run(VsgTripletOut* out, int topk) {
       float* xa = ar.get<float>((int64_t)N * E);      // per-layer outputs (N x E floats each: small next to the R-row buffers)
       float* xb = ar.get<float>((int64_t)N * E);
       gemm(x, E, lw.qkv, qkv, 3 * E, N);
-      FWD_CALL(vsg_mha(qkv, 3 * E, qkv + E, 3 * E, qkv + 2 * E, 3 * E, b->seg64, V, 0, b->max_tracks, H, E / H, att, E, b->mha_blk_seg,
-                       b->mha_blk_q0, b->n_mha_blk, stream));
+      if (w->tc_attention == 1 && mode != VSG_GEMM_SIMT && E / H == 64) {      // ragged tracks-per-video sequences on the fused tcgen05 kernel
+        const int products = (mode == VSG_GEMM_3XTF32 || mode == VSG_GEMM_TF32_BF16X2 || mode == VSG_GEMM_FP16X3) ? 3 : 1;
+        FWD_CALL(vsg_mha_tc64(qkv, 3 * E, qkv + E, 3 * E, qkv + 2 * E, 3 * E, b->seg64, V, 0, H, att, E, b->mha_blk_seg, b->mha_blk_q0, b->n_mha_blk,
+                              products, stream));
+      } else {
+        FWD_CALL(vsg_mha(qkv, 3 * E, qkv + E, 3 * E, qkv + 2 * E, 3 * E, b->seg64, V, 0, b->max_tracks, H, E / H, att, E, b->mha_blk_seg,
+                         b->mha_blk_q0, b->n_mha_blk, stream));
+      }
       gemm(att, E, lw.out, t1, E, N);
       add_ln(x, t1, lw.n1, nullptr, 0, N, E, xa);
       gemm(xa, E, lw.l1, t2, lw.l1.N, N, true);
