@@ -312,3 +312,17 @@ def test_cpulist_parsing_and_numa_binding_is_best_effort():
     assert info["device"] == 0 and isinstance(info["bound"], bool)
     if not info["bound"]:
         assert os.sched_getaffinity(0) == before
+
+
+def test_fp16x3_weight_image_scale():
+    """linalg.fp16_image_scale_log2: max |w| * 2^s in [2^13, 2^14) for every magnitude, exact powers of two included; degenerate weights -> 0."""
+    import math
+    from vidsgg_big_b200 import linalg
+    for wmax in (1.0, 0.5, 0.022, 3.7e-5, 1e-12, 40.0, 8191.9, 8192.0, 16384.0, 65504.0, 2.0 ** -20, 1e20):
+        s = linalg.fp16_image_scale_log2(wmax)
+        assert 2.0 ** 13 <= wmax * 2.0 ** s < 2.0 ** 14, (wmax, s)
+        assert math.isfinite(2.0 ** s) and math.isfinite(2.0 ** -s)
+    assert linalg.fp16_image_scale_log2(0.0) == 0 and linalg.fp16_image_scale_log2(float("nan")) == 0 and linalg.fp16_image_scale_log2(float("inf")) == 0
+    assert linalg.fp16_image_scale_log2(1e-45) == 100          # clamped: 2^100 is still a finite fp32
+    assert set(linalg.FP32_CLASS) == {linalg.X3TF32, linalg.TF32_BF16X2, linalg.FP16X3} and linalg.MODES["fp16x3"] == 5
+    assert linalg.attention_mode(linalg.FP16X3) == linalg.X3TF32 and linalg.attention_mode(linalg.BF16) == linalg.TF32

@@ -825,6 +825,7 @@ role_attention_hid_kernel(const float* __restrict__ p2a, const float* __restrict
   const int v = blockIdx.x, q0 = blockIdx.y * RA2_QB;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int t0 = seg[v], n = seg[v + 1] - t0;
+  if (n > ld_t) __trap();                                          // the caller's max_tracks sized the shared-memory tables: fail loudly, never overrun
   const int hl = lane & 15, role1 = lane >> 4;
   // ---- pass 1: logits of this warp's two queries ----
   // a lane's dims: float4 number j * 16 + hl (j < PER / 4) of its role half -- a quarter-warp then reads 128 contiguous bytes of a staged row

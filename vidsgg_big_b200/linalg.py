@@ -29,6 +29,16 @@ def attention_mode(mode: int) -> int:
     return X3TF32 if mode in (TF32_BF16X2, FP16X3) else mode
 
 
+def fp16_image_scale_log2(wmax: float) -> int:
+    """Exponent s of the power-of-two scale of an fp16x3 weight image: max |w| * 2^s lies in [2^13, 2^14) -- below fp16's 65504 with room for
+    rounding, and high enough that the low part fp16(w 2^s - hi) stays a normal number for |w| >= 2^-16 max |w| (csrc/gemm.cu mode 5).
+    0 for an all-zero / non-finite weight; clamped to +-100 so that 2^s and 2^-s stay finite fp32 values."""
+    import math
+    if not (wmax > 0.0) or not math.isfinite(wmax):
+        return 0
+    return max(-100, min(100, 14 - math.frexp(wmax)[1]))
+
+
 class Weight(object):
     """A [N,K] fp32 weight resident in HBM with its (optional) tf32 hi/lo split."""
 
@@ -45,10 +55,7 @@ class Weight(object):
         self.a_scale = 1.0         # fp16x3: optional power of two applied to the A operand before its fp16 split (csrc/gemm.cu mode 5)
         if split == "fp16":
             # fp16x3 mode: power-of-two scale that puts max |w| into [2^13, 2^14) (exact; undone by alpha in the GEMM epilogue)
-            import math
-            wmax = float(self.w.abs().max()) if self.w.numel() else 0.0
-            s = 13 - math.frexp(wmax)[1] + 1 if wmax > 0 and math.isfinite(wmax) else 0
-            s = max(-100, min(100, s))
+            s = fp16_image_scale_log2(float(self.w.abs().max()) if self.w.numel() else 0.0)
             self.alpha = 2.0 ** (-s)
             self.img16_bn = int(lib().vsg_gemm_tile_n(self.N))
             nbytes = int(lib().vsg_weight_image_fp16_bytes(self.N, self.K, self.img16_bn))
