@@ -57,7 +57,7 @@ def parse():
     ap.add_argument("--vidor-videos", type=int, default=835, help="size of the VidOR-val-shaped set of the 'vidor' leg (0: skip the leg)")
     ap.add_argument("--vidor-passes", type=int, default=2, help="timed passes over the VidOR set")
     ap.add_argument("--chunk-rows", type=int, default=2_500_000, help="feature rows per resident chunk of the VidOR set")
-    ap.add_argument("--no-graph", action="store_true", help="issue the BIG-C forward's ~150 launches from Python every step instead of "
+    ap.add_argument("--no-graph", action="store_true", help="issue the BIG-C forward's ~115 launches from Python every step instead of "
                     "replaying the CUDA graph captured for the resident batch")
     ap.add_argument("--modes", default="fp16x3,bf16", help="comma list of extra precisions timed on the top-level workload next to --precision, with their decision-flip report "
                     "('' = none)")

@@ -453,7 +453,7 @@ typedef struct VsgTripletOut {   /* video v owns rows [v*cap, v*cap + counts[v][
 
 /* Bytes of workspace vsg_bigc_forward needs for this batch / mode (256-byte aligned carve-up, peak over the forward). */
 int64_t vsg_bigc_workspace_bytes(const VsgBigCWeights* w, const VsgVideoBatch* b, int topk, int precision_mode);
-/* precision_mode = a VSG_GEMM_* mode.  workspace: device memory, 256-byte aligned.  Enqueues ~150 launches on `stream`; no sync. */
+/* precision_mode = a VSG_GEMM_* mode.  workspace: device memory, 256-byte aligned.  Enqueues ~115 launches on `stream`; no sync. */
 int vsg_bigc_forward(const VsgBigCWeights* w, const VsgVideoBatch* b, VsgTripletOut* out, int topk, int precision_mode,
                      void* workspace, int64_t workspace_bytes, void* stream);
 

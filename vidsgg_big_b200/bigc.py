@@ -700,7 +700,7 @@ class BIG_C(object):
     def forward_packed(self, proposal_list, topk=None, packed_videos=None, sync=True, graph=False):
         """Same computation as ``forward`` for a batch of non-empty videos, but the result stays packed on the device
         (``PackedTriplets``): no per-video slicing -- the fast path into ``evalapi.PackedRelations``.
-        ``graph=True`` (needs ``packed_videos``): the ~150 launches of the forward are captured ONCE per packed batch into a CUDA graph
+        ``graph=True`` (needs ``packed_videos``): the ~115 launches of the forward are captured ONCE per packed batch into a CUDA graph
         and replayed on later calls -- same kernels, same buffers, one launch call instead of ~150 Python-issued ones (the decoder's
         launches are shorter than the time Python needs to issue them).  The batch's input buffers must stay at their addresses."""
         if self._w is None:
