@@ -639,7 +639,12 @@ def instrumented_step(pipe, props, graphs, precision, ms_step):
                                               {"grounding_stage_ms": grd_ms, "grounding_stage_useful_flops": timers["grd_flops"],
                                                "grounding_stage_tflops": timers["grd_flops"] / (grd_ms * 1e-3) / 1e12 if grd_ms > 0 else 0.0,
                                                "queries": timers["n_queries"],
-                                               "note": "N = K = 128 GEMMs: 64 flop/B unfused, i.e. HBM-bound (SURVEY 8d K6); stage flops = flops_grd formula"})
+                                               "hbm_model": (lambda b: {"algorithmic_bytes": int(b), "achieved": b / (ms * 1e-3) / 1e9 if ms > 0 else 0.0,
+                                                                        "peak": hbm_peak, "unit": "GB/s", "frac": b / (ms * 1e-3) / 1e9 / hbm_peak if ms > 0 else 0.0,
+                                                                        "note": "the bound that applies: compulsory bytes of these launches (A + C + residual, "
+                                                                                "fp32) / their time against the measured HBM copy rate"})(P.summary_bytes("gemm", "grounding")),
+                                               "note": "N = K = 128 GEMMs: 64 flop/B unfused, i.e. HBM-bound (SURVEY 8d K6), so `frac` against the TENSOR peak is "
+                                                       "small by construction -- see hbm_model; stage flops = flops_grd formula"})
         n, fl, ms = P.summary("mha", "grounding")
         out["k6_grounding_attention"] = tensor_leg("grounding mh_attn (8 heads x 16)", n, fl, ms)
     return out

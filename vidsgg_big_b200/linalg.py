@@ -136,6 +136,11 @@ class _Profile(object):
         return out
 
     @classmethod
+    def summary_bytes(cls, kind="gemm", stage=None):
+        """Sum of the compulsory-HBM-bytes field of the records that carry one (plain fp32 GEMM launches)."""
+        return sum(r[6] for r in cls.records if r[3] == kind and (stage is None or r[4] == stage) and len(r) > 6)
+
+    @classmethod
     def summary(cls, kind="gemm", stage=None):
         sel = [r for r in cls.records if r[3] == kind and (stage is None or r[4] == stage)]
         return len(sel), sum(r[2] for r in sel), sum(r[0].elapsed_time(r[1]) for r in sel)
@@ -229,7 +234,9 @@ def gemm(mode: int, A: torch.Tensor, W: Weight, out: Optional[torch.Tensor] = No
                              _raw(out), ldc, stream_ptr(A.device)), "vsg_gemm")
     if _Profile.enabled:
         ev1.record()
-        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage, (M, W.N, K)))
+        # 7th field: compulsory HBM bytes of the launch (A + C (+ residual), fp32; W is L2-resident) for the HBM-model view of narrow GEMMs
+        _Profile.records.append((ev0, ev1, 2.0 * M * W.N * K, "gemm", _Profile.stage, (M, W.N, K),
+                                 4.0 * M * (K + W.N * (2 if residual is not None else 1))))
     return out
 
 
